@@ -1,0 +1,335 @@
+"""`AIMNet2Calculator` — drop-in for the reference's calculator facade on the E / F / charges / stress path
+(aimnet/calculators/calculator.py:130-165, 377-515, 638-783, 879-947), backed by the sm_100a engine through the C ABI.
+
+Same constructor signature, `keys_in` / `keys_in_optional` / `keys_out`, input conventions (flat `(N,3)` + `mol_idx`, or
+dense `(B,N,3)` with `numbers == 0` padding; numpy / lists / tensors accepted), output dtypes/shapes (energy `(B,)` f64,
+charges / forces in the input's atom layout, stress `(3,3)` or `(B,3,3)`), errors and warnings (PBC auto-switch
+simple -> DSF scoped to one eval, Ewald without a cell, unsupported species).  Out of this path's scope and rejected
+loudly: Hessians, training mode, torch.compile.
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+from types import MappingProxyType
+from typing import Any, ClassVar, Mapping
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from .engine import Engine
+from .model_spec import ModelSpec
+
+
+def _load_model_source(model) -> tuple[dict, dict | None, int]:
+    """Return (state_dict, metadata, num_charge_channels) from the accepted model sources."""
+    if isinstance(model, tuple) and len(model) == 2 and isinstance(model[1], ModelSpec):
+        sd, spec = model
+        return dict(sd), spec.metadata(), spec.num_charge_channels
+    if isinstance(model, nn.Module):
+        meta = getattr(model, "metadata", None)
+        if meta is None or callable(meta):
+            meta = getattr(model, "_metadata", None)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        return sd, (dict(meta) if meta is not None else None), int(getattr(model, "num_charge_channels", 1))
+    if isinstance(model, str):
+        path = model
+        if not os.path.isfile(path):
+            cache = os.environ.get("AIMNET_CACHE_DIR", os.path.expanduser("~/.cache/aimnet"))
+            for cand in (os.path.join(cache, model), os.path.join(cache, model + ".pt")):
+                if os.path.isfile(cand):
+                    path = cand
+                    break
+            else:
+                raise FileNotFoundError(
+                    f"model '{model}' is neither a file nor present in {cache}; registry / Hugging Face downloads are "
+                    "outside this engine's scope (SURVEY.md §2 row 13) — pass a v2 .pt path, a (state_dict, ModelSpec) "
+                    "pair or an nn.Module")
+        model = torch.load(path, map_location="cpu", weights_only=True)
+    if isinstance(model, Mapping):
+        if "state_dict" not in model:
+            raise TypeError("model mapping must be a v2 artifact with a 'state_dict' entry (docs/model_format.md)")
+        meta = {k: v for k, v in model.items() if k not in ("state_dict", "model_yaml")}
+        C = 1
+        yml = model.get("model_yaml")
+        if isinstance(yml, str):
+            import yaml
+
+            yml = yaml.safe_load(yml)
+        if isinstance(yml, Mapping):
+            C = int(yml.get("kwargs", {}).get("num_charge_channels", 1))
+        elif "conv_q.agh" in model["state_dict"]:
+            C = int(model["state_dict"]["conv_q.agh"].shape[0])
+        return dict(model["state_dict"]), meta, C
+    raise TypeError("Invalid model type/name.")
+
+
+class AIMNet2Calculator:
+    keys_in: ClassVar[dict[str, torch.dtype]] = {"coord": torch.float, "numbers": torch.int, "charge": torch.float}
+    keys_in_optional: ClassVar[dict[str, torch.dtype]] = {
+        "mult": torch.float, "mol_idx": torch.int, "nbmat": torch.int, "nbmat_lr": torch.int,
+        "nb_pad_mask": torch.bool, "nb_pad_mask_lr": torch.bool, "shifts": torch.float, "shifts_lr": torch.float,
+        "cell": torch.float, "pbc": torch.bool,
+    }
+    keys_out: ClassVar[list[str]] = ["energy", "charges", "spin_charges", "forces", "hessian", "stress"]
+    atom_feature_keys: ClassVar[list[str]] = ["coord", "numbers", "charges", "spin_charges", "forces"]
+
+    def __init__(self, model: Any = "aimnet2", nb_threshold: int = 120, needs_coulomb: bool | None = None,
+                 needs_dispersion: bool | None = None, device: str | None = None, compile_model: bool = False,
+                 compile_kwargs: dict | None = None, cache_static: bool = False, train: bool = False,
+                 deterministic: bool = False, ensemble_member: int = 0, revision: str | None = None,
+                 token: str | None = None, *, model_import_paths=None, model_import_mode: str = "extend"):
+        if device is None:
+            device = "cuda"
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("aimnetcentral_b200.AIMNet2Calculator needs a CUDA device: the hot path is hand-written "
+                               "sm_100a kernels with no CPU fallback")
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available")
+        if train:
+            raise NotImplementedError("training mode is outside the inference engine's scope (SURVEY.md §2 row 18)")
+        if compile_model:
+            warnings.warn("compile_model is ignored: the engine does not use torch.compile", stacklevel=2)
+        self.device = str(torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device()))
+        sd, metadata, C = _load_model_source(model)
+        self._metadata = metadata
+        self._num_charge_channels = C
+        self.cutoff = float(metadata.get("cutoff", 5.0)) if metadata else 5.0
+        final_needs_coulomb = needs_coulomb if needs_coulomb is not None else bool(metadata and metadata.get("needs_coulomb", False))
+        final_needs_dispersion = needs_dispersion if needs_dispersion is not None else bool(metadata and metadata.get("needs_dispersion", False))
+        sr_embedded = bool(metadata) and metadata.get("coulomb_mode") == "sr_embedded"
+        if not sr_embedded and "outputs.srcoulomb.rc" not in sd and metadata is not None and metadata.get("coulomb_mode") not in (None, "sr_embedded"):
+            raise NotImplementedError("only v2 models with embedded SRCoulomb (coulomb_mode='sr_embedded') are supported")
+        sr_rc = (metadata or {}).get("coulomb_sr_rc") or 4.6
+        sr_env = (metadata or {}).get("coulomb_sr_envelope") or "exp"
+        self._d3_params = None
+        if final_needs_dispersion:
+            self._d3_params = (metadata or {}).get("d3_params")
+            if self._d3_params is None:
+                raise ValueError("needs_dispersion=True but d3_params not found in metadata. "
+                                 "Provide d3_params in model metadata or set needs_dispersion=False.")
+        self._has_coulomb = bool(final_needs_coulomb)
+        self._has_dftd3 = bool(final_needs_dispersion)
+        self.nb_threshold = nb_threshold
+        self.cache_static = bool(cache_static)
+        self._deterministic = bool(deterministic)
+        self._coulomb_method: str | None = "simple" if self._has_coulomb else None
+        self._dsf_alpha, self._dsf_rc, self._ewald_accuracy = 0.2, 15.0, 1e-6
+        self._default_dsf_cutoff = 15.0
+        self._default_dftd3_cutoff = 15.0
+        self._default_dftd3_smoothing = 0.2
+        self._coulomb_cutoff: float | None = float("inf") if self._has_coulomb else None
+        self._dftd3_cutoff = self._default_dftd3_cutoff
+        self._dftd3_smoothing = self._default_dftd3_smoothing
+        self.cutoff_lr = float("inf") if self._has_coulomb else (self._dftd3_cutoff if self._has_dftd3 else None)
+        self._mult_ignored_checked = False
+        self._batch: int | None = None
+        self.engine = Engine(sd, C, self.device, sr_rc=float(sr_rc), sr_envelope=sr_env, load_d3=self._has_dftd3)
+        self._push_options()
+
+    # ---- properties (calculator.py:380-515) ------------------------------------------------------------------
+    @property
+    def metadata(self):
+        return MappingProxyType(self._metadata) if self._metadata is not None else None
+
+    @property
+    def is_nse(self) -> bool:
+        return self._num_charge_channels == 2
+
+    @property
+    def has_external_coulomb(self) -> bool:
+        return self._has_coulomb
+
+    @property
+    def has_external_dftd3(self) -> bool:
+        return self._has_dftd3
+
+    @property
+    def coulomb_method(self) -> str | None:
+        return self._coulomb_method if self._has_coulomb else None
+
+    @property
+    def coulomb_cutoff(self) -> float | None:
+        return self._coulomb_cutoff
+
+    @property
+    def dftd3_cutoff(self) -> float:
+        return self._dftd3_cutoff
+
+    # ---- LR configuration (calculator.py:638-783) ------------------------------------------------------------
+    def _push_options(self, coulomb_override: str | None = None):
+        method = coulomb_override or self._coulomb_method
+        d3 = self._d3_params or {}
+        self.engine.set_options(
+            coulomb_method=method if self._has_coulomb else None, dsf_alpha=float(self._dsf_alpha),
+            dsf_rc=float(self._dsf_rc), ewald_accuracy=float(self._ewald_accuracy), dispersion=self._has_dftd3,
+            d3_s6=float(d3.get("s6", 1.0)), d3_s8=float(d3.get("s8", 0.0)), d3_a1=float(d3.get("a1", 0.0)),
+            d3_a2=float(d3.get("a2", 0.0)), d3_cutoff=float(self._dftd3_cutoff), d3_smoothing=float(self._dftd3_smoothing),
+            sr_cutoff=float(self.cutoff))
+
+    def set_lrcoulomb_method(self, method: str, cutoff: float = 15.0, dsf_alpha: float = 0.2, ewald_accuracy: float = 1e-6):
+        if method not in ("simple", "dsf", "ewald", "pme"):
+            raise ValueError(f"Invalid method: {method}")
+        if method == "pme":
+            raise NotImplementedError("PME is outside the configured hot path (SURVEY.md §2 row 9)")
+        if not self._has_coulomb:
+            return
+        self._coulomb_method = method
+        if method == "dsf":
+            self._dsf_alpha, self._dsf_rc = dsf_alpha, cutoff
+            self._coulomb_cutoff = cutoff
+        elif method == "simple":
+            self._coulomb_cutoff = float("inf")
+        else:
+            self._ewald_accuracy = ewald_accuracy
+            self._coulomb_cutoff = None
+        self.cutoff_lr = self._coulomb_cutoff if self._coulomb_cutoff is not None else (
+            self._dftd3_cutoff if self._has_dftd3 else None)
+        self._push_options()
+
+    def set_lr_cutoff(self, cutoff: float) -> None:
+        if self._coulomb_method not in ("ewald", "pme"):
+            self._coulomb_cutoff = cutoff
+            if self._coulomb_method == "dsf":
+                self._dsf_rc = cutoff
+        self._dftd3_cutoff = cutoff
+        self.cutoff_lr = cutoff
+        self._push_options()
+
+    def set_dftd3_cutoff(self, cutoff: float | None = None, smoothing_fraction: float | None = None) -> None:
+        self._dftd3_cutoff = self._default_dftd3_cutoff if cutoff is None else cutoff
+        self._dftd3_smoothing = self._default_dftd3_smoothing if smoothing_fraction is None else smoothing_fraction
+        self._push_options()
+
+    # ---- validation (calculator.py:785-851) ------------------------------------------------------------------
+    def _validate_species_and_charge(self, data: dict) -> None:
+        if "numbers" not in data:
+            return
+        impl = (self._metadata or {}).get("implemented_species") or []
+        if impl:
+            seen = {int(z) for z in torch.as_tensor(data["numbers"]).flatten().tolist() if int(z) > 0}
+            unsupported = sorted(seen - set(int(z) for z in impl))
+            if unsupported:
+                raise ValueError(f"Atomic numbers {unsupported} are not in this model's implemented_species "
+                                 f"{sorted(impl)}. Pass validate_species=False to bypass.")
+        if (self._metadata or {}).get("supports_charged_systems") is False:
+            charge_t = torch.as_tensor(data.get("charge", 0.0))
+            if charge_t.numel() > 0 and float(charge_t.abs().max().item()) > 1e-6:
+                raise ValueError("This model does not support net-charged systems. Pass validate_species=False to bypass.")
+
+    def _maybe_warn_mult_ignored(self, data: dict) -> None:
+        if self._mult_ignored_checked or self.is_nse or data.get("mult") is None:
+            return
+        self._mult_ignored_checked = True
+        mult_t = torch.as_tensor(data["mult"]).detach().cpu()
+        if bool((mult_t != 1).any()):
+            warnings.warn(f"Input mult={mult_t.flatten().tolist()} is ignored: this model is closed-shell "
+                          "(num_charge_channels=1). For radicals/open-shell systems use an NSE model.",
+                          UserWarning, stacklevel=3)
+
+    # ---- evaluation ------------------------------------------------------------------------------------------
+    def __call__(self, *args, **kwargs) -> dict[str, Any]:
+        return self.eval(*args, **kwargs)
+
+    def to_input_tensors(self, data: dict) -> dict[str, Tensor]:
+        """calculator.py:1452-1473."""
+        ret = {}
+        for k, dt in self.keys_in.items():
+            if k not in data:
+                raise KeyError(f"Missing key {k} in the input data")
+            ret[k] = torch.as_tensor(data[k], device=self.device, dtype=dt).detach()
+        for k, dt in self.keys_in_optional.items():
+            if k in data and data[k] is not None:
+                if k == "shifts":
+                    dt = torch.int  # kernels take the integer lattice shifts the neighbor builder produces
+                ret[k] = torch.as_tensor(data[k], device=self.device, dtype=dt).detach()
+        for k, v in ret.items():
+            if v.ndim == 0:
+                ret[k] = v.unsqueeze(0)
+        return ret
+
+    def eval(self, data: dict, forces=False, stress=False, hessian=False, *, validate_species: bool = True) -> dict:
+        if validate_species:
+            self._validate_species_and_charge(data)
+        self._maybe_warn_mult_ignored(data)
+        if hessian:
+            raise NotImplementedError("Hessians are outside this engine's hot path (SURVEY.md §8f f4)")
+        d = self.to_input_tensors(data)
+        coord, numbers, charge = d["coord"], d["numbers"], d["charge"]
+        cell = d.get("cell")
+        method = self._coulomb_method
+        if cell is not None and method == "simple":
+            warnings.warn("Switching to DSF Coulomb for PBC for this evaluation; call set_lrcoulomb_method() to select "
+                          "a periodic method persistently.", stacklevel=2)
+            method = "dsf"  # scoped to this evaluation (calculator.py:1044-1062, 939-947)
+        if method in ("ewald", "pme") and cell is None:
+            raise ValueError(f"Coulomb method '{method}' requires a periodic 'cell' in the input data. Provide a (3,3) "
+                             "or (B,3,3) cell tensor, or switch to a non-periodic method via "
+                             "set_lrcoulomb_method('simple' | 'dsf').")
+        if method == "ewald":
+            raise NotImplementedError("Ewald Coulomb is not available in this build of the engine")
+        if stress and cell is None:
+            raise AssertionError("Stress calculation requires cell")
+        # ---- flatten (mol_flatten, calculator.py:1475-1511): the engine always runs the sparse layout ----
+        batch_shape = None
+        keep = None
+        mult = d.get("mult")
+        if coord.ndim == 3:
+            Bn, Nn = coord.shape[:2]
+            batch_shape = (Bn, Nn)
+            numbers2 = numbers.reshape(Bn, Nn)
+            real = numbers2 > 0
+            mol_idx = torch.arange(Bn, device=self.device, dtype=torch.int32).unsqueeze(1).expand(Bn, Nn)
+            if bool(real.all()):
+                coord_f, numbers_f, mol_f = coord.reshape(-1, 3), numbers2.reshape(-1), mol_idx.reshape(-1)
+            else:
+                keep = real.reshape(-1).nonzero().squeeze(1)
+                coord_f = coord.reshape(-1, 3).index_select(0, keep)
+                numbers_f = numbers2.reshape(-1).index_select(0, keep)
+                mol_f = mol_idx.reshape(-1).index_select(0, keep)
+            if charge.shape[0] != Bn:
+                charge = charge.expand(Bn)
+        else:
+            coord_f, numbers_f = coord, numbers
+            mol_f = d.get("mol_idx")
+            if mol_f is None and charge.shape[0] != 1:
+                raise ValueError("mol_idx is required when charge has more than one entry")
+        coord_f = coord_f.contiguous()
+        numbers_f = numbers_f.to(torch.int32).contiguous()
+        mol_f = None if mol_f is None else mol_f.to(torch.int32).contiguous()
+        charge = charge.to(torch.float32).contiguous()
+        if self.is_nse:
+            if mult is None:
+                raise ValueError("mult key is required for NSE if two channels for charge are not provided")
+            mult = mult.to(torch.float32).expand(charge.shape[0]).contiguous()
+        else:
+            mult = None
+        if cell is not None:
+            cell = cell.to(torch.float32).contiguous()
+        nbmat, shifts = d.get("nbmat"), d.get("shifts")
+        if nbmat is not None:
+            nbmat = nbmat.to(torch.int32).contiguous()
+            shifts = None if shifts is None else shifts.to(torch.int32).contiguous()
+        if method != self._coulomb_method:
+            self._push_options(coulomb_override=method)
+        try:
+            out = self.engine.eval(coord_f, numbers_f, charge, mol_idx=mol_f, mult=mult, cell=cell, pbc=d.get("pbc"),
+                                   nbmat=nbmat, shifts=shifts, forces=bool(forces), stress=bool(stress))
+        finally:
+            if method != self._coulomb_method:
+                self._push_options()
+        # ---- un-flatten (process_output, calculator.py:1240-1245) ----
+        if batch_shape is not None:
+            Bn, Nn = batch_shape
+            for k in ("charges", "spin_charges", "forces"):
+                if k in out:
+                    v = out[k]
+                    if keep is not None:
+                        full = torch.zeros((Bn * Nn, *v.shape[1:]), dtype=v.dtype, device=v.device)
+                        full.index_copy_(0, keep, v)
+                        v = full
+                    out[k] = v.view(Bn, Nn, *v.shape[1:])
+        return {k: v for k, v in out.items() if k in self.keys_out}

@@ -1,0 +1,132 @@
+// Shared helpers for the AIMNet2 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/aimnet2_b200.h"
+
+namespace aimnet {
+
+constexpr int kA = 16;   // nfeature        (aimnet/models/aimnet2.yaml)
+constexpr int kG = 16;   // nshifts_s
+constexpr int kH = 12;   // ncomb_v
+constexpr int kAG = kA * kG;       // 256
+constexpr int kAH = kA * kH;       // 192
+constexpr int kTA = kA * kH * 3;   // 576  saved vector mixing T[a,h,d]
+constexpr float kPi = 3.14159265358979323846f;
+constexpr double kHartree = 27.211386024367243;   // aimnet/constants.py:6
+constexpr double kBohr = 0.5291772105638411;      // aimnet/constants.py:8
+
+void set_error(const std::string& msg);
+extern thread_local int g_launch_count;
+
+#define AIM_CUDA_CHECK(expr)                                                                        \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::aimnet::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+            return AIMNET_ECUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define AIM_LAUNCH_CHECK()                                                                          \
+    do {                                                                                            \
+        ::aimnet::g_launch_count++;                                                                 \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) {                                                                    \
+            ::aimnet::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) +   \
+                                " at " + __FILE__ + ":" + std::to_string(__LINE__));                \
+            return AIMNET_ECUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define AIM_REQUIRE(cond, msg)                                                                      \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            ::aimnet::set_error(std::string("invalid argument: ") + msg);                          \
+            return AIMNET_EINVAL;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+struct AevParams {
+    float shifts[kG];
+    float eta;
+    float rc;
+};
+
+// Where the geometry of neighbor slot (i, m) comes from.
+struct NbView {
+    const int32_t* nbmat;    // (n_atoms[+1], width) or nullptr in segment mode
+    const int32_t* shifts;   // (rows, width, 3) or nullptr
+    const int32_t* count;    // (n_atoms) valid-prefix length per row, or nullptr = scan full width
+    int width;
+    int sentinel;            // n_atoms
+};
+
+struct CellView {
+    const float* cell;       // (n_cells,3,3) or nullptr
+    int n_cells;             // 0, 1, or n_mol
+};
+
+
+// neighbour source of the pair-potential walkers (lr.cu): matrix row, or the molecule's own atom segment
+struct PairSource {
+    NbView nb;                   // nb.nbmat == nullptr -> segment mode
+    const int32_t* mol_idx;
+    const int32_t* mol_ptr;
+    float seg_cut2;              // segment mode only: skip pairs with d2 >= seg_cut2 (<= 0: no cutoff)
+};
+
+struct CoulombParams {
+    float rc;         // SR envelope radius or DSF cutoff
+    float alpha;      // DSF
+    float shift_val, shift_slope, self_coeff;   // DSF constants (aimnet/modules/lr.py:594-606)
+    double factor;    // signed prefactor c (eV*A): -k for the embedded SR term, +k for the external term
+};
+
+struct D3Params {
+    const float* c6ref;   // (95,95,5,5)
+    const float* cnref;   // (95,5)
+    const float* rcov;    // (95)
+    const float* r4r2;    // (95)
+    float s6, s8, a1, a2;
+    float r_on, r_off;    // Bohr
+};
+
+enum { PAIR_SR_EXP = 0, PAIR_SR_COS = 1, PAIR_SIMPLE = 2, PAIR_DSF = 3 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// exact-erf GELU and its derivative (nn.GELU() default, aimnet/modules/core.py:11-46)
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float z) {
+    return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+}
+
+// r_ij = x_j + s @ cell - x_i   (aimnet/ops.py:37-66)
+__device__ __forceinline__ void pair_vector(const float* __restrict__ coord, int i, int j, const int32_t* sh,
+                                            const float* __restrict__ cell, float& rx, float& ry, float& rz) {
+    float xj = coord[3 * j + 0], yj = coord[3 * j + 1], zj = coord[3 * j + 2];
+    if (sh != nullptr) {
+        float s0 = (float)sh[0], s1 = (float)sh[1], s2 = (float)sh[2];
+        xj += s0 * cell[0] + s1 * cell[3] + s2 * cell[6];
+        yj += s0 * cell[1] + s1 * cell[4] + s2 * cell[7];
+        zj += s0 * cell[2] + s1 * cell[5] + s2 * cell[8];
+    }
+    rx = xj - coord[3 * i + 0];
+    ry = yj - coord[3 * i + 1];
+    rz = zj - coord[3 * i + 2];
+}
+
+}  // namespace aimnet

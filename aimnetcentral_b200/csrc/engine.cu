@@ -1,0 +1,675 @@
+// Engine: weights resident in HBM + one-call E/F/stress evaluation (C ABI in include/aimnet2_b200.h).
+// Orchestrates the kernels of nblist.cu / conv.cu / gemm*.cu / pointwise.cu / lr.cu in the order of
+// AIMNet2Calculator.eval (aimnet/calculators/calculator.py:879-947) and AIMNet2.forward
+// (aimnet/models/aimnet2.py:141-187); the reverse pass replaces the reference's single torch.autograd.grad call
+// (aimnet/calculators/derivatives.py:96-146) with analytic kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace aimnet {
+
+static thread_local std::string g_error;
+thread_local int g_launch_count = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+
+// ---- declarations of the launchers living in the other translation units -----------------------------------
+int neighbor_matrix_impl(const float*, int, float, const float*, const float*, const uint8_t*, int, const int32_t*, int,
+                         int, int, int, int32_t*, int32_t*, int32_t*, int*, cudaStream_t, bool);
+int wrap_positions_impl(const float*, float*, int, const float*, int, const uint8_t*, const int32_t*, cudaStream_t);
+int launch_conv_fwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
+                    const float*, const float*, const float*, const float*, float*, int, float*, float*, int,
+                    cudaStream_t);
+int launch_conv_bwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
+                    const float*, const float*, const float*, int, const float*, const float*, const float*,
+                    const float*, float*, float*, float*, float*, float*, double*, int, int, cudaStream_t);
+int gemm_nt(const float*, int, const float*, int, const float*, float*, int, float*, int, int, int, int, int, int,
+            cudaStream_t);
+bool gemm_tc_available();
+int launch_embed(int, const int32_t*, const float*, float*, cudaStream_t);
+int launch_mol_ptr(const int32_t*, int, int, int32_t*, cudaStream_t);
+int launch_nse_fwd(int, int, int, const int32_t*, const int32_t*, const float*, const float*, const float*, int,
+                   const float*, float*, float*, const float*, float*, float*, cudaStream_t);
+int launch_nse_bwd(int, int, int, const int32_t*, const int32_t*, const float*, const float*, const float*, int,
+                   const float*, const float*, const float*, float*, const float*, const float*, int, float*, int,
+                   float*, cudaStream_t);
+int launch_accum_grads(int, int, const float*, int, const float*, const float*, const float*, int, float*, int, float*,
+                       cudaStream_t);
+int launch_head_tail(int, const float*, int, const float*, const float*, float, const int32_t*, const double*, double*,
+                     float*, cudaStream_t);
+int launch_energy_reduce(int, const int32_t*, const double*, const double*, const double*, const double*, double*,
+                         cudaStream_t);
+int launch_stress_reduce(const int32_t*, int, int, const double*, const float*, float*, cudaStream_t);
+int launch_charges_out(int, int, const float*, float*, float*, cudaStream_t);
+
+int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, const float*, const CoulombParams&,
+                   double*, float*, float*, double*, int, cudaStream_t);
+int launch_d3(int, const PairSource&, const float*, const CellView&, const int32_t*, const D3Params&, float*, float*,
+              double*, float*, double*, cudaStream_t);
+
+static inline int pad32(int x) { return (x + 31) / 32 * 32; }
+static inline int round16(int x) { return (x + 15) / 16 * 16; }
+
+struct Linear {
+    int in = 0, out = 0, in_pad = 0, out_pad = 0;
+    float* W = nullptr;    // (out_pad, in_pad)
+    float* Wt = nullptr;   // (in_pad, out_pad)
+    float* b = nullptr;    // (out_pad)
+};
+
+}  // namespace aimnet
+
+using namespace aimnet;
+
+struct aimnet2_engine {
+    int device = 0;
+    int C = 1;
+    AevParams aev{};
+    float *afv = nullptr, *agh_a = nullptr, *agh_q = nullptr, *w3 = nullptr;
+    float b3 = 0.f;
+    double* sae = nullptr;
+    std::vector<Linear> mlp[3];
+    Linear head[2];
+    float sr_rc = 4.6f;
+    int sr_envelope = 0;
+    float *d3_c6ref = nullptr, *d3_cnref = nullptr, *d3_rcov = nullptr, *d3_r4r2 = nullptr;
+    aimnet2_options_t opt{};
+    int gemm_backend = 0;
+    // workspace (grow-only)
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    int sr_cap = 64, lr_cap = 256;
+    int last_sr_width = 0, last_lr_width = 0;
+    int last_launches = 0;
+    // host staging for eval_host
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    // timing
+    int timing = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[5] = {0, 0, 0, 0, 0};
+    std::vector<void*> owned;
+};
+
+namespace aimnet {
+
+template <typename T>
+static int upload(aimnet2_engine* e, T** dst, const T* src, size_t count) {
+    AIM_CUDA_CHECK(cudaMalloc((void**)dst, sizeof(T) * count));
+    e->owned.push_back(*dst);
+    AIM_CUDA_CHECK(cudaMemcpy(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+    return AIMNET_OK;
+}
+
+static int make_linear(aimnet2_engine* e, Linear& L, const float* w, const float* b, int in, int out) {
+    L.in = in;
+    L.out = out;
+    L.in_pad = pad32(in);
+    L.out_pad = pad32(out);
+    std::vector<float> W((size_t)L.out_pad * L.in_pad, 0.f), Wt((size_t)L.in_pad * L.out_pad, 0.f), B(L.out_pad, 0.f);
+    for (int o = 0; o < out; ++o) {
+        for (int i = 0; i < in; ++i) {
+            float v = w[(size_t)o * in + i];
+            W[(size_t)o * L.in_pad + i] = v;
+            Wt[(size_t)i * L.out_pad + o] = v;
+        }
+        B[o] = b[o];
+    }
+    int rc;
+    if ((rc = upload(e, &L.W, W.data(), W.size()))) return rc;
+    if ((rc = upload(e, &L.Wt, Wt.data(), Wt.size()))) return rc;
+    if ((rc = upload(e, &L.b, B.data(), B.size()))) return rc;
+    return AIMNET_OK;
+}
+
+struct Bump {
+    char* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += sizeof(T) * count;
+        return p;
+    }
+};
+
+struct Buffers {
+    float* coord_w;
+    int32_t* mol_ptr;
+    int32_t *nb_sr, *sh_sr, *cnt_sr, *nb_lr, *sh_lr, *cnt_lr;
+    float* a[3];
+    float* q[2];
+    float* x;
+    float *hA, *hB;
+    float* y[2];
+    float* aim;
+    float* gp[3][4];
+    float *h1, *h2, *gp_h1, *gp_h2;
+    float* T_a[3];
+    float* T_q[3];
+    float *sumq[2], *sumf[2], *s1;
+    double *e_nn, *e_sr, *e_lr, *e_d3;
+    float *gq, *cn, *dEdCN;
+    float *dzA, *dzB, *dx, *dS_a, *dS_q, *grad_a, *grad_q, *da_tot, *dq, *dq_base;
+    double* virial_atom;
+    float* forces_tmp;
+};
+
+static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_cap, int lr_cap, bool pbc,
+                  bool need_lr, int ldx) {
+    int C = e->C;
+    size_t n = (size_t)std::max(N, 1);
+    b.coord_w = bp.take<float>(n * 3);
+    b.mol_ptr = bp.take<int32_t>(B + 2);
+    b.nb_sr = bp.take<int32_t>(n * sr_cap);
+    b.sh_sr = pbc ? bp.take<int32_t>(n * sr_cap * 3) : nullptr;
+    b.cnt_sr = bp.take<int32_t>(n);
+    b.nb_lr = need_lr ? bp.take<int32_t>(n * lr_cap) : nullptr;
+    b.sh_lr = need_lr ? bp.take<int32_t>(n * lr_cap * 3) : nullptr;
+    b.cnt_lr = bp.take<int32_t>(n);
+    for (int p = 0; p < 3; ++p) b.a[p] = bp.take<float>(n * kAG);
+    for (int p = 0; p < 2; ++p) b.q[p] = bp.take<float>(n * C);
+    b.x = bp.take<float>(n * ldx);
+    b.hA = bp.take<float>(n * 512);
+    b.hB = bp.take<float>(n * 512);
+    for (int p = 0; p < 2; ++p) b.y[p] = bp.take<float>(n * 288);
+    b.aim = bp.take<float>(n * 256);
+    for (int p = 0; p < 3; ++p)
+        for (int l = 0; l < 4; ++l)
+            b.gp[p][l] = (l < (int)e->mlp[p].size()) ? bp.take<float>(n * e->mlp[p][l].out_pad) : nullptr;
+    b.h1 = bp.take<float>(n * 128);
+    b.h2 = bp.take<float>(n * 128);
+    b.gp_h1 = bp.take<float>(n * 128);
+    b.gp_h2 = bp.take<float>(n * 128);
+    for (int p = 0; p < 3; ++p) {
+        b.T_a[p] = bp.take<float>(n * kTA);
+        b.T_q[p] = bp.take<float>(n * C * kH * 3);
+    }
+    for (int p = 0; p < 2; ++p) {
+        b.sumq[p] = bp.take<float>((size_t)B * C);
+        b.sumf[p] = bp.take<float>((size_t)B * C);
+    }
+    b.s1 = bp.take<float>((size_t)B * C);
+    b.e_nn = bp.take<double>(n);
+    b.e_sr = bp.take<double>(n);
+    b.e_lr = bp.take<double>(n);
+    b.e_d3 = bp.take<double>(n);
+    b.gq = bp.take<float>(n);
+    b.cn = bp.take<float>(n);
+    b.dEdCN = bp.take<float>(n);
+    b.dzA = bp.take<float>(n * 512);
+    b.dzB = bp.take<float>(n * 512);
+    b.dx = bp.take<float>(n * ldx);
+    b.dS_a = bp.take<float>(n * kAG * 4);
+    b.dS_q = bp.take<float>(n * C * kG * 4);
+    b.grad_a = bp.take<float>(n * kAG);
+    b.grad_q = bp.take<float>(n * C);
+    b.da_tot = bp.take<float>(n * kAG);
+    b.dq = bp.take<float>(n * C);
+    b.dq_base = bp.take<float>(n * C);
+    b.virial_atom = bp.take<double>(n * 9);
+    b.forces_tmp = bp.take<float>(n * 3);
+}
+
+static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ldx, int K, float* Y, float* gp, bool act,
+                      int M, cudaStream_t st) {
+    return gemm_nt(X, ldx, L.W, L.in_pad, L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1,
+                   e->gemm_backend, st);
+}
+// dX[M,in_pad] = dZ[M,out_pad] @ W  (* gp_prev)
+static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float* dX, int lddx, const float* gp_prev,
+                      int ldgp, int M, cudaStream_t st) {
+    return gemm_nt(dZ, L.out_pad, L.Wt, L.out_pad, nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad,
+                   L.out_pad, gp_prev ? 3 : 0, e->gemm_backend, st);
+}
+
+#define AIM_TRY(expr)                      \
+    do {                                   \
+        int _rc = (expr);                  \
+        if (_rc != AIMNET_OK) return _rc;  \
+    } while (0)
+
+static int build_list(aimnet2_engine* e, const float* coord, int N, float cutoff, const aimnet2_system_t* sys,
+                      const int32_t* mol_idx, int sorted, int cap, int32_t* nb, int32_t* sh, int32_t* cnt, int* maxc,
+                      cudaStream_t st) {
+    return neighbor_matrix_impl(coord, N, cutoff, sys->cell, sys->host_cell, sys->pbc_host, sys->n_cells, mol_idx,
+                                sys->n_mol, cap, N, sorted, nb, sh, cnt, maxc, st, true);
+}
+
+static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
+                     cudaStream_t st) {
+    AIM_REQUIRE(e && sys && res, "engine_eval: null argument");
+    const int N = sys->n_atoms, B = sys->n_mol, C = e->C;
+    AIM_REQUIRE(N >= 0 && B >= 1, "engine_eval: need n_atoms >= 0 and n_mol >= 1");
+    AIM_REQUIRE(sys->coord && sys->numbers && sys->charge, "engine_eval: coord, numbers and charge are required");
+    AIM_REQUIRE(res->energy && res->charges, "engine_eval: energy and charges outputs are required");
+    AIM_REQUIRE(B == 1 || sys->mol_idx != nullptr, "engine_eval: mol_idx required for more than one molecule");
+    AIM_REQUIRE((sys->cell == nullptr) == (sys->n_cells == 0), "engine_eval: cell / n_cells mismatch");
+    AIM_REQUIRE(sys->n_cells == 0 || sys->n_cells == 1 || sys->n_cells == B, "engine_eval: n_cells must be 0, 1 or n_mol");
+    AIM_REQUIRE(sys->cell == nullptr || sys->host_cell != nullptr, "engine_eval: host_cell required with cell");
+    const bool want_f = (flags & AIMNET_WANT_FORCES) != 0, want_s = (flags & AIMNET_WANT_STRESS) != 0;
+    AIM_REQUIRE(!want_f || res->forces, "engine_eval: forces requested without an output buffer");
+    AIM_REQUIRE(!want_s || (res->stress && sys->cell), "engine_eval: stress needs a cell and an output buffer");
+    const aimnet2_options_t& o = e->opt;
+    AIM_REQUIRE(o.coulomb_method != AIMNET_COULOMB_EWALD, "engine_eval: Ewald Coulomb is not implemented in this build");
+    AIM_REQUIRE(!o.dispersion || e->d3_c6ref, "engine_eval: dispersion requested but no D3 tables were loaded");
+    g_launch_count = 0;
+    const bool pbc = sys->cell != nullptr;
+    const bool backward = want_f || want_s;
+    const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
+    const bool need_lr_terms = (o.coulomb_method == AIMNET_COULOMB_SIMPLE || o.coulomb_method == AIMNET_COULOMB_DSF ||
+                                o.dispersion);
+    const bool need_lr_list = need_lr_terms && pbc;
+    AIM_REQUIRE(!(pbc && o.coulomb_method == AIMNET_COULOMB_SIMPLE),
+                "engine_eval: 'simple' Coulomb is not defined for periodic systems (host switches to DSF)");
+    float lr_cut = 0.f;
+    if (o.coulomb_method == AIMNET_COULOMB_DSF) lr_cut = std::max(lr_cut, o.dsf_rc);
+    if (o.dispersion) lr_cut = std::max(lr_cut, o.d3_cutoff);
+    const bool own_sr = sys->nbmat == nullptr;
+    if (e->timing) cudaEventRecord(e->ev[0], st);
+
+    Buffers b;
+    for (int attempt = 0;; ++attempt) {
+        AIM_REQUIRE(attempt < 8, "engine_eval: neighbor buffers failed to converge");
+        Bump probe{nullptr};
+        carve(e, probe, b, N, B, e->sr_cap, e->lr_cap, pbc, need_lr_list, ldx);
+        size_t need = probe.off + 1024;
+        if (need > e->ws_bytes) {
+            AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (e->ws) AIM_CUDA_CHECK(cudaFree(e->ws));
+            e->ws = nullptr;
+            size_t want = need + need / 8;
+            AIM_CUDA_CHECK(cudaMalloc((void**)&e->ws, want));
+            e->ws_bytes = want;
+        }
+        Bump bp{e->ws};
+        carve(e, bp, b, N, B, e->sr_cap, e->lr_cap, pbc, need_lr_list, ldx);
+        if (N == 0) break;
+        const float* coord = sys->coord;
+        if (pbc) {
+            AIM_TRY(wrap_positions_impl(sys->coord, b.coord_w, N, sys->cell, sys->n_cells, sys->pbc_host, sys->mol_idx, st));
+            coord = b.coord_w;
+        }
+        bool retry = false;
+        if (own_sr) {
+            int maxc = 0;
+            int rc = build_list(e, coord, N, o.sr_cutoff, sys, sys->mol_idx, 1, e->sr_cap, b.nb_sr, b.sh_sr, b.cnt_sr,
+                                &maxc, st);
+            if (rc == AIMNET_NEIGHBOR_OVERFLOW) {
+                e->sr_cap = round16(maxc + maxc / 4 + 1);
+                retry = true;
+            } else if (rc != AIMNET_OK)
+                return rc;
+            e->last_sr_width = std::max(1, maxc);
+        }
+        if (!retry && need_lr_list) {
+            int maxc = 0;
+            int rc = build_list(e, coord, N, lr_cut, sys, sys->mol_idx, 0, e->lr_cap, b.nb_lr, b.sh_lr, b.cnt_lr, &maxc, st);
+            if (rc == AIMNET_NEIGHBOR_OVERFLOW) {
+                e->lr_cap = round16(maxc + maxc / 8 + 1);
+                retry = true;
+            } else if (rc != AIMNET_OK)
+                return rc;
+            e->last_lr_width = std::max(1, maxc);
+        }
+        if (!retry) break;
+    }
+    if (e->timing) cudaEventRecord(e->ev[1], st);
+    const float* coord = pbc ? b.coord_w : sys->coord;
+    AIM_TRY(launch_mol_ptr(sys->mol_idx, N, B, b.mol_ptr, st));
+
+    NbView sr;
+    if (own_sr) {
+        sr = NbView{b.nb_sr, b.sh_sr, b.cnt_sr, e->sr_cap, N};
+    } else {
+        AIM_REQUIRE(sys->nb_width >= 1, "engine_eval: nb_width must be >= 1 with a caller-supplied nbmat");
+        AIM_REQUIRE(!pbc || sys->shifts, "engine_eval: shifts required with a caller-supplied nbmat and a cell");
+        sr = NbView{sys->nbmat, pbc ? sys->shifts : nullptr, nullptr, sys->nb_width, N};
+        e->last_sr_width = sys->nb_width;
+    }
+    CellView cv{sys->cell, sys->n_cells};
+
+    // ---------------- forward (aimnet/models/aimnet2.py:141-187) ----------------
+    AIM_TRY(launch_embed(N, sys->numbers, e->afv, b.a[0], st));
+    for (int p = 0; p < 3; ++p) {
+        const std::vector<Linear>& L = e->mlp[p];
+        const int nl = (int)L.size();
+        const float* qin = (p == 0) ? nullptr : b.q[p - 1];
+        AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
+                                b.T_a[p], b.T_q[p], p > 0, st));
+        const float* in = b.x;
+        int ldin = ldx;
+        float* bufs[2] = {b.hA, b.hB};
+        for (int l = 0; l < nl; ++l) {
+            bool last = (l == nl - 1);
+            bool act = !last || p > 0;   // last_linear only for pass 0 (aimnet2.py:56,65,75)
+            float* out = last ? (p < 2 ? b.y[p] : b.aim) : bufs[l & 1];
+            AIM_TRY(linear_fwd(e, L[l], in, ldin, L[l].in_pad, out, act ? b.gp[p][l] : nullptr, act, N, st));
+            in = out;
+            ldin = L[l].out_pad;
+        }
+        if (p < 2) {
+            AIM_TRY(launch_nse_fwd(C, N, B, sys->mol_idx, b.mol_ptr, sys->charge, sys->mult, b.y[p], 288, qin,
+                                   b.sumq[p], b.sumf[p], b.a[p], b.a[p + 1], b.q[p], st));
+        }
+    }
+    // energy head (aimnet/modules/core.py:114-132) + SAE (core.py:71-97)
+    AIM_TRY(linear_fwd(e, e->head[0], b.aim, 256, 256, b.h1, b.gp_h1, true, N, st));
+    AIM_TRY(linear_fwd(e, e->head[1], b.h1, 128, 128, b.h2, b.gp_h2, true, N, st));
+    AIM_TRY(launch_head_tail(N, b.h2, 128, b.gp_h2, e->w3, e->b3, sys->numbers, e->sae, b.e_nn, b.dzA, st));
+    AIM_TRY(launch_charges_out(C, N, b.q[1], res->charges, res->spin_charges, st));
+    if (e->timing) cudaEventRecord(e->ev[2], st);
+
+    // ---------------- pair terms on the final charges ----------------
+    float* F = want_f ? res->forces : (backward ? b.forces_tmp : nullptr);
+    double* vir = want_s ? b.virial_atom : nullptr;
+    if (N > 0) {
+        if (F) AIM_CUDA_CHECK(cudaMemsetAsync(F, 0, sizeof(float) * 3 * N, st));
+        if (vir) AIM_CUDA_CHECK(cudaMemsetAsync(vir, 0, sizeof(double) * 9 * N, st));
+        AIM_CUDA_CHECK(cudaMemsetAsync(b.gq, 0, sizeof(float) * N, st));
+    }
+    const double k = 0.5 * kHartree * kBohr;
+    const float* qfin = res->charges;   // total charges (qa + qb for NSE)
+    {   // embedded SRCoulomb: E -= k sum fc q_i q_j / d (lr.py:21-62, 986-1032)
+        PairSource ps{sr, sys->mol_idx, b.mol_ptr, 0.f};
+        CoulombParams cp{e->sr_rc, 0.f, 0.f, 0.f, 0.f, -k};
+        AIM_TRY(launch_coulomb(e->sr_envelope == 0 ? PAIR_SR_EXP : PAIR_SR_COS, N, ps, coord, cv, qfin, cp, b.e_sr, b.gq,
+                               backward ? F : nullptr, vir, 0, st));
+    }
+    PairSource lrs;
+    if (need_lr_list)
+        lrs = PairSource{NbView{b.nb_lr, b.sh_lr, b.cnt_lr, e->lr_cap, N}, sys->mol_idx, b.mol_ptr, 0.f};
+    else
+        lrs = PairSource{NbView{nullptr, nullptr, nullptr, 0, N}, sys->mol_idx, b.mol_ptr,
+                         o.coulomb_method == AIMNET_COULOMB_SIMPLE ? 0.f : lr_cut * lr_cut};
+    bool have_lr = false, have_d3 = false;
+    if (o.coulomb_method == AIMNET_COULOMB_SIMPLE) {
+        CoulombParams cp{0.f, 0.f, 0.f, 0.f, 0.f, k};
+        AIM_TRY(launch_coulomb(PAIR_SIMPLE, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        have_lr = true;
+    } else if (o.coulomb_method == AIMNET_COULOMB_DSF) {
+        double a = o.dsf_alpha, R = o.dsf_rc;
+        double erfc_rc = std::erfc(a * R);
+        CoulombParams cp;
+        cp.rc = o.dsf_rc;
+        cp.alpha = o.dsf_alpha;
+        cp.shift_val = (float)(erfc_rc / R);
+        cp.shift_slope = (float)(erfc_rc / (R * R) + 2.0 * a / std::sqrt(M_PI) * std::exp(-a * a * R * R) / R);
+        cp.self_coeff = (float)(-(erfc_rc / R / 2.0 + a / std::sqrt(M_PI)));
+        cp.factor = k;
+        AIM_TRY(launch_coulomb(PAIR_DSF, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        have_lr = true;
+    }
+    if (o.dispersion) {
+        D3Params dp{e->d3_c6ref, e->d3_cnref, e->d3_rcov, e->d3_r4r2, o.d3_s6, o.d3_s8, o.d3_a1, o.d3_a2,
+                    (float)(o.d3_cutoff * (1.0 - o.d3_smoothing) / kBohr), (float)(o.d3_cutoff / kBohr)};
+        AIM_TRY(launch_d3(N, lrs, coord, cv, sys->numbers, dp, b.cn, b.dEdCN, b.e_d3, backward ? F : nullptr, vir, st));
+        have_d3 = true;
+    }
+    AIM_TRY(launch_energy_reduce(B, b.mol_ptr, b.e_nn, b.e_sr, have_lr ? b.e_lr : nullptr, have_d3 ? b.e_d3 : nullptr,
+                                 res->energy, st));
+    if (e->timing) cudaEventRecord(e->ev[3], st);
+
+    // ---------------- analytic reverse pass ----------------
+    if (backward && N > 0) {
+        // head: dzA holds dz2 = w3 * gelu'(z2)
+        AIM_TRY(linear_bwd(e, e->head[1], b.dzA, b.dzB, 128, b.gp_h1, 128, N, st));
+        AIM_TRY(linear_bwd(e, e->head[0], b.dzB, b.dzA, 256, b.gp[2][e->mlp[2].size() - 1], 256, N, st));
+        float* cur = b.dzA;   // gradient w.r.t. pre-activation of the last Linear of pass 2
+        float* other = b.dzB;
+        for (int p = 2; p >= 0; --p) {
+            const std::vector<Linear>& L = e->mlp[p];
+            const int nl = (int)L.size();
+            for (int l = nl - 1; l >= 0; --l) {
+                if (l > 0) {
+                    AIM_TRY(linear_bwd(e, L[l], cur, other, L[l].in_pad, b.gp[p][l - 1], L[l - 1].out_pad, N, st));
+                    std::swap(cur, other);
+                } else {
+                    AIM_TRY(linear_bwd(e, L[0], cur, b.dx, ldx, nullptr, 0, N, st));
+                }
+            }
+            const float* qin = (p == 0) ? nullptr : b.q[p - 1];
+            AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
+                                    e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
+            if (p == 0) break;
+            // dE/da_p and dE/dq_{p-1}
+            if (p == 2)
+                AIM_TRY(launch_accum_grads(C, N, b.dx, ldx, b.grad_a, b.grad_q, b.gq, 1, b.da_tot, 0, b.dq, st));
+            else
+                AIM_TRY(launch_accum_grads(C, N, b.dx, ldx, b.grad_a, b.grad_q, b.dq_base, C, b.da_tot, 1, b.dq, st));
+            // NSE backward of pass p-1 -> dz of the last Linear of pass p-1
+            int pp = p - 1;
+            const float* qprev = (pp == 0) ? nullptr : b.q[pp - 1];
+            (void)qprev;
+            cur = b.dzA;
+            other = b.dzB;
+            AIM_TRY(launch_nse_bwd(C, N, B, sys->mol_idx, b.mol_ptr, sys->charge, sys->mult, b.y[pp], 288, b.dq,
+                                   b.sumq[pp], b.sumf[pp], b.s1, b.da_tot, pp > 0 ? b.gp[pp][e->mlp[pp].size() - 1] : nullptr,
+                                   288, cur, 288, pp > 0 ? b.dq_base : nullptr, st));
+        }
+        if (want_s)
+            AIM_TRY(launch_stress_reduce(b.mol_ptr, sys->n_cells, N, b.virial_atom, sys->cell, res->stress, st));
+    }
+    if (e->timing) cudaEventRecord(e->ev[4], st);
+
+    // optional: hand the short-range matrix back in the reference layout (padding row appended)
+    if (res->nbmat_out && own_sr && N > 0) {
+        int w = res->nbmat_out_width;
+        AIM_REQUIRE(w >= 1 && w <= e->sr_cap, "engine_eval: nbmat_out_width out of range");
+        AIM_CUDA_CHECK(cudaMemcpy2DAsync(res->nbmat_out, sizeof(int32_t) * w, b.nb_sr, sizeof(int32_t) * e->sr_cap,
+                                         sizeof(int32_t) * w, N, cudaMemcpyDeviceToDevice, st));
+        if (res->shifts_out && pbc)
+            AIM_CUDA_CHECK(cudaMemcpy2DAsync(res->shifts_out, sizeof(int32_t) * 3 * w, b.sh_sr,
+                                             sizeof(int32_t) * 3 * e->sr_cap, sizeof(int32_t) * 3 * w, N,
+                                             cudaMemcpyDeviceToDevice, st));
+    }
+    e->last_launches = g_launch_count;
+    return AIMNET_OK;
+}
+
+}  // namespace aimnet
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" const char* aimnet2_last_error(void) { return aimnet::g_error.c_str(); }
+extern "C" int aimnet2_abi_version(void) { return 1; }
+
+extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weights_t* w, int device) {
+    AIM_REQUIRE(out && w, "engine_create: null argument");
+    AIM_REQUIRE(w->num_charge_channels == 1 || w->num_charge_channels == 2, "engine_create: num_charge_channels must be 1 or 2");
+    AIM_CUDA_CHECK(cudaSetDevice(device));
+    aimnet2_engine* e = new aimnet2_engine();
+    e->device = device;
+    e->C = w->num_charge_channels;
+    int C = e->C, rc;
+    for (int g = 0; g < kG; ++g) e->aev.shifts[g] = w->shifts_s[g];
+    e->aev.eta = w->eta_s;
+    e->aev.rc = w->rc_s;
+    // embedding rows of unimplemented species are NaN in exported models (train/export_model.py:74-80): kept as is
+    if ((rc = upload(e, &e->afv, w->afv, (size_t)64 * kAG))) return rc;
+    if ((rc = upload(e, &e->agh_a, w->agh_a, (size_t)kA * kG * kH))) return rc;
+    if ((rc = upload(e, &e->agh_q, w->agh_q, (size_t)C * kG * kH))) return rc;
+    if ((rc = upload(e, &e->sae, w->sae, 64))) return rc;
+    for (int p = 0; p < 3; ++p) {
+        int nl = w->n_layers[p];
+        AIM_REQUIRE(nl >= 2 && nl <= 4, "engine_create: 2..4 Linear layers per pass are supported");
+        e->mlp[p].resize(nl);
+        for (int l = 0; l < nl; ++l) {
+            int in = w->layer_dims[p][l], outd = w->layer_dims[p][l + 1];
+            AIM_REQUIRE(in >= 1 && outd >= 1 && in <= 768 && outd <= 512, "engine_create: layer size out of range");
+            if ((rc = make_linear(e, e->mlp[p][l], w->mlp_w[p][l], w->mlp_b[p][l], in, outd))) return rc;
+        }
+        int in0 = 2 * kAG + kAH + (p > 0 ? C * (1 + kG + kH) : 0);
+        int out_last = (p < 2) ? kAG + 2 * C : 256;
+        AIM_REQUIRE(w->layer_dims[p][0] == in0, "engine_create: first layer width does not match the AEV/conv layout");
+        AIM_REQUIRE(w->layer_dims[p][nl] == out_last, "engine_create: last layer width mismatch");
+    }
+    if ((rc = make_linear(e, e->head[0], w->head_w[0], w->head_b[0], 256, 128))) return rc;
+    if ((rc = make_linear(e, e->head[1], w->head_w[1], w->head_b[1], 128, 128))) return rc;
+    if ((rc = upload(e, &e->w3, w->head_w[2], 128))) return rc;
+    e->b3 = w->head_b[2][0];
+    e->sr_rc = w->sr_rc;
+    e->sr_envelope = w->sr_envelope;
+    if (w->d3_c6ref) {
+        if ((rc = upload(e, &e->d3_c6ref, w->d3_c6ref, (size_t)95 * 95 * 25))) return rc;
+        if ((rc = upload(e, &e->d3_cnref, w->d3_cnref, (size_t)95 * 5))) return rc;
+        if ((rc = upload(e, &e->d3_rcov, w->d3_rcov, 95))) return rc;
+        if ((rc = upload(e, &e->d3_r4r2, w->d3_r4r2, 95))) return rc;
+    }
+    e->opt.coulomb_method = AIMNET_COULOMB_SIMPLE;
+    e->opt.dsf_alpha = 0.2f;
+    e->opt.dsf_rc = 15.0f;
+    e->opt.ewald_accuracy = 1e-6f;
+    e->opt.dispersion = 0;
+    e->opt.d3_s6 = 1.0f;
+    e->opt.d3_s8 = 0.3908f;
+    e->opt.d3_a1 = 0.566f;
+    e->opt.d3_a2 = 3.128f;
+    e->opt.d3_cutoff = 15.0f;
+    e->opt.d3_smoothing = 0.2f;
+    e->opt.sr_cutoff = 5.0f;
+    e->gemm_backend = gemm_tc_available() ? 1 : 0;
+    AIM_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 6; ++k) AIM_CUDA_CHECK(cudaEventCreate(&e->ev[k]));
+    *out = e;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_destroy(aimnet2_engine_t* e) {
+    if (!e) return AIMNET_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (void* p : e->owned) cudaFree(p);
+    if (e->ws) cudaFree(e->ws);
+    if (e->stage) cudaFree(e->stage);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    for (int k = 0; k < 6; ++k)
+        if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    delete e;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt) {
+    AIM_REQUIRE(e && opt, "set_options: null argument");
+    AIM_REQUIRE(opt->coulomb_method >= 0 && opt->coulomb_method <= 3, "set_options: bad coulomb_method");
+    AIM_REQUIRE(opt->sr_cutoff > 0.f, "set_options: sr_cutoff must be positive");
+    e->opt = *opt;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend) {
+    AIM_REQUIRE(e, "set_gemm_backend: null engine");
+    AIM_REQUIRE(backend == 0 || backend == 1, "set_gemm_backend: backend must be 0 or 1");
+    AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backend not available in this build");
+    e->gemm_backend = backend;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
+                                   void* stream) {
+    AIM_REQUIRE(e, "engine_eval: null engine");
+    AIM_CUDA_CHECK(cudaSetDevice(e->device));
+    int rc = eval_impl(e, sys, res, flags, (cudaStream_t)stream);
+    if (rc == AIMNET_OK && e->timing) {
+        cudaStream_t st = (cudaStream_t)stream;
+        AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev[k], e->ev[k + 1]);
+        cudaEventElapsedTime(&e->last_ms[4], e->ev[0], e->ev[4]);
+    }
+    return rc;
+}
+
+extern "C" int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res,
+                                        int flags) {
+    AIM_REQUIRE(e && sys && res, "engine_eval_host: null argument");
+    AIM_CUDA_CHECK(cudaSetDevice(e->device));
+    cudaStream_t st = e->own_stream;
+    const int N = sys->n_atoms, B = sys->n_mol, nc = sys->n_cells;
+    AIM_REQUIRE(N >= 0 && B >= 1, "engine_eval_host: bad sizes");
+    AIM_REQUIRE(sys->nbmat == nullptr, "engine_eval_host: caller-supplied nbmat is only supported by engine_eval");
+    size_t n = (size_t)std::max(N, 1);
+    Bump probe{nullptr};
+    auto carve_stage = [&](Bump& bp, aimnet2_system_t& ds, aimnet2_result_t& dr) {
+        ds = *sys;
+        dr = *res;
+        ds.coord = bp.take<float>(n * 3);
+        ds.numbers = bp.take<int32_t>(n);
+        ds.mol_idx = sys->mol_idx ? bp.take<int32_t>(n) : nullptr;
+        ds.charge = bp.take<float>(B);
+        ds.mult = sys->mult ? bp.take<float>(B) : nullptr;
+        ds.cell = sys->cell ? bp.take<float>((size_t)9 * nc) : nullptr;
+        ds.host_cell = sys->cell;   // the caller's cell IS host memory here
+        dr.energy = bp.take<double>(B);
+        dr.charges = bp.take<float>(n);
+        dr.spin_charges = res->spin_charges ? bp.take<float>(n) : nullptr;
+        dr.forces = res->forces ? bp.take<float>(n * 3) : nullptr;
+        dr.stress = res->stress ? bp.take<float>((size_t)9 * std::max(nc, 1)) : nullptr;
+        dr.nbmat_out = nullptr;
+        dr.shifts_out = nullptr;
+    };
+    aimnet2_system_t ds;
+    aimnet2_result_t dr;
+    carve_stage(probe, ds, dr);
+    if (probe.off + 1024 > e->stage_bytes) {
+        if (e->stage) AIM_CUDA_CHECK(cudaFree(e->stage));
+        e->stage = nullptr;
+        AIM_CUDA_CHECK(cudaMalloc((void**)&e->stage, probe.off + 1024));
+        e->stage_bytes = probe.off + 1024;
+    }
+    Bump bp{e->stage};
+    carve_stage(bp, ds, dr);
+#define H2D(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st))
+    if (N > 0) {
+        H2D(ds.coord, sys->coord, sizeof(float) * 3 * N);
+        H2D(ds.numbers, sys->numbers, sizeof(int32_t) * N);
+        if (sys->mol_idx) H2D(ds.mol_idx, sys->mol_idx, sizeof(int32_t) * N);
+    }
+    H2D(ds.charge, sys->charge, sizeof(float) * B);
+    if (sys->mult) H2D(ds.mult, sys->mult, sizeof(float) * B);
+    if (sys->cell) H2D(ds.cell, sys->cell, sizeof(float) * 9 * nc);
+    int rc = eval_impl(e, &ds, &dr, flags, st);
+    if (rc != AIMNET_OK) return rc;
+    D2H(res->energy, dr.energy, sizeof(double) * B);
+    if (N > 0) {
+        D2H(res->charges, dr.charges, sizeof(float) * N);
+        if (res->spin_charges) D2H(res->spin_charges, dr.spin_charges, sizeof(float) * N);
+        if (res->forces && (flags & AIMNET_WANT_FORCES)) D2H(res->forces, dr.forces, sizeof(float) * 3 * N);
+    }
+    if (res->stress && (flags & AIMNET_WANT_STRESS)) D2H(res->stress, dr.stress, sizeof(float) * 9 * nc);
+#undef H2D
+#undef D2H
+    AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (e->timing) {
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev[k], e->ev[k + 1]);
+        cudaEventElapsedTime(&e->last_ms[4], e->ev[0], e->ev[4]);
+    }
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_last_launches(const aimnet2_engine_t* e) { return e ? e->last_launches : 0; }
+
+extern "C" int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int* lr_width, int64_t* workspace_bytes) {
+    AIM_REQUIRE(e, "engine_info: null engine");
+    if (sr_width) *sr_width = e->last_sr_width;
+    if (lr_width) *lr_width = e->last_lr_width;
+    if (workspace_bytes) *workspace_bytes = (int64_t)e->ws_bytes;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_enable_timing(aimnet2_engine_t* e, int on) {
+    AIM_REQUIRE(e, "enable_timing: null engine");
+    e->timing = on ? 1 : 0;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, int n) {
+    AIM_REQUIRE(e && ms, "last_timing: null argument");
+    int k = 0;
+    for (; k < n && k < 5; ++k) ms[k] = e->last_ms[k];
+    return k;
+}

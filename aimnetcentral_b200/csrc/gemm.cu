@@ -1,0 +1,136 @@
+// Per-atom MLP GEMMs: Y[M,N] = epilogue(A[M,K] @ W[N,K]^T)   (aimnet/modules/core.py:11-46)
+//
+// Both operands are K-major ("NT"), which is how torch stores Linear weights (out,in) and how the activations are
+// laid out, and it is the native operand layout of tcgen05.mma.  Epilogue modes:
+//   0  plain store                       (input-gradient GEMM of the first layer of a stack)
+//   1  + bias                            (last Linear without activation)
+//   2  + bias, exact-erf GELU; also stores gelu'(z) to aux so the backward pass never recomputes erf
+//   3  * aux[M,N]                        (input-gradient GEMM fused with the GELU derivative of the layer below)
+//
+// Backend 0 (this file): fp32 SIMT, 128x64x16 tiles, 8x4 register micro-tiles — the bit-faithful baseline.
+// Backend 1 (gemm_tc.cu): tcgen05 3xTF32 with TMEM accumulators.
+#include "common.cuh"
+
+namespace aimnet {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restrict__ A, int lda,
+                                                           const float* __restrict__ W, int ldw,
+                                                           const float* __restrict__ bias, float* __restrict__ Y,
+                                                           int ldy, float* __restrict__ aux, int ldaux, int M, int N,
+                                                           int K) {
+    __shared__ float As[2][BK][BM + 4];
+    __shared__ float Ws[2][BK][BN + 4];
+    int tid = threadIdx.x;
+    int tx = tid & 15, ty = tid >> 4;
+    int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // global->smem mapping: A tile 128 rows x 16 k = 512 float4 (2 per thread); W tile 64 x 16 = 256 float4
+    int ar = tid >> 2, ak = (tid & 3) * 4;          // rows ar and ar+64
+    int wr = tid >> 2, wk = (tid & 3) * 4;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    float4 ra0, ra1, rw;
+    auto gload = [&](int k0) {
+        int r0 = m0 + ar, r1 = m0 + ar + 64;
+        ra0 = (r0 < M) ? *reinterpret_cast<const float4*>(A + (size_t)r0 * lda + k0 + ak) : make_float4(0, 0, 0, 0);
+        ra1 = (r1 < M) ? *reinterpret_cast<const float4*>(A + (size_t)r1 * lda + k0 + ak) : make_float4(0, 0, 0, 0);
+        int n = n0 + wr;
+        rw = (n < N) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k0 + wk) : make_float4(0, 0, 0, 0);
+    };
+    auto sstore = [&](int buf) {
+        As[buf][ak + 0][ar] = ra0.x;
+        As[buf][ak + 1][ar] = ra0.y;
+        As[buf][ak + 2][ar] = ra0.z;
+        As[buf][ak + 3][ar] = ra0.w;
+        As[buf][ak + 0][ar + 64] = ra1.x;
+        As[buf][ak + 1][ar + 64] = ra1.y;
+        As[buf][ak + 2][ar + 64] = ra1.z;
+        As[buf][ak + 3][ar + 64] = ra1.w;
+        Ws[buf][wk + 0][wr] = rw.x;
+        Ws[buf][wk + 1][wr] = rw.y;
+        Ws[buf][wk + 2][wr] = rw.z;
+        Ws[buf][wk + 3][wr] = rw.w;
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int nk = K / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        if (kt + 1 < nk) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    int col = n0 + tx * 4;
+    if (col >= N) return;
+    float4 bz = make_float4(0, 0, 0, 0);
+    if (MODE == 1 || MODE == 2) bz = *reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int row = m0 + ty * 8 + r;
+        if (row >= M) continue;
+        float4 z = make_float4(acc[r][0] + bz.x, acc[r][1] + bz.y, acc[r][2] + bz.z, acc[r][3] + bz.w);
+        if (MODE == 2) {
+            if (aux != nullptr) {
+                float4 gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
+                *reinterpret_cast<float4*>(aux + (size_t)row * ldaux + col) = gp;
+            }
+            z = make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w));
+        } else if (MODE == 3) {
+            float4 gp = *reinterpret_cast<const float4*>(aux + (size_t)row * ldaux + col);
+            z = make_float4(z.x * gp.x, z.y * gp.y, z.z * gp.z, z.w * gp.w);
+        }
+        *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = z;
+    }
+}
+
+int gemm_nt_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy, float* aux,
+               int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
+bool gemm_tc_available();
+
+int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy, float* aux,
+            int ldaux, int M, int N, int K, int mode, int backend, cudaStream_t st) {
+    AIM_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes");
+    AIM_REQUIRE(K % BK == 0, "gemm: K must be a multiple of 16 (pad the operands)");
+    AIM_REQUIRE(N % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0, "gemm: N and leading dims must be multiples of 4");
+    AIM_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad epilogue mode");
+    AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
+    AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
+    if (M == 0) return AIMNET_OK;
+    if (backend == 1) return gemm_nt_tc(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    switch (mode) {
+        case 0: gemm_nt_simt_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+        case 1: gemm_nt_simt_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+        case 2: gemm_nt_simt_kernel<2><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+        default: gemm_nt_simt_kernel<3><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+    }
+    AIM_LAUNCH_CHECK();
+    return AIMNET_OK;
+}
+
+}  // namespace aimnet
+
+extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                               float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {
+    return aimnet::gemm_nt(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, backend, (cudaStream_t)stream);
+}

@@ -1,0 +1,320 @@
+// Small per-atom / per-molecule kernels around the GEMMs: embedding, charge equilibration (NSE) forward and
+// backward, energy head tail, fp64 per-molecule reductions.
+#include "common.cuh"
+
+namespace aimnet {
+
+// a0[i] = afv[Z_i]   (aimnet/models/aimnet2.py:144-147)
+__global__ void embed_kernel(int n, const int32_t* __restrict__ numbers, const float* __restrict__ afv,
+                             float* __restrict__ a0) {
+    int i = blockIdx.x, t = threadIdx.x;
+    int z = numbers[i];
+    z = (z < 0 || z > 63) ? 0 : z;
+    a0[(size_t)i * kAG + t] = afv[(size_t)z * kAG + t];
+}
+
+// molecule segment pointers from sorted mol_idx (nullptr = one molecule)
+__global__ void mol_ptr_kernel(const int32_t* __restrict__ mol_idx, int n, int n_mol, int32_t* __restrict__ ptr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (mol_idx == nullptr) {
+        if (i == 0) {
+            ptr[0] = 0;
+            for (int s = 1; s <= n_mol; ++s) ptr[s] = n;
+        }
+        return;
+    }
+    int prev = (i == 0) ? -1 : mol_idx[i - 1];
+    int cur = (i == n) ? n_mol : mol_idx[i];
+    for (int s = prev + 1; s <= cur && s <= n_mol; ++s) ptr[s] = i;
+}
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    T r = 0;
+    int nw = (blockDim.x + 31) >> 5;
+    for (int k = 0; k < nw; ++k) r += smem[k];
+    return r;
+}
+
+__device__ __forceinline__ float target_charge(int C, int c, const float* charge, const float* mult, int m) {
+    // NSE split (aimnet/models/aimnet2.py:94-100)
+    if (C == 1) return charge[m];
+    float hs = 0.5f * ((mult ? mult[m] : 1.0f) - 1.0f), hq = 0.5f * charge[m];
+    return c == 0 ? hq + hs : hq - hs;
+}
+
+// per molecule: sumq[m,c] = sum_i q_u, sumf[m,c] = sum_i f_raw^2   (aimnet/ops.py:99-145, nbops.py:309-377)
+__global__ void __launch_bounds__(256) nse_reduce_fwd_kernel(int C, const int32_t* __restrict__ mol_ptr,
+                                                             const float* __restrict__ y, int ldy,
+                                                             const float* __restrict__ q_prev,
+                                                             float* __restrict__ sumq, float* __restrict__ sumf) {
+    __shared__ float red[8];
+    int m = blockIdx.x;
+    int s0 = mol_ptr[m], s1 = mol_ptr[m + 1];
+    for (int c = 0; c < C; ++c) {
+        float aq = 0.f, af = 0.f;
+        for (int i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+            float dq = y[(size_t)i * ldy + c];
+            float fr = y[(size_t)i * ldy + C + c];
+            aq += (q_prev ? q_prev[(size_t)i * C + c] : 0.f) + dq;
+            af += fr * fr;
+        }
+        aq = block_sum(aq, red);
+        af = block_sum(af, red);
+        if (threadIdx.x == 0) {
+            sumq[m * C + c] = aq;
+            sumf[m * C + c] = af;
+        }
+    }
+}
+
+// per atom: q <- q_u + f (Q - sumq)/(sumf + eps) ; a <- a + delta_a     (aimnet/models/aimnet2.py:122-139)
+__global__ void __launch_bounds__(256) nse_apply_fwd_kernel(int C, int n, const int32_t* __restrict__ mol_idx,
+                                                            const float* __restrict__ charge,
+                                                            const float* __restrict__ mult,
+                                                            const float* __restrict__ y, int ldy,
+                                                            const float* __restrict__ q_prev,
+                                                            const float* __restrict__ sumq,
+                                                            const float* __restrict__ sumf,
+                                                            const float* __restrict__ a_old, float* __restrict__ a_new,
+                                                            float* __restrict__ q_new) {
+    int i = blockIdx.x, t = threadIdx.x;
+    a_new[(size_t)i * kAG + t] = a_old[(size_t)i * kAG + t] + y[(size_t)i * ldy + 2 * C + t];
+    if (t < C) {
+        int m = mol_idx ? mol_idx[i] : 0;
+        float qu = (q_prev ? q_prev[(size_t)i * C + t] : 0.f) + y[(size_t)i * ldy + t];
+        float fr = y[(size_t)i * ldy + C + t];
+        float f = fr * fr;
+        float Q = target_charge(C, t, charge, mult, m);
+        float F = sumf[m * C + t] + 1.0e-6f;
+        float dQ = Q - sumq[m * C + t];
+        q_new[(size_t)i * C + t] = qu + f / F * dQ;
+    }
+}
+
+// backward of the NSE update.  With q_i = qu_i + f_i D/G (D = Q - sum qu, G = sum f + eps) and g_i = dE/dq_i:
+//   S1 = sum_i g_i f_i ;  h_i = g_i - S1/G ;  dE/dqu_i = h_i ;  dE/df_raw_i = 2 f_raw_i (D/G) h_i
+__global__ void __launch_bounds__(256) nse_reduce_bwd_kernel(int C, const int32_t* __restrict__ mol_ptr,
+                                                             const float* __restrict__ y, int ldy,
+                                                             const float* __restrict__ gq, float* __restrict__ s1) {
+    __shared__ float red[8];
+    int m = blockIdx.x;
+    int p0 = mol_ptr[m], p1 = mol_ptr[m + 1];
+    for (int c = 0; c < C; ++c) {
+        float acc = 0.f;
+        for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+            float fr = y[(size_t)i * ldy + C + c];
+            acc += gq[(size_t)i * C + c] * fr * fr;
+        }
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) s1[m * C + c] = acc;
+    }
+}
+
+// writes dz[i, :] (gradient w.r.t. the pre-activation of the pass MLP's last Linear) and dq_prev (dE/dq of the
+// previous pass through qu = q_prev + dq)
+__global__ void __launch_bounds__(288) nse_apply_bwd_kernel(int C, int n, const int32_t* __restrict__ mol_idx,
+                                                            const float* __restrict__ charge,
+                                                            const float* __restrict__ mult,
+                                                            const float* __restrict__ y, int ldy,
+                                                            const float* __restrict__ gq,
+                                                            const float* __restrict__ sumq,
+                                                            const float* __restrict__ sumf,
+                                                            const float* __restrict__ s1,
+                                                            const float* __restrict__ da_tot,
+                                                            const float* __restrict__ gp_last, int ldgp,
+                                                            float* __restrict__ dz, int lddz,
+                                                            float* __restrict__ dq_prev) {
+    int i = blockIdx.x, t = threadIdx.x;
+    if (t >= lddz) return;
+    float v = 0.f;
+    int m = mol_idx ? mol_idx[i] : 0;
+    if (t < 2 * C) {
+        int c = (t < C) ? t : t - C;
+        float G = sumf[m * C + c] + 1.0e-6f;
+        float h = gq[(size_t)i * C + c] - s1[m * C + c] / G;
+        if (t < C) {
+            v = h;
+            if (dq_prev) dq_prev[(size_t)i * C + c] = h;
+        } else {
+            float D = target_charge(C, c, charge, mult, m) - sumq[m * C + c];
+            v = 2.0f * y[(size_t)i * ldy + C + c] * (D / G) * h;
+        }
+    } else if (t < 2 * C + kAG) {
+        v = da_tot[(size_t)i * kAG + (t - 2 * C)];
+    }
+    if (gp_last != nullptr && t < 2 * C + kAG) v *= gp_last[(size_t)i * ldgp + t];
+    dz[(size_t)i * lddz + t] = v;
+}
+
+// da_tot (+)= dx[:, :256] + grad_a ;  dq = base_q + dx[:, 704+c] + grad_q
+__global__ void __launch_bounds__(256) accum_grads_kernel(int C, int n, const float* __restrict__ dx, int ldx,
+                                                          const float* __restrict__ grad_a,
+                                                          const float* __restrict__ grad_q,
+                                                          const float* __restrict__ base_q, int base_q_stride,
+                                                          float* __restrict__ da_tot, int accumulate,
+                                                          float* __restrict__ dq) {
+    int i = blockIdx.x, t = threadIdx.x;
+    float v = dx[(size_t)i * ldx + t] + grad_a[(size_t)i * kAG + t];
+    if (accumulate) v += da_tot[(size_t)i * kAG + t];
+    da_tot[(size_t)i * kAG + t] = v;
+    if (t < C) {
+        float b = base_q[(size_t)i * base_q_stride + (base_q_stride == 1 ? 0 : t)];
+        dq[(size_t)i * C + t] = b + dx[(size_t)i * ldx + (2 * kAG + kAH) + t] + grad_q[(size_t)i * C + t];
+    }
+}
+
+// energy head tail: e_i = w3 . h2_i + b3 (+ SAE in fp64); seeds the backward pass with dz2 = w3 * gelu'(z2)
+// (aimnet/modules/core.py:114-132, 71-97).  One warp per atom.
+__global__ void __launch_bounds__(256) head_tail_kernel(int n, const float* __restrict__ h2, int ldh,
+                                                        const float* __restrict__ gp2, const float* __restrict__ w3,
+                                                        float b3, const int32_t* __restrict__ numbers,
+                                                        const double* __restrict__ sae, double* __restrict__ e_atom,
+                                                        float* __restrict__ dz2) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    int i = warp;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int c = lane + 32 * k;
+        float w = w3[c];
+        acc += w * h2[(size_t)i * ldh + c];
+        dz2[(size_t)i * ldh + c] = w * gp2[(size_t)i * ldh + c];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        int z = numbers[i];
+        z = (z < 0 || z > 63) ? 0 : z;
+        e_atom[i] = (double)(acc + b3) + sae[z];
+    }
+}
+
+// energy[m] = sum_{i in m} (e_nn + e_sr + e_lr + e_d3)   fp64 (aimnet/modules/core.py:100-111)
+__global__ void __launch_bounds__(256) energy_reduce_kernel(const int32_t* __restrict__ mol_ptr,
+                                                            const double* __restrict__ e0,
+                                                            const double* __restrict__ e1,
+                                                            const double* __restrict__ e2,
+                                                            const double* __restrict__ e3,
+                                                            double* __restrict__ energy) {
+    __shared__ double red[8];
+    int m = blockIdx.x;
+    int p0 = mol_ptr[m], p1 = mol_ptr[m + 1];
+    double acc = 0.0;
+    for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+        double v = e0[i];
+        if (e1) v += e1[i];
+        if (e2) v += e2[i];
+        if (e3) v += e3[i];
+        acc += v;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) energy[m] = acc;
+}
+
+// stress[s] = sum_{i in s} virial_atom[i] / |det cell_s|   (aimnet/calculators/derivatives.py:122-137)
+__global__ void __launch_bounds__(256) stress_reduce_kernel(const int32_t* __restrict__ mol_ptr, int n_cells, int n,
+                                                            const double* __restrict__ virial_atom,
+                                                            const float* __restrict__ cell, float* __restrict__ stress) {
+    __shared__ double red[8];
+    int s = blockIdx.x;
+    int p0 = (n_cells == 1) ? 0 : mol_ptr[s], p1 = (n_cells == 1) ? n : mol_ptr[s + 1];
+    const float* c = cell + 9 * s;
+    double det = (double)c[0] * ((double)c[4] * c[8] - (double)c[5] * c[7]) -
+                 (double)c[1] * ((double)c[3] * c[8] - (double)c[5] * c[6]) +
+                 (double)c[2] * ((double)c[3] * c[7] - (double)c[4] * c[6]);
+    double vol = fabs(det);
+    for (int k = 0; k < 9; ++k) {
+        double acc = 0.0;
+        for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) acc += virial_atom[(size_t)i * 9 + k];
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) stress[9 * s + k] = (float)(acc / vol);
+    }
+}
+
+// final charges: C==1 copy; C==2: charges = qa+qb, spin = qa-qb (aimnet/models/aimnet2.py:102-106)
+__global__ void charges_out_kernel(int C, int n, const float* __restrict__ q, float* __restrict__ charges,
+                                   float* __restrict__ spin) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (C == 1) {
+        charges[i] = q[i];
+    } else {
+        float a = q[2 * i], b = q[2 * i + 1];
+        charges[i] = a + b;
+        if (spin) spin[i] = a - b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+#define AIM_K(...)          \
+    do {                    \
+        __VA_ARGS__;        \
+        AIM_LAUNCH_CHECK(); \
+    } while (0)
+
+int launch_embed(int n, const int32_t* numbers, const float* afv, float* a0, cudaStream_t st) {
+    if (n) AIM_K(embed_kernel<<<n, 256, 0, st>>>(n, numbers, afv, a0));
+    return AIMNET_OK;
+}
+int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, cudaStream_t st) {
+    AIM_K(mol_ptr_kernel<<<(n + 256) / 256, 256, 0, st>>>(mol_idx, n, n_mol, ptr));
+    return AIMNET_OK;
+}
+int launch_nse_fwd(int C, int n, int n_mol, const int32_t* mol_idx, const int32_t* mol_ptr, const float* charge,
+                   const float* mult, const float* y, int ldy, const float* q_prev, float* sumq, float* sumf,
+                   const float* a_old, float* a_new, float* q_new, cudaStream_t st) {
+    if (!n) return AIMNET_OK;
+    AIM_K(nse_reduce_fwd_kernel<<<n_mol, 256, 0, st>>>(C, mol_ptr, y, ldy, q_prev, sumq, sumf));
+    AIM_K(nse_apply_fwd_kernel<<<n, 256, 0, st>>>(C, n, mol_idx, charge, mult, y, ldy, q_prev, sumq, sumf, a_old, a_new,
+                                                 q_new));
+    return AIMNET_OK;
+}
+int launch_nse_bwd(int C, int n, int n_mol, const int32_t* mol_idx, const int32_t* mol_ptr, const float* charge,
+                   const float* mult, const float* y, int ldy, const float* gq, const float* sumq, const float* sumf,
+                   float* s1, const float* da_tot, const float* gp_last, int ldgp, float* dz, int lddz, float* dq_prev,
+                   cudaStream_t st) {
+    if (!n) return AIMNET_OK;
+    if (lddz > 288) {
+        set_error("nse_bwd: lddz > 288");
+        return AIMNET_EINVAL;
+    }
+    AIM_K(nse_reduce_bwd_kernel<<<n_mol, 256, 0, st>>>(C, mol_ptr, y, ldy, gq, s1));
+    AIM_K(nse_apply_bwd_kernel<<<n, 288, 0, st>>>(C, n, mol_idx, charge, mult, y, ldy, gq, sumq, sumf, s1, da_tot,
+                                                 gp_last, ldgp, dz, lddz, dq_prev));
+    return AIMNET_OK;
+}
+int launch_accum_grads(int C, int n, const float* dx, int ldx, const float* grad_a, const float* grad_q,
+                       const float* base_q, int base_q_stride, float* da_tot, int accumulate, float* dq,
+                       cudaStream_t st) {
+    if (n) AIM_K(accum_grads_kernel<<<n, 256, 0, st>>>(C, n, dx, ldx, grad_a, grad_q, base_q, base_q_stride, da_tot,
+                                                      accumulate, dq));
+    return AIMNET_OK;
+}
+int launch_head_tail(int n, const float* h2, int ldh, const float* gp2, const float* w3, float b3,
+                     const int32_t* numbers, const double* sae, double* e_atom, float* dz2, cudaStream_t st) {
+    if (n) AIM_K(head_tail_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, h2, ldh, gp2, w3, b3, numbers, sae, e_atom, dz2));
+    return AIMNET_OK;
+}
+int launch_energy_reduce(int n_mol, const int32_t* mol_ptr, const double* e0, const double* e1, const double* e2,
+                         const double* e3, double* energy, cudaStream_t st) {
+    AIM_K(energy_reduce_kernel<<<n_mol, 256, 0, st>>>(mol_ptr, e0, e1, e2, e3, energy));
+    return AIMNET_OK;
+}
+int launch_stress_reduce(const int32_t* mol_ptr, int n_cells, int n, const double* virial_atom, const float* cell,
+                         float* stress, cudaStream_t st) {
+    AIM_K(stress_reduce_kernel<<<n_cells, 256, 0, st>>>(mol_ptr, n_cells, n, virial_atom, cell, stress));
+    return AIMNET_OK;
+}
+int launch_charges_out(int C, int n, const float* q, float* charges, float* spin, cudaStream_t st) {
+    if (n) AIM_K(charges_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(C, n, q, charges, spin));
+    return AIMNET_OK;
+}
+
+}  // namespace aimnet

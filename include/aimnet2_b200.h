@@ -1,0 +1,184 @@
+/*
+ * aimnet2_b200.h — C ABI of the B200-native AIMNet2 hot path (libaimnet2_b200.so).
+ *
+ * Plain pointers and sizes only; no torch types.  Every entry returns an int status:
+ *     0  AIMNET_OK
+ *     1  AIMNET_NEIGHBOR_OVERFLOW   a row needs more slots than `max_neighbors`; the host retries with a wider buffer,
+ *                                   the contract of NeighborOverflowError in the reference
+ *                                   (aimnet/calculators/neighbors.py:127-130)
+ *    <0  invalid argument / CUDA failure (aimnet2_last_error() has the text); the Python host raises
+ *        ValueError / RuntimeError like aimnet/kernels/conv_sv_2d_sp_wp.py:649-658
+ *
+ * All device pointers are plain CUDA device memory owned by the caller (torch on the Python side); work is
+ * enqueued on `stream` (a cudaStream_t passed as void*), like the reference's Warp ops launch on
+ * torch.cuda.current_stream (aimnet/kernels/conv_sv_2d_sp_wp.py:78-82).
+ *
+ * Which reference interface each entry replaces (paths relative to the reference tree):
+ *   aimnet2_neighbor_matrix      nvalchemiops.torch.neighbors.neighbor_list as called at
+ *                                aimnet/calculators/neighbors.py:106-125 and aimnet/modules/lr.py:388-396
+ *   aimnet2_conv_sv_2d_sp_fwd    torch.ops.aimnet.conv_sv_2d_sp_fwd   aimnet/kernels/conv_sv_2d_sp_wp.py:252-276
+ *   aimnet2_conv_sv_2d_sp_bwd    torch.ops.aimnet.conv_sv_2d_sp_bwd   aimnet/kernels/conv_sv_2d_sp_wp.py:285-330
+ *   aimnet2_engine_*             AIMNet2Calculator.eval hot path       aimnet/calculators/calculator.py:879-947
+ *                                = AIMNet2.forward (aimnet/models/aimnet2.py:141-187) + SRCoulomb/LRCoulomb/DFTD3
+ *                                (aimnet/modules/lr.py:311-331, 559-615, 986-1032, 1580-1657) + the autograd
+ *                                force/stress pass (aimnet/calculators/derivatives.py:96-146), as analytic kernels
+ */
+#ifndef AIMNET2_B200_H
+#define AIMNET2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIMNET_OK 0
+#define AIMNET_NEIGHBOR_OVERFLOW 1
+#define AIMNET_EINVAL (-1)
+#define AIMNET_ECUDA (-2)
+
+/* Coulomb method of the external LRCoulomb module (aimnet/modules/lr.py:212-331) */
+#define AIMNET_COULOMB_NONE 0
+#define AIMNET_COULOMB_SIMPLE 1
+#define AIMNET_COULOMB_DSF 2
+#define AIMNET_COULOMB_EWALD 3
+
+/* output request flags */
+#define AIMNET_WANT_FORCES 1
+#define AIMNET_WANT_STRESS 2
+
+const char* aimnet2_last_error(void);
+int aimnet2_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Neighbor matrix (full list, both directions).  Canonical form: `d2 < cutoff^2` in float32, rows sorted by
+ * (j, sx, sy, sz), unused slots = fill_value, zero shifts.
+ *   positions   (n_atoms,3) f32 device        batch_idx  (n_atoms) i32 device, sorted, or NULL (one system)
+ *   cell        (n_cells,3,3) f32 device or NULL ; host_cell = the same values in host memory (grid sizing)
+ *   pbc         3*n_cells bytes on host (0/1), or NULL = all periodic when cell != NULL
+ *   nbmat       (n_atoms, max_neighbors) i32 device out
+ *   shifts      (n_atoms, max_neighbors, 3) i32 device out, or NULL when cell == NULL
+ *   num_neighbors (n_atoms) i32 device out (true counts, may exceed max_neighbors on overflow)
+ *   max_count_host   optional host int*, receives max(num_neighbors) (forces a stream sync)
+ *   sorted      1 = canonical row order (always for the naive builder; per-row sort for the cell-list builder)
+ * ------------------------------------------------------------------------------------------------------------- */
+int aimnet2_neighbor_matrix(const float* positions, int n_atoms, float cutoff, const float* cell,
+                            const float* host_cell, const uint8_t* pbc, int n_cells, const int32_t* batch_idx,
+                            int n_systems, int max_neighbors, int fill_value, int sorted, int32_t* nbmat,
+                            int32_t* shifts, int32_t* num_neighbors, int* max_count_host, void* stream);
+
+/* wrap positions into the cell on periodic axes: ((x @ inv(cell)) mod 1) @ cell  (aimnet/calculators/neighbors.py:331) */
+int aimnet2_wrap_positions(const float* positions, float* wrapped, int n_atoms, const float* cell, int n_cells,
+                           const uint8_t* pbc_host, const int32_t* batch_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * conv_sv_2d_sp operator seam:  a (B,A,G) f32, idx (B,M) i32 with padding value B-1, g (B,M,G,4) f32.
+ * out (B,A,G,4); row B-1 is the padding row and is written as zero.
+ * ------------------------------------------------------------------------------------------------------------- */
+int aimnet2_conv_sv_2d_sp_fwd(const float* a, const int32_t* idx, const float* g, float* out, int B, int A, int G,
+                              int M, void* stream);
+int aimnet2_conv_sv_2d_sp_bwd(const float* grad_out, const float* a, const int32_t* idx, const float* g,
+                              float* grad_a, float* grad_g, int B, int A, int G, int M, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Engine: weights resident in HBM, one call = one E(+F, +stress) evaluation.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct aimnet2_engine aimnet2_engine_t;
+
+/* Weights in the reference's state_dict layout, host pointers, float32 unless noted.
+ * Linear weights are (out,in) row-major as torch stores them. */
+typedef struct {
+    int num_charge_channels;          /* 1 closed-shell, 2 NSE */
+    const float* afv;                 /* (64, 256) */
+    const float* agh_a;               /* (16,16,12) conv_a.agh */
+    const float* agh_q;               /* (C,16,12)  conv_q.agh */
+    const float* shifts_s;            /* (16) aev.shifts_s */
+    float eta_s;                      /* aev.eta_s */
+    float rc_s;                       /* aev.rc_s */
+    int n_layers[3];                  /* Linear layers per pass MLP (3,3,4) */
+    const int* layer_dims[3];         /* per pass: n_layers+1 ints: in, hidden..., out */
+    const float* const* mlp_w[3];     /* per pass: n_layers pointers */
+    const float* const* mlp_b[3];
+    const float* head_w[3];           /* 256->128->128->1 */
+    const float* head_b[3];
+    const double* sae;                /* (64) outputs.atomic_shift.shifts.weight, float64 */
+    float sr_rc;                      /* outputs.srcoulomb.rc (4.6) */
+    int sr_envelope;                  /* 0 exp, 1 cosine */
+    /* DFT-D3 tables (aimnet/dftd3_data.pt), may be NULL when dispersion is never requested */
+    const float* d3_c6ref;            /* (95,95,5,5) */
+    const float* d3_cnref;            /* (95,5) */
+    const float* d3_rcov;             /* (95) */
+    const float* d3_r4r2;             /* (95) */
+} aimnet2_weights_t;
+
+typedef struct {
+    int coulomb_method;               /* AIMNET_COULOMB_* ; external LRCoulomb(subtract_sr=False) */
+    float dsf_alpha, dsf_rc;          /* 0.2, 15.0 */
+    float ewald_accuracy;             /* 1e-6 */
+    int dispersion;                   /* 1 = external DFTD3 */
+    float d3_s6, d3_s8, d3_a1, d3_a2;
+    float d3_cutoff, d3_smoothing;    /* 15.0, 0.2 */
+    float sr_cutoff;                  /* 5.0 */
+} aimnet2_options_t;
+
+/* One evaluation.  Flat (mode-1) layout, real atoms only (the engine adds no padding atom; sentinel = n_atoms).
+ * Device pointers unless noted. */
+typedef struct {
+    int n_atoms, n_mol;
+    const float* coord;               /* (n_atoms,3) */
+    const int32_t* numbers;           /* (n_atoms) */
+    const int32_t* mol_idx;           /* (n_atoms) sorted; NULL = single molecule */
+    const float* charge;              /* (n_mol) */
+    const float* mult;                /* (n_mol) or NULL (NSE only) */
+    const float* cell;                /* (n_cells,3,3) or NULL */
+    const float* host_cell;           /* host copy of cell (grid sizing), NULL iff cell NULL */
+    int n_cells;                      /* 0, 1 or n_mol */
+    const uint8_t* pbc_host;          /* 3*n_cells host bytes or NULL */
+    /* optional caller-supplied short-range neighbor matrix in the reference layout (n_atoms+1 or n_atoms rows) */
+    const int32_t* nbmat;             /* (rows, nb_width) sentinel = n_atoms, or NULL = build it */
+    const int32_t* shifts;            /* (rows, nb_width, 3) or NULL */
+    int nb_width;
+} aimnet2_system_t;
+
+typedef struct {
+    double* energy;                   /* (n_mol) f64 */
+    float* charges;                   /* (n_atoms) */
+    float* spin_charges;              /* (n_atoms) or NULL */
+    float* forces;                    /* (n_atoms,3) or NULL */
+    float* stress;                    /* (n_cells,3,3) or NULL */
+    /* optional: the short-range neighbor matrix the engine built, reference layout with the padding row */
+    int32_t* nbmat_out;               /* (n_atoms+1, nbmat_out_width) or NULL */
+    int32_t* shifts_out;              /* (n_atoms+1, nbmat_out_width, 3) or NULL */
+    int nbmat_out_width;
+} aimnet2_result_t;
+
+int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weights_t* w, int device);
+int aimnet2_engine_destroy(aimnet2_engine_t* e);
+int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt);
+/* GEMM backend for the per-atom MLPs: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (default when available) */
+int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
+
+/* device-resident inputs/outputs; flags = AIMNET_WANT_* */
+int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
+                        void* stream);
+/* same with every pointer of sys/res in HOST memory: H2D copies, evaluation, D2H copies, stream sync inside */
+int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags);
+
+/* introspection: kernels launched by the last eval, last short-range / long-range list widths, workspace bytes */
+int aimnet2_engine_last_launches(const aimnet2_engine_t* e);
+int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int* lr_width, int64_t* workspace_bytes);
+/* per-phase device times (ms) of the last eval when timing was enabled; phases: 0 neighbors, 1 forward,
+ * 2 long-range, 3 backward, 4 total; returns number of phases written */
+int aimnet2_engine_enable_timing(aimnet2_engine_t* e, int on);
+int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, int n);
+
+/* standalone NT GEMM with fused epilogue (test seam for the MLP kernels):
+ * Y[M,N] = act(A[M,K] @ W[N,K]^T + bias); mode 0 none, 1 bias, 2 bias+GELU (also writes gelu'(z) to aux when non-NULL),
+ * 3 multiply by aux[M,N].  lda/ldw/ldy in elements. */
+int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                    float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

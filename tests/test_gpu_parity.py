@@ -1,0 +1,192 @@
+"""GPU parity: the CUDA path (through the C ABI / AIMNet2Calculator) against the committed golden outputs of the
+unmodified reference and against the CPU oracle on the same seeded inputs."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import CHARGE_ATOL, ENERGY_ATOL, FORCE_ATOL, golden_state_dict, load_golden
+
+pytestmark = pytest.mark.gpu
+
+_CALCS = {}
+
+
+def get_calc(meta):
+    from aimnetcentral_b200 import AIMNet2Calculator
+
+    key = (meta["weights_seed"], meta["num_charge_channels"])
+    if key not in _CALCS:
+        sd, spec = golden_state_dict(meta)
+        _CALCS[key] = AIMNet2Calculator((sd, spec), device="cuda:0")
+    return _CALCS[key]
+
+
+CASES = [
+    ("taxol_q0", {}),
+    ("taxol_q1", {}),
+    ("caffeine", {}),
+    ("mols_8x50", {}),
+    ("mols_ragged", {}),
+    ("pbc_box60_dsf", {"stress": True}),
+    ("pbc_slab60_dsf", {}),
+    ("allose_1x1x1_dsf", {"stress": True}),
+    ("allose_2x1x1_dsf", {"stress": True}),
+    ("nse_4x20", {}),
+]
+
+
+def _report(name, out, ref, n):
+    de = np.abs(out["energy"] - ref["energy"]).max()
+    df = np.abs(out["forces"] - ref["forces"]).max()
+    dq = np.abs(out["charges"] - ref["charges"]).max()
+    print(f"[parity] {name}: N={n} max|dE|={de:.3e} eV  max|dF|={df:.3e} eV/A  max|dq|={dq:.3e}")
+    return de, df, dq
+
+
+@pytest.mark.parametrize("name,kw", CASES, ids=[c[0] for c in CASES])
+def test_calculator_matches_reference_golden(name, kw):
+    inputs, ref, meta = load_golden(name)
+    calc = get_calc(meta)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = calc(dict(inputs), forces=True, stress=bool(kw.get("stress")))
+    out = {k: v.detach().cpu().numpy() for k, v in res.items()}
+    assert out["energy"].dtype == np.float64 and out["forces"].dtype == np.float32
+    de, df, dq = _report(name, out, ref, len(inputs["numbers"]))
+    assert de < ENERGY_ATOL, f"energy off by {de}"
+    assert df < FORCE_ATOL, f"forces off by {df}"
+    assert dq < CHARGE_ATOL, f"charges off by {dq}"
+    if "spin_charges" in ref:
+        assert np.abs(out["spin_charges"] - ref["spin_charges"]).max() < CHARGE_ATOL
+    if kw.get("stress"):
+        ds = np.abs(out["stress"] - ref["stress"]).max()
+        print(f"[parity] {name}: max|dstress|={ds:.3e} eV/A^3")
+        assert ds < 1e-5
+
+
+def test_components_against_reference():
+    """NN-only and NN+Coulomb (no D3) goldens isolate the terms."""
+    from aimnetcentral_b200 import AIMNet2Calculator
+
+    inputs, ref, meta = load_golden("taxol_q1")
+    sd, spec = golden_state_dict(meta)
+    nn_only = AIMNet2Calculator((sd, spec), device="cuda:0", needs_coulomb=False, needs_dispersion=False)
+    out = {k: v.cpu().numpy() for k, v in nn_only(dict(inputs), forces=True).items()}
+    print("[parity] nn-only dE", abs(out["energy"][0] - ref["energy_nn"][0]), "dF", np.abs(out["forces"] - ref["forces_nn"]).max())
+    assert abs(out["energy"][0] - ref["energy_nn"][0]) < ENERGY_ATOL
+    assert np.abs(out["forces"] - ref["forces_nn"]).max() < FORCE_ATOL
+    nod3 = AIMNet2Calculator((sd, spec), device="cuda:0", needs_dispersion=False)
+    out = {k: v.cpu().numpy() for k, v in nod3(dict(inputs), forces=True).items()}
+    print("[parity] no-d3 dE", abs(out["energy"][0] - ref["energy_nod3"][0]), "dF", np.abs(out["forces"] - ref["forces_nod3"]).max())
+    assert abs(out["energy"][0] - ref["energy_nod3"][0]) < ENERGY_ATOL
+    assert np.abs(out["forces"] - ref["forces_nod3"]).max() < FORCE_ATOL
+
+
+def test_dense_batch_equals_flat():
+    """(B,N,3) input == flat + mol_idx input (tests/test_calculator.py:1017-1218 of the reference)."""
+    inputs, ref, meta = load_golden("mols_8x50")
+    calc = get_calc(meta)
+    dense = {"coord": inputs["coord"].reshape(8, 50, 3), "numbers": inputs["numbers"].reshape(8, 50),
+             "charge": inputs["charge"]}
+    res = calc(dense, forces=True)
+    assert res["forces"].shape == (8, 50, 3) and res["charges"].shape == (8, 50) and res["energy"].shape == (8,)
+    assert np.abs(res["forces"].cpu().numpy().reshape(-1, 3) - ref["forces"]).max() < FORCE_ATOL
+    assert np.abs(res["energy"].cpu().numpy() - ref["energy"]).max() < ENERGY_ATOL
+
+
+def test_padded_dense_batch():
+    """numbers == 0 padding in a dense batch: padded atoms get zero outputs, real atoms unchanged."""
+    inputs, ref, meta = load_golden("mols_ragged")
+    calc = get_calc(meta)
+    mi = inputs["mol_idx"]
+    B, nmax = int(mi.max()) + 1, int(np.bincount(mi).max())
+    coord = np.zeros((B, nmax, 3), np.float32)
+    numbers = np.zeros((B, nmax), np.int32)
+    for b in range(B):
+        sel = mi == b
+        coord[b, : sel.sum()] = inputs["coord"][sel]
+        numbers[b, : sel.sum()] = inputs["numbers"][sel]
+    res = calc({"coord": coord, "numbers": numbers, "charge": inputs["charge"]}, forces=True)
+    f = res["forces"].cpu().numpy()
+    flat = np.concatenate([f[b, : (mi == b).sum()] for b in range(B)])
+    assert np.abs(flat - ref["forces"]).max() < FORCE_ATOL
+    assert np.abs(res["energy"].cpu().numpy() - ref["energy"]).max() < ENERGY_ATOL
+    assert float(np.abs(f[numbers == 0]).max()) == 0.0
+
+
+def test_oracle_parity_random_batch():
+    """Seeded batch bigger than the fixtures: CUDA vs the CPU oracle run here (64 x 50 atoms)."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import random_molecules
+    from oracle.calculator_oracle import oracle_calculate
+
+    spec = ModelSpec()
+    sd = random_state_dict(0, spec)
+    coord, numbers = random_molecules(64, 50, seed=99)
+    inp = {"coord": coord, "numbers": numbers, "charge": np.zeros(64, np.float32)}
+    ref = oracle_calculate(sd, inp)
+    calc = AIMNet2Calculator((sd, spec), device="cuda:0")
+    res = calc(inp, forces=True)
+    df = np.abs(res["forces"].cpu().numpy() - ref["forces"]).max()
+    de = np.abs(res["energy"].cpu().numpy() - ref["energy"]).max()
+    dq = np.abs(res["charges"].cpu().numpy() - ref["charges"]).max()
+    print(f"[parity] random 64x50: max|dE|={de:.3e} max|dF|={df:.3e} max|dq|={dq:.3e}")
+    assert de < ENERGY_ATOL and df < FORCE_ATOL and dq < CHARGE_ATOL
+
+
+def test_invariances_full_size():
+    """cfg-2 sized batch (1024 x 50): size-independent properties — total force on each isolated molecule vanishes,
+    rigid translation + permutation of molecules leaves per-molecule results unchanged, charges sum to the target."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import random_molecules
+
+    spec = ModelSpec()
+    sd = random_state_dict(0, spec)
+    calc = AIMNet2Calculator((sd, spec), device="cuda:0")
+    coord, numbers = random_molecules(1024, 50, seed=1234)
+    charge = np.zeros(1024, np.float32)
+    charge[::7] = 1.0
+    r1 = calc({"coord": coord, "numbers": numbers, "charge": charge}, forces=True)
+    f1 = r1["forces"].cpu().numpy()
+    assert np.abs(f1.sum(axis=1)).max() < 2e-4
+    assert np.abs(r1["charges"].cpu().numpy().sum(axis=1) - charge).max() < 1e-4
+    perm = np.random.default_rng(0).permutation(1024)
+    shift = np.random.default_rng(1).normal(0, 3.0, (1024, 1, 3)).astype(np.float32)
+    r2 = calc({"coord": (coord + shift)[perm], "numbers": numbers[perm], "charge": charge[perm]}, forces=True)
+    assert np.abs(r2["energy"].cpu().numpy() - r1["energy"].cpu().numpy()[perm]).max() < 2e-4
+    assert np.abs(r2["forces"].cpu().numpy() - f1[perm]).max() < 2e-4
+
+
+def test_host_buffer_entry_matches_device_entry():
+    """aimnet2_engine_eval_host (H2D + compute + D2H inside the C call) == device-resident call."""
+    inputs, ref, meta = load_golden("mols_8x50")
+    calc = get_calc(meta)
+    calc.engine.set_options(coulomb_method="simple", dispersion=True)
+    out = calc.engine.eval_host(inputs["coord"], inputs["numbers"].astype(np.int32), inputs["charge"],
+                                mol_idx=inputs["mol_idx"].astype(np.int32), forces=True)
+    assert np.abs(out["forces"] - ref["forces"]).max() < FORCE_ATOL
+    assert np.abs(out["energy"] - ref["energy"]).max() < ENERGY_ATOL
+    assert calc.engine.last_launches() > 20
+
+
+def test_errors_and_warnings():
+    inputs, ref, meta = load_golden("caffeine")
+    calc = get_calc(meta)
+    with pytest.raises(KeyError):
+        calc({"coord": inputs["coord"], "numbers": inputs["numbers"]})
+    bad = dict(inputs)
+    bad["numbers"] = inputs["numbers"].copy()
+    bad["numbers"][0] = 26
+    with pytest.raises(ValueError):
+        calc(bad)
+    with pytest.raises(NotImplementedError):
+        calc(dict(inputs), hessian=True)
+    inputs_p, _, _ = load_golden("pbc_box60_dsf")
+    with pytest.warns(UserWarning, match="Switching to DSF"):
+        calc(dict(inputs_p), forces=True)
+    assert calc.coulomb_method == "simple"  # the auto-switch is scoped to one evaluation
+    calc.set_lrcoulomb_method("ewald")
+    with pytest.raises(ValueError):
+        calc(dict(inputs))
+    calc.set_lrcoulomb_method("simple")
