@@ -92,6 +92,11 @@ struct aimnet2_engine {
     int timing = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
+    // per-GEMM events (timing level 2): pairs (begin, end) in launch order
+    std::vector<cudaEvent_t> gemm_ev;
+    int gemm_ev_used = 0;
+    float last_gemm_ms = 0.f;
+    int last_gemm_launches = 0;
     std::vector<void*> owned;
 };
 
@@ -216,16 +221,44 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.forces_tmp = bp.take<float>(n * 3);
 }
 
+static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
+    if (e->timing < 2) return;
+    if (e->gemm_ev_used == (int)e->gemm_ev.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->gemm_ev.push_back(ev);
+    }
+    cudaEventRecord(e->gemm_ev[e->gemm_ev_used++], st);
+}
+
 static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ldx, int K, float* Y, float* gp, bool act,
                       int M, cudaStream_t st) {
-    return gemm_nt(X, ldx, L.W, L.in_pad, L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1,
-                   e->gemm_backend, st);
+    gemm_mark(e, st);
+    int rc = gemm_nt(X, ldx, L.W, L.in_pad, L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1,
+                     e->gemm_backend, st);
+    gemm_mark(e, st);
+    return rc;
 }
 // dX[M,in_pad] = dZ[M,out_pad] @ W  (* gp_prev)
 static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float* dX, int lddx, const float* gp_prev,
                       int ldgp, int M, cudaStream_t st) {
-    return gemm_nt(dZ, L.out_pad, L.Wt, L.out_pad, nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad,
-                   L.out_pad, gp_prev ? 3 : 0, e->gemm_backend, st);
+    gemm_mark(e, st);
+    int rc = gemm_nt(dZ, L.out_pad, L.Wt, L.out_pad, nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad,
+                     L.out_pad, gp_prev ? 3 : 0, e->gemm_backend, st);
+    gemm_mark(e, st);
+    return rc;
+}
+
+static void collect_timing(aimnet2_engine* e) {
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev[k], e->ev[k + 1]);
+    cudaEventElapsedTime(&e->last_ms[4], e->ev[0], e->ev[4]);
+    e->last_gemm_ms = 0.f;
+    e->last_gemm_launches = e->gemm_ev_used / 2;
+    for (int k = 0; k + 1 < e->gemm_ev_used; k += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->gemm_ev[k], e->gemm_ev[k + 1]);
+        e->last_gemm_ms += ms;
+    }
 }
 
 #define AIM_TRY(expr)                      \
@@ -259,6 +292,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     AIM_REQUIRE(o.coulomb_method != AIMNET_COULOMB_EWALD, "engine_eval: Ewald Coulomb is not implemented in this build");
     AIM_REQUIRE(!o.dispersion || e->d3_c6ref, "engine_eval: dispersion requested but no D3 tables were loaded");
     g_launch_count = 0;
+    e->gemm_ev_used = 0;
     const bool pbc = sys->cell != nullptr;
     const bool backward = want_f || want_s;
     const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
@@ -549,6 +583,7 @@ extern "C" int aimnet2_engine_destroy(aimnet2_engine_t* e) {
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     for (int k = 0; k < 6; ++k)
         if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    for (cudaEvent_t ev : e->gemm_ev) cudaEventDestroy(ev);
     delete e;
     return AIMNET_OK;
 }
@@ -577,8 +612,7 @@ extern "C" int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* 
     if (rc == AIMNET_OK && e->timing) {
         cudaStream_t st = (cudaStream_t)stream;
         AIM_CUDA_CHECK(cudaStreamSynchronize(st));
-        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev[k], e->ev[k + 1]);
-        cudaEventElapsedTime(&e->last_ms[4], e->ev[0], e->ev[4]);
+        collect_timing(e);
     }
     return rc;
 }
@@ -644,10 +678,7 @@ extern "C" int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_syste
 #undef H2D
 #undef D2H
     AIM_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (e->timing) {
-        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev[k], e->ev[k + 1]);
-        cudaEventElapsedTime(&e->last_ms[4], e->ev[0], e->ev[4]);
-    }
+    if (e->timing) collect_timing(e);
     return AIMNET_OK;
 }
 
@@ -663,7 +694,7 @@ extern "C" int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int
 
 extern "C" int aimnet2_engine_enable_timing(aimnet2_engine_t* e, int on) {
     AIM_REQUIRE(e, "enable_timing: null engine");
-    e->timing = on ? 1 : 0;
+    e->timing = on < 0 ? 0 : (on > 2 ? 2 : on);   // 1: phase events, 2: + one event pair per GEMM launch
     return AIMNET_OK;
 }
 
@@ -671,5 +702,7 @@ extern "C" int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, 
     AIM_REQUIRE(e && ms, "last_timing: null argument");
     int k = 0;
     for (; k < n && k < 5; ++k) ms[k] = e->last_ms[k];
+    if (k < n) ms[k++] = e->last_gemm_ms;                    // summed GEMM device time (timing level 2)
+    if (k < n) ms[k++] = (float)e->last_gemm_launches;
     return k;
 }

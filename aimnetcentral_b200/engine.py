@@ -20,6 +20,13 @@ def _np32(t) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
 
 
+def _pbc_bytes(pbc, n_cells: int) -> np.ndarray:
+    if isinstance(pbc, torch.Tensor):
+        pbc = pbc.detach().cpu().numpy()
+    p = np.asarray(pbc).astype(np.uint8).reshape(-1, 3)
+    return np.ascontiguousarray(np.broadcast_to(p, (n_cells, 3)))
+
+
 def _ptr(a) -> int | None:
     if a is None:
         return None
@@ -85,6 +92,8 @@ class Engine:
         _capi.check(self._lib.aimnet2_engine_create(C.byref(h), C.byref(w), self.device.index), "engine_create")
         self._h = h
         self._keep = []
+        # engine_create selects the tcgen05 backend when it was built in; mirror that choice here
+        self.gemm_backend = 1 if self._lib.aimnet2_engine_set_gemm_backend(h, 1) == 0 else 0
         self.options = dict(coulomb_method="simple", dsf_alpha=0.2, dsf_rc=15.0, ewald_accuracy=1e-6, dispersion=False,
                             d3_s6=1.0, d3_s8=0.3908, d3_a1=0.566, d3_a2=3.128, d3_cutoff=15.0, d3_smoothing=0.2,
                             sr_cutoff=5.0)
@@ -114,14 +123,17 @@ class Engine:
 
     def set_gemm_backend(self, backend: int):
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
+        self.gemm_backend = int(backend)
 
-    def enable_timing(self, on: bool = True):
-        _capi.check(self._lib.aimnet2_engine_enable_timing(self._h, 1 if on else 0))
+    def enable_timing(self, level: int = 1):
+        """0 off, 1 phase events, 2 additionally one CUDA-event pair around every GEMM launch."""
+        _capi.check(self._lib.aimnet2_engine_enable_timing(self._h, int(level)))
 
     def last_timing(self) -> dict:
-        buf = (C.c_float * 5)()
-        self._lib.aimnet2_engine_last_timing(self._h, buf, 5)
-        return dict(zip(("neighbors_ms", "forward_ms", "pair_terms_ms", "backward_ms", "total_ms"), list(buf)))
+        buf = (C.c_float * 7)()
+        self._lib.aimnet2_engine_last_timing(self._h, buf, 7)
+        return dict(zip(("neighbors_ms", "forward_ms", "pair_terms_ms", "backward_ms", "total_ms", "gemm_ms",
+                         "gemm_launches"), list(buf)))
 
     def last_launches(self) -> int:
         return int(self._lib.aimnet2_engine_last_launches(self._h))
@@ -168,8 +180,7 @@ class Engine:
             host_cell = np.ascontiguousarray(cell.detach().cpu().numpy().reshape(n_cells, 3, 3).astype(np.float32))
             sys_.cell, sys_.host_cell = cell.data_ptr(), host_cell.ctypes.data
             if pbc is not None:
-                pbc_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(pbc, dtype=np.uint8).reshape(-1, 3),
-                                                               (n_cells, 3)))
+                pbc_arr = _pbc_bytes(pbc, n_cells)
                 sys_.pbc_host = pbc_arr.ctypes.data
         sys_.n_cells = n_cells
         if nbmat is not None:
@@ -226,8 +237,7 @@ class Engine:
             n_cells = 1 if cell.ndim == 2 else cell.shape[0]
             sys_.cell = sys_.host_cell = cell.ctypes.data
             if pbc is not None:
-                pbc_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(pbc, dtype=np.uint8).reshape(-1, 3),
-                                                               (n_cells, 3)))
+                pbc_arr = _pbc_bytes(pbc, n_cells)
                 sys_.pbc_host = pbc_arr.ctypes.data
         sys_.n_cells = n_cells
         if out is None:

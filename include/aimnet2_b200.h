@@ -167,7 +167,8 @@ int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_system_t* sys, c
 /* introspection: kernels launched by the last eval, last short-range / long-range list widths, workspace bytes */
 int aimnet2_engine_last_launches(const aimnet2_engine_t* e);
 int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int* lr_width, int64_t* workspace_bytes);
-/* per-phase device times (ms) of the last eval when timing was enabled; phases: 0 neighbors, 1 forward,
+/* per-phase device times (ms) of the last eval when timing was enabled (level 1: phase events, level 2: also one
+ * event pair around every GEMM launch); slots: 0 neighbors, 1 forward,
  * 2 long-range, 3 backward, 4 total; returns number of phases written */
 int aimnet2_engine_enable_timing(aimnet2_engine_t* e, int on);
 int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, int n);
