@@ -3,7 +3,20 @@
 // Reference semantics: calc_distances (aimnet/ops.py:37-66), AEVSV._calc_aev (aimnet/modules/aev.py:94-110),
 // ConvSV.forward (aimnet/modules/aev.py:156-189), Warp kernels aimnet/kernels/conv_sv_2d_sp_wp.py:90-164.
 // The reference materialises g_sv (N,M,16,4) in HBM (256 B per pair) and re-reads it for every convolution and for
-// the autograd pass; here the radial basis is recomputed per neighbour tile in shared memory and never stored.
+// the autograd pass; here the radial basis is recomputed from a small per-tile pair table in shared memory.
+//
+// Thread mapping (forward and backward): one CTA = 16 centre atoms x 16 radial shifts; thread (atom, g) owns the
+// full 16(a) x 4(d) register tile of S[i,:,g,:].  Per neighbour it loads the 64-byte row aT[j][g][0..15] and does a
+// 16x4 outer-product update: 64 FMAs for 5 vector loads, no cross-thread traffic.  Features are therefore kept in the
+// gather-friendly transposed layout aT (N, 16 g, 16 a); dS^T (N, 16 g, 16 a, 4 d) likewise.
+//
+// Backward: the neighbour matrix is full (both directions), so everything atom i needs is in its own row:
+//   grad_a[i,a,g]  = sum_m <dS[j_m,a,g,:], g_sv(j_m->i)[g,:]>            g_sv(j->i) = (gs, -gs u_{i->j})
+//   F_i            = sum_m ( w(i->j_m) - w(j_m->i) )                       w = dE/dr of a slot
+//   virial_i       = sum_m r_im (x) w(i->j_m)
+// w is linear in the per-g partial contractions, so every thread accumulates its own g-share of the force over all
+// pairs and the 16 lanes of an atom are reduced once at the end: no per-pair reductions, no atomics, deterministic
+// (the reference's backward kernel scatters with wp.atomic_add, conv_sv_2d_sp_wp.py:115-136).
 //
 // Layout of one MLP input row x (ld = ldx, zero padded):
 //   [0,256)   a[i] flat (a*16+g)            [256,512) S_s[a,g]          [512,704) avf_v[a,h]
@@ -12,172 +25,213 @@
 
 namespace aimnet {
 
-constexpr int kTile = 32;   // neighbour slots staged per shared-memory tile
+constexpr int kAtomsPerCta = 16;
+constexpr int kSlotsPerTile = 16;
 
-struct PairTile {
-    int j[kTile];          // neighbour index (0 when slot invalid)
-    float valid[kTile];    // 1 / 0
-    float d[kTile];
-    float u[kTile][3];
-    float gs[kTile][kG];   // radial basis * cutoff   (0 for invalid slots)
-    float dgs[kTile][kG];  // d gs / d d
+struct PairEntry {
+    float ux, uy, uz, d;
+    float fc, dfc;
+    int j;
+    int pad;
 };
 
-// stage geometry + radial basis for slots [m0, m0+kTile) of centre atom i; all 256 threads participate
+// stage geometry + cutoff for slots [m0, m0+16) of the CTA's 16 atoms: thread (atom = tid>>4, slot = tid&15)
 template <bool kWithDeriv>
-__device__ __forceinline__ void stage_tile(PairTile& t, int i, int m0, int row_len, const NbView& nb,
-                                           const float* __restrict__ coord, const float* __restrict__ cell,
-                                           const AevParams& aev) {
+__device__ __forceinline__ void stage_pairs(PairEntry* tile, int i, bool atom_ok, int m0, int row_len, const NbView& nb,
+                                            const float* __restrict__ coord, const float* __restrict__ cell,
+                                            const AevParams& aev) {
     int tid = threadIdx.x;
-    if (tid < kTile) {
-        int m = m0 + tid;
-        int j = nb.sentinel;
-        if (m < row_len) j = nb.nbmat[(size_t)i * nb.width + m];
-        bool ok = (j != nb.sentinel) && (j >= 0);
-        float rx = 1.f, ry = 1.f, rz = 1.f;
-        if (ok) {
-            const int32_t* sh = nb.shifts ? nb.shifts + ((size_t)i * nb.width + m) * 3 : nullptr;
-            pair_vector(coord, i, j, sh, cell, rx, ry, rz);
-        }
-        float d = sqrtf(rx * rx + ry * ry + rz * rz);
-        float inv = 1.0f / d;
-        t.j[tid] = ok ? j : 0;
-        t.valid[tid] = ok ? 1.f : 0.f;
-        t.d[tid] = d;
-        t.u[tid][0] = rx * inv;
-        t.u[tid][1] = ry * inv;
-        t.u[tid][2] = rz * inv;
+    int m = m0 + (tid & 15);
+    int j = nb.sentinel;
+    if (atom_ok && m < row_len) j = nb.nbmat[(size_t)i * nb.width + m];
+    bool ok = atom_ok && (j != nb.sentinel) && (j >= 0);
+    float rx = 1.f, ry = 1.f, rz = 1.f;
+    if (ok) {
+        const int32_t* sh = nb.shifts ? nb.shifts + ((size_t)i * nb.width + m) * 3 : nullptr;
+        pair_vector(coord, i, j, sh, cell, rx, ry, rz);
     }
-    __syncthreads();
-    // 32 slots x 16 shifts = 512 basis values, 2 per thread
-#pragma unroll
-    for (int k = 0; k < (kTile * kG) / 256; ++k) {
-        int e = tid + 256 * k;
-        int s = e >> 4, g = e & 15;
-        float d = t.d[s];
-        float v = t.valid[s];
-        // cosine cutoff, aimnet/ops.py:82-85
-        float dc = fminf(fmaxf(d, 1e-6f), aev.rc);
-        float arg = dc * (kPi / aev.rc);
-        float sn, cs;
-        sincosf(arg, &sn, &cs);
-        float fc = 0.5f * (cs + 1.0f) * v;
-        float x = d - aev.shifts[g];
-        float ex = expf(-aev.eta * x * x);
-        t.gs[s][g] = ex * fc;
-        if (kWithDeriv) {
-            float dfc = (d > 1e-6f && d < aev.rc) ? (-0.5f * (kPi / aev.rc) * sn * v) : 0.f;
-            t.dgs[s][g] = ex * (dfc - 2.0f * aev.eta * x * fc);
-        }
-    }
-    __syncthreads();
+    float d = sqrtf(rx * rx + ry * ry + rz * rz);
+    float inv = 1.0f / d;
+    // cosine cutoff, aimnet/ops.py:82-85
+    float dc = fminf(fmaxf(d, 1e-6f), aev.rc);
+    float sn, cs;
+    sincosf(dc * (kPi / aev.rc), &sn, &cs);
+    PairEntry e;
+    e.ux = rx * inv;
+    e.uy = ry * inv;
+    e.uz = rz * inv;
+    e.d = d;
+    e.fc = ok ? 0.5f * (cs + 1.0f) : 0.f;
+    e.dfc = (kWithDeriv && ok && d > 1e-6f && d < aev.rc) ? -0.5f * (kPi / aev.rc) * sn : 0.f;
+    e.j = ok ? j : (atom_ok ? i : 0);
+    e.pad = 0;
+    tile[tid] = e;
 }
 
 __device__ __forceinline__ int row_length(const NbView& nb, int i) {
     return nb.count ? min(nb.count[i], nb.width) : nb.width;
 }
 
+__device__ __forceinline__ int block_max_int(int v, int* scratch) {
+    // 256 threads; value identical within each 16-thread atom group
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = scratch[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = max(r, scratch[k]);
+    __syncthreads();
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// forward: one block (256 threads = (a,g)) per atom
+// forward
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
                                                        CellView cv, const int32_t* __restrict__ mol_idx,
-                                                       AevParams aev, const float* __restrict__ a,
+                                                       AevParams aev, const float* __restrict__ aT,
                                                        const float* __restrict__ q, const float* __restrict__ agh_a,
                                                        const float* __restrict__ agh_q, float* __restrict__ x,
                                                        int ldx, float* __restrict__ T_a, float* __restrict__ T_q,
                                                        int with_q) {
-    __shared__ PairTile tile;
-    __shared__ float sv[kAG][3];       // vector part of S^a
-    __shared__ float svq[2 * kG][3];   // vector part of S^q
-    __shared__ float sT[kTA];
-    __shared__ float sTq[2 * kH * 3];
-    int i = blockIdx.x;
-    int tid = threadIdx.x;
-    int g = tid & 15;
-    const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[i] : 0)) : nullptr;
-    int len = row_length(nb, i);
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    float qa0 = 0.f, qa1 = 0.f, qa2 = 0.f, qa3 = 0.f;
-    bool qthread = with_q && tid < C * kG;
-    int qc = tid >> 4;
-    for (int m0 = 0; m0 < len; m0 += kTile) {
-        stage_tile<false>(tile, i, m0, len, nb, coord, cell, aev);
-        int lim = min(kTile, len - m0);
-#pragma unroll 4
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairEntry* tile = reinterpret_cast<PairEntry*>(smem_raw);                       // 256 entries, 8 KB
+    float* sv = reinterpret_cast<float*>(smem_raw + 256 * sizeof(PairEntry));       // [16 atoms][16 a][16 g][3]
+    float* svq = sv + kAtomsPerCta * kAG * 3;                                       // [16 atoms][C][16 g][3]
+    __shared__ int scratch[8];
+    const int tid = threadIdx.x;
+    const int al = tid >> 4, g = tid & 15;
+    const int i = blockIdx.x * kAtomsPerCta + al;
+    const bool atom_ok = i < n_atoms;
+    const int ic = atom_ok ? i : 0;
+    const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
+    const int len = atom_ok ? row_length(nb, i) : 0;
+    const int maxlen = block_max_int(len, scratch);
+    const float shift_g = aev.shifts[g];
+    float S[kA][4];
+#pragma unroll
+    for (int a = 0; a < kA; ++a) S[a][0] = S[a][1] = S[a][2] = S[a][3] = 0.f;
+    float Sq[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) Sq[c][0] = Sq[c][1] = Sq[c][2] = Sq[c][3] = 0.f;
+    for (int m0 = 0; m0 < maxlen; m0 += kSlotsPerTile) {
+        __syncthreads();
+        stage_pairs<false>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
+        __syncthreads();
+        int lim = min(kSlotsPerTile, len - m0);
         for (int s = 0; s < lim; ++s) {
-            int j = tile.j[s];
-            float w = tile.gs[s][g];
-            float aj = a[(size_t)j * kAG + tid];
-            float p = aj * w;
-            acc0 += p;
-            acc1 += p * tile.u[s][0];
-            acc2 += p * tile.u[s][1];
-            acc3 += p * tile.u[s][2];
-            if (qthread) {
-                float pq = q[(size_t)j * C + qc] * w;
-                qa0 += pq;
-                qa1 += pq * tile.u[s][0];
-                qa2 += pq * tile.u[s][1];
-                qa3 += pq * tile.u[s][2];
+            const PairEntry e = tile[al * 16 + s];
+            const float4* row = reinterpret_cast<const float4*>(aT + ((size_t)e.j * kAG + g * kA));
+            float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+            float xg = e.d - shift_g;
+            float w0 = expf(-aev.eta * xg * xg) * e.fc;
+            float w1 = w0 * e.ux, w2 = w0 * e.uy, w3 = w0 * e.uz;
+            float av[kA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+            for (int a = 0; a < kA; ++a) {
+                S[a][0] = fmaf(av[a], w0, S[a][0]);
+                S[a][1] = fmaf(av[a], w1, S[a][1]);
+                S[a][2] = fmaf(av[a], w2, S[a][2]);
+                S[a][3] = fmaf(av[a], w3, S[a][3]);
+            }
+            if (with_q) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float qj = q[(size_t)e.j * C + c];
+                    Sq[c][0] = fmaf(qj, w0, Sq[c][0]);
+                    Sq[c][1] = fmaf(qj, w1, Sq[c][1]);
+                    Sq[c][2] = fmaf(qj, w2, Sq[c][2]);
+                    Sq[c][3] = fmaf(qj, w3, Sq[c][3]);
+                }
             }
         }
-        __syncthreads();
     }
-    sv[tid][0] = acc1;
-    sv[tid][1] = acc2;
-    sv[tid][2] = acc3;
-    if (qthread) {
-        svq[tid][0] = qa1;
-        svq[tid][1] = qa2;
-        svq[tid][2] = qa3;
-    }
-    __syncthreads();
-    // T[a,h,d] = sum_g agh[a,g,h] * Sv[a,g,d]      (aimnet/modules/aev.py:188)
-    for (int e = tid; e < kTA; e += 256) {
-        int aa = e / (kH * 3), rem = e % (kH * 3);
-        int h = rem / 3, d = rem % 3;
-        float s = 0.f;
+    // ---- epilogue: scalar part straight to x, vector part through shared memory for the agh mixing ----
+    float* svl = sv + al * (kAG * 3);
 #pragma unroll
-        for (int gg = 0; gg < kG; ++gg) s += agh_a[(aa * kG + gg) * kH + h] * sv[aa * kG + gg][d];
-        sT[e] = s;
-        T_a[(size_t)i * kTA + e] = s;
+    for (int a = 0; a < kA; ++a) {
+        svl[(a * kG + g) * 3 + 0] = S[a][1];
+        svl[(a * kG + g) * 3 + 1] = S[a][2];
+        svl[(a * kG + g) * 3 + 2] = S[a][3];
     }
+    float* svql = svq + al * (C * kG * 3);
     if (with_q) {
-        for (int e = tid; e < C * kH * 3; e += 256) {
-            int cc = e / (kH * 3), rem = e % (kH * 3);
-            int h = rem / 3, d = rem % 3;
-            float s = 0.f;
 #pragma unroll
-            for (int gg = 0; gg < kG; ++gg) s += agh_q[(cc * kG + gg) * kH + h] * svq[cc * kG + gg][d];
-            sTq[e] = s;
-            T_q[(size_t)i * (C * kH * 3) + e] = s;
+        for (int c = 0; c < C; ++c) {
+            svql[(c * kG + g) * 3 + 0] = Sq[c][1];
+            svql[(c * kG + g) * 3 + 1] = Sq[c][2];
+            svql[(c * kG + g) * 3 + 2] = Sq[c][3];
         }
     }
-    __syncthreads();
-    float* xr = x + (size_t)i * ldx;
-    xr[tid] = a[(size_t)i * kAG + tid];
-    xr[kAG + tid] = acc0;
-    if (tid < kAH) {
-        float t0 = sT[tid * 3], t1 = sT[tid * 3 + 1], t2 = sT[tid * 3 + 2];
-        xr[2 * kAG + tid] = t0 * t0 + t1 * t1 + t2 * t2;
-    }
-    int base = 2 * kAG + kAH;   // 704
-    if (with_q) {
-        if (tid < C) xr[base + tid] = q[(size_t)i * C + tid];
-        if (qthread) xr[base + C + tid] = qa0;
-        if (tid < C * kH) {
-            float t0 = sTq[tid * 3], t1 = sTq[tid * 3 + 1], t2 = sTq[tid * 3 + 2];
-            xr[base + C + C * kG + tid] = t0 * t0 + t1 * t1 + t2 * t2;
+    if (atom_ok) {
+        float* xr = x + (size_t)i * ldx;
+        const float4* own = reinterpret_cast<const float4*>(aT + ((size_t)i * kAG + g * kA));
+        float4 o0 = own[0], o1 = own[1], o2 = own[2], o3 = own[3];
+        float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+#pragma unroll
+        for (int a = 0; a < kA; ++a) {
+            xr[a * kG + g] = ov[a];
+            xr[kAG + a * kG + g] = S[a][0];
         }
-        base += C * (1 + kG + kH);
+        int base = 2 * kAG + kAH;
+        if (with_q) {
+            if (g < C) xr[base + g] = q[(size_t)i * C + g];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq[c][0];
+            base += C * (1 + kG + kH);
+        }
+        for (int c = base + g; c < ldx; c += 16) xr[c] = 0.f;
     }
-    for (int c = base + tid; c < ldx; c += 256) xr[c] = 0.f;
+    __syncthreads();
+    // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); thread g handles 12 (a,h) pairs
+    if (atom_ok) {
+        float* xr = x + (size_t)i * ldx;
+#pragma unroll 1
+        for (int e = g; e < kAH; e += 16) {
+            int a = e / kH, h = e % kH;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < kG; ++gg) {
+                float w = agh_a[(a * kG + gg) * kH + h];
+                const float* p = svl + (a * kG + gg) * 3;
+                t0 = fmaf(w, p[0], t0);
+                t1 = fmaf(w, p[1], t1);
+                t2 = fmaf(w, p[2], t2);
+            }
+            float* To = T_a + (size_t)i * kTA + e * 3;
+            To[0] = t0;
+            To[1] = t1;
+            To[2] = t2;
+            xr[2 * kAG + e] = t0 * t0 + t1 * t1 + t2 * t2;
+        }
+        if (with_q) {
+            int base = 2 * kAG + kAH;
+            for (int e = g; e < C * kH; e += 16) {
+                int c = e / kH, h = e % kH;
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int gg = 0; gg < kG; ++gg) {
+                    float w = agh_q[(c * kG + gg) * kH + h];
+                    const float* p = svql + (c * kG + gg) * 3;
+                    t0 = fmaf(w, p[0], t0);
+                    t1 = fmaf(w, p[1], t1);
+                    t2 = fmaf(w, p[2], t2);
+                }
+                float* To = T_q + (size_t)i * (C * kH * 3) + e * 3;
+                To[0] = t0;
+                To[1] = t1;
+                To[2] = t2;
+                xr[base + C + C * kG + e] = t0 * t0 + t1 * t1 + t2 * t2;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward step 1: per atom, turn d(loss)/d(x row) into d(loss)/dS^a (16,16,4) and d(loss)/dS^q (C,16,4)
+// backward step 1: per atom, turn d(loss)/d(x row) into d(loss)/dS^a and d(loss)/dS^q, stored transposed for the
+// gather: dS_a^T (N,16 g,16 a,4), dS_q^T (N,16 g,C,4)
 //   d avf_v[a,h] -> dT[a,h,d] = 2 T[a,h,d] * d avf_v[a,h] -> dSv[a,g,d] = sum_h agh[a,g,h] dT[a,h,d]
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
@@ -197,9 +251,10 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
         for (int e = tid; e < C * kH * 3; e += 256)
             dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
     __syncthreads();
-    int aa = tid >> 4, g = tid & 15;
+    // thread t = g*16 + a so that the transposed store is coalesced
+    int g = tid >> 4, aa = tid & 15;
     float4 o;
-    o.x = dxr[kAG + tid];
+    o.x = dxr[kAG + aa * kG + g];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int h = 0; h < kH; ++h) {
@@ -213,13 +268,13 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
     o.w = s2;
     reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + tid] = o;
     if (with_q && tid < C * kG) {
-        int cc = tid >> 4;
+        int gq = tid / C, cc = tid % C;
         float4 oq;
-        oq.x = dxr[base + C + tid];
+        oq.x = dxr[base + C + cc * kG + gq];
         float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
-            float w = agh_q[(cc * kG + g) * kH + h];
+            float w = agh_q[(cc * kG + gq) * kH + h];
             q0 += w * dTq[(cc * kH + h) * 3 + 0];
             q1 += w * dTq[(cc * kH + h) * 3 + 1];
             q2 += w * dTq[(cc * kH + h) * 3 + 2];
@@ -232,151 +287,174 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward step 2: one block per atom i.  Over the (symmetric, full) neighbour row of i:
-//   (1) grad_a[i,a,g]  = sum_m  <dS^a[j_m,a,g,:], g_sv(j_m -> i)[g,:]>     g_sv(j->i) = (gs, -gs*u_{i->j})
-//   (2) grad_q[i,c]    = sum_m sum_g <dS^q[j_m,c,g,:], g_sv(j_m -> i)[g,:]>
-//   (3) w_im = dE/dr_im through g_sv(i -> j_m): P[g,d] = sum_a a[j,a,g] dS^a[i,a,g,d] + sum_c q[j,c] dS^q[i,c,g,d]
-//       dE/dr = u*(A + C.u) + (B - u (B.u))/d,  A = sum_g P[g,0] gs'_g, B_k = sum_g P[g,1+k] gs_g, C_k = sum_g P[g,1+k] gs'_g
-//   forces: F_i += w_im, F_j -= w_im  (r_ij = x_j + s.cell - x_i);  virial_i += r_im (x) w_im
-// (1),(2) are the gather form of the reference's atomic scatter kernel conv_sv_2d_sp_wp.py:115-136: with a full
-// list every pair appears in both rows, so the contribution of centre j to neighbour i can be evaluated from i's
-// own row -> no atomics, deterministic.
+// backward step 2 (see the header comment)
 // ------------------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(256) conv_bwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
-                                                       CellView cv, const int32_t* __restrict__ mol_idx,
-                                                       AevParams aev, const float* __restrict__ a,
-                                                       const float* __restrict__ q, const float* __restrict__ dS_a,
-                                                       const float* __restrict__ dS_q, float* __restrict__ grad_a,
-                                                       float* __restrict__ grad_q, float* __restrict__ forces,
-                                                       double* __restrict__ virial_atom, int with_q,
-                                                       int want_grad_a) {
-    __shared__ PairTile tile;
-    __shared__ float red[8][kTile][8];   // per-warp partials of (A, B0..2, C0..2) per slot
-    int i = blockIdx.x, tid = threadIdx.x;
-    int g = tid & 15, lane = tid & 31, warp = tid >> 5;
-    const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[i] : 0)) : nullptr;
-    int len = row_length(nb, i);
-    float4 dSi = reinterpret_cast<const float4*>(dS_a)[(size_t)i * kAG + tid];
-    bool qthread = with_q && tid < C * kG;
-    int qc = tid >> 4;
-    float4 dSqi = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (qthread) dSqi = reinterpret_cast<const float4*>(dS_q)[(size_t)i * (C * kG) + tid];
-    float ga = 0.f, gq = 0.f;
+template <int C, bool kGradA>
+__global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
+                                                          CellView cv, const int32_t* __restrict__ mol_idx,
+                                                          AevParams aev, const float* __restrict__ aT,
+                                                          const float* __restrict__ q, const float* __restrict__ dS_a,
+                                                          const float* __restrict__ dS_q, float* __restrict__ grad_a,
+                                                          float* __restrict__ grad_q, float* __restrict__ forces,
+                                                          double* __restrict__ virial_atom, int with_q) {
+    __shared__ PairEntry tile[256];
+    __shared__ int scratch[8];
+    const int tid = threadIdx.x;
+    const int al = tid >> 4, g = tid & 15;
+    const int i = blockIdx.x * kAtomsPerCta + al;
+    const bool atom_ok = i < n_atoms;
+    const int ic = atom_ok ? i : 0;
+    const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
+    const int len = atom_ok ? row_length(nb, i) : 0;
+    const int maxlen = block_max_int(len, scratch);
+    const float shift_g = aev.shifts[g];
+    // own atom: dS_i[g][a][d] and a_i[g][a] in registers
+    float4 dSi[kA];
+    float ai[kA];
+    {
+        const float4* p = reinterpret_cast<const float4*>(dS_a) + ((size_t)ic * kAG + g * kA);
+#pragma unroll
+        for (int a = 0; a < kA; ++a) dSi[a] = p[a];
+        const float4* r = reinterpret_cast<const float4*>(aT + ((size_t)ic * kAG + g * kA));
+        float4 o0 = r[0], o1 = r[1], o2 = r[2], o3 = r[3];
+        float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+#pragma unroll
+        for (int a = 0; a < kA; ++a) ai[a] = ov[a];
+    }
+    float4 dSqi[C];
+    float qi[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        dSqi[c] = with_q ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + g * C + c] : make_float4(0, 0, 0, 0);
+        qi[c] = with_q ? q[(size_t)ic * C + c] : 0.f;
+    }
+    float ga[kA];
+#pragma unroll
+    for (int a = 0; a < kA; ++a) ga[a] = 0.f;
+    float gq[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) gq[c] = 0.f;
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    double vir[9];
+    float vir[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) vir[k] = 0.0;
-    for (int m0 = 0; m0 < len; m0 += kTile) {
-        stage_tile<true>(tile, i, m0, len, nb, coord, cell, aev);
-        int lim = min(kTile, len - m0);
+    for (int k = 0; k < 9; ++k) vir[k] = 0.f;
+
+    for (int m0 = 0; m0 < maxlen; m0 += kSlotsPerTile) {
+        __syncthreads();
+        stage_pairs<true>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
+        __syncthreads();
+        int lim = min(kSlotsPerTile, len - m0);
         for (int s = 0; s < lim; ++s) {
-            int j = tile.j[s];
-            float gsv = tile.gs[s][g], dg = tile.dgs[s][g];
-            float ux = tile.u[s][0], uy = tile.u[s][1], uz = tile.u[s][2];
-            float aj = a[(size_t)j * kAG + tid];
-            if (want_grad_a) {
-                float4 dj = reinterpret_cast<const float4*>(dS_a)[(size_t)j * kAG + tid];
-                ga += gsv * (dj.x - (dj.y * ux + dj.z * uy + dj.w * uz));
-            }
-            float p0 = aj * dSi.x, p1 = aj * dSi.y, p2 = aj * dSi.z, p3 = aj * dSi.w;
-            if (qthread) {
-                float qj = q[(size_t)j * C + qc];
-                p0 += qj * dSqi.x;
-                p1 += qj * dSqi.y;
-                p2 += qj * dSqi.z;
-                p3 += qj * dSqi.w;
-                if (want_grad_a) {
-                    float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)j * (C * kG) + tid];
-                    gq += gsv * (dqj.x - (dqj.y * ux + dqj.z * uy + dqj.w * uz));
-                }
-            }
-            float vA = p0 * dg, vB0 = p1 * gsv, vB1 = p2 * gsv, vB2 = p3 * gsv, vC0 = p1 * dg, vC1 = p2 * dg,
-                  vC2 = p3 * dg;
-            vA = warp_sum(vA);
-            vB0 = warp_sum(vB0);
-            vB1 = warp_sum(vB1);
-            vB2 = warp_sum(vB2);
-            vC0 = warp_sum(vC0);
-            vC1 = warp_sum(vC1);
-            vC2 = warp_sum(vC2);
-            if (lane == 0) {
-                red[warp][s][0] = vA;
-                red[warp][s][1] = vB0;
-                red[warp][s][2] = vB1;
-                red[warp][s][3] = vB2;
-                red[warp][s][4] = vC0;
-                red[warp][s][5] = vC1;
-                red[warp][s][6] = vC2;
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // kTile == 32: slot s <-> lane s of warp 0
-            int s = lane;
-            bool act = s < lim;
-            float A = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-            if (act) {
+            const PairEntry e = tile[al * 16 + s];
+            const float4* arow = reinterpret_cast<const float4*>(aT + ((size_t)e.j * kAG + g * kA));
+            const float4* drow = reinterpret_cast<const float4*>(dS_a) + ((size_t)e.j * kAG + g * kA);
+            float4 v0 = arow[0], v1 = arow[1], v2 = arow[2], v3 = arow[3];
+            float aj[kA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+            float xg = e.d - shift_g;
+            float ex = expf(-aev.eta * xg * xg);
+            float gs = ex * e.fc;
+            float dgs = ex * (e.dfc - 2.0f * aev.eta * xg * e.fc);
+            // p = contraction for slot (i -> j), pr = for the reverse slot (j -> i)
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                    A += red[w][s][0];
-                    B0 += red[w][s][1];
-                    B1 += red[w][s][2];
-                    B2 += red[w][s][3];
-                    C0 += red[w][s][4];
-                    C1 += red[w][s][5];
-                    C2 += red[w][s][6];
+            for (int a = 0; a < kA; ++a) {
+                float4 dj = drow[a];
+                if (kGradA) {
+                    float t = dj.x - (dj.y * e.ux + dj.z * e.uy + dj.w * e.uz);
+                    ga[a] = fmaf(gs, t, ga[a]);
+                }
+                p0 = fmaf(aj[a], dSi[a].x, p0);
+                p1 = fmaf(aj[a], dSi[a].y, p1);
+                p2 = fmaf(aj[a], dSi[a].z, p2);
+                p3 = fmaf(aj[a], dSi[a].w, p3);
+                r0 = fmaf(ai[a], dj.x, r0);
+                r1 = fmaf(ai[a], dj.y, r1);
+                r2 = fmaf(ai[a], dj.z, r2);
+                r3 = fmaf(ai[a], dj.w, r3);
+            }
+            if (with_q) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float qj = q[(size_t)e.j * C + c];
+                    float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)e.j * (C * kG) + g * C + c];
+                    if (kGradA) gq[c] = fmaf(gs, dqj.x - (dqj.y * e.ux + dqj.z * e.uy + dqj.w * e.uz), gq[c]);
+                    p0 = fmaf(qj, dSqi[c].x, p0);
+                    p1 = fmaf(qj, dSqi[c].y, p1);
+                    p2 = fmaf(qj, dSqi[c].z, p2);
+                    p3 = fmaf(qj, dSqi[c].w, p3);
+                    r0 = fmaf(qi[c], dqj.x, r0);
+                    r1 = fmaf(qi[c], dqj.y, r1);
+                    r2 = fmaf(qi[c], dqj.z, r2);
+                    r3 = fmaf(qi[c], dqj.w, r3);
                 }
             }
-            float ux = tile.u[s][0], uy = tile.u[s][1], uz = tile.u[s][2];
-            float d = tile.d[s], v = act ? tile.valid[s] : 0.f;
-            float cu = C0 * ux + C1 * uy + C2 * uz;
-            float bu = B0 * ux + B1 * uy + B2 * uz;
-            float inv = 1.0f / d;
-            float wx = (ux * (A + cu) + (B0 - ux * bu) * inv) * v;
-            float wy = (uy * (A + cu) + (B1 - uy * bu) * inv) * v;
-            float wz = (uz * (A + cu) + (B2 - uz * bu) * inv) * v;
-            if (v != 0.f) {
-                int j = tile.j[s];
-                atomicAdd(&forces[3 * j + 0], -wx);
-                atomicAdd(&forces[3 * j + 1], -wy);
-                atomicAdd(&forces[3 * j + 2], -wz);
-            }
-            fx += warp_sum(wx);
-            fy += warp_sum(wy);
-            fz += warp_sum(wz);
+            float inv = 1.0f / e.d;
+            // this thread's g-share of w(i->j) = u (A + C.u) + (B - u (B.u))/d
+            float pu = p1 * e.ux + p2 * e.uy + p3 * e.uz;
+            float sc = p0 * dgs + pu * dgs - pu * gs * inv;
+            float wx = e.ux * sc + p1 * gs * inv;
+            float wy = e.uy * sc + p2 * gs * inv;
+            float wz = e.uz * sc + p3 * gs * inv;
+            // reverse slot (j->i): u' = -u;  w' = -u (A' - (r.u) dgs) + (B' - u (B'.u))/d
+            float ru = r1 * e.ux + r2 * e.uy + r3 * e.uz;
+            float scr = -(r0 * dgs - ru * dgs) - ru * gs * inv;
+            float vx = e.ux * scr + r1 * gs * inv;
+            float vy = e.uy * scr + r2 * gs * inv;
+            float vz = e.uz * scr + r3 * gs * inv;
+            fx += wx - vx;
+            fy += wy - vy;
+            fz += wz - vz;
             if (virial_atom) {
-                float rx = ux * d, ry = uy * d, rz = uz * d;
-                vir[0] += warp_sum((double)(rx * wx));
-                vir[1] += warp_sum((double)(rx * wy));
-                vir[2] += warp_sum((double)(rx * wz));
-                vir[3] += warp_sum((double)(ry * wx));
-                vir[4] += warp_sum((double)(ry * wy));
-                vir[5] += warp_sum((double)(ry * wz));
-                vir[6] += warp_sum((double)(rz * wx));
-                vir[7] += warp_sum((double)(rz * wy));
-                vir[8] += warp_sum((double)(rz * wz));
+                float rx = e.ux * e.d, ry = e.uy * e.d, rz = e.uz * e.d;
+                vir[0] = fmaf(rx, wx, vir[0]);
+                vir[1] = fmaf(rx, wy, vir[1]);
+                vir[2] = fmaf(rx, wz, vir[2]);
+                vir[3] = fmaf(ry, wx, vir[3]);
+                vir[4] = fmaf(ry, wy, vir[4]);
+                vir[5] = fmaf(ry, wz, vir[5]);
+                vir[6] = fmaf(rz, wx, vir[6]);
+                vir[7] = fmaf(rz, wy, vir[7]);
+                vir[8] = fmaf(rz, wz, vir[8]);
             }
         }
-        __syncthreads();
     }
-    if (want_grad_a) {
-        grad_a[(size_t)i * kAG + tid] = ga;
-        if (with_q) {
-            // reduce gq over g (16 lanes) then over the two half-warps of each charge channel
-            float v = qthread ? gq : 0.f;
+    // reduce the force / virial / grad_q shares over the 16 g-lanes of the atom
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (qthread && g == 0) grad_q[(size_t)i * C + qc] = v;
+    for (int o = 8; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (virial_atom) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) vir[k] += __shfl_xor_sync(0xffffffffu, vir[k], o);
+    }
+    if (kGradA && with_q) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) gq[c] += __shfl_xor_sync(0xffffffffu, gq[c], o);
+    }
+    if (!atom_ok) return;
+    if (kGradA) {
+#pragma unroll
+        for (int a = 0; a < kA; ++a) grad_a[(size_t)i * kAG + a * kG + g] = ga[a];
+        if (with_q && g < C) {
+            float v = gq[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) v = (g == c) ? gq[c] : v;
+            grad_q[(size_t)i * C + g] = v;
         }
     }
-    if (tid == 0) {
-        atomicAdd(&forces[3 * i + 0], fx);
-        atomicAdd(&forces[3 * i + 1], fy);
-        atomicAdd(&forces[3 * i + 2], fz);
+    if (g == 0) {
+        forces[3 * i + 0] += fx;
+        forces[3 * i + 1] += fy;
+        forces[3 * i + 2] += fz;
         if (virial_atom)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += vir[k];
+            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += (double)vir[k];
     }
 }
 
@@ -452,39 +530,64 @@ __global__ void conv_op_bwd_a_kernel(const float* __restrict__ grad_out, const i
 // ------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------
-int launch_conv_fwd(int C, int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
-                    const int32_t* mol_idx, const AevParams& aev, const float* a, const float* q, const float* agh_a,
-                    const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q, cudaStream_t st) {
-    if (n_atoms == 0) return AIMNET_OK;
-    if (C == 1)
-        conv_fwd_kernel<1><<<n_atoms, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, a, q, agh_a, agh_q, x, ldx,
-                                                   T_a, T_q, with_q);
-    else
-        conv_fwd_kernel<2><<<n_atoms, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, a, q, agh_a, agh_q, x, ldx,
-                                                   T_a, T_q, with_q);
+template <int C>
+static int conv_fwd_launch(int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
+                           const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
+                           const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q,
+                           int with_q, cudaStream_t st) {
+    size_t smem = 256 * sizeof(PairEntry) + sizeof(float) * (kAtomsPerCta * kAG * 3 + kAtomsPerCta * C * kG * 3);
+    static bool configured = false;
+    if (!configured) {
+        AIM_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    conv_fwd_kernel<C><<<grid, 256, smem, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a,
+                                               T_q, with_q);
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }
 
+int launch_conv_fwd(int C, int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
+                    const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q, const float* agh_a,
+                    const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q, cudaStream_t st) {
+    if (n_atoms == 0) return AIMNET_OK;
+    if (C == 1)
+        return conv_fwd_launch<1>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q, with_q, st);
+    return conv_fwd_launch<2>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q, with_q, st);
+}
+
+template <int C>
+static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
+                           const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
+                           const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
+                           const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
+                           double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
+    conv_bwd_prep_kernel<C><<<n_atoms, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q);
+    AIM_LAUNCH_CHECK();
+    int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    if (want_grad_a)
+        conv_bwd_kernel<C, true><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a,
+                                                      grad_q, forces, virial_atom, with_q);
+    else
+        conv_bwd_kernel<C, false><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a,
+                                                       grad_q, forces, virial_atom, with_q);
+    AIM_LAUNCH_CHECK();
+    return AIMNET_OK;
+}
+
+// `forces` must not be written concurrently by another stream: every atom's total is accumulated with a plain +=
 int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
-                    const int32_t* mol_idx, const AevParams& aev, const float* a, const float* q, const float* dx,
+                    const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q, const float* dx,
                     int ldx, const float* T_a, const float* T_q, const float* agh_a, const float* agh_q, float* dS_a,
                     float* dS_q, float* grad_a, float* grad_q, float* forces, double* virial_atom, int with_q,
                     int want_grad_a, cudaStream_t st) {
     if (n_atoms == 0) return AIMNET_OK;
-    if (C == 1) {
-        conv_bwd_prep_kernel<1><<<n_atoms, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q);
-        AIM_LAUNCH_CHECK();
-        conv_bwd_kernel<1><<<n_atoms, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, a, q, dS_a, dS_q, grad_a,
-                                                   grad_q, forces, virial_atom, with_q, want_grad_a);
-    } else {
-        conv_bwd_prep_kernel<2><<<n_atoms, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q);
-        AIM_LAUNCH_CHECK();
-        conv_bwd_kernel<2><<<n_atoms, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, a, q, dS_a, dS_q, grad_a,
-                                                   grad_q, forces, virial_atom, with_q, want_grad_a);
-    }
-    AIM_LAUNCH_CHECK();
-    return AIMNET_OK;
+    if (C == 1)
+        return conv_bwd_launch<1>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q,
+                                  grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, st);
+    return conv_bwd_launch<2>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q,
+                              grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, st);
 }
 
 }  // namespace aimnet
