@@ -26,8 +26,9 @@ int launch_conv_fwd(int, int, const NbView&, const float*, const CellView&, cons
 int launch_conv_bwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
                     const float*, const float*, const float*, int, const float*, const float*, const float*,
                     const float*, float*, float*, float*, float*, float*, double*, int, int, cudaStream_t);
-int gemm_nt(const float*, int, const float*, int, const float*, float*, int, float*, int, int, int, int, int, int,
-            cudaStream_t);
+int gemm_nt(const float*, int, const float*, const float*, const float*, int, const float*, float*, int, float*, int, int,
+            int, int, int, int, cudaStream_t);
+int split_tf32(const float*, float*, float*, size_t, cudaStream_t);
 bool gemm_tc_available();
 int launch_embed(int, const int32_t*, const float*, float*, cudaStream_t);
 int launch_mol_ptr(const int32_t*, int, int, int32_t*, cudaStream_t);
@@ -58,6 +59,8 @@ struct Linear {
     float* W = nullptr;    // (out_pad, in_pad)
     float* Wt = nullptr;   // (in_pad, out_pad)
     float* b = nullptr;    // (out_pad)
+    // tf32 hi/lo splits of W and Wt for the tcgen05 3xTF32 backend
+    float *Whi = nullptr, *Wlo = nullptr, *Wthi = nullptr, *Wtlo = nullptr;
 };
 
 }  // namespace aimnet
@@ -128,6 +131,30 @@ static int make_linear(aimnet2_engine* e, Linear& L, const float* w, const float
     if ((rc = upload(e, &L.W, W.data(), W.size()))) return rc;
     if ((rc = upload(e, &L.Wt, Wt.data(), Wt.size()))) return rc;
     if ((rc = upload(e, &L.b, B.data(), B.size()))) return rc;
+    auto split = [](const std::vector<float>& src, std::vector<float>& hi, std::vector<float>& lo) {
+        hi.resize(src.size());
+        lo.resize(src.size());
+        for (size_t k = 0; k < src.size(); ++k) {
+            uint32_t v, h, l;
+            std::memcpy(&v, &src[k], 4);
+            h = v & 0xffffe000u;
+            float hf, lf;
+            std::memcpy(&hf, &h, 4);
+            lf = src[k] - hf;
+            std::memcpy(&l, &lf, 4);
+            l &= 0xffffe000u;
+            std::memcpy(&lf, &l, 4);
+            hi[k] = hf;
+            lo[k] = lf;
+        }
+    };
+    std::vector<float> hi, lo;
+    split(W, hi, lo);
+    if ((rc = upload(e, &L.Whi, hi.data(), hi.size()))) return rc;
+    if ((rc = upload(e, &L.Wlo, lo.data(), lo.size()))) return rc;
+    split(Wt, hi, lo);
+    if ((rc = upload(e, &L.Wthi, hi.data(), hi.size()))) return rc;
+    if ((rc = upload(e, &L.Wtlo, lo.data(), lo.size()))) return rc;
     return AIMNET_OK;
 }
 
@@ -234,7 +261,7 @@ static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
 static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ldx, int K, float* Y, float* gp, bool act,
                       int M, cudaStream_t st) {
     gemm_mark(e, st);
-    int rc = gemm_nt(X, ldx, L.W, L.in_pad, L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1,
+    int rc = gemm_nt(X, ldx, L.W, L.Whi, L.Wlo, L.in_pad, L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1,
                      e->gemm_backend, st);
     gemm_mark(e, st);
     return rc;
@@ -243,8 +270,8 @@ static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ld
 static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float* dX, int lddx, const float* gp_prev,
                       int ldgp, int M, cudaStream_t st) {
     gemm_mark(e, st);
-    int rc = gemm_nt(dZ, L.out_pad, L.Wt, L.out_pad, nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad,
-                     L.out_pad, gp_prev ? 3 : 0, e->gemm_backend, st);
+    int rc = gemm_nt(dZ, L.out_pad, L.Wt, L.Wthi, L.Wtlo, L.out_pad, nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M,
+                     L.in_pad, L.out_pad, gp_prev ? 3 : 0, e->gemm_backend, st);
     gemm_mark(e, st);
     return rc;
 }

@@ -103,12 +103,14 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
     }
 }
 
-int gemm_nt_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy, float* aux,
-               int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
+int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int ldw, const float* bias, float* Y, int ldy,
+               float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
+int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st);
 bool gemm_tc_available();
 
-int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy, float* aux,
-            int ldaux, int M, int N, int K, int mode, int backend, cudaStream_t st) {
+// W: fp32 weights (SIMT backend); Whi / Wlo: their tf32 hi/lo split (tcgen05 backend), same leading dimension
+int gemm_nt(const float* A, int lda, const float* W, const float* Whi, const float* Wlo, int ldw, const float* bias,
+            float* Y, int ldy, float* aux, int ldaux, int M, int N, int K, int mode, int backend, cudaStream_t st) {
     AIM_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes");
     AIM_REQUIRE(K % BK == 0, "gemm: K must be a multiple of 16 (pad the operands)");
     AIM_REQUIRE(N % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0, "gemm: N and leading dims must be multiples of 4");
@@ -116,7 +118,10 @@ int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias,
     AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
     AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
     if (M == 0) return AIMNET_OK;
-    if (backend == 1) return gemm_nt_tc(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
+    if (backend == 1) {
+        AIM_REQUIRE(Whi != nullptr && Wlo != nullptr, "gemm: tcgen05 backend needs the split weights");
+        return gemm_nt_tc(A, lda, Whi, Wlo, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     switch (mode) {
         case 0: gemm_nt_simt_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
@@ -132,5 +137,17 @@ int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias,
 
 extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                                float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {
-    return aimnet::gemm_nt(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, backend, (cudaStream_t)stream);
+    using namespace aimnet;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (backend != 1) return gemm_nt(A, lda, W, nullptr, nullptr, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, backend, st);
+    AIM_REQUIRE(gemm_tc_available(), "gemm: tcgen05 backend not available");
+    AIM_REQUIRE(N > 0 && ldw > 0, "gemm: bad sizes");
+    float *hi = nullptr, *lo = nullptr;
+    size_t n = (size_t)N * ldw;
+    AIM_CUDA_CHECK(cudaMallocAsync(&hi, sizeof(float) * n * 2, st));
+    lo = hi + n;
+    int rc = split_tf32(W, hi, lo, n, st);
+    if (rc == AIMNET_OK) rc = gemm_nt(A, lda, W, hi, lo, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, 1, st);
+    cudaFreeAsync(hi, st);
+    return rc;
 }
