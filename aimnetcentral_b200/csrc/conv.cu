@@ -7,8 +7,9 @@
 //
 // Thread mapping (forward and backward): one CTA = 16 centre atoms x 16 radial shifts; thread (atom, g) owns the
 // full 16(a) x 4(d) register tile of S[i,:,g,:].  Per neighbour it loads the 64-byte row aT[j][g][0..15] and does a
-// 16x4 outer-product update: 64 FMAs for 5 vector loads, no cross-thread traffic.  Features are therefore kept in the
-// gather-friendly transposed layout aT (N, 16 g, 16 a); dS^T (N, 16 g, 16 a, 4 d) likewise.
+// 16x4 outer-product update: 64 FMAs for 5 vector loads, no cross-thread traffic.  Features are kept in a gather
+// layout aX (N, 4 a-quads, 16 g, 4 a) so that the 16 g-lanes of an atom read 256 contiguous bytes per float4 load
+// (index(a,g) = ((a>>2)*16 + g)*4 + (a&3)); dS (N, 16 a, 16 g, 4 d) is lane-contiguous as is.
 //
 // Backward: the neighbour matrix is full (both directions), so everything atom i needs is in its own row:
 //   grad_a[i,a,g]  = sum_m <dS[j_m,a,g,:], g_sv(j_m->i)[g,:]>            g_sv(j->i) = (gs, -gs u_{i->j})
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
         int lim = min(kSlotsPerTile, len - m0);
         for (int s = 0; s < lim; ++s) {
             const PairEntry e = tile[al * 16 + s];
-            const float4* row = reinterpret_cast<const float4*>(aT + ((size_t)e.j * kAG + g * kA));
-            float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+            const float4* row = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g;
+            float4 v0 = row[0], v1 = row[16], v2 = row[32], v3 = row[48];
             float xg = e.d - shift_g;
             float w0 = expf(-aev.eta * xg * xg) * e.fc;
             float w1 = w0 * e.ux, w2 = w0 * e.uy, w3 = w0 * e.uz;
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
     }
     if (atom_ok) {
         float* xr = x + (size_t)i * ldx;
-        const float4* own = reinterpret_cast<const float4*>(aT + ((size_t)i * kAG + g * kA));
-        float4 o0 = own[0], o1 = own[1], o2 = own[2], o3 = own[3];
+        const float4* own = reinterpret_cast<const float4*>(aT + (size_t)i * kAG) + g;
+        float4 o0 = own[0], o1 = own[16], o2 = own[32], o3 = own[48];
         float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
 #pragma unroll
         for (int a = 0; a < kA; ++a) {
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
 
 // ------------------------------------------------------------------------------------------------------------
 // backward step 1: per atom, turn d(loss)/d(x row) into d(loss)/dS^a and d(loss)/dS^q, stored transposed for the
-// gather: dS_a^T (N,16 g,16 a,4), dS_q^T (N,16 g,C,4)
+// gather: dS_a (N,16 a,16 g,4), dS_q (N,C,16 g,4)
 //   d avf_v[a,h] -> dT[a,h,d] = 2 T[a,h,d] * d avf_v[a,h] -> dSv[a,g,d] = sum_h agh[a,g,h] dT[a,h,d]
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
@@ -251,10 +252,9 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
         for (int e = tid; e < C * kH * 3; e += 256)
             dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
     __syncthreads();
-    // thread t = g*16 + a so that the transposed store is coalesced
-    int g = tid >> 4, aa = tid & 15;
+    int aa = tid >> 4, g = tid & 15;
     float4 o;
-    o.x = dxr[kAG + aa * kG + g];
+    o.x = dxr[kAG + tid];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int h = 0; h < kH; ++h) {
@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
     o.w = s2;
     reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + tid] = o;
     if (with_q && tid < C * kG) {
-        int gq = tid / C, cc = tid % C;
+        int cc = tid >> 4, gq = tid & 15;
         float4 oq;
-        oq.x = dxr[base + C + cc * kG + gq];
+        oq.x = dxr[base + C + tid];
         float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
     float4 dSi[kA];
     float ai[kA];
     {
-        const float4* p = reinterpret_cast<const float4*>(dS_a) + ((size_t)ic * kAG + g * kA);
+        const float4* p = reinterpret_cast<const float4*>(dS_a) + (size_t)ic * kAG + g;
 #pragma unroll
-        for (int a = 0; a < kA; ++a) dSi[a] = p[a];
-        const float4* r = reinterpret_cast<const float4*>(aT + ((size_t)ic * kAG + g * kA));
-        float4 o0 = r[0], o1 = r[1], o2 = r[2], o3 = r[3];
+        for (int a = 0; a < kA; ++a) dSi[a] = p[a * kG];
+        const float4* r = reinterpret_cast<const float4*>(aT + (size_t)ic * kAG) + g;
+        float4 o0 = r[0], o1 = r[16], o2 = r[32], o3 = r[48];
         float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
 #pragma unroll
         for (int a = 0; a < kA; ++a) ai[a] = ov[a];
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
     float qi[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        dSqi[c] = with_q ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + g * C + c] : make_float4(0, 0, 0, 0);
+        dSqi[c] = with_q ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
         qi[c] = with_q ? q[(size_t)ic * C + c] : 0.f;
     }
     float ga[kA];
@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
         int lim = min(kSlotsPerTile, len - m0);
         for (int s = 0; s < lim; ++s) {
             const PairEntry e = tile[al * 16 + s];
-            const float4* arow = reinterpret_cast<const float4*>(aT + ((size_t)e.j * kAG + g * kA));
-            const float4* drow = reinterpret_cast<const float4*>(dS_a) + ((size_t)e.j * kAG + g * kA);
-            float4 v0 = arow[0], v1 = arow[1], v2 = arow[2], v3 = arow[3];
+            const float4* arow = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g;
+            const float4* drow = reinterpret_cast<const float4*>(dS_a) + (size_t)e.j * kAG + g;
+            float4 v0 = arow[0], v1 = arow[16], v2 = arow[32], v3 = arow[48];
             float aj[kA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
             float xg = e.d - shift_g;
             float ex = expf(-aev.eta * xg * xg);
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
             for (int a = 0; a < kA; ++a) {
-                float4 dj = drow[a];
+                float4 dj = drow[a * kG];
                 if (kGradA) {
                     float t = dj.x - (dj.y * e.ux + dj.z * e.uy + dj.w * e.uz);
                     ga[a] = fmaf(gs, t, ga[a]);
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     float qj = q[(size_t)e.j * C + c];
-                    float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)e.j * (C * kG) + g * C + c];
+                    float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)e.j * (C * kG) + c * kG + g];
                     if (kGradA) gq[c] = fmaf(gs, dqj.x - (dqj.y * e.ux + dqj.z * e.uy + dqj.w * e.uz), gq[c]);
                     p0 = fmaf(qj, dSqi[c].x, p0);
                     p1 = fmaf(qj, dSqi[c].y, p1);

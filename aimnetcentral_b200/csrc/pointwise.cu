@@ -4,13 +4,17 @@
 
 namespace aimnet {
 
-// a0[i] = afv[Z_i]   (aimnet/models/aimnet2.py:144-147), stored in the gather layout aT[i][g][a]
+// gather layout of the features (see conv.cu): slot t of a row holds (a, g) with
+//   a = (t >> 6) * 4 + (t & 3),  g = (t >> 2) & 15 ;  canonical flat index = a*16 + g
+__device__ __forceinline__ int gather_slot_to_canonical(int t) { return (((t >> 6) << 2) + (t & 3)) * kG + ((t >> 2) & 15); }
+
+// a0[i] = afv[Z_i]   (aimnet/models/aimnet2.py:144-147), stored in the gather layout
 __global__ void embed_kernel(int n, const int32_t* __restrict__ numbers, const float* __restrict__ afv,
                              float* __restrict__ aT0) {
-    int i = blockIdx.x, t = threadIdx.x;   // t = g*16 + a
+    int i = blockIdx.x, t = threadIdx.x;
     int z = numbers[i];
     z = (z < 0 || z > 63) ? 0 : z;
-    aT0[(size_t)i * kAG + t] = afv[(size_t)z * kAG + (t & 15) * kG + (t >> 4)];
+    aT0[(size_t)i * kAG + t] = afv[(size_t)z * kAG + gather_slot_to_canonical(t)];
 }
 
 // molecule segment pointers from sorted mol_idx (nullptr = one molecule)
@@ -84,8 +88,8 @@ __global__ void __launch_bounds__(256) nse_apply_fwd_kernel(int C, int n, const 
                                                             const float* __restrict__ sumf,
                                                             const float* __restrict__ a_old, float* __restrict__ a_new,
                                                             float* __restrict__ q_new) {
-    int i = blockIdx.x, t = threadIdx.x;   // features live in the gather layout aT[i][g][a], t = g*16 + a
-    a_new[(size_t)i * kAG + t] = a_old[(size_t)i * kAG + t] + y[(size_t)i * ldy + 2 * C + (t & 15) * kG + (t >> 4)];
+    int i = blockIdx.x, t = threadIdx.x;   // features live in the gather layout
+    a_new[(size_t)i * kAG + t] = a_old[(size_t)i * kAG + t] + y[(size_t)i * ldy + 2 * C + gather_slot_to_canonical(t)];
     if (t < C) {
         int m = mol_idx ? mol_idx[i] : 0;
         float qu = (q_prev ? q_prev[(size_t)i * C + t] : 0.f) + y[(size_t)i * ldy + t];
