@@ -135,14 +135,15 @@ static int make_linear(aimnet2_engine* e, Linear& L, const float* w, const float
         hi.resize(src.size());
         lo.resize(src.size());
         for (size_t k = 0; k < src.size(); ++k) {
+            // round-to-nearest (ties away) to tf32, like cvt.rna.tf32.f32
             uint32_t v, h, l;
             std::memcpy(&v, &src[k], 4);
-            h = v & 0xffffe000u;
+            h = (v + 0x1000u) & 0xffffe000u;
             float hf, lf;
             std::memcpy(&hf, &h, 4);
             lf = src[k] - hf;
             std::memcpy(&l, &lf, 4);
-            l &= 0xffffe000u;
+            l = (l + 0x1000u) & 0xffffe000u;
             std::memcpy(&lf, &l, 4);
             hi[k] = hf;
             lo[k] = lf;

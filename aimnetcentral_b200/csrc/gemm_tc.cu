@@ -1,19 +1,24 @@
 // tcgen05 backend of the per-atom MLP GEMMs: Y[M,N] = epilogue(A[M,K] @ W[N,K]^T) with fp32-faithful accuracy.
 //
-// Precision scheme ("3xTF32"): the reference forbids TF32/autocast on the inference path (aimnet/train/utils.py:19-34,
-// aimnet/validation/gpu_observables.py:33-40) and parity is 1e-4 eV/A, so every fp32 operand is split exactly into
-// hi = top 10 mantissa bits (a valid tf32) and lo = tf32(x - hi); the product is accumulated in fp32 TMEM as
-// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (the dropped lo*lo term and the truncation of lo are ~2^-21 relative).
-// Weights are split once on the host; activations are split in shared memory by a dedicated warpgroup.
+// Precision scheme ("3xTF32" with two-level accumulation): the reference forbids TF32/autocast on the inference path
+// (aimnet/train/utils.py:19-34, aimnet/validation/gpu_observables.py:33-40) and parity is 1e-4 eV/A, so every fp32
+// operand is split into hi = rn_tf32(x) and lo = rn_tf32(x - hi) and the product is formed as
+// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (dropped lo*lo and the rounding of lo are ~2^-22 relative, unbiased).
+// The tensor core adds into its fp32 accumulator with truncation (measured: -4.8e-6 relative shrinkage over K=704,
+// tools/gemm_error.py), so TMEM only accumulates chunks of K=128; the epilogue warps drain each chunk and sum the
+// chunks in registers with round-to-nearest.  Weights are split once on the host; activations are split in shared
+// memory by a dedicated warpgroup.
 //
 // Structure (one persistent CTA per SM, 512 threads, warp-specialised):
 //   warp 0       TMA producer   cp.async.bulk.tensor 2D, 64B-swizzled K-major tiles: A 128x16, W_hi 256x16, W_lo 256x16
 //   warps 4-7    splitter       A tile -> A_hi (in place) + A_lo, then fence.proxy.async + mbarrier arrive
 //   warp 1       MMA issuer     one elected thread: 2 k-steps x 3 tcgen05.mma.kind::tf32 (M128 x N<=256 x K8) per stage,
-//                               tcgen05.commit releases the stage; accumulators double-buffered in TMEM (2 x 256 cols)
+//                               tcgen05.commit releases the stage; chunk accumulators double-buffered in TMEM (2 x 256 cols)
 //   warp 2       TMEM allocator
-//   warps 8-15   epilogue       tcgen05.ld 32x32b.x32 -> bias / exact-erf GELU (+ gelu' side output) / *aux -> global
-// Four 48 KB stages (192 KB shared memory).  Epilogue of tile t overlaps the main loop of tile t+1.
+//   warps 8-15   epilogue       per K-chunk: tcgen05.ld 32x32b.x32 += into 128 fp32 registers per thread; per tile:
+//                               bias / exact-erf GELU (+ gelu' side output) / *aux -> global
+// Four 48 KB stages (192 KB shared memory); setmaxnreg moves registers from the control/splitter warpgroups to the
+// epilogue warpgroups.  Draining chunk c overlaps the MMAs of chunk c+1.
 #include <cuda.h>
 
 #include <mutex>
@@ -26,6 +31,7 @@ namespace aimnet {
 namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4;
+constexpr int CHUNK = 8;                   // stages (of K=16) accumulated inside TMEM before the fp32 register add
 constexpr int A_BYTES = BM * BK * 4;       // 8 KB
 constexpr int B_BYTES = BN * BK * 4;       // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB
@@ -63,6 +69,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
             smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ uint32_t rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -155,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
@@ -176,43 +188,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            int cit = 0;   // running chunk counter -> TMEM buffer / phase
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 int n0 = (t % n_tiles) * BN;
                 int n_tile = min(BN, p.N - n0);
                 uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-                int b = it & 1;
-                uint32_t aph = (uint32_t)(it >> 1) & 1;
-                mbar_wait(&tmem_empty[b], aph ^ 1);
-                tc_fence_after();
-                uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
-                for (int ks = 0; ks < nk; ++ks) {
-                    mbar_wait(&full_split[s], ph);
+                for (int ks0 = 0; ks0 < nk; ks0 += CHUNK, ++cit) {
+                    int b = cit & 1;
+                    uint32_t aph = (uint32_t)(cit >> 1) & 1;
+                    mbar_wait(&tmem_empty[b], aph ^ 1);
                     tc_fence_after();
-                    uint32_t sa = smem_u32(stage_ptr(s));
-                    uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
-                    uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES);
+                    uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+                    int ks1 = min(nk, ks0 + CHUNK);
+                    for (int ks = ks0; ks < ks1; ++ks) {
+                        mbar_wait(&full_split[s], ph);
+                        tc_fence_after();
+                        uint32_t sa = smem_u32(stage_ptr(s));
+                        uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+                        uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {
-                        uint64_t adv = (uint64_t)(kk * 32 >> 4);   // 8 tf32 = 32 bytes along K inside the swizzle atom
-                        tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (ks | kk) ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                        tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            uint64_t adv = (uint64_t)(kk * 32 >> 4);   // 8 tf32 = 32 bytes along K inside the swizzle atom
+                            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (ks > ks0 || kk > 0) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        }
+                        tc_commit(&empty[s]);   // frees the stage once these MMAs have read it
+                        if (++s == STAGES) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
-                    tc_commit(&empty[s]);   // frees the stage once these MMAs have read it
-                    if (++s == STAGES) {
-                        s = 0;
-                        ph ^= 1;
-                    }
+                    tc_commit(&tmem_full[b]);
                 }
-                tc_commit(&tmem_full[b]);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    } else if (warp < 8) {
         // ------------------------------------------------ splitter: A -> (A_hi in place, A_lo)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         int s = 0;
         uint32_t ph = 0;
         const int tsp = threadIdx.x - 128;
@@ -226,14 +245,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     int idx = tsp + 128 * r;
                     uint4 v = hi[idx];
                     uint4 h, l;
-                    h.x = v.x & 0xffffe000u;
-                    h.y = v.y & 0xffffe000u;
-                    h.z = v.z & 0xffffe000u;
-                    h.w = v.w & 0xffffe000u;
-                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
-                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
-                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
-                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+                    h.x = rn_tf32(__uint_as_float(v.x));
+                    h.y = rn_tf32(__uint_as_float(v.y));
+                    h.z = rn_tf32(__uint_as_float(v.z));
+                    h.w = rn_tf32(__uint_as_float(v.w));
+                    l.x = rn_tf32(__uint_as_float(v.x) - __uint_as_float(h.x));
+                    l.y = rn_tf32(__uint_as_float(v.y) - __uint_as_float(h.y));
+                    l.z = rn_tf32(__uint_as_float(v.z) - __uint_as_float(h.z));
+                    l.w = rn_tf32(__uint_as_float(v.w) - __uint_as_float(h.w));
                     hi[idx] = h;
                     lo[idx] = l;
                 }
@@ -247,59 +266,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 8) {
         // ------------------------------------------------ epilogue
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         const int ql = warp & 3;            // TMEM lane quarter this warp may access
         const int ch = (warp - 8) >> 2;     // column half of the 256-wide accumulator
-        int it = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        int cit = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
             int n_tile = min(BN, p.N - n0);
-            int b = it & 1;
-            uint32_t aph = (uint32_t)(it >> 1) & 1;
-            mbar_wait(&tmem_full[b], aph);
-            tc_fence_after();
-            int row = m0 + ql * 32 + lane;
-            bool row_ok = row < p.M;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                int col0 = ch * 128 + c * 32;
-                if (col0 >= n_tile) break;
-                uint32_t r[32];
-                uint32_t taddr = tmem_base + ((uint32_t)(ql * 32) << 16) + (uint32_t)(b * BN + col0);
-                tc_ld32(taddr, r);
-                if (row_ok) {
-                    int col = n0 + col0;
-                    float* yrow = p.Y + (size_t)row * p.ldy + col;
+            float acc[128];
 #pragma unroll
-                    for (int v4 = 0; v4 < 8; ++v4) {
-                        float4 z = make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]),
-                                               __uint_as_float(r[4 * v4 + 2]), __uint_as_float(r[4 * v4 + 3]));
-                        if (p.mode == 1 || p.mode == 2) {
-                            float4 bz = *reinterpret_cast<const float4*>(p.bias + col + 4 * v4);
-                            z.x += bz.x;
-                            z.y += bz.y;
-                            z.z += bz.z;
-                            z.w += bz.w;
-                        }
-                        if (p.mode == 2) {
-                            if (p.aux != nullptr) {
-                                float4 gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
-                                *reinterpret_cast<float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4) = gp;
+            for (int k = 0; k < 128; ++k) acc[k] = 0.f;
+            for (int ks0 = 0; ks0 < nk; ks0 += CHUNK, ++cit) {
+                int b = cit & 1;
+                uint32_t aph = (uint32_t)(cit >> 1) & 1;
+                mbar_wait(&tmem_full[b], aph);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int col0 = ch * 128 + c * 32;
+                    if (col0 < n_tile) {
+                        uint32_t r[32];
+                        uint32_t taddr = tmem_base + ((uint32_t)(ql * 32) << 16) + (uint32_t)(b * BN + col0);
+                        tc_ld32(taddr, r);
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) acc[c * 32 + k] += __uint_as_float(r[k]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[b]);
+            }
+            int row = m0 + ql * 32 + lane;
+            if (row < p.M) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int col0 = ch * 128 + c * 32;
+                    if (col0 < n_tile) {
+                        int col = n0 + col0;
+                        float* yrow = p.Y + (size_t)row * p.ldy + col;
+#pragma unroll
+                        for (int v4 = 0; v4 < 8; ++v4) {
+                            float4 z = make_float4(acc[c * 32 + 4 * v4], acc[c * 32 + 4 * v4 + 1], acc[c * 32 + 4 * v4 + 2],
+                                                   acc[c * 32 + 4 * v4 + 3]);
+                            if (p.mode == 1 || p.mode == 2) {
+                                float4 bz = *reinterpret_cast<const float4*>(p.bias + col + 4 * v4);
+                                z.x += bz.x;
+                                z.y += bz.y;
+                                z.z += bz.z;
+                                z.w += bz.w;
                             }
-                            z = make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w));
-                        } else if (p.mode == 3) {
-                            float4 gp = *reinterpret_cast<const float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4);
-                            z.x *= gp.x;
-                            z.y *= gp.y;
-                            z.z *= gp.z;
-                            z.w *= gp.w;
+                            if (p.mode == 2) {
+                                if (p.aux != nullptr) {
+                                    float4 gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
+                                    *reinterpret_cast<float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4) = gp;
+                                }
+                                z = make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w));
+                            } else if (p.mode == 3) {
+                                float4 gp = *reinterpret_cast<const float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4);
+                                z.x *= gp.x;
+                                z.y *= gp.y;
+                                z.z *= gp.z;
+                                z.w *= gp.w;
+                            }
+                            *reinterpret_cast<float4*>(yrow + 4 * v4) = z;
                         }
-                        *reinterpret_cast<float4*>(yrow + 4 * v4) = z;
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[b]);
         }
     }
     tc_fence_before();
@@ -314,10 +347,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t v = __float_as_uint(w[i]);
-    uint32_t h = v & 0xffffe000u;
+    uint32_t h = rn_tf32(w[i]);
     hi[i] = __uint_as_float(h);
-    lo[i] = __uint_as_float(__float_as_uint(w[i] - __uint_as_float(h)) & 0xffffe000u);
+    lo[i] = __uint_as_float(rn_tf32(w[i] - __uint_as_float(h)));
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
