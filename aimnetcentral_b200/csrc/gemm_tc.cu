@@ -5,7 +5,7 @@
 // operand is split into hi = rn_tf32(x) and lo = rn_tf32(x - hi) and the product is formed as
 // A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (dropped lo*lo and the rounding of lo are ~2^-22 relative, unbiased).
 // The tensor core adds into its fp32 accumulator with truncation (measured: -4.8e-6 relative shrinkage over K=704,
-// tools/gemm_error.py), so TMEM only accumulates chunks of K=128; the epilogue warps drain each chunk and sum the
+// tools/gemm_error.py), so TMEM only accumulates chunks of K=32 (rms error 3.2e-7 vs 6.1e-7 for fp32 FMA); the epilogue warps drain each chunk and sum the
 // chunks in registers with round-to-nearest.  Weights are split once on the host; activations are split in shared
 // memory by a dedicated warpgroup.
 //
@@ -21,6 +21,7 @@
 // epilogue warpgroups.  Draining chunk c overlaps the MMAs of chunk c+1.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -31,7 +32,7 @@ namespace aimnet {
 namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4;
-constexpr int CHUNK = 8;                   // stages (of K=16) accumulated inside TMEM before the fp32 register add
+constexpr int CHUNK = 2;                   // stages (of K=16) accumulated inside TMEM before the fp32 register add (K=32)
 constexpr int A_BYTES = BM * BK * 4;       // 8 KB
 constexpr int B_BYTES = BN * BK * 4;       // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB
@@ -121,6 +122,7 @@ struct Params {
     float* Y;
     float* aux;
     int ldy, ldaux, M, N, K, mode;
+    int chunk;   // stages (K=16 each) accumulated in TMEM before the fp32 register add
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -197,13 +199,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int n0 = (t % n_tiles) * BN;
                 int n_tile = min(BN, p.N - n0);
                 uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-                for (int ks0 = 0; ks0 < nk; ks0 += CHUNK, ++cit) {
+                for (int ks0 = 0; ks0 < nk; ks0 += p.chunk, ++cit) {
                     int b = cit & 1;
                     uint32_t aph = (uint32_t)(cit >> 1) & 1;
                     mbar_wait(&tmem_empty[b], aph ^ 1);
                     tc_fence_after();
                     uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
-                    int ks1 = min(nk, ks0 + CHUNK);
+                    int ks1 = min(nk, ks0 + p.chunk);
                     for (int ks = ks0; ks < ks1; ++ks) {
                         mbar_wait(&full_split[s], ph);
                         tc_fence_after();
@@ -276,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float acc[128];
 #pragma unroll
             for (int k = 0; k < 128; ++k) acc[k] = 0.f;
-            for (int ks0 = 0; ks0 < nk; ks0 += CHUNK, ++cit) {
+            for (int ks0 = 0; ks0 < nk; ks0 += p.chunk, ++cit) {
                 int b = cit & 1;
                 uint32_t aph = (uint32_t)(cit >> 1) & 1;
                 mbar_wait(&tmem_full[b], aph);
@@ -420,7 +422,13 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     if ((rc = make_map(&tmA, A, M, K, lda, BM))) return rc;
     if ((rc = make_map(&tmBh, Whi, N, K, ldw, BN))) return rc;
     if ((rc = make_map(&tmBl, Wlo, N, K, ldw, BN))) return rc;
-    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode};
+    static int chunk = 0;
+    if (chunk == 0) {
+        const char* env = getenv("AIMNET_TC_CHUNK");
+        chunk = env ? atoi(env) : CHUNK;
+        if (chunk < 1) chunk = 1;
+    }
+    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk};
     int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int grid = tiles < num_sms ? tiles : num_sms;
     gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p);

@@ -1,0 +1,26 @@
+"""Time the MLP GEMM shapes of cfg-2 (M=51200) per backend / epilogue mode; report TFLOP/s (1x flops)."""
+import ctypes as C, sys, os
+import torch
+sys.path.insert(0, ".")
+from aimnetcentral_b200 import _capi
+lib = _capi.load()
+dev = "cuda:0"
+M = 51200
+shapes = [(512, 704, 2), (384, 512, 2), (288, 384, 1), (512, 384, 3), (736, 512, 0), (256, 384, 2), (128, 256, 2)]
+backends = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1").split(",")]
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for N, K, mode in shapes:
+    A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * 0.05; b = torch.randn(N, device=dev)
+    Y = torch.empty(M, N, device=dev); aux = torch.randn(M, N, device=dev)
+    from aimnetcentral_b200 import _capi as cap
+    for be in backends:
+        # pre-split weights are re-made inside aimnet2_gemm_nt for backend 1 (small, included in the timing)
+        for _ in range(3):
+            lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode, be, st)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(10):
+            rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode, be, st)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"backend={be} chunk={os.environ.get('AIMNET_TC_CHUNK','8')} N={N:4d} K={K:4d} mode={mode} {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:7.1f} TFLOP/s")
