@@ -90,11 +90,12 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
         if (row >= M) continue;
         float4 z = make_float4(acc[r][0] + bz.x, acc[r][1] + bz.y, acc[r][2] + bz.z, acc[r][3] + bz.w);
         if (MODE == 2) {
-            if (aux != nullptr) {
-                float4 gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
-                *reinterpret_cast<float4*>(aux + (size_t)row * ldaux + col) = gp;
-            }
-            z = make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w));
+            float4 gp;
+            gelu_pair(z.x, z.x, gp.x);
+            gelu_pair(z.y, z.y, gp.y);
+            gelu_pair(z.z, z.z, gp.z);
+            gelu_pair(z.w, z.w, gp.w);
+            if (aux != nullptr) *reinterpret_cast<float4*>(aux + (size_t)row * ldaux + col) = gp;
         } else if (MODE == 3) {
             float4 gp = *reinterpret_cast<const float4*>(aux + (size_t)row * ldaux + col);
             z = make_float4(z.x * gp.x, z.y * gp.y, z.z * gp.z, z.w * gp.w);

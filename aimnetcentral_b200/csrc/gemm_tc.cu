@@ -123,6 +123,7 @@ struct Params {
     float* aux;
     int ldy, ldaux, M, N, K, mode;
     int chunk;   // stages (K=16 each) accumulated in TMEM before the fp32 register add
+    int bn;      // N-tile width (multiple of 16, <= 256): N is cut into equal tiles so that no CTA gets a sliver
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -139,7 +140,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + p.bn - 1) / p.bn;
+    const uint32_t tx_bytes = (uint32_t)(A_BYTES + 2 * p.bn * BK * 4);
     const int tiles = m_tiles * n_tiles;
     const int nk = p.K / BK;
 
@@ -173,11 +175,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int s = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-                int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+                int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * p.bn;
                 for (int ks = 0; ks < nk; ++ks) {
                     mbar_wait(&empty[s], ph ^ 1);
                     unsigned char* sp = stage_ptr(s);
-                    mbar_expect_tx(&full_tma[s], TX_BYTES);
+                    mbar_expect_tx(&full_tma[s], tx_bytes);
                     tma_load_2d(sp, &tmA, &full_tma[s], ks * BK, m0);
                     tma_load_2d(sp + 2 * A_BYTES, &tmBh, &full_tma[s], ks * BK, n0);
                     tma_load_2d(sp + 2 * A_BYTES + B_BYTES, &tmBl, &full_tma[s], ks * BK, n0);
@@ -196,8 +198,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t ph = 0;
             int cit = 0;   // running chunk counter -> TMEM buffer / phase
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-                int n0 = (t % n_tiles) * BN;
-                int n_tile = min(BN, p.N - n0);
+                int n0 = (t % n_tiles) * p.bn;
+                int n_tile = min(p.bn, p.N - n0);
                 uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
                 for (int ks0 = 0; ks0 < nk; ks0 += p.chunk, ++cit) {
                     int b = cit & 1;
@@ -273,8 +275,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ch = (warp - 8) >> 2;     // column half of the 256-wide accumulator
         int cit = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-            int n_tile = min(BN, p.N - n0);
+            int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * p.bn;
+            int n_tile = min(p.bn, p.N - n0);
             float acc[128];
 #pragma unroll
             for (int k = 0; k < 128; ++k) acc[k] = 0.f;
@@ -308,6 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float* yrow = p.Y + (size_t)row * p.ldy + col;
 #pragma unroll
                         for (int v4 = 0; v4 < 8; ++v4) {
+                            if (col0 + 4 * v4 >= n_tile) continue;
                             float4 z = make_float4(acc[c * 32 + 4 * v4], acc[c * 32 + 4 * v4 + 1], acc[c * 32 + 4 * v4 + 2],
                                                    acc[c * 32 + 4 * v4 + 3]);
                             if (p.mode == 1 || p.mode == 2) {
@@ -318,11 +321,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 z.w += bz.w;
                             }
                             if (p.mode == 2) {
-                                if (p.aux != nullptr) {
-                                    float4 gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
+                                float4 gp;
+                                gelu_pair(z.x, z.x, gp.x);
+                                gelu_pair(z.y, z.y, gp.y);
+                                gelu_pair(z.z, z.z, gp.z);
+                                gelu_pair(z.w, z.w, gp.w);
+                                if (p.aux != nullptr)
                                     *reinterpret_cast<float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4) = gp;
-                                }
-                                z = make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w));
                             } else if (p.mode == 3) {
                                 float4 gp = *reinterpret_cast<const float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4);
                                 z.x *= gp.x;
@@ -420,16 +425,18 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     CUtensorMap tmA, tmBh, tmBl;
     int rc;
     if ((rc = make_map(&tmA, A, M, K, lda, BM))) return rc;
-    if ((rc = make_map(&tmBh, Whi, N, K, ldw, BN))) return rc;
-    if ((rc = make_map(&tmBl, Wlo, N, K, ldw, BN))) return rc;
+    int n_tiles = (N + BN - 1) / BN;
+    int bn = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+    if ((rc = make_map(&tmBh, Whi, N, K, ldw, bn))) return rc;
+    if ((rc = make_map(&tmBl, Wlo, N, K, ldw, bn))) return rc;
     static int chunk = 0;
     if (chunk == 0) {
         const char* env = getenv("AIMNET_TC_CHUNK");
         chunk = env ? atoi(env) : CHUNK;
         if (chunk < 1) chunk = 1;
     }
-    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk};
-    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, bn};
+    int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
     gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p);
     AIM_LAUNCH_CHECK();
