@@ -37,8 +37,7 @@ constexpr int A_BYTES = BM * BK * 4;       // 8 KB
 constexpr int B_BYTES = BN * BK * 4;       // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB
 constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
-constexpr int EPI_BYTES = 8 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose buffers
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,7 +123,6 @@ struct Params {
     float* aux;
     int ldy, ldaux, M, N, K, mode;
     int chunk;   // stages (K=16 each) accumulated in TMEM before the fp32 register add
-    int exp;     // debug experiments (AIMNET_TC_EXP bitmask): 1 = hi*hi MMA only, 2 = splitter skips the split, 4 = no stores
     int bn;      // N-tile width (multiple of 16, <= 256): N is cut into equal tiles so that no CTA gets a sliver
 };
 
@@ -140,7 +138,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = bars + 3 * STAGES;    // [2]
     uint64_t* tmem_empty = bars + 3 * STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
-    float* stage_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + p.bn - 1) / p.bn;
@@ -220,13 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int kk = 0; kk < BK / 8; ++kk) {
                             uint64_t adv = (uint64_t)(kk * 32 >> 4);   // 8 tf32 = 32 bytes along K inside the swizzle atom
-                            if (p.exp & 1) {
-                                tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (ks > ks0 || kk > 0) ? 1u : 0u);
-                            } else {
-                                tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (ks > ks0 || kk > 0) ? 1u : 0u);
-                                tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                                tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-                            }
+                            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (ks > ks0 || kk > 0) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
                         }
                         tc_commit(&empty[s]);   // frees the stage once these MMAs have read it
                         if (++s == STAGES) {
@@ -253,7 +246,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint4* lo = reinterpret_cast<uint4*>(stage_ptr(s) + A_BYTES);
 #pragma unroll
                 for (int r = 0; r < (A_BYTES / 16) / 128; ++r) {
-                    if (p.exp & 2) break;
                     int idx = tsp + 128 * r;
                     uint4 v = hi[idx];
                     uint4 h, l;
@@ -308,69 +300,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[b]);
             }
-            // ---- tile epilogue.  Each thread holds one row (lane) x 128 columns; going straight to global would make
-            // every store instruction touch 32 different 128-byte lines, so each 32x32 block is transposed through a
-            // padded per-warp shared-memory buffer and written (and, for mode 3, read) as whole 128-byte rows.
-            if (!(p.exp & 4)) {
-                float* sw = stage_buf + (warp - 8) * (32 * 33);
-                const int row_base = m0 + ql * 32;
+            int row = m0 + ql * 32 + lane;
+            if (row < p.M) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int col0 = ch * 128 + c * 32;
+                    int col0 = ch * 128 + c * 32;
                     if (col0 < n_tile) {
-                        const int col = n0 + col0;
-                        const bool col_ok = (col0 + lane) < n_tile;
-                        if (p.mode == 3) {
-#pragma unroll 4
-                            for (int r = 0; r < 32; ++r) {
-                                int rg = row_base + r;
-                                sw[r * 33 + lane] = (rg < p.M && col_ok) ? p.aux[(size_t)rg * p.ldaux + col + lane] : 0.f;
+                        int col = n0 + col0;
+                        float* yrow = p.Y + (size_t)row * p.ldy + col;
+#pragma unroll
+                        for (int v4 = 0; v4 < 8; ++v4) {
+                            if (col0 + 4 * v4 >= n_tile) continue;
+                            float4 z = make_float4(acc[c * 32 + 4 * v4], acc[c * 32 + 4 * v4 + 1], acc[c * 32 + 4 * v4 + 2],
+                                                   acc[c * 32 + 4 * v4 + 3]);
+                            if (p.mode == 1 || p.mode == 2) {
+                                float4 bz = *reinterpret_cast<const float4*>(p.bias + col + 4 * v4);
+                                z.x += bz.x;
+                                z.y += bz.y;
+                                z.z += bz.z;
+                                z.w += bz.w;
                             }
-                            __syncwarp();
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) acc[c * 32 + k] *= sw[lane * 33 + k];
-                            __syncwarp();
-                        } else if (p.mode == 1 || p.mode == 2) {
-#pragma unroll
-                            for (int v4 = 0; v4 < 8; ++v4) {
-                                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (col0 + 4 * v4 < n_tile) bz = *reinterpret_cast<const float4*>(p.bias + col + 4 * v4);
-                                acc[c * 32 + 4 * v4 + 0] += bz.x;
-                                acc[c * 32 + 4 * v4 + 1] += bz.y;
-                                acc[c * 32 + 4 * v4 + 2] += bz.z;
-                                acc[c * 32 + 4 * v4 + 3] += bz.w;
+                            if (p.mode == 2) {
+                                float4 gp;
+                                gelu_pair(z.x, z.x, gp.x);
+                                gelu_pair(z.y, z.y, gp.y);
+                                gelu_pair(z.z, z.z, gp.z);
+                                gelu_pair(z.w, z.w, gp.w);
+                                if (p.aux != nullptr)
+                                    *reinterpret_cast<float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4) = gp;
+                            } else if (p.mode == 3) {
+                                float4 gp = *reinterpret_cast<const float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4);
+                                z.x *= gp.x;
+                                z.y *= gp.y;
+                                z.z *= gp.z;
+                                z.w *= gp.w;
                             }
-                        }
-                        if (p.mode == 2) {
-                            // y goes to the staging buffer, gelu' takes over the accumulator registers
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                float y, g;
-                                gelu_pair(acc[c * 32 + k], y, g);
-                                sw[lane * 33 + k] = y;
-                                acc[c * 32 + k] = g;
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) sw[lane * 33 + k] = acc[c * 32 + k];
-                        }
-                        __syncwarp();
-#pragma unroll 4
-                        for (int r = 0; r < 32; ++r) {
-                            int rg = row_base + r;
-                            if (rg < p.M && col_ok) p.Y[(size_t)rg * p.ldy + col + lane] = sw[r * 33 + lane];
-                        }
-                        __syncwarp();
-                        if (p.mode == 2 && p.aux != nullptr) {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) sw[lane * 33 + k] = acc[c * 32 + k];
-                            __syncwarp();
-#pragma unroll 4
-                            for (int r = 0; r < 32; ++r) {
-                                int rg = row_base + r;
-                                if (rg < p.M && col_ok) p.aux[(size_t)rg * p.ldaux + col + lane] = sw[r * 33 + lane];
-                            }
-                            __syncwarp();
+                            *reinterpret_cast<float4*>(yrow + 4 * v4) = z;
                         }
                     }
                 }
@@ -470,12 +435,7 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
         chunk = env ? atoi(env) : CHUNK;
         if (chunk < 1) chunk = 1;
     }
-    static int expm = -1;
-    if (expm < 0) {
-        const char* env = getenv("AIMNET_TC_EXP");
-        expm = env ? atoi(env) : 0;
-    }
-    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, expm, bn};
+    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, bn};
     int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
     gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p);
