@@ -120,7 +120,7 @@ __device__ __forceinline__ float gelu_grad_f(float z) {
 // fp32 evaluation: max |gelu - exact| = 3.8e-7 on [-9, 9] (torch's own fp32 GELU: 1.2e-6), max |gelu' - exact| = 2.9e-7.
 __device__ __forceinline__ void gelu_pair(float z, float& y, float& gp) {
     const float ax = fabsf(z) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.47f, ax, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.47f, ax, 1.0f));
     float P = -0.019820483937064207f;
     P = fmaf(P, t, 0.14386611213498762f);
     P = fmaf(P, t, -0.3281399463335257f);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void gelu_pair(float z, float& y, float& gp) {
     P = fmaf(P, t, 0.23444773423159065f);
     P = fmaf(P, t, 0.2652225546919865f);
     P = fmaf(P, t, 0.26516877756878143f);
-    const float E = expf(-0.5f * z * z);
+    const float E = __expf(-0.5f * z * z);
     const float e = t * P * E;
     const float Phi = z > 0.f ? fmaf(-0.5f, e, 1.0f) : 0.5f * e;
     y = z * Phi;

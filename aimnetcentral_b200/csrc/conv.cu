@@ -5,9 +5,9 @@
 // The reference materialises g_sv (N,M,16,4) in HBM (256 B per pair) and re-reads it for every convolution and for
 // the autograd pass; here the radial basis is recomputed from a small per-tile pair table in shared memory.
 //
-// Thread mapping (forward and backward): one CTA = 16 centre atoms x 16 radial shifts; thread (atom, g) owns the
-// full 16(a) x 4(d) register tile of S[i,:,g,:].  Per neighbour it loads the 64-byte row aT[j][g][0..15] and does a
-// 16x4 outer-product update: 64 FMAs for 5 vector loads, no cross-thread traffic.  Features are kept in a gather
+// Thread mapping (forward and backward): one warp = one centre atom; lane = (half h, radial shift g) owns the
+// 8(a) x 4(d) register tile of S[i, 8h..8h+7, g, :].  Per neighbour it loads two float4 of a[j] and does an 8x4
+// outer-product update: 32 FMAs for 2 vector loads, no cross-thread traffic; 8 atoms (warps) per CTA.  Features are kept in a gather
 // layout aX (N, 4 a-quads, 16 g, 4 a) so that the 16 g-lanes of an atom read 256 contiguous bytes per float4 load
 // (index(a,g) = ((a>>2)*16 + g)*4 + (a&3)); dS (N, 16 a, 16 g, 4 d) is lane-contiguous as is.
 //
@@ -26,8 +26,9 @@
 
 namespace aimnet {
 
-constexpr int kAtomsPerCta = 16;
-constexpr int kSlotsPerTile = 16;
+constexpr int kAtomsPerCta = 8;     // one warp per atom
+constexpr int kSlotsPerTile = 32;   // neighbour slots staged per tile and atom (one per lane)
+constexpr int kHalfA = 8;           // feature channels per thread (two half-warps split the 16 channels)
 
 struct PairEntry {
     float ux, uy, uz, d;
@@ -36,13 +37,13 @@ struct PairEntry {
     int pad;
 };
 
-// stage geometry + cutoff for slots [m0, m0+16) of the CTA's 16 atoms: thread (atom = tid>>4, slot = tid&15)
+// stage geometry + cutoff for slots [m0, m0+32) of the CTA's 8 atoms: thread (atom = warp, slot = lane)
 template <bool kWithDeriv>
 __device__ __forceinline__ void stage_pairs(PairEntry* tile, int i, bool atom_ok, int m0, int row_len, const NbView& nb,
                                             const float* __restrict__ coord, const float* __restrict__ cell,
                                             const AevParams& aev) {
     int tid = threadIdx.x;
-    int m = m0 + (tid & 15);
+    int m = m0 + (tid & 31);
     int j = nb.sentinel;
     if (atom_ok && m < row_len) j = nb.nbmat[(size_t)i * nb.width + m];
     bool ok = atom_ok && (j != nb.sentinel) && (j >= 0);
@@ -74,9 +75,7 @@ __device__ __forceinline__ int row_length(const NbView& nb, int i) {
 }
 
 __device__ __forceinline__ int block_max_int(int v, int* scratch) {
-    // 256 threads; value identical within each 16-thread atom group
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    // value is warp-uniform (one atom per warp)
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     int r = scratch[0];
@@ -90,20 +89,19 @@ __device__ __forceinline__ int block_max_int(int v, int* scratch) {
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
-                                                       CellView cv, const int32_t* __restrict__ mol_idx,
-                                                       AevParams aev, const float* __restrict__ aT,
-                                                       const float* __restrict__ q, const float* __restrict__ agh_a,
-                                                       const float* __restrict__ agh_q, float* __restrict__ x,
-                                                       int ldx, float* __restrict__ T_a, float* __restrict__ T_q,
-                                                       int with_q) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PairEntry* tile = reinterpret_cast<PairEntry*>(smem_raw);                       // 256 entries, 8 KB
-    float* sv = reinterpret_cast<float*>(smem_raw + 256 * sizeof(PairEntry));       // [16 atoms][16 a][16 g][3]
-    float* svq = sv + kAtomsPerCta * kAG * 3;                                       // [16 atoms][C][16 g][3]
+__global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
+                                                          CellView cv, const int32_t* __restrict__ mol_idx,
+                                                          AevParams aev, const float* __restrict__ aT,
+                                                          const float* __restrict__ q, const float* __restrict__ agh_a,
+                                                          const float* __restrict__ agh_q, float* __restrict__ x,
+                                                          int ldx, float* __restrict__ T_a, float* __restrict__ T_q,
+                                                          int with_q) {
+    __shared__ PairEntry tile[256];                      // 8 atoms x 32 slots
+    __shared__ float sv[kAtomsPerCta][kAG * 3];          // vector part of S^a per atom: [a][g][3]
+    __shared__ float svq[kAtomsPerCta][2 * kG * 3];      // vector part of S^q per atom: [c][g][3]
     __shared__ int scratch[8];
     const int tid = threadIdx.x;
-    const int al = tid >> 4, g = tid & 15;
+    const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
     const int i = blockIdx.x * kAtomsPerCta + al;
     const bool atom_ok = i < n_atoms;
     const int ic = atom_ok ? i : 0;
@@ -111,9 +109,9 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
     const int len = atom_ok ? row_length(nb, i) : 0;
     const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
-    float S[kA][4];
+    float S[kHalfA][4];
 #pragma unroll
-    for (int a = 0; a < kA; ++a) S[a][0] = S[a][1] = S[a][2] = S[a][3] = 0.f;
+    for (int a = 0; a < kHalfA; ++a) S[a][0] = S[a][1] = S[a][2] = S[a][3] = 0.f;
     float Sq[C][4];
 #pragma unroll
     for (int c = 0; c < C; ++c) Sq[c][0] = Sq[c][1] = Sq[c][2] = Sq[c][3] = 0.f;
@@ -122,16 +120,17 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
         stage_pairs<false>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
         __syncthreads();
         int lim = min(kSlotsPerTile, len - m0);
+#pragma unroll 2
         for (int s = 0; s < lim; ++s) {
-            const PairEntry e = tile[al * 16 + s];
-            const float4* row = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g;
-            float4 v0 = row[0], v1 = row[16], v2 = row[32], v3 = row[48];
+            const PairEntry e = tile[al * 32 + s];
+            const float4* row = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g + 32 * h;
+            float4 v0 = row[0], v1 = row[16];
             float xg = e.d - shift_g;
             float w0 = expf(-aev.eta * xg * xg) * e.fc;
             float w1 = w0 * e.ux, w2 = w0 * e.uy, w3 = w0 * e.uz;
-            float av[kA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+            float av[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int a = 0; a < kA; ++a) {
+            for (int a = 0; a < kHalfA; ++a) {
                 S[a][0] = fmaf(av[a], w0, S[a][0]);
                 S[a][1] = fmaf(av[a], w1, S[a][1]);
                 S[a][2] = fmaf(av[a], w2, S[a][2]);
@@ -150,15 +149,16 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
         }
     }
     // ---- epilogue: scalar part straight to x, vector part through shared memory for the agh mixing ----
-    float* svl = sv + al * (kAG * 3);
+    float* svl = sv[al];
 #pragma unroll
-    for (int a = 0; a < kA; ++a) {
-        svl[(a * kG + g) * 3 + 0] = S[a][1];
-        svl[(a * kG + g) * 3 + 1] = S[a][2];
-        svl[(a * kG + g) * 3 + 2] = S[a][3];
+    for (int a = 0; a < kHalfA; ++a) {
+        int aa = kHalfA * h + a;
+        svl[(aa * kG + g) * 3 + 0] = S[a][1];
+        svl[(aa * kG + g) * 3 + 1] = S[a][2];
+        svl[(aa * kG + g) * 3 + 2] = S[a][3];
     }
-    float* svql = svq + al * (C * kG * 3);
-    if (with_q) {
+    float* svql = svq[al];
+    if (with_q && h == 0) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             svql[(c * kG + g) * 3 + 0] = Sq[c][1];
@@ -168,34 +168,37 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
     }
     if (atom_ok) {
         float* xr = x + (size_t)i * ldx;
-        const float4* own = reinterpret_cast<const float4*>(aT + (size_t)i * kAG) + g;
-        float4 o0 = own[0], o1 = own[16], o2 = own[32], o3 = own[48];
-        float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+        const float4* own = reinterpret_cast<const float4*>(aT + (size_t)i * kAG) + g + 32 * h;
+        float4 o0 = own[0], o1 = own[16];
+        float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
-        for (int a = 0; a < kA; ++a) {
-            xr[a * kG + g] = ov[a];
-            xr[kAG + a * kG + g] = S[a][0];
+        for (int a = 0; a < kHalfA; ++a) {
+            int aa = kHalfA * h + a;
+            xr[aa * kG + g] = ov[a];
+            xr[kAG + aa * kG + g] = S[a][0];
         }
         int base = 2 * kAG + kAH;
         if (with_q) {
-            if (g < C) xr[base + g] = q[(size_t)i * C + g];
+            if (lane < C) xr[base + lane] = q[(size_t)i * C + lane];
+            if (h == 0) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq[c][0];
+                for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq[c][0];
+            }
             base += C * (1 + kG + kH);
         }
-        for (int c = base + g; c < ldx; c += 16) xr[c] = 0.f;
+        for (int c = base + lane; c < ldx; c += 32) xr[c] = 0.f;
     }
-    __syncthreads();
-    // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); thread g handles 12 (a,h) pairs
+    __syncwarp();
+    // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); each lane handles 6 (a,h) pairs
     if (atom_ok) {
         float* xr = x + (size_t)i * ldx;
 #pragma unroll 1
-        for (int e = g; e < kAH; e += 16) {
-            int a = e / kH, h = e % kH;
+        for (int e = lane; e < kAH; e += 32) {
+            int a = e / kH, hh = e % kH;
             float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
             for (int gg = 0; gg < kG; ++gg) {
-                float w = agh_a[(a * kG + gg) * kH + h];
+                float w = agh_a[(a * kG + gg) * kH + hh];
                 const float* p = svl + (a * kG + gg) * 3;
                 t0 = fmaf(w, p[0], t0);
                 t1 = fmaf(w, p[1], t1);
@@ -209,12 +212,12 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(int n_atoms, NbView nb, c
         }
         if (with_q) {
             int base = 2 * kAG + kAH;
-            for (int e = g; e < C * kH; e += 16) {
-                int c = e / kH, h = e % kH;
+            for (int e = lane; e < C * kH; e += 32) {
+                int c = e / kH, hh = e % kH;
                 float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
                 for (int gg = 0; gg < kG; ++gg) {
-                    float w = agh_q[(c * kG + gg) * kH + h];
+                    float w = agh_q[(c * kG + gg) * kH + hh];
                     const float* p = svql + (c * kG + gg) * 3;
                     t0 = fmaf(w, p[0], t0);
                     t1 = fmaf(w, p[1], t1);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
 // backward step 2 (see the header comment)
 // ------------------------------------------------------------------------------------------------------------
 template <int C, bool kGradA>
-__global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
+__global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
                                                           CellView cv, const int32_t* __restrict__ mol_idx,
                                                           AevParams aev, const float* __restrict__ aT,
                                                           const float* __restrict__ q, const float* __restrict__ dS_a,
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
     __shared__ PairEntry tile[256];
     __shared__ int scratch[8];
     const int tid = threadIdx.x;
-    const int al = tid >> 4, g = tid & 15;
+    const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
     const int i = blockIdx.x * kAtomsPerCta + al;
     const bool atom_ok = i < n_atoms;
     const int ic = atom_ok ? i : 0;
@@ -308,29 +311,31 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
     const int len = atom_ok ? row_length(nb, i) : 0;
     const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
-    // own atom: dS_i[g][a][d] and a_i[g][a] in registers
-    float4 dSi[kA];
-    float ai[kA];
+    // own atom: dS_i[a][g][d] and a_i[a][g] for this thread's 8 channels
+    float4 dSi[kHalfA];
+    float ai[kHalfA];
     {
-        const float4* p = reinterpret_cast<const float4*>(dS_a) + (size_t)ic * kAG + g;
+        const float4* p = reinterpret_cast<const float4*>(dS_a) + (size_t)ic * kAG + (kHalfA * h) * kG + g;
 #pragma unroll
-        for (int a = 0; a < kA; ++a) dSi[a] = p[a * kG];
-        const float4* r = reinterpret_cast<const float4*>(aT + (size_t)ic * kAG) + g;
-        float4 o0 = r[0], o1 = r[16], o2 = r[32], o3 = r[48];
-        float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+        for (int a = 0; a < kHalfA; ++a) dSi[a] = p[a * kG];
+        const float4* r = reinterpret_cast<const float4*>(aT + (size_t)ic * kAG) + g + 32 * h;
+        float4 o0 = r[0], o1 = r[16];
+        float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
-        for (int a = 0; a < kA; ++a) ai[a] = ov[a];
+        for (int a = 0; a < kHalfA; ++a) ai[a] = ov[a];
     }
+    // the charge channels are handled by the h == 0 half only (their partial sums are added once)
+    const bool qhalf = with_q && h == 0;
     float4 dSqi[C];
     float qi[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        dSqi[c] = with_q ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
-        qi[c] = with_q ? q[(size_t)ic * C + c] : 0.f;
+        dSqi[c] = qhalf ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
+        qi[c] = qhalf ? q[(size_t)ic * C + c] : 0.f;
     }
-    float ga[kA];
+    float ga[kHalfA];
 #pragma unroll
-    for (int a = 0; a < kA; ++a) ga[a] = 0.f;
+    for (int a = 0; a < kHalfA; ++a) ga[a] = 0.f;
     float gq[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) gq[c] = 0.f;
@@ -345,19 +350,19 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
         __syncthreads();
         int lim = min(kSlotsPerTile, len - m0);
         for (int s = 0; s < lim; ++s) {
-            const PairEntry e = tile[al * 16 + s];
-            const float4* arow = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g;
-            const float4* drow = reinterpret_cast<const float4*>(dS_a) + (size_t)e.j * kAG + g;
-            float4 v0 = arow[0], v1 = arow[16], v2 = arow[32], v3 = arow[48];
-            float aj[kA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+            const PairEntry e = tile[al * 32 + s];
+            const float4* arow = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g + 32 * h;
+            const float4* drow = reinterpret_cast<const float4*>(dS_a) + (size_t)e.j * kAG + (kHalfA * h) * kG + g;
+            float4 v0 = arow[0], v1 = arow[16];
+            float aj[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             float xg = e.d - shift_g;
             float ex = expf(-aev.eta * xg * xg);
             float gs = ex * e.fc;
             float dgs = ex * (e.dfc - 2.0f * aev.eta * xg * e.fc);
-            // p = contraction for slot (i -> j), pr = for the reverse slot (j -> i)
+            // p = contraction for slot (i -> j), r = for the reverse slot (j -> i); partial over this thread's channels
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-            for (int a = 0; a < kA; ++a) {
+            for (int a = 0; a < kHalfA; ++a) {
                 float4 dj = drow[a * kG];
                 if (kGradA) {
                     float t = dj.x - (dj.y * e.ux + dj.z * e.uy + dj.w * e.uz);
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
                 r2 = fmaf(ai[a], dj.z, r2);
                 r3 = fmaf(ai[a], dj.w, r3);
             }
-            if (with_q) {
+            if (qhalf) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     float qj = q[(size_t)e.j * C + c];
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
                 }
             }
             float inv = 1.0f / e.d;
-            // this thread's g-share of w(i->j) = u (A + C.u) + (B - u (B.u))/d
+            // this thread's share of w(i->j) = u (A + C.u) + (B - u (B.u))/d
             float pu = p1 * e.ux + p2 * e.uy + p3 * e.uz;
             float sc = p0 * dgs + pu * dgs - pu * gs * inv;
             float wx = e.ux * sc + p1 * gs * inv;
@@ -418,37 +423,30 @@ __global__ void __launch_bounds__(256, 1) conv_bwd_kernel(int n_atoms, NbView nb
             }
         }
     }
-    // reduce the force / virial / grad_q shares over the 16 g-lanes of the atom
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, o);
-        fy += __shfl_xor_sync(0xffffffffu, fy, o);
-        fz += __shfl_xor_sync(0xffffffffu, fz, o);
-    }
+    // reduce the force / virial / grad_q shares over the 32 lanes of the atom
+    fx = warp_sum(fx);
+    fy = warp_sum(fy);
+    fz = warp_sum(fz);
     if (virial_atom) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) vir[k] += __shfl_xor_sync(0xffffffffu, vir[k], o);
+        for (int k = 0; k < 9; ++k) vir[k] = warp_sum(vir[k]);
     }
     if (kGradA && with_q) {
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) gq[c] += __shfl_xor_sync(0xffffffffu, gq[c], o);
+        for (int c = 0; c < C; ++c) gq[c] = warp_sum(gq[c]);
     }
     if (!atom_ok) return;
     if (kGradA) {
 #pragma unroll
-        for (int a = 0; a < kA; ++a) grad_a[(size_t)i * kAG + a * kG + g] = ga[a];
-        if (with_q && g < C) {
+        for (int a = 0; a < kHalfA; ++a) grad_a[(size_t)i * kAG + (kHalfA * h + a) * kG + g] = ga[a];
+        if (with_q && lane < C) {
             float v = gq[0];
 #pragma unroll
-            for (int c = 1; c < C; ++c) v = (g == c) ? gq[c] : v;
-            grad_q[(size_t)i * C + g] = v;
+            for (int c = 1; c < C; ++c) v = (lane == c) ? gq[c] : v;
+            grad_q[(size_t)i * C + lane] = v;
         }
     }
-    if (g == 0) {
+    if (lane == 0) {
         forces[3 * i + 0] += fx;
         forces[3 * i + 1] += fy;
         forces[3 * i + 2] += fz;
@@ -535,15 +533,9 @@ static int conv_fwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
                            const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q,
                            int with_q, cudaStream_t st) {
-    size_t smem = 256 * sizeof(PairEntry) + sizeof(float) * (kAtomsPerCta * kAG * 3 + kAtomsPerCta * C * kG * 3);
-    static bool configured = false;
-    if (!configured) {
-        AIM_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    conv_fwd_kernel<C><<<grid, 256, smem, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a,
-                                               T_q, with_q);
+    conv_fwd_kernel<C><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q,
+                                            with_q);
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }

@@ -37,7 +37,7 @@ constexpr int A_BYTES = BM * BK * 4;       // 8 KB
 constexpr int B_BYTES = BN * BK * 4;       // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB
 constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
 constexpr int NUM_THREADS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,6 +126,7 @@ struct Params {
     int bn;      // N-tile width (multiple of 16, <= 256): N is cut into equal tiles so that no CTA gets a sliver
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                const __grid_constant__ CUtensorMap tmBl, Params p) {
@@ -138,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = bars + 3 * STAGES;    // [2]
     uint64_t* tmem_empty = bars + 3 * STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + p.bn - 1) / p.bn;
@@ -280,6 +282,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float acc[128];
 #pragma unroll
             for (int k = 0; k < 128; ++k) acc[k] = 0.f;
+            if (MODE == 1 || MODE == 2) {
+                // bias of this tile's columns -> shared memory (read back as warp-wide broadcasts in the epilogue)
+                asm volatile("bar.sync 1, 256;");   // previous tile's readers are done
+                int cb = threadIdx.x - 256;
+                sbias[cb] = (cb < n_tile) ? p.bias[n0 + cb] : 0.f;
+                asm volatile("bar.sync 1, 256;");
+            }
             for (int ks0 = 0; ks0 < nk; ks0 += p.chunk, ++cit) {
                 int b = cit & 1;
                 uint32_t aph = (uint32_t)(cit >> 1) & 1;
@@ -313,14 +322,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (col0 + 4 * v4 >= n_tile) continue;
                             float4 z = make_float4(acc[c * 32 + 4 * v4], acc[c * 32 + 4 * v4 + 1], acc[c * 32 + 4 * v4 + 2],
                                                    acc[c * 32 + 4 * v4 + 3]);
-                            if (p.mode == 1 || p.mode == 2) {
-                                float4 bz = *reinterpret_cast<const float4*>(p.bias + col + 4 * v4);
+                            if (MODE == 1 || MODE == 2) {
+                                float4 bz = *reinterpret_cast<const float4*>(sbias + col0 + 4 * v4);
                                 z.x += bz.x;
                                 z.y += bz.y;
                                 z.z += bz.z;
                                 z.w += bz.w;
                             }
-                            if (p.mode == 2) {
+                            if (MODE == 2) {
                                 float4 gp;
                                 gelu_pair(z.x, z.x, gp.x);
                                 gelu_pair(z.y, z.y, gp.y);
@@ -328,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 gelu_pair(z.w, z.w, gp.w);
                                 if (p.aux != nullptr)
                                     *reinterpret_cast<float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4) = gp;
-                            } else if (p.mode == 3) {
+                            } else if (MODE == 3) {
                                 float4 gp = *reinterpret_cast<const float4*>(p.aux + (size_t)row * p.ldaux + col + 4 * v4);
                                 z.x *= gp.x;
                                 z.y *= gp.y;
@@ -416,7 +425,10 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     static bool configured = false;
     static int num_sms = 148;
     if (!configured) {
-        AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         int dev = 0;
         AIM_CUDA_CHECK(cudaGetDevice(&dev));
         AIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -438,7 +450,12 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, bn};
     int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p);
+    switch (mode) {
+        case 0: gemm_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p); break;
+        case 1: gemm_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p); break;
+        case 2: gemm_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p); break;
+        default: gemm_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p); break;
+    }
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }
