@@ -95,7 +95,7 @@ struct D3Params {
     float r_on, r_off;    // Bohr
 };
 
-enum { PAIR_SR_EXP = 0, PAIR_SR_COS = 1, PAIR_SIMPLE = 2, PAIR_DSF = 3 };
+enum { PAIR_SR_EXP = 0, PAIR_SR_COS = 1, PAIR_SIMPLE = 2, PAIR_DSF = 3, PAIR_EWALD = 4 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

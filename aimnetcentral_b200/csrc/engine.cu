@@ -51,6 +51,21 @@ int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, c
 int launch_d3(int, const PairSource&, const float*, const CellView&, const int32_t*, const D3Params&, float*, float*,
               double*, float*, double*, cudaStream_t);
 
+struct EwaldPlan {
+    double cell[9] = {0};
+    double accuracy = 0, rc_cap = 0;
+    int n_atoms = 0;
+    double alpha = 0, rc = 0, kc = 0, volume = 0;
+    int nk = 0;
+    double* d_kvec = nullptr;
+    double* d_ck = nullptr;
+    double* d_S = nullptr;
+    int cap = 0;
+};
+int ewald_prepare(EwaldPlan&, const float*, int, double, double, cudaStream_t);
+void ewald_release(EwaldPlan&);
+int launch_ewald_recip(const EwaldPlan&, int, const float*, const float*, double*, float*, float*, double*, cudaStream_t);
+
 static inline int pad32(int x) { return (x + 31) / 32 * 32; }
 static inline int round16(int x) { return (x + 15) / 16 * 16; }
 
@@ -100,6 +115,7 @@ struct aimnet2_engine {
     int gemm_ev_used = 0;
     float last_gemm_ms = 0.f;
     int last_gemm_launches = 0;
+    EwaldPlan ewald;
     std::vector<void*> owned;
 };
 
@@ -317,7 +333,11 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     AIM_REQUIRE(!want_f || res->forces, "engine_eval: forces requested without an output buffer");
     AIM_REQUIRE(!want_s || (res->stress && sys->cell), "engine_eval: stress needs a cell and an output buffer");
     const aimnet2_options_t& o = e->opt;
-    AIM_REQUIRE(o.coulomb_method != AIMNET_COULOMB_EWALD, "engine_eval: Ewald Coulomb is not implemented in this build");
+    const bool ewald = o.coulomb_method == AIMNET_COULOMB_EWALD;
+    if (ewald) {
+        AIM_REQUIRE(sys->cell != nullptr && sys->n_cells == 1 && B == 1, "engine_eval: Ewald needs one periodic system with a cell");
+        if (sys->pbc_host) AIM_REQUIRE(sys->pbc_host[0] && sys->pbc_host[1] && sys->pbc_host[2], "engine_eval: Ewald needs pbc on all three axes");
+    }
     AIM_REQUIRE(!o.dispersion || e->d3_c6ref, "engine_eval: dispersion requested but no D3 tables were loaded");
     g_launch_count = 0;
     e->gemm_ev_used = 0;
@@ -325,13 +345,17 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     const bool backward = want_f || want_s;
     const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
     const bool need_lr_terms = (o.coulomb_method == AIMNET_COULOMB_SIMPLE || o.coulomb_method == AIMNET_COULOMB_DSF ||
-                                o.dispersion);
+                                ewald || o.dispersion);
     const bool need_lr_list = need_lr_terms && pbc;
     AIM_REQUIRE(!(pbc && o.coulomb_method == AIMNET_COULOMB_SIMPLE),
                 "engine_eval: 'simple' Coulomb is not defined for periodic systems (host switches to DSF)");
     float lr_cut = 0.f;
     if (o.coulomb_method == AIMNET_COULOMB_DSF) lr_cut = std::max(lr_cut, o.dsf_rc);
     if (o.dispersion) lr_cut = std::max(lr_cut, o.d3_cutoff);
+    if (ewald) {
+        AIM_TRY(ewald_prepare(e->ewald, sys->host_cell, N, o.ewald_accuracy, 15.0, st));
+        lr_cut = std::max(lr_cut, (float)e->ewald.rc);
+    }
     const bool own_sr = sys->nbmat == nullptr;
     if (e->timing) cudaEventRecord(e->ev[0], st);
 
@@ -465,6 +489,12 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         cp.self_coeff = (float)(-(erfc_rc / R / 2.0 + a / std::sqrt(M_PI)));
         cp.factor = k;
         AIM_TRY(launch_coulomb(PAIR_DSF, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        have_lr = true;
+    }
+    else if (ewald) {
+        CoulombParams cp{(float)e->ewald.rc, (float)e->ewald.alpha, 0.f, 0.f, 0.f, k};
+        AIM_TRY(launch_coulomb(PAIR_EWALD, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        AIM_TRY(launch_ewald_recip(e->ewald, N, coord, qfin, b.e_lr, b.gq, backward ? F : nullptr, vir, st));
         have_lr = true;
     }
     if (o.dispersion) {
@@ -608,6 +638,7 @@ extern "C" int aimnet2_engine_destroy(aimnet2_engine_t* e) {
     for (void* p : e->owned) cudaFree(p);
     if (e->ws) cudaFree(e->ws);
     if (e->stage) cudaFree(e->stage);
+    ewald_release(e->ewald);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     for (int k = 0; k < 6; ++k)
         if (e->ev[k]) cudaEventDestroy(e->ev[k]);

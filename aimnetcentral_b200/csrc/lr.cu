@@ -70,6 +70,15 @@ __device__ __forceinline__ void pair_phi(float d, const CoulombParams& p, float&
         float dfc = (d > 1e-6f && d < p.rc) ? -0.5f * (kPi / p.rc) * sn : 0.f;
         phi = fc * inv;
         dphi = dfc * inv - fc * inv * inv;
+    } else if (MODE == PAIR_EWALD) {   // real-space Ewald term
+        if (d < p.rc) {
+            float ec = erfcf(p.alpha * d);
+            phi = ec * inv;
+            dphi = -ec * inv * inv - 1.1283791670955126f * p.alpha * expf(-p.alpha * p.alpha * d * d) * inv;
+        } else {
+            phi = 0.f;
+            dphi = 0.f;
+        }
     } else {   // DSF, lr.py:594-600
         if (d < p.rc) {
             float ec = erfcf(p.alpha * d);
@@ -401,6 +410,9 @@ int launch_coulomb(int mode, int n, const PairSource& ps, const float* coord, co
             break;
         case PAIR_SIMPLE:
             coulomb_pair_kernel<PAIR_SIMPLE><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
+            break;
+        case PAIR_EWALD:
+            coulomb_pair_kernel<PAIR_EWALD><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
             break;
         default:
             coulomb_pair_kernel<PAIR_DSF><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);

@@ -170,6 +170,29 @@ def test_host_buffer_entry_matches_device_entry():
     assert calc.engine.last_launches() > 20
 
 
+def test_ewald_against_oracle():
+    """Row a16: Ewald Coulomb (real-space pair walker + reciprocal structure factors) vs the fp32 oracle with its
+    fp64 textbook Ewald.  Upstream parity is unpinned (third-party kernel); tolerance = the north-star 1e-4."""
+    from aimnetcentral_b200 import AIMNet2Calculator
+    from oracle.calculator_oracle import oracle_calculate
+
+    for name in ("allose_1x1x1_dsf", "pbc_box60_dsf"):
+        inputs, _, meta = load_golden(name)
+        sd, spec = golden_state_dict(meta)
+        inputs = dict(inputs)
+        inputs["charge"] = np.array([1.0], np.float32) if name.startswith("pbc") else inputs["charge"]  # background term
+        ref = oracle_calculate(sd, inputs, coulomb="ewald", stress=True)
+        calc = AIMNet2Calculator((sd, spec), device="cuda:0")
+        calc.set_lrcoulomb_method("ewald", ewald_accuracy=1e-6)
+        out = {k: v.cpu().numpy() for k, v in calc(inputs, forces=True, stress=True).items()}
+        de = abs(out["energy"][0] - ref["energy"][0])
+        df = np.abs(out["forces"] - ref["forces"]).max()
+        ds = np.abs(out["stress"] - ref["stress"]).max()
+        dq = np.abs(out["charges"] - ref["charges"]).max()
+        print(f"[parity] ewald {name}: dE={de:.3e} dF={df:.3e} dstress={ds:.3e} dq={dq:.3e}")
+        assert de < ENERGY_ATOL and df < FORCE_ATOL and dq < CHARGE_ATOL and ds < 1e-5
+
+
 def test_errors_and_warnings():
     inputs, ref, meta = load_golden("caffeine")
     calc = get_calc(meta)
