@@ -12,7 +12,7 @@ from __future__ import annotations
 import math
 import os
 import warnings
-from types import MappingProxyType
+from types import MappingProxyType, SimpleNamespace
 from typing import Any, ClassVar, Mapping
 
 import numpy as np
@@ -128,6 +128,10 @@ class AIMNet2Calculator:
         self._mult_ignored_checked = False
         self._batch: int | None = None
         self.engine = Engine(sd, C, self.device, sr_rc=float(sr_rc), sr_envelope=sr_env, load_d3=self._has_dftd3)
+        # duck-typed `model` handle for the adapters that read `base_calc.model._metadata` / `.num_charge_channels`
+        # (aimnet/calculators/aimnet2ase.py:69, aimnet2torchsim.py:78-125)
+        self.model = SimpleNamespace(_metadata=metadata, metadata=metadata, num_charge_channels=C)
+        self.engine.set_deterministic(self._deterministic)
         self._push_options()
 
     # ---- properties (calculator.py:380-515) ------------------------------------------------------------------

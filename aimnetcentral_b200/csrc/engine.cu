@@ -30,6 +30,7 @@ int gemm_nt(const float*, int, const float*, const float*, const float*, int, co
             int, int, int, int, cudaStream_t);
 int split_tf32(const float*, float*, float*, size_t, cudaStream_t);
 bool gemm_tc_available();
+void gemm_tc_set_deterministic(bool);
 int launch_embed(int, const int32_t*, const float*, float*, cudaStream_t);
 int launch_mol_ptr(const int32_t*, int, int, int32_t*, cudaStream_t);
 int launch_nse_fwd(int, int, int, const int32_t*, const int32_t*, const float*, const float*, const float*, int,
@@ -660,6 +661,12 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
     AIM_REQUIRE(backend == 0 || backend == 1, "set_gemm_backend: backend must be 0 or 1");
     AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backend not available in this build");
     e->gemm_backend = backend;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on) {
+    AIM_REQUIRE(e, "set_deterministic: null engine");
+    gemm_tc_set_deterministic(on != 0);   // process-wide switch of the GEMM chunking policy
     return AIMNET_OK;
 }
 

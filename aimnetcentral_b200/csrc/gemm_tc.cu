@@ -64,6 +64,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -122,7 +135,8 @@ struct Params {
     float* Y;
     float* aux;
     int ldy, ldaux, M, N, K, mode;
-    int chunk;   // stages (K=16 each) accumulated in TMEM before the fp32 register add
+    int chunk;   // minimum stages (K=16 each) accumulated in TMEM before the fp32 register add
+    int chunk_max;   // elastic upper bound (== chunk: fixed, reproducible chunking)
     int bn;      // N-tile width (multiple of 16, <= 256): N is cut into equal tiles so that no CTA gets a sliver
 };
 
@@ -139,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = bars + 3 * STAGES;    // [2]
     uint64_t* tmem_empty = bars + 3 * STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    volatile int* chunk_last = reinterpret_cast<volatile int*>(bars + 3 * STAGES + 5);   // [2] last chunk of its tile?
     float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,14 +218,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int n0 = (t % n_tiles) * p.bn;
                 int n_tile = min(p.bn, p.N - n0);
                 uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-                for (int ks0 = 0; ks0 < nk; ks0 += p.chunk, ++cit) {
+                // Elastic chunking: a chunk is at least p.chunk stages; it keeps growing (up to p.chunk_max) while the
+                // epilogue warps are still busy with the other TMEM buffer, so the tensor pipe never idles behind a
+                // tile epilogue.  chunk_max == chunk gives fixed chunks (bitwise run-to-run reproducible).
+                int ks = 0;
+                while (ks < nk) {
                     int b = cit & 1;
                     uint32_t aph = (uint32_t)(cit >> 1) & 1;
                     mbar_wait(&tmem_empty[b], aph ^ 1);
                     tc_fence_after();
                     uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
-                    int ks1 = min(nk, ks0 + p.chunk);
-                    for (int ks = ks0; ks < ks1; ++ks) {
+                    int len = 0;
+                    for (;;) {
                         mbar_wait(&full_split[s], ph);
                         tc_fence_after();
                         uint32_t sa = smem_u32(stage_ptr(s));
@@ -219,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int kk = 0; kk < BK / 8; ++kk) {
                             uint64_t adv = (uint64_t)(kk * 32 >> 4);   // 8 tf32 = 32 bytes along K inside the swizzle atom
-                            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (ks > ks0 || kk > 0) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (len > 0 || kk > 0) ? 1u : 0u);
                             tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                             tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
                         }
@@ -228,8 +247,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             s = 0;
                             ph ^= 1;
                         }
+                        ++ks;
+                        ++len;
+                        if (ks == nk || len >= p.chunk_max) break;
+                        if (len >= p.chunk) {
+                            int nb = (cit + 1) & 1;
+                            uint32_t nph = (uint32_t)((cit + 1) >> 1) & 1;
+                            if (mbar_test(&tmem_empty[nb], nph ^ 1)) break;   // the other buffer is free: hand over
+                        }
                     }
+                    chunk_last[b] = (ks == nk) ? 1 : 0;
+                    __threadfence_block();
                     tc_commit(&tmem_full[b]);
+                    ++cit;
                 }
             }
         }
@@ -289,11 +319,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 sbias[cb] = (cb < n_tile) ? p.bias[n0 + cb] : 0.f;
                 asm volatile("bar.sync 1, 256;");
             }
-            for (int ks0 = 0; ks0 < nk; ks0 += p.chunk, ++cit) {
+            for (int last = 0; !last; ++cit) {
                 int b = cit & 1;
                 uint32_t aph = (uint32_t)(cit >> 1) & 1;
                 mbar_wait(&tmem_full[b], aph);
                 tc_fence_after();
+                last = chunk_last[b];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     int col0 = ch * 128 + c * 32;
@@ -407,6 +438,9 @@ static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld
 }  // namespace tc
 
 bool gemm_tc_available() { return tc::get_encode() != nullptr; }
+
+static bool g_tc_deterministic = false;
+void gemm_tc_set_deterministic(bool on) { g_tc_deterministic = on; }
 
 int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st) {
     if (n == 0) return AIMNET_OK;

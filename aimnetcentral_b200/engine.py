@@ -125,6 +125,9 @@ class Engine:
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
         self.gemm_backend = int(backend)
 
+    def set_deterministic(self, on: bool = True):
+        _capi.check(self._lib.aimnet2_engine_set_deterministic(self._h, 1 if on else 0), "set_deterministic")
+
     def enable_timing(self, level: int = 1):
         """0 off, 1 phase events, 2 additionally one CUDA-event pair around every GEMM launch."""
         _capi.check(self._lib.aimnet2_engine_enable_timing(self._h, int(level)))

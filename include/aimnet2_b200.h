@@ -157,6 +157,9 @@ int aimnet2_engine_destroy(aimnet2_engine_t* e);
 int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt);
 /* GEMM backend for the per-atom MLPs: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (default when available) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
+/* 1 = bitwise run-to-run reproducible results (fixed K-chunking in the tcgen05 GEMM; every other kernel is atomics-free
+ * already) — the counterpart of AIMNet2Calculator(deterministic=True), aimnet/calculators/calculator.py:76-84 */
+int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on);
 
 /* device-resident inputs/outputs; flags = AIMNET_WANT_* */
 int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
