@@ -481,7 +481,13 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
         chunk = env ? atoi(env) : CHUNK;
         if (chunk < 1) chunk = 1;
     }
-    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, bn};
+    static int chunk_max = 0;
+    if (chunk_max == 0) {
+        const char* env = getenv("AIMNET_TC_CHUNK_MAX");
+        chunk_max = env ? atoi(env) : 8;
+        if (chunk_max < chunk) chunk_max = chunk;
+    }
+    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, g_tc_deterministic ? chunk : chunk_max, bn};
     int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
     switch (mode) {
