@@ -50,7 +50,7 @@ int launch_charges_out(int, int, const float*, float*, float*, cudaStream_t);
 int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, const float*, const CoulombParams&,
                    double*, float*, float*, double*, int, cudaStream_t);
 int launch_d3(int, const PairSource&, const float*, const CellView&, const int32_t*, const D3Params&, float*, float*,
-              double*, float*, double*, cudaStream_t);
+              float*, double*, float*, double*, cudaStream_t);
 
 struct EwaldPlan {
     double cell[9] = {0};
@@ -204,7 +204,7 @@ struct Buffers {
     float* T_q[3];
     float *sumq[2], *sumf[2], *s1;
     double *e_nn, *e_sr, *e_lr, *e_d3;
-    float *gq, *cn, *dEdCN;
+    float *gq, *cn, *dEdCN, *d3w;
     float *dzA, *dzB, *dx, *dS_a, *dS_q, *grad_a, *grad_q, *da_tot, *dq, *dq_base;
     double* virial_atom;
     float* forces_tmp;
@@ -252,6 +252,7 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.gq = bp.take<float>(n);
     b.cn = bp.take<float>(n);
     b.dEdCN = bp.take<float>(n);
+    b.d3w = bp.take<float>(n * 16);
     b.dzA = bp.take<float>(n * 512);
     b.dzB = bp.take<float>(n * 512);
     b.dx = bp.take<float>(n * ldx);
@@ -501,7 +502,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     if (o.dispersion) {
         D3Params dp{e->d3_c6ref, e->d3_cnref, e->d3_rcov, e->d3_r4r2, o.d3_s6, o.d3_s8, o.d3_a1, o.d3_a2,
                     (float)(o.d3_cutoff * (1.0 - o.d3_smoothing) / kBohr), (float)(o.d3_cutoff / kBohr)};
-        AIM_TRY(launch_d3(N, lrs, coord, cv, sys->numbers, dp, b.cn, b.dEdCN, b.e_d3, backward ? F : nullptr, vir, st));
+        AIM_TRY(launch_d3(N, lrs, coord, cv, sys->numbers, dp, b.cn, b.d3w, b.dEdCN, b.e_d3, backward ? F : nullptr, vir, st));
         have_d3 = true;
     }
     AIM_TRY(launch_energy_reduce(B, b.mol_ptr, b.e_nn, b.e_sr, have_lr ? b.e_lr : nullptr, have_d3 ? b.e_d3 : nullptr,

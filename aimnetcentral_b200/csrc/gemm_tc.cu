@@ -6,7 +6,7 @@
 // A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (dropped lo*lo and the rounding of lo are ~2^-22 relative, unbiased).
 // The tensor core adds into its fp32 accumulator with truncation (measured: -4.8e-6 relative shrinkage over K=704,
 // tools/gemm_error.py), so TMEM only accumulates chunks of K=32 (rms error 3.2e-7 vs 6.1e-7 for fp32 FMA); the epilogue warps drain each chunk and sum the
-// chunks in registers with round-to-nearest.  Weights are split once on the host; activations are split in shared
+// chunks in registers with round-to-nearest (fixed chunking: results are bitwise run-to-run reproducible).  Weights are split once on the host; activations are split in shared
 // memory by a dedicated warpgroup.
 //
 // Structure (one persistent CTA per SM, 512 threads, warp-specialised):
@@ -218,9 +218,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int n0 = (t % n_tiles) * p.bn;
                 int n_tile = min(p.bn, p.N - n0);
                 uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-                // Elastic chunking: a chunk is at least p.chunk stages; it keeps growing (up to p.chunk_max) while the
-                // epilogue warps are still busy with the other TMEM buffer, so the tensor pipe never idles behind a
-                // tile epilogue.  chunk_max == chunk gives fixed chunks (bitwise run-to-run reproducible).
+                // A chunk is p.chunk stages.  Experimental (AIMNET_TC_CHUNK_MAX > chunk): let it grow while the epilogue
+                // warps still hold the other TMEM buffer.  Measured: no gain (the MMA issuer is not what waits), so the
+                // default is chunk_max == chunk: fixed chunks, bitwise run-to-run reproducible.
                 int ks = 0;
                 while (ks < nk) {
                     int b = cit & 1;
@@ -484,7 +484,7 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     static int chunk_max = 0;
     if (chunk_max == 0) {
         const char* env = getenv("AIMNET_TC_CHUNK_MAX");
-        chunk_max = env ? atoi(env) : 8;
+        chunk_max = env ? atoi(env) : chunk;   // elastic growth is experimental and off by default
         if (chunk_max < chunk) chunk_max = chunk;
     }
     Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, g_tc_deterministic ? chunk : chunk_max, bn};

@@ -196,45 +196,64 @@ __global__ void __launch_bounds__(256) d3_cn_kernel(int n, PairSource ps, const 
     if (lane == 0) cn[i] = acc;
 }
 
-// C6 interpolation with the reference's max-shifted, thresholded Gaussian weights (lr.py:1605-1624)
-__device__ __forceinline__ void d3_c6(const D3Params& p, int zi, int zj, float cni, float cnj, float& c6,
-                                      float& dc6_dcni) {
-    const float* cr = p.c6ref + ((size_t)zi * 95 + zj) * 25;
-    float di[5], dj[5];
+// C6 interpolation with the reference's max-shifted, thresholded Gaussian weights (lr.py:1605-1624).
+// The validity mask of the reference table is separable (c6ref[zi,zj,a,b] != 0  <=>  a valid for zi and b valid for zj;
+// verified for every element pair when the table is packed), so max_ab(-4(da^2+db^2)) = m_i + m_j and the weight
+// factorises: exp(shifted_ab) = exp(s_i[a]) exp(s_j[b]) with s = -4 d^2 - m <= 0.  The five (s, w = exp(s),
+// dw = w * (-8 d)) triples are computed once per atom; a pair then needs 25 multiply-adds and no exponential.
+__global__ void d3_weights_kernel(int n, const int32_t* __restrict__ numbers, D3Params p, const float* __restrict__ cn,
+                                  float* __restrict__ wtab) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int z = clampz(numbers[i]);
+    float c = cn[i];
+    float d[5], arg[5];
+    float mx = -INFINITY;
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-        di[a] = cni - p.cnref[zi * 5 + a];
-        dj[a] = cnj - p.cnref[zj * 5 + a];
+        float ref = p.cnref[z * 5 + a];
+        d[a] = c - ref;
+        arg[a] = (ref >= 0.f) ? -4.0f * d[a] * d[a] : -INFINITY;
+        mx = fmaxf(mx, arg[a]);
     }
-    float cv[25];
-    float mx = -INFINITY;
+    float* o = wtab + (size_t)i * 16;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        bool ok = arg[a] > -INFINITY;
+        float sft = ok ? arg[a] - mx : -1.0e30f;
+        float w = ok ? expf(sft) : 0.f;
+        o[a] = sft;
+        o[5 + a] = w;
+        o[10 + a] = w * (-8.0f * d[a]);
+    }
+    o[15] = 0.f;
+}
+
+__device__ __forceinline__ void d3_c6(const D3Params& p, int zi, int zj, const float* __restrict__ wi,
+                                      const float* __restrict__ wj, float& c6, float& dc6_dcni) {
+    const float* cr = p.c6ref + ((size_t)zi * 95 + zj) * 25;
+    float si[5], ei[5], di[5], sj[5], ej[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        si[a] = wi[a];
+        ei[a] = wi[5 + a];
+        di[a] = wi[10 + a];
+        sj[a] = wj[a];
+        ej[a] = wj[5 + a];
+    }
+    float wsum = 0.f, csum = 0.f, dwsum = 0.f, dcsum = 0.f;
 #pragma unroll
     for (int a = 0; a < 5; ++a)
 #pragma unroll
         for (int b = 0; b < 5; ++b) {
+            float keep = (si[a] + sj[b] >= -12.0f) ? ej[b] : 0.f;   // invalid references carry w = 0 and s = -1e30
             float c = cr[a * 5 + b];
-            cv[a * 5 + b] = c;
-            float arg = -4.0f * (di[a] * di[a] + dj[b] * dj[b]);
-            if (c != 0.f) mx = fmaxf(mx, arg);
+            float w = ei[a] * keep, dw = di[a] * keep;
+            wsum += w;
+            csum = fmaf(c, w, csum);
+            dwsum += dw;
+            dcsum = fmaf(c, dw, dcsum);
         }
-    float wsum = 0.f, csum = 0.f, dwsum = 0.f, dcsum = 0.f;
-    if (mx > -INFINITY) {
-#pragma unroll
-        for (int a = 0; a < 5; ++a)
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                float c = cv[a * 5 + b];
-                float sh = -4.0f * (di[a] * di[a] + dj[b] * dj[b]) - mx;
-                if (c != 0.f && sh >= -12.0f) {
-                    float w = expf(sh);
-                    float dw = w * (-8.0f * di[a]);
-                    wsum += w;
-                    csum += c * w;
-                    dwsum += dw;
-                    dcsum += c * dw;
-                }
-            }
-    }
     if (wsum > 1e-12f) {
         float inv = 1.0f / fmaxf(wsum, 1e-12f);
         c6 = csum * inv;
@@ -248,7 +267,7 @@ __device__ __forceinline__ void d3_c6(const D3Params& p, int zi, int zj, float c
 // E_i = c sum_m e(d), e = -C6 * damp * sw ; dEdCN_i = 2c sum_m -(dC6/dCN_i) damp sw ; direct pair force + virial
 __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, const float* __restrict__ coord,
                                                         CellView cv, const int32_t* __restrict__ numbers, D3Params p,
-                                                        const float* __restrict__ cn, double* __restrict__ e_atom,
+                                                        const float* __restrict__ wtab, double* __restrict__ e_atom,
                                                         float* __restrict__ dEdCN, float* __restrict__ forces,
                                                         double* __restrict__ virial_atom) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -258,7 +277,10 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
     int b, e;
     row_range(ps, i, b, e);
     int zi = clampz(numbers[i]);
-    float cni = cn[i], r4i = p.r4r2[zi];
+    float r4i = p.r4r2[zi];
+    float wi[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) wi[k] = wtab[(size_t)i * 16 + k];
     const float ib = (float)(1.0 / kBohr);
     double esum = 0.0;
     float gsum = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
@@ -282,7 +304,7 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
         if (sw == 0.f && dsw == 0.f) continue;
         int zj = clampz(numbers[j]);
         float c6, dc6;
-        d3_c6(p, zi, zj, cni, cn[j], c6, dc6);
+        d3_c6(p, zi, zj, wi, wtab + (size_t)j * 16, c6, dc6);
         float rr = 3.0f * r4i * p.r4r2[zj];
         float r0 = p.a1 * sqrtf(rr) + p.a2;
         float d2 = d * d, d4 = d2 * d2, d6 = d4 * d2, d8 = d4 * d4;
@@ -423,13 +445,15 @@ int launch_coulomb(int mode, int n, const PairSource& ps, const float* coord, co
 }
 
 int launch_d3(int n, const PairSource& ps, const float* coord, const CellView& cv, const int32_t* numbers,
-              const D3Params& p, float* cn, float* dEdCN, double* e_atom, float* forces, double* virial_atom,
+              const D3Params& p, float* cn, float* wtab, float* dEdCN, double* e_atom, float* forces, double* virial_atom,
               cudaStream_t st) {
     if (n == 0) return AIMNET_OK;
     dim3 grid((n + 7) / 8);
     d3_cn_kernel<<<grid, 256, 0, st>>>(n, ps, coord, cv, numbers, p, cn);
     AIM_LAUNCH_CHECK();
-    d3_energy_kernel<<<grid, 256, 0, st>>>(n, ps, coord, cv, numbers, p, cn, e_atom, dEdCN, forces, virial_atom);
+    d3_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, numbers, p, cn, wtab);
+    AIM_LAUNCH_CHECK();
+    d3_energy_kernel<<<grid, 256, 0, st>>>(n, ps, coord, cv, numbers, p, wtab, e_atom, dEdCN, forces, virial_atom);
     AIM_LAUNCH_CHECK();
     if (forces) {
         d3_cn_force_kernel<<<grid, 256, 0, st>>>(n, ps, coord, cv, numbers, p, dEdCN, forces, virial_atom);

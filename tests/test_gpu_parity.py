@@ -266,7 +266,7 @@ def test_ase_adapter_with_stand_in_atoms(monkeypatch):
     assert np.abs(ase_calc.results["forces"] - ref["forces"]).max() < FORCE_ATOL
     assert ase_calc.results["charges"].shape == (len(inputs["numbers"]),)
     inputs, ref, meta = load_golden("allose_1x1x1_dsf")
-    atoms = Atoms(inputs["numbers"], inputs["coord"], cell=inputs["cell"], pbc=True)
+    atoms = Atoms(inputs["numbers"], inputs["coord"], cell=inputs["cell"], pbc=True, info={"charge": 0})
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         ase_calc.calculate(atoms, properties=["energy", "forces", "stress"])
