@@ -289,3 +289,80 @@ def test_deterministic_mode_is_bitwise_reproducible():
         assert (a[k] == b[k]).all(), k
     assert np.abs(a["forces"].cpu().numpy() - ref["forces"]).max() < FORCE_ATOL
     calc.engine.set_deterministic(False)
+
+
+def test_single_atom_and_tiny_systems():
+    """Edge cases: one atom (no neighbours at all), two atoms beyond the cutoff, a diatomic."""
+    from oracle.calculator_oracle import oracle_calculate
+
+    inputs, _, meta = load_golden("caffeine")
+    sd, spec = golden_state_dict(meta)
+    calc = get_calc(meta)
+    for coord, numbers in (([[0.0, 0.0, 0.0]], [8]), ([[0.0, 0.0, 0.0], [9.0, 0.0, 0.0]], [6, 1]),
+                           ([[0.0, 0.0, 0.0], [1.1, 0.0, 0.0]], [7, 7])):
+        inp = {"coord": np.array(coord, np.float32), "numbers": np.array(numbers, np.int32), "charge": np.array([0.0], np.float32)}
+        ref = oracle_calculate(sd, inp)
+        out = {k: v.cpu().numpy() for k, v in calc(inp, forces=True).items()}
+        assert abs(out["energy"][0] - ref["energy"][0]) < ENERGY_ATOL
+        assert np.abs(out["forces"] - ref["forces"]).max() < FORCE_ATOL
+        assert np.abs(out["charges"] - ref["charges"]).max() < CHARGE_ATOL
+
+
+def test_batched_periodic_cells_equal_individual():
+    """Flat coordinates + mol_idx + per-system cells (B,3,3): batch == individual evaluations, incl. per-system stress
+    (tests/test_pbc.py:551-745 of the reference)."""
+    from aimnetcentral_b200.structures import random_periodic_box
+
+    inputs, _, meta = load_golden("caffeine")
+    calc = get_calc(meta)
+    systems = [random_periodic_box(40, seed=21), random_periodic_box(56, seed=22, triclinic=False)]
+    singles = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for z, x, cell in systems:
+            singles.append({k: v.cpu().numpy() for k, v in calc({"coord": x, "numbers": z, "charge": 0.0, "cell": cell},
+                                                                 forces=True, stress=True).items()})
+        batch = {"coord": np.concatenate([s[1] for s in systems]), "numbers": np.concatenate([s[0] for s in systems]),
+                 "charge": np.zeros(2, np.float32), "mol_idx": np.repeat([0, 1], [40, 56]).astype(np.int64),
+                 "cell": np.stack([s[2] for s in systems])}
+        out = {k: v.cpu().numpy() for k, v in calc(batch, forces=True, stress=True).items()}
+    assert out["stress"].shape == (2, 3, 3) and out["energy"].shape == (2,)
+    f = np.concatenate([s["forces"] for s in singles])
+    assert np.abs(out["forces"] - f).max() < 2e-5
+    for b in range(2):
+        assert abs(out["energy"][b] - singles[b]["energy"][0]) < 2e-5
+        assert np.abs(out["stress"][b] - singles[b]["stress"]).max() < 1e-6
+
+
+def test_large_nonperiodic_molecule_vs_oracle():
+    """One 300-atom non-periodic system: naive all-pairs builder path, long rows, Coulomb over the whole molecule."""
+    from aimnetcentral_b200.structures import random_molecules
+    from oracle.calculator_oracle import oracle_calculate
+
+    inputs, _, meta = load_golden("caffeine")
+    sd, spec = golden_state_dict(meta)
+    calc = get_calc(meta)
+    coord, numbers = random_molecules(1, 300, seed=77, box=16.0)
+    inp = {"coord": coord[0], "numbers": numbers[0], "charge": np.array([-1.0], np.float32)}
+    ref = oracle_calculate(sd, inp)
+    out = {k: v.cpu().numpy() for k, v in calc(inp, forces=True).items()}
+    print(f"[parity] 300-atom molecule: dE={abs(out['energy'][0] - ref['energy'][0]):.3e} "
+          f"dF={np.abs(out['forces'] - ref['forces']).max():.3e}")
+    assert abs(out["energy"][0] - ref["energy"][0]) < 3e-4   # total energy of 300 atoms: fp32 round-off of the reference itself
+    # dense 300-atom blob: |F| reaches 36 eV/A; reference CPU<->GPU practice is rtol 1e-4 / atol 1e-5 (tests/test_calculator_gpu.py:106-137)
+    assert np.abs(out["forces"] - ref["forces"]).max() < FORCE_ATOL + 1e-5 * np.abs(ref["forces"]).max()
+    assert np.abs(out["charges"] - ref["charges"]).max() < CHARGE_ATOL
+
+
+def test_user_supplied_neighbor_matrix():
+    """Caller-provided nbmat (+ padding row, sentinel N) as in keys_in_optional (calculator.py:130-142)."""
+    from oracle.nblist_oracle import neighbor_matrix
+
+    inputs, ref, meta = load_golden("caffeine")
+    calc = get_calc(meta)
+    N = len(inputs["numbers"])
+    nb, _, _ = neighbor_matrix(inputs["coord"], 5.0)
+    nb = np.concatenate([nb, np.full((1, nb.shape[1]), N, np.int32)])
+    out = {k: v.cpu().numpy() for k, v in calc(dict(inputs, nbmat=nb), forces=True).items()}
+    assert np.abs(out["forces"] - ref["forces"]).max() < FORCE_ATOL
+    assert abs(out["energy"][0] - ref["energy"][0]) < ENERGY_ATOL
