@@ -245,47 +245,56 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
                                                             const float* __restrict__ agh_a,
                                                             const float* __restrict__ agh_q, float* __restrict__ dS_a,
                                                             float* __restrict__ dS_q, int with_q) {
-    __shared__ float dT[kTA];
-    __shared__ float dTq[2 * kH * 3];
-    int i = blockIdx.x, tid = threadIdx.x;
+    // one warp per atom, 8 atoms per block
+    __shared__ float dT_s[kAtomsPerCta][kTA];
+    __shared__ float dTq_s[kAtomsPerCta][2 * kH * 3];
+    const int al = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kAtomsPerCta + al;
+    if (i >= n_atoms) return;
+    float* dT = dT_s[al];
+    float* dTq = dTq_s[al];
     const float* dxr = dx + (size_t)i * ldx;
-    for (int e = tid; e < kTA; e += 256) dT[e] = 2.0f * T_a[(size_t)i * kTA + e] * dxr[2 * kAG + e / 3];
-    int base = 2 * kAG + kAH;
+    for (int e = lane; e < kTA; e += 32) dT[e] = 2.0f * T_a[(size_t)i * kTA + e] * dxr[2 * kAG + e / 3];
+    const int base = 2 * kAG + kAH;
     if (with_q)
-        for (int e = tid; e < C * kH * 3; e += 256)
+        for (int e = lane; e < C * kH * 3; e += 32)
             dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
-    __syncthreads();
-    int aa = tid >> 4, g = tid & 15;
-    float4 o;
-    o.x = dxr[kAG + tid];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    __syncwarp();
+#pragma unroll 2
+    for (int k = 0; k < kAG / 32; ++k) {
+        int e = lane + 32 * k;
+        int aa = e >> 4, g = e & 15;
+        float4 o;
+        o.x = dxr[kAG + e];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int h = 0; h < kH; ++h) {
-        float w = agh_a[(aa * kG + g) * kH + h];
-        s0 += w * dT[(aa * kH + h) * 3 + 0];
-        s1 += w * dT[(aa * kH + h) * 3 + 1];
-        s2 += w * dT[(aa * kH + h) * 3 + 2];
+        for (int h = 0; h < kH; ++h) {
+            float w = agh_a[(aa * kG + g) * kH + h];
+            s0 = fmaf(w, dT[(aa * kH + h) * 3 + 0], s0);
+            s1 = fmaf(w, dT[(aa * kH + h) * 3 + 1], s1);
+            s2 = fmaf(w, dT[(aa * kH + h) * 3 + 2], s2);
+        }
+        o.y = s0;
+        o.z = s1;
+        o.w = s2;
+        reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + e] = o;
     }
-    o.y = s0;
-    o.z = s1;
-    o.w = s2;
-    reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + tid] = o;
-    if (with_q && tid < C * kG) {
-        int cc = tid >> 4, gq = tid & 15;
+    if (with_q && lane < C * kG) {
+        int cc = lane >> 4, gq = lane & 15;
         float4 oq;
-        oq.x = dxr[base + C + tid];
+        oq.x = dxr[base + C + lane];
         float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
             float w = agh_q[(cc * kG + gq) * kH + h];
-            q0 += w * dTq[(cc * kH + h) * 3 + 0];
-            q1 += w * dTq[(cc * kH + h) * 3 + 1];
-            q2 += w * dTq[(cc * kH + h) * 3 + 2];
+            q0 = fmaf(w, dTq[(cc * kH + h) * 3 + 0], q0);
+            q1 = fmaf(w, dTq[(cc * kH + h) * 3 + 1], q1);
+            q2 = fmaf(w, dTq[(cc * kH + h) * 3 + 2], q2);
         }
         oq.y = q0;
         oq.z = q1;
         oq.w = q2;
-        reinterpret_cast<float4*>(dS_q)[(size_t)i * (C * kG) + tid] = oq;
+        reinterpret_cast<float4*>(dS_q)[(size_t)i * (C * kG) + lane] = oq;
     }
 }
 
@@ -555,7 +564,8 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                            const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
                            double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
-    conv_bwd_prep_kernel<C><<<n_atoms, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q);
+    conv_bwd_prep_kernel<C><<<(n_atoms + kAtomsPerCta - 1) / kAtomsPerCta, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a,
+                                                                                          agh_q, dS_a, dS_q, with_q);
     AIM_LAUNCH_CHECK();
     int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
     if (want_grad_a)

@@ -18,7 +18,7 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 // ---- declarations of the launchers living in the other translation units -----------------------------------
 int neighbor_matrix_impl(const float*, int, float, const float*, const float*, const uint8_t*, int, const int32_t*, int,
-                         int, int, int, int32_t*, int32_t*, int32_t*, int*, cudaStream_t, bool);
+                         int, int, int, int32_t*, int32_t*, int32_t*, int*, cudaStream_t, bool, int32_t*, int32_t*);
 int wrap_positions_impl(const float*, float*, int, const float*, int, const uint8_t*, const int32_t*, cudaStream_t);
 int launch_conv_fwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
                     const float*, const float*, const float*, const float*, float*, int, float*, float*, int,
@@ -107,6 +107,7 @@ struct aimnet2_engine {
     char* stage = nullptr;
     size_t stage_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    int32_t* pinned_int = nullptr;   // page-locked scratch for small device->host read-backs
     // timing
     int timing = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -191,6 +192,7 @@ struct Bump {
 struct Buffers {
     float* coord_w;
     int32_t* mol_ptr;
+    int32_t* nb_scratch;
     int32_t *nb_sr, *sh_sr, *cnt_sr, *nb_lr, *sh_lr, *cnt_lr;
     float* a[3];
     float* q[2];
@@ -216,6 +218,7 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     size_t n = (size_t)std::max(N, 1);
     b.coord_w = bp.take<float>(n * 3);
     b.mol_ptr = bp.take<int32_t>(B + 2);
+    b.nb_scratch = bp.take<int32_t>((size_t)B * 4 + 16);
     b.nb_sr = bp.take<int32_t>(n * sr_cap);
     b.sh_sr = pbc ? bp.take<int32_t>(n * sr_cap * 3) : nullptr;
     b.cnt_sr = bp.take<int32_t>(n);
@@ -315,9 +318,9 @@ static void collect_timing(aimnet2_engine* e) {
 
 static int build_list(aimnet2_engine* e, const float* coord, int N, float cutoff, const aimnet2_system_t* sys,
                       const int32_t* mol_idx, int sorted, int cap, int32_t* nb, int32_t* sh, int32_t* cnt, int* maxc,
-                      cudaStream_t st) {
+                      int32_t* scratch, cudaStream_t st) {
     return neighbor_matrix_impl(coord, N, cutoff, sys->cell, sys->host_cell, sys->pbc_host, sys->n_cells, mol_idx,
-                                sys->n_mol, cap, N, sorted, nb, sh, cnt, maxc, st, true);
+                                sys->n_mol, cap, N, sorted, nb, sh, cnt, maxc, st, true, scratch, e->pinned_int);
 }
 
 static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
@@ -387,7 +390,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         if (own_sr) {
             int maxc = 0;
             int rc = build_list(e, coord, N, o.sr_cutoff, sys, sys->mol_idx, 1, e->sr_cap, b.nb_sr, b.sh_sr, b.cnt_sr,
-                                &maxc, st);
+                                &maxc, b.nb_scratch, st);
             if (rc == AIMNET_NEIGHBOR_OVERFLOW) {
                 e->sr_cap = round16(maxc + maxc / 4 + 1);
                 retry = true;
@@ -397,7 +400,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         }
         if (!retry && need_lr_list) {
             int maxc = 0;
-            int rc = build_list(e, coord, N, lr_cut, sys, sys->mol_idx, 0, e->lr_cap, b.nb_lr, b.sh_lr, b.cnt_lr, &maxc, st);
+            int rc = build_list(e, coord, N, lr_cut, sys, sys->mol_idx, 0, e->lr_cap, b.nb_lr, b.sh_lr, b.cnt_lr, &maxc, b.nb_scratch, st);
             if (rc == AIMNET_NEIGHBOR_OVERFLOW) {
                 e->lr_cap = round16(maxc + maxc / 8 + 1);
                 retry = true;
@@ -628,6 +631,7 @@ extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weigh
     e->opt.sr_cutoff = 5.0f;
     e->gemm_backend = gemm_tc_available() ? 1 : 0;
     AIM_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    AIM_CUDA_CHECK(cudaMallocHost((void**)&e->pinned_int, 64));
     for (int k = 0; k < 6; ++k) AIM_CUDA_CHECK(cudaEventCreate(&e->ev[k]));
     *out = e;
     return AIMNET_OK;
@@ -642,6 +646,7 @@ extern "C" int aimnet2_engine_destroy(aimnet2_engine_t* e) {
     if (e->stage) cudaFree(e->stage);
     ewald_release(e->ewald);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->pinned_int) cudaFreeHost(e->pinned_int);
     for (int k = 0; k < 6; ++k)
         if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     for (cudaEvent_t ev : e->gemm_ev) cudaEventDestroy(ev);

@@ -415,15 +415,18 @@ static bool make_grid(const float* hc, const uint8_t* pbc, float cutoff, int n_a
 int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, const float* cell, const float* host_cell,
                          const uint8_t* pbc_host, int n_cells, const int32_t* batch_idx, int n_systems, int max_nb,
                          int fill_value, int sorted, int32_t* nbmat, int32_t* shifts, int32_t* nnb,
-                         int* max_count_host, cudaStream_t st, bool prefer_cells) {
+                         int* max_count_host, cudaStream_t st, bool prefer_cells, int32_t* scratch = nullptr,
+                         int32_t* pinned_host = nullptr) {
+    // scratch (optional, device): >= n_systems + 3*n_cells + 8 ints owned by the caller, avoids the stream-ordered
+    // allocations below; pinned_host (optional): page-locked int for the overflow read-back
     AIM_REQUIRE(n_atoms >= 0 && max_nb >= 1, "neighbor_matrix: bad sizes");
     AIM_REQUIRE(cutoff > 0.f, "neighbor_matrix: cutoff must be positive");
     AIM_REQUIRE((cell == nullptr) == (n_cells == 0), "neighbor_matrix: cell / n_cells mismatch");
     AIM_REQUIRE(cell == nullptr || shifts != nullptr, "neighbor_matrix: shifts output required with a cell");
     AIM_REQUIRE(n_cells == 0 || n_cells == 1 || n_cells == n_systems, "neighbor_matrix: n_cells must be 0, 1 or n_systems");
     if (n_systems < 1) n_systems = 1;
-    int32_t* d_max = nullptr;
-    AIM_CUDA_CHECK(cudaMallocAsync(&d_max, sizeof(int32_t), st));
+    int32_t* d_max = scratch;
+    if (!scratch) AIM_CUDA_CHECK(cudaMallocAsync(&d_max, sizeof(int32_t), st));
     AIM_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
     float rc2 = cutoff * cutoff;
     if (n_atoms > 0) {
@@ -482,13 +485,16 @@ int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, cons
             AIM_CUDA_CHECK(cudaFreeAsync(bin_start, st));
             AIM_CUDA_CHECK(cudaFreeAsync(tmp, st));
         } else {
-            int32_t *seg = nullptr, *nimg = nullptr;
+            int32_t *seg = scratch ? scratch + 2 : nullptr, *nimg = nullptr;
             uint8_t* d_pbc = nullptr;
-            AIM_CUDA_CHECK(cudaMallocAsync(&seg, sizeof(int32_t) * (n_systems + 1), st));
+            if (!scratch) AIM_CUDA_CHECK(cudaMallocAsync(&seg, sizeof(int32_t) * (n_systems + 1), st));
             seg_ptr_kernel<<<(n_atoms + 256) / 256, 256, 0, st>>>(batch_idx, n_atoms, n_systems, seg);
             AIM_LAUNCH_CHECK();
             if (cell != nullptr) {
-                AIM_CUDA_CHECK(cudaMallocAsync(&nimg, sizeof(int32_t) * 3 * n_cells, st));
+                if (scratch)
+                    nimg = scratch + 2 + n_systems + 2;
+                else
+                    AIM_CUDA_CHECK(cudaMallocAsync(&nimg, sizeof(int32_t) * 3 * n_cells, st));
                 if (pbc_host != nullptr) {
                     AIM_CUDA_CHECK(cudaMallocAsync(&d_pbc, 3 * n_cells, st));
                     AIM_CUDA_CHECK(cudaMemcpyAsync(d_pbc, pbc_host, 3 * n_cells, cudaMemcpyHostToDevice, st));
@@ -499,20 +505,24 @@ int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, cons
             nb_naive_kernel<<<(n_atoms + 7) / 8, 256, 0, st>>>(positions, n_atoms, rc2, cell, n_cells, nimg, batch_idx,
                                                               seg, max_nb, fill_value, nbmat, shifts, nnb, d_max);
             AIM_LAUNCH_CHECK();
-            AIM_CUDA_CHECK(cudaFreeAsync(seg, st));
-            if (nimg) AIM_CUDA_CHECK(cudaFreeAsync(nimg, st));
+            if (!scratch) {
+                AIM_CUDA_CHECK(cudaFreeAsync(seg, st));
+                if (nimg) AIM_CUDA_CHECK(cudaFreeAsync(nimg, st));
+            }
             if (d_pbc) AIM_CUDA_CHECK(cudaFreeAsync(d_pbc, st));
         }
     }
     int rc = AIMNET_OK;
     if (max_count_host != nullptr) {
         int32_t h = 0;
-        AIM_CUDA_CHECK(cudaMemcpyAsync(&h, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        int32_t* dst = pinned_host ? pinned_host : &h;
+        AIM_CUDA_CHECK(cudaMemcpyAsync(dst, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+        h = *dst;
         *max_count_host = h;
         if (h > max_nb) rc = AIMNET_NEIGHBOR_OVERFLOW;
     }
-    AIM_CUDA_CHECK(cudaFreeAsync(d_max, st));
+    if (!scratch) AIM_CUDA_CHECK(cudaFreeAsync(d_max, st));
     return rc;
 }
 
