@@ -52,6 +52,27 @@ def make_workload(name: str, seed: int):
         z, x, cell = allose_supercell((7, 3, 5), jitter=0.02, seed=seed)
         return dict(coord=x, numbers=z.astype(np.int32), charge=np.zeros(1, np.float32), mol_idx=None, cell=cell,
                     desc="cfg-3: 10 080-atom allose supercell, PBC, DSF Coulomb + DFT-D3, E+F+stress", stress=True)
+    if name == "cfg5":
+        z, x, cell = allose_supercell((14, 6, 10), jitter=0.02, seed=seed)
+        return dict(coord=x, numbers=z.astype(np.int32), charge=np.zeros(1, np.float32), mol_idx=None, cell=cell,
+                    desc="cfg-5: 80 640-atom allose supercell, PBC, Ewald Coulomb (1e-6) + DFT-D3, E+F+stress (one "
+                         "replica per GPU)", stress=True, coulomb="ewald")
+    if name == "cfg1":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "taxol_q0.npz"))
+        return dict(coord=g["in_coord"].astype(np.float32), numbers=g["in_numbers"].astype(np.int32),
+                    charge=np.zeros(1, np.float32), mol_idx=None, cell=None,
+                    desc="cfg-1: taxol, 113 atoms, single molecule, E+F, Coulomb simple + DFT-D3", stress=False)
+    if name == "cfg4":
+        coord, numbers = random_molecules(512, 80, seed=4321 + seed, box=8.5)
+        B, n = coord.shape[:2]
+        rng = np.random.default_rng(seed)
+        charge = rng.integers(-1, 2, size=B).astype(np.float32)
+        nelec = numbers.sum(axis=1) - charge.astype(np.int64)
+        mult = np.where(nelec % 2 == 0, rng.choice([1, 3], size=B), 2).astype(np.float32)
+        return dict(coord=coord.reshape(-1, 3), numbers=numbers.reshape(-1).astype(np.int32), charge=charge, mult=mult,
+                    mol_idx=np.repeat(np.arange(B), n).astype(np.int32), cell=None, channels=2,
+                    desc="cfg-4: aimnet2-nse graph (2 charge channels), 512 x 80-atom molecules, E+F+charges+spin charges",
+                    stress=False)
     raise ValueError(name)
 
 
@@ -173,7 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--gemm-backend", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -197,14 +218,14 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
-    spec = ModelSpec()
+    w = make_workload(args.workload, args.seed + rank)  # weak scaling: every rank owns its own batch
+    spec = ModelSpec(num_charge_channels=w.get("channels", 1))
     sd = random_state_dict(0, spec)
     eng = Engine(sd, spec.C, dev)
     if args.gemm_backend is not None:
         eng.set_gemm_backend(args.gemm_backend)
-    w = make_workload(args.workload, args.seed + rank)  # weak scaling: every rank owns its own batch
     pbc = w["cell"] is not None
-    eng.set_options(coulomb_method="dsf" if pbc else "simple", dispersion=True)
+    eng.set_options(coulomb_method=w.get("coulomb", "dsf" if pbc else "simple"), dispersion=True)
     N = len(w["numbers"])
     B = len(w["charge"])
     rng = np.random.default_rng(args.seed + 17 * rank)
@@ -217,6 +238,8 @@ def main():
     charge_h = torch.from_numpy(w["charge"]).pin_memory()
     mol_h = torch.from_numpy(w["mol_idx"]).pin_memory() if w["mol_idx"] is not None else None
     numbers_d, charge_d = numbers_h.to(dev), charge_h.to(dev)
+    mult_h = torch.from_numpy(w["mult"]).pin_memory() if w.get("mult") is not None else None
+    mult_d = mult_h.to(dev) if mult_h is not None else None
     mol_d = mol_h.to(dev) if mol_h is not None else None
     cell_d = torch.from_numpy(w["cell"]).to(dev) if pbc else None
     gather_e = gather_f = None
@@ -225,7 +248,8 @@ def main():
         gather_f = torch.empty(world * N, 3, dtype=torch.float32, device=dev)
 
     def step(i):
-        out = eng.eval(coords_d[i], numbers_d, charge_d, mol_idx=mol_d, cell=cell_d, forces=True, stress=w["stress"])
+        out = eng.eval(coords_d[i], numbers_d, charge_d, mol_idx=mol_d, mult=mult_d, cell=cell_d, forces=True,
+                       stress=w["stress"])
         if world > 1:  # result gather of the batch split (NCCL over NVLink)
             dist.all_gather_into_tensor(gather_e, out["energy"])
             dist.all_gather_into_tensor(gather_f, out["forces"])
@@ -263,10 +287,12 @@ def main():
              "forces": torch.empty(N, 3, dtype=torch.float32).pin_memory().numpy()}
     if w["stress"]:
         out_h["stress"] = torch.empty(3, 3, dtype=torch.float32).pin_memory().numpy()
+    if spec.C == 2:
+        out_h["spin_charges"] = torch.empty(N, dtype=torch.float32).pin_memory().numpy()
 
     def step_host(i):
-        eng.eval_host(coords_h[i], numbers_h, charge_h, mol_idx=mol_h, cell=w["cell"], forces=True, stress=w["stress"],
-                      out=out_h)
+        eng.eval_host(coords_h[i], numbers_h, charge_h, mol_idx=mol_h, mult=mult_h, cell=w["cell"], forces=True,
+                      stress=w["stress"], out=out_h)
 
     for i in range(2):
         step_host(i)
@@ -332,7 +358,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload in ("cfg2", "cfg3"):
             v, sample, cores, dtc, n = cpu_baseline(args.workload, args.seed, budget_s=15.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "s_per_step": dtc, "steps": n}
