@@ -79,3 +79,38 @@ def test_nblist_oracle_properties():
         assert (nb[i, nnb[i]:] == N).all()
     for (i, j, a, b, c) in pairs:
         assert (j, i, -a, -b, -c) in pairs
+
+
+def test_model_sources_v2_artifact_and_module(tmp_path):
+    """B2: the weights ABI — a v2 `.pt` dict (docs/model_format.md:205-222) and an nn.Module carrying `_metadata`
+    resolve to the same (state_dict, metadata, channels) triple the engine consumes."""
+    import torch
+    import yaml
+
+    from aimnetcentral_b200 import ModelSpec, random_state_dict
+    from aimnetcentral_b200.calculator import _load_model_source
+
+    spec = ModelSpec(num_charge_channels=2)
+    sd = random_state_dict(3, spec)
+    artifact = {"format_version": 2, "model_yaml": yaml.safe_dump({"class": "aimnet.models.AIMNet2",
+                                                                  "kwargs": {"num_charge_channels": 2}}),
+                **{k: v for k, v in spec.metadata().items() if k != "format_version"}, "state_dict": sd}
+    path = tmp_path / "model.pt"
+    torch.save(artifact, path)
+    sd2, meta, C = _load_model_source(str(path))
+    assert C == 2 and meta["coulomb_mode"] == "sr_embedded" and meta["d3_params"]["s8"] == 0.3908
+    assert set(sd2) == set(sd) and torch.equal(sd2["mlps.1.0.weight"], sd["mlps.1.0.weight"])
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_charge_channels = 1
+            self.lin = torch.nn.Linear(2, 2)
+            self.__dict__["_metadata"] = {"cutoff": 5.0}
+
+    sd3, meta3, C3 = _load_model_source(Tiny())
+    assert C3 == 1 and meta3["cutoff"] == 5.0 and "lin.weight" in sd3
+    with pytest.raises(FileNotFoundError):
+        _load_model_source("aimnet2")  # registry names need a download: outside scope, reported clearly
+    with pytest.raises(TypeError):
+        _load_model_source(42)
