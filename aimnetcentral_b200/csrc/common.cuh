@@ -108,6 +108,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Packed fp32 FMA (sm_100 FFMA2, PTX fma.rn.f32x2): two independent IEEE fp32 FMAs per issued instruction; bitwise
+// identical to two fmaf() calls.  ptxas folds the mov.b64 packs away when the halves sit in an aligned register pair
+// (float4 loads, accumulators) and takes a plain 32-bit register as a broadcast multiplicand (ffma2s).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rc) : "l"(ra), "l"(rb), "l"(rc));
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+    return r;
+}
+__device__ __forceinline__ float2 ffma2s(float a, float2 b, float2 c) { return ffma2(make_float2(a, a), b, c); }
+
 // exact-erf GELU and its derivative (nn.GELU() default, aimnet/modules/core.py:11-46), library form
 __device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float z) {

@@ -34,8 +34,13 @@ struct PairEntry {
     float ux, uy, uz, d;
     float fc, dfc;
     int j;
-    int pad;
+    float inv;   // 1/d
 };
+
+// Gaussian of the radial basis, aimnet/ops.py:93-96 (exp_expand).  ex2.approx of x*log2(e): relative error <= 2^-22 + |x| 2^-24
+// (x in [-20, 0] wherever the result matters), far inside the 1e-4 parity budget; forward and backward use the same
+// function, so the forces stay the exact gradient of the energy that is returned.
+__device__ __forceinline__ float aev_exp(float x) { return __expf(x); }
 
 // stage geometry + cutoff for slots [m0, m0+32) of the CTA's 8 atoms: thread (atom = warp, slot = lane)
 template <bool kWithDeriv>
@@ -66,7 +71,7 @@ __device__ __forceinline__ void stage_pairs(PairEntry* tile, int i, bool atom_ok
     e.fc = ok ? 0.5f * (cs + 1.0f) : 0.f;
     e.dfc = (kWithDeriv && ok && d > 1e-6f && d < aev.rc) ? -0.5f * (kPi / aev.rc) * sn : 0.f;
     e.j = ok ? j : (atom_ok ? i : 0);
-    e.pad = 0;
+    e.inv = inv;
     tile[tid] = e;
 }
 
@@ -109,12 +114,13 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
     const int len = atom_ok ? row_length(nb, i) : 0;
     const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
-    float S[kHalfA][4];
+    // accumulators as (scalar, x) / (y, z) register pairs: the 8x4 outer-product update is 16 packed FFMA2 per pair
+    float2 S01[kHalfA], S23[kHalfA];
 #pragma unroll
-    for (int a = 0; a < kHalfA; ++a) S[a][0] = S[a][1] = S[a][2] = S[a][3] = 0.f;
-    float Sq[C][4];
+    for (int a = 0; a < kHalfA; ++a) S01[a] = S23[a] = make_float2(0.f, 0.f);
+    float2 Sq01[C], Sq23[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) Sq[c][0] = Sq[c][1] = Sq[c][2] = Sq[c][3] = 0.f;
+    for (int c = 0; c < C; ++c) Sq01[c] = Sq23[c] = make_float2(0.f, 0.f);
     for (int m0 = 0; m0 < maxlen; m0 += kSlotsPerTile) {
         __syncthreads();
         stage_pairs<false>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
@@ -126,24 +132,20 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
             const float4* row = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g + 32 * h;
             float4 v0 = row[0], v1 = row[16];
             float xg = e.d - shift_g;
-            float w0 = expf(-aev.eta * xg * xg) * e.fc;
-            float w1 = w0 * e.ux, w2 = w0 * e.uy, w3 = w0 * e.uz;
+            float w0 = aev_exp(-aev.eta * xg * xg) * e.fc;
+            const float2 w01 = make_float2(w0, w0 * e.ux), w23 = make_float2(w0 * e.uy, w0 * e.uz);
             float av[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int a = 0; a < kHalfA; ++a) {
-                S[a][0] = fmaf(av[a], w0, S[a][0]);
-                S[a][1] = fmaf(av[a], w1, S[a][1]);
-                S[a][2] = fmaf(av[a], w2, S[a][2]);
-                S[a][3] = fmaf(av[a], w3, S[a][3]);
+                S01[a] = ffma2s(av[a], w01, S01[a]);
+                S23[a] = ffma2s(av[a], w23, S23[a]);
             }
             if (with_q) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     float qj = q[(size_t)e.j * C + c];
-                    Sq[c][0] = fmaf(qj, w0, Sq[c][0]);
-                    Sq[c][1] = fmaf(qj, w1, Sq[c][1]);
-                    Sq[c][2] = fmaf(qj, w2, Sq[c][2]);
-                    Sq[c][3] = fmaf(qj, w3, Sq[c][3]);
+                    Sq01[c] = ffma2s(qj, w01, Sq01[c]);
+                    Sq23[c] = ffma2s(qj, w23, Sq23[c]);
                 }
             }
         }
@@ -153,17 +155,17 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
 #pragma unroll
     for (int a = 0; a < kHalfA; ++a) {
         int aa = kHalfA * h + a;
-        svl[(aa * kG + g) * 3 + 0] = S[a][1];
-        svl[(aa * kG + g) * 3 + 1] = S[a][2];
-        svl[(aa * kG + g) * 3 + 2] = S[a][3];
+        svl[(aa * kG + g) * 3 + 0] = S01[a].y;
+        svl[(aa * kG + g) * 3 + 1] = S23[a].x;
+        svl[(aa * kG + g) * 3 + 2] = S23[a].y;
     }
     float* svql = svq[al];
     if (with_q && h == 0) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            svql[(c * kG + g) * 3 + 0] = Sq[c][1];
-            svql[(c * kG + g) * 3 + 1] = Sq[c][2];
-            svql[(c * kG + g) * 3 + 2] = Sq[c][3];
+            svql[(c * kG + g) * 3 + 0] = Sq01[c].y;
+            svql[(c * kG + g) * 3 + 1] = Sq23[c].x;
+            svql[(c * kG + g) * 3 + 2] = Sq23[c].y;
         }
     }
     if (atom_ok) {
@@ -175,14 +177,14 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
         for (int a = 0; a < kHalfA; ++a) {
             int aa = kHalfA * h + a;
             xr[aa * kG + g] = ov[a];
-            xr[kAG + aa * kG + g] = S[a][0];
+            xr[kAG + aa * kG + g] = S01[a].x;
         }
         int base = 2 * kAG + kAH;
         if (with_q) {
             if (lane < C) xr[base + lane] = q[(size_t)i * C + lane];
             if (h == 0) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq[c][0];
+                for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq01[c].x;
             }
             base += C * (1 + kG + kH);
         }
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
 // ------------------------------------------------------------------------------------------------------------
 // backward step 2 (see the header comment)
 // ------------------------------------------------------------------------------------------------------------
-template <int C, bool kGradA>
+template <int C, bool kGradA, bool kVirial>
 __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
                                                           CellView cv, const int32_t* __restrict__ mol_idx,
                                                           AevParams aev, const float* __restrict__ aT,
@@ -320,13 +322,17 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
     const int len = atom_ok ? row_length(nb, i) : 0;
     const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
-    // own atom: dS_i[a][g][d] and a_i[a][g] for this thread's 8 channels
-    float4 dSi[kHalfA];
+    // own atom: dS_i[a][g][d] (as (scalar,x) / (y,z) register pairs) and a_i[a][g] for this thread's 8 channels
+    float2 dSi01[kHalfA], dSi23[kHalfA];
     float ai[kHalfA];
     {
         const float4* p = reinterpret_cast<const float4*>(dS_a) + (size_t)ic * kAG + (kHalfA * h) * kG + g;
 #pragma unroll
-        for (int a = 0; a < kHalfA; ++a) dSi[a] = p[a * kG];
+        for (int a = 0; a < kHalfA; ++a) {
+            float4 v = p[a * kG];
+            dSi01[a] = make_float2(v.x, v.y);
+            dSi23[a] = make_float2(v.z, v.w);
+        }
         const float4* r = reinterpret_cast<const float4*>(aT + (size_t)ic * kAG) + g + 32 * h;
         float4 o0 = r[0], o1 = r[16];
         float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
@@ -335,19 +341,22 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
     }
     // the charge channels are handled by the h == 0 half only (their partial sums are added once)
     const bool qhalf = with_q && h == 0;
-    float4 dSqi[C];
+    float2 dSqi01[C], dSqi23[C];
     float qi[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        dSqi[c] = qhalf ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
+        float4 v = qhalf ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
+        dSqi01[c] = make_float2(v.x, v.y);
+        dSqi23[c] = make_float2(v.z, v.w);
         qi[c] = qhalf ? q[(size_t)ic * C + c] : 0.f;
     }
-    float ga[kHalfA];
+    // grad_a / grad_q as two partial sums each (the halves of one packed accumulator), added at the end
+    float2 ga2[kHalfA];
 #pragma unroll
-    for (int a = 0; a < kHalfA; ++a) ga[a] = 0.f;
-    float gq[C];
+    for (int a = 0; a < kHalfA; ++a) ga2[a] = make_float2(0.f, 0.f);
+    float2 gq2[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) gq[c] = 0.f;
+    for (int c = 0; c < C; ++c) gq2[c] = make_float2(0.f, 0.f);
     float fx = 0.f, fy = 0.f, fz = 0.f;
     float vir[9];
 #pragma unroll
@@ -365,60 +374,65 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
             float4 v0 = arow[0], v1 = arow[16];
             float aj[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             float xg = e.d - shift_g;
-            float ex = expf(-aev.eta * xg * xg);
+            float ex = aev_exp(-aev.eta * xg * xg);
             float gs = ex * e.fc;
             float dgs = ex * (e.dfc - 2.0f * aev.eta * xg * e.fc);
+            // g_sv(j->i)[g,:] = (gs, -gs u): grad_a[i] += <dS[j], g_sv(j->i)> as two packed FMAs per channel
+            const float2 G01 = make_float2(gs, -gs * e.ux), G23 = make_float2(-gs * e.uy, -gs * e.uz);
             // p = contraction for slot (i -> j), r = for the reverse slot (j -> i); partial over this thread's channels
-            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+            float2 p01 = make_float2(0.f, 0.f), p23 = p01, r01 = p01, r23 = p01;
 #pragma unroll
             for (int a = 0; a < kHalfA; ++a) {
                 float4 dj = drow[a * kG];
+                const float2 dj01 = make_float2(dj.x, dj.y), dj23 = make_float2(dj.z, dj.w);
                 if (kGradA) {
-                    float t = dj.x - (dj.y * e.ux + dj.z * e.uy + dj.w * e.uz);
-                    ga[a] = fmaf(gs, t, ga[a]);
+                    ga2[a] = ffma2(dj01, G01, ga2[a]);
+                    ga2[a] = ffma2(dj23, G23, ga2[a]);
                 }
-                p0 = fmaf(aj[a], dSi[a].x, p0);
-                p1 = fmaf(aj[a], dSi[a].y, p1);
-                p2 = fmaf(aj[a], dSi[a].z, p2);
-                p3 = fmaf(aj[a], dSi[a].w, p3);
-                r0 = fmaf(ai[a], dj.x, r0);
-                r1 = fmaf(ai[a], dj.y, r1);
-                r2 = fmaf(ai[a], dj.z, r2);
-                r3 = fmaf(ai[a], dj.w, r3);
+                p01 = ffma2s(aj[a], dSi01[a], p01);
+                p23 = ffma2s(aj[a], dSi23[a], p23);
+                r01 = ffma2s(ai[a], dj01, r01);
+                r23 = ffma2s(ai[a], dj23, r23);
             }
             if (qhalf) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     float qj = q[(size_t)e.j * C + c];
                     float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)e.j * (C * kG) + c * kG + g];
-                    if (kGradA) gq[c] = fmaf(gs, dqj.x - (dqj.y * e.ux + dqj.z * e.uy + dqj.w * e.uz), gq[c]);
-                    p0 = fmaf(qj, dSqi[c].x, p0);
-                    p1 = fmaf(qj, dSqi[c].y, p1);
-                    p2 = fmaf(qj, dSqi[c].z, p2);
-                    p3 = fmaf(qj, dSqi[c].w, p3);
-                    r0 = fmaf(qi[c], dqj.x, r0);
-                    r1 = fmaf(qi[c], dqj.y, r1);
-                    r2 = fmaf(qi[c], dqj.z, r2);
-                    r3 = fmaf(qi[c], dqj.w, r3);
+                    const float2 dq01 = make_float2(dqj.x, dqj.y), dq23 = make_float2(dqj.z, dqj.w);
+                    if (kGradA) {
+                        gq2[c] = ffma2(dq01, G01, gq2[c]);
+                        gq2[c] = ffma2(dq23, G23, gq2[c]);
+                    }
+                    p01 = ffma2s(qj, dSqi01[c], p01);
+                    p23 = ffma2s(qj, dSqi23[c], p23);
+                    r01 = ffma2s(qi[c], dq01, r01);
+                    r23 = ffma2s(qi[c], dq23, r23);
                 }
             }
-            float inv = 1.0f / e.d;
+            const float gsi = gs * e.inv;
             // this thread's share of w(i->j) = u (A + C.u) + (B - u (B.u))/d
-            float pu = p1 * e.ux + p2 * e.uy + p3 * e.uz;
-            float sc = p0 * dgs + pu * dgs - pu * gs * inv;
-            float wx = e.ux * sc + p1 * gs * inv;
-            float wy = e.uy * sc + p2 * gs * inv;
-            float wz = e.uz * sc + p3 * gs * inv;
+            float pu = p01.y * e.ux + p23.x * e.uy + p23.y * e.uz;
+            float sc = (p01.x + pu) * dgs - pu * gsi;
             // reverse slot (j->i): u' = -u;  w' = -u (A' - (r.u) dgs) + (B' - u (B'.u))/d
-            float ru = r1 * e.ux + r2 * e.uy + r3 * e.uz;
-            float scr = -(r0 * dgs - ru * dgs) - ru * gs * inv;
-            float vx = e.ux * scr + r1 * gs * inv;
-            float vy = e.uy * scr + r2 * gs * inv;
-            float vz = e.uz * scr + r3 * gs * inv;
-            fx += wx - vx;
-            fy += wy - vy;
-            fz += wz - vz;
-            if (virial_atom) {
+            float ru = r01.y * e.ux + r23.x * e.uy + r23.y * e.uz;
+            float scr = (ru - r01.x) * dgs - ru * gsi;
+            if (!kVirial) {
+                // F_i += w - w' = u (sc - scr) + (B - B') gs/d
+                float ds = sc - scr;
+                fx += fmaf(e.ux, ds, (p01.y - r01.y) * gsi);
+                fy += fmaf(e.uy, ds, (p23.x - r23.x) * gsi);
+                fz += fmaf(e.uz, ds, (p23.y - r23.y) * gsi);
+            } else {
+                float wx = e.ux * sc + p01.y * gsi;
+                float wy = e.uy * sc + p23.x * gsi;
+                float wz = e.uz * sc + p23.y * gsi;
+                float vx = e.ux * scr + r01.y * gsi;
+                float vy = e.uy * scr + r23.x * gsi;
+                float vz = e.uz * scr + r23.y * gsi;
+                fx += wx - vx;
+                fy += wy - vy;
+                fz += wz - vz;
                 float rx = e.ux * e.d, ry = e.uy * e.d, rz = e.uz * e.d;
                 vir[0] = fmaf(rx, wx, vir[0]);
                 vir[1] = fmaf(rx, wy, vir[1]);
@@ -436,18 +450,21 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
-    if (virial_atom) {
+    if (kVirial) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) vir[k] = warp_sum(vir[k]);
     }
+    float gq[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) gq[c] = 0.f;
     if (kGradA && with_q) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) gq[c] = warp_sum(gq[c]);
+        for (int c = 0; c < C; ++c) gq[c] = warp_sum(gq2[c].x + gq2[c].y);
     }
     if (!atom_ok) return;
     if (kGradA) {
 #pragma unroll
-        for (int a = 0; a < kHalfA; ++a) grad_a[(size_t)i * kAG + (kHalfA * h + a) * kG + g] = ga[a];
+        for (int a = 0; a < kHalfA; ++a) grad_a[(size_t)i * kAG + (kHalfA * h + a) * kG + g] = ga2[a].x + ga2[a].y;
         if (with_q && lane < C) {
             float v = gq[0];
 #pragma unroll
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
         forces[3 * i + 0] += fx;
         forces[3 * i + 1] += fy;
         forces[3 * i + 2] += fz;
-        if (virial_atom)
+        if (kVirial)
 #pragma unroll
             for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += (double)vir[k];
     }
@@ -568,12 +585,15 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                                                                                           agh_q, dS_a, dS_q, with_q);
     AIM_LAUNCH_CHECK();
     int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    if (want_grad_a)
-        conv_bwd_kernel<C, true><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a,
-                                                      grad_q, forces, virial_atom, with_q);
-    else
-        conv_bwd_kernel<C, false><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a,
-                                                       grad_q, forces, virial_atom, with_q);
+#define AIM_CONV_BWD(GA, VIR)                                                                                       \
+    conv_bwd_kernel<C, GA, VIR><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a, \
+                                                      grad_q, forces, virial_atom, with_q)
+    if (want_grad_a) {
+        if (virial_atom) AIM_CONV_BWD(true, true); else AIM_CONV_BWD(true, false);
+    } else {
+        if (virial_atom) AIM_CONV_BWD(false, true); else AIM_CONV_BWD(false, false);
+    }
+#undef AIM_CONV_BWD
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }
