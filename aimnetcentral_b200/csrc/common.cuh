@@ -71,6 +71,17 @@ struct CellView {
 };
 
 
+// one Linear's weight matrix (N, ldw) in the forms the GEMM backends consume
+struct WeightView {
+    const float* W;            // fp32 (SIMT backend 0)
+    const float* Whi;          // tf32 hi / lo split (tcgen05 3xTF32 backend 1)
+    const float* Wlo;
+    const void* Wh16;          // fp16 hi / lo split of s_w * W (tcgen05 3xFP16 backend 2)
+    const void* Wl16;
+    const float* inv_scale16;  // device scalar 1 / s_w
+    int ldw;
+};
+
 // neighbour source of the pair-potential walkers (lr.cu): matrix row, or the molecule's own atom segment
 struct PairSource {
     NbView nb;                   // nb.nbmat == nullptr -> segment mode

@@ -3,6 +3,8 @@
 // AIMNet2Calculator.eval (aimnet/calculators/calculator.py:879-947) and AIMNet2.forward
 // (aimnet/models/aimnet2.py:141-187); the reverse pass replaces the reference's single torch.autograd.grad call
 // (aimnet/calculators/derivatives.py:96-146) with analytic kernels.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -26,8 +28,8 @@ int launch_conv_fwd(int, int, const NbView&, const float*, const CellView&, cons
 int launch_conv_bwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
                     const float*, const float*, const float*, int, const float*, const float*, const float*,
                     const float*, float*, float*, float*, float*, float*, double*, int, int, cudaStream_t);
-int gemm_nt(const float*, int, const float*, const float*, const float*, int, const float*, float*, int, float*, int, int,
-            int, int, int, int, cudaStream_t);
+int gemm_nt(const float*, int, const WeightView&, const float*, float*, int, float*, int, int, int, int, int, int,
+            cudaStream_t);
 int split_tf32(const float*, float*, float*, size_t, cudaStream_t);
 bool gemm_tc_available();
 void gemm_tc_set_deterministic(bool);
@@ -77,6 +79,11 @@ struct Linear {
     float* b = nullptr;    // (out_pad)
     // tf32 hi/lo splits of W and Wt for the tcgen05 3xTF32 backend
     float *Whi = nullptr, *Wlo = nullptr, *Wthi = nullptr, *Wtlo = nullptr;
+    // fp16 hi/lo splits of s_w * W and s_w * Wt (one power-of-two scale per tensor) for the 3xFP16 backend
+    __half *Wh16 = nullptr, *Wl16 = nullptr, *Wth16 = nullptr, *Wtl16 = nullptr;
+    float* inv_scale16 = nullptr;   // device scalar 1 / s_w
+    WeightView fwd() const { return WeightView{W, Whi, Wlo, Wh16, Wl16, inv_scale16, in_pad}; }
+    WeightView bwd() const { return WeightView{Wt, Wthi, Wtlo, Wth16, Wtl16, inv_scale16, out_pad}; }
 };
 
 }  // namespace aimnet
@@ -174,6 +181,30 @@ static int make_linear(aimnet2_engine* e, Linear& L, const float* w, const float
     split(Wt, hi, lo);
     if ((rc = upload(e, &L.Wthi, hi.data(), hi.size()))) return rc;
     if ((rc = upload(e, &L.Wtlo, lo.data(), lo.size()))) return rc;
+    // 3xFP16: scale the tensor so that max|W| lands in [2^13, 2^14) (gemm_tc16.cu), then hi = rn(sW), lo = rn(sW - hi)
+    float wmax = 0.f;
+    for (float v : W) wmax = std::max(wmax, std::fabs(v));
+    int ex = 0;
+    if (wmax > 0.f) std::frexp(wmax, &ex);   // wmax = f * 2^ex, f in [0.5, 1)  ->  floor(log2) = ex - 1
+    ex = std::min(std::max(ex - 1, -113), 127);
+    const float sw = std::ldexp(1.0f, 13 - ex), inv_sw = std::ldexp(1.0f, ex - 13);
+    auto split16 = [sw](const std::vector<float>& src, std::vector<__half>& h, std::vector<__half>& l) {
+        h.resize(src.size());
+        l.resize(src.size());
+        for (size_t k = 0; k < src.size(); ++k) {
+            float x = src[k] * sw;
+            h[k] = __float2half_rn(x);
+            l[k] = __float2half_rn(x - __half2float(h[k]));
+        }
+    };
+    std::vector<__half> h16, l16;
+    split16(W, h16, l16);
+    if ((rc = upload(e, &L.Wh16, h16.data(), h16.size()))) return rc;
+    if ((rc = upload(e, &L.Wl16, l16.data(), l16.size()))) return rc;
+    split16(Wt, h16, l16);
+    if ((rc = upload(e, &L.Wth16, h16.data(), h16.size()))) return rc;
+    if ((rc = upload(e, &L.Wtl16, l16.data(), l16.size()))) return rc;
+    if ((rc = upload(e, &L.inv_scale16, &inv_sw, 1))) return rc;
     return AIMNET_OK;
 }
 
@@ -283,8 +314,7 @@ static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
 static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ldx, int K, float* Y, float* gp, bool act,
                       int M, cudaStream_t st) {
     gemm_mark(e, st);
-    int rc = gemm_nt(X, ldx, L.W, L.Whi, L.Wlo, L.in_pad, L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1,
-                     e->gemm_backend, st);
+    int rc = gemm_nt(X, ldx, L.fwd(), L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1, e->gemm_backend, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -292,8 +322,8 @@ static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ld
 static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float* dX, int lddx, const float* gp_prev,
                       int ldgp, int M, cudaStream_t st) {
     gemm_mark(e, st);
-    int rc = gemm_nt(dZ, L.out_pad, L.Wt, L.Wthi, L.Wtlo, L.out_pad, nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M,
-                     L.in_pad, L.out_pad, gp_prev ? 3 : 0, e->gemm_backend, st);
+    int rc = gemm_nt(dZ, L.out_pad, L.bwd(), nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
+                     gp_prev ? 3 : 0, e->gemm_backend, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -629,7 +659,7 @@ extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weigh
     e->opt.d3_cutoff = 15.0f;
     e->opt.d3_smoothing = 0.2f;
     e->opt.sr_cutoff = 5.0f;
-    e->gemm_backend = gemm_tc_available() ? 1 : 0;
+    e->gemm_backend = gemm_tc_available() ? 2 : 0;
     AIM_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     AIM_CUDA_CHECK(cudaMallocHost((void**)&e->pinned_int, 64));
     for (int k = 0; k < 6; ++k) AIM_CUDA_CHECK(cudaEventCreate(&e->ev[k]));
@@ -664,8 +694,8 @@ extern "C" int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_opt
 
 extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend) {
     AIM_REQUIRE(e, "set_gemm_backend: null engine");
-    AIM_REQUIRE(backend == 0 || backend == 1, "set_gemm_backend: backend must be 0 or 1");
-    AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backend not available in this build");
+    AIM_REQUIRE(backend >= 0 && backend <= 2, "set_gemm_backend: backend must be 0 (SIMT), 1 (3xTF32) or 2 (3xFP16)");
+    AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backends not available in this build");
     e->gemm_backend = backend;
     return AIMNET_OK;
 }

@@ -9,6 +9,7 @@
 //
 // Backend 0 (this file): fp32 SIMT, 128x64x16 tiles, 8x4 register micro-tiles — the bit-faithful baseline.
 // Backend 1 (gemm_tc.cu): tcgen05 3xTF32 with TMEM accumulators.
+// Backend 2 (gemm_tc16.cu): tcgen05 3xFP16 with per-(row, K-chunk) power-of-two scaling — the default.
 #include "common.cuh"
 
 namespace aimnet {
@@ -106,23 +107,33 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
 
 int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int ldw, const float* bias, float* Y, int ldy,
                float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
+int gemm_nt_tc16(const float* A, int lda, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw,
+                 const float* bias, float* Y, int ldy, float* aux, int ldaux, int M, int N, int K, int mode,
+                 cudaStream_t st);                                                        // gemm_tc16.cu
 int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st);
+int split_fp16_device(const float* w, void* hi, void* lo, float* inv_scale, unsigned int* scratch, size_t n, cudaStream_t st);
 bool gemm_tc_available();
 
-// W: fp32 weights (SIMT backend); Whi / Wlo: their tf32 hi/lo split (tcgen05 backend), same leading dimension
-int gemm_nt(const float* A, int lda, const float* W, const float* Whi, const float* Wlo, int ldw, const float* bias,
-            float* Y, int ldy, float* aux, int ldaux, int M, int N, int K, int mode, int backend, cudaStream_t st) {
+int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, float* Y, int ldy, float* aux, int ldaux, int M,
+            int N, int K, int mode, int backend, cudaStream_t st) {
     AIM_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes");
     AIM_REQUIRE(K % BK == 0, "gemm: K must be a multiple of 16 (pad the operands)");
-    AIM_REQUIRE(N % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0, "gemm: N and leading dims must be multiples of 4");
+    AIM_REQUIRE(N % 4 == 0 && lda % 4 == 0 && w.ldw % 4 == 0 && ldy % 4 == 0, "gemm: N and leading dims must be multiples of 4");
     AIM_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad epilogue mode");
     AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
     AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
     if (M == 0) return AIMNET_OK;
-    if (backend == 1) {
-        AIM_REQUIRE(Whi != nullptr && Wlo != nullptr, "gemm: tcgen05 backend needs the split weights");
-        return gemm_nt_tc(A, lda, Whi, Wlo, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
+    if (backend == 2) {
+        AIM_REQUIRE(w.Wh16 != nullptr && w.Wl16 != nullptr, "gemm: 3xFP16 backend needs the fp16 split weights");
+        return gemm_nt_tc16(A, lda, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
     }
+    if (backend == 1) {
+        AIM_REQUIRE(w.Whi != nullptr && w.Wlo != nullptr, "gemm: 3xTF32 backend needs the tf32 split weights");
+        return gemm_nt_tc(A, lda, w.Whi, w.Wlo, w.ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
+    }
+    AIM_REQUIRE(w.W != nullptr, "gemm: SIMT backend needs the fp32 weights");
+    const float* W = w.W;
+    const int ldw = w.ldw;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     switch (mode) {
         case 0: gemm_nt_simt_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
@@ -136,19 +147,33 @@ int gemm_nt(const float* A, int lda, const float* W, const float* Whi, const flo
 
 }  // namespace aimnet
 
+// Operator seam for tests / tools: fp32 weights in, split on the device for the tensor-core backends.
 extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                                float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {
     using namespace aimnet;
     cudaStream_t st = (cudaStream_t)stream;
-    if (backend != 1) return gemm_nt(A, lda, W, nullptr, nullptr, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, backend, st);
-    AIM_REQUIRE(gemm_tc_available(), "gemm: tcgen05 backend not available");
+    AIM_REQUIRE(backend >= 0 && backend <= 2, "gemm: backend must be 0 (SIMT), 1 (3xTF32) or 2 (3xFP16)");
+    WeightView wv{W, nullptr, nullptr, nullptr, nullptr, nullptr, ldw};
+    if (backend == 0) return gemm_nt(A, lda, wv, bias, Y, ldy, aux, ldaux, M, N, K, mode, 0, st);
+    AIM_REQUIRE(gemm_tc_available(), "gemm: tcgen05 backends not available");
     AIM_REQUIRE(N > 0 && ldw > 0, "gemm: bad sizes");
-    float *hi = nullptr, *lo = nullptr;
     size_t n = (size_t)N * ldw;
-    AIM_CUDA_CHECK(cudaMallocAsync(&hi, sizeof(float) * n * 2, st));
-    lo = hi + n;
-    int rc = split_tf32(W, hi, lo, n, st);
-    if (rc == AIMNET_OK) rc = gemm_nt(A, lda, W, hi, lo, ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, 1, st);
-    cudaFreeAsync(hi, st);
+    float* buf = nullptr;
+    AIM_CUDA_CHECK(cudaMallocAsync(&buf, sizeof(float) * (n * 2 + 64), st));
+    int rc;
+    if (backend == 1) {
+        wv.Whi = buf;
+        wv.Wlo = buf + n;
+        rc = split_tf32(W, buf, buf + n, n, st);
+    } else {
+        // [hi halfs | lo halfs | inv_scale | absmax scratch]
+        wv.Wh16 = buf;
+        wv.Wl16 = reinterpret_cast<char*>(buf) + n * 2;
+        float* inv = buf + n;
+        wv.inv_scale16 = inv;
+        rc = split_fp16_device(W, buf, reinterpret_cast<char*>(buf) + n * 2, inv, reinterpret_cast<unsigned int*>(inv + 16), n, st);
+    }
+    if (rc == AIMNET_OK) rc = gemm_nt(A, lda, wv, bias, Y, ldy, aux, ldaux, M, N, K, mode, backend, st);
+    cudaFreeAsync(buf, st);
     return rc;
 }

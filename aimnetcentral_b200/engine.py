@@ -93,7 +93,7 @@ class Engine:
         self._h = h
         self._keep = []
         # engine_create selects the tcgen05 backend when it was built in; mirror that choice here
-        self.gemm_backend = 1 if self._lib.aimnet2_engine_set_gemm_backend(h, 1) == 0 else 0
+        self.gemm_backend = 2 if self._lib.aimnet2_engine_set_gemm_backend(h, 2) == 0 else 0
         self.options = dict(coulomb_method="simple", dsf_alpha=0.2, dsf_rc=15.0, ewald_accuracy=1e-6, dispersion=False,
                             d3_s6=1.0, d3_s8=0.3908, d3_a1=0.566, d3_a2=3.128, d3_cutoff=15.0, d3_smoothing=0.2,
                             sr_cutoff=5.0)

@@ -30,4 +30,5 @@ for nm, f in (("trunc", trunc), ("rn", rn)):
     stats(f"emulated 3xTF32 split={nm} (exact acc)", emu)
 stats("fp32 torch matmul (highest)", (A @ W.T).double())
 stats("simt backend", run(0))
-stats("tcgen05 backend", run(1))
+stats("tcgen05 3xTF32 backend", run(1))
+stats("tcgen05 3xFP16 backend", run(2))
