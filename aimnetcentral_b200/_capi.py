@@ -65,7 +65,7 @@ EXPORTS = [
     "aimnet2_conv_sv_2d_sp_fwd", "aimnet2_conv_sv_2d_sp_bwd", "aimnet2_engine_create", "aimnet2_engine_destroy",
     "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
     "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_enable_timing",
-    "aimnet2_engine_last_timing", "aimnet2_gemm_nt",
+    "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace",
 ]
 
 
@@ -103,6 +103,7 @@ def load():
     lib.aimnet2_engine_enable_timing.argtypes = [vp, ci]
     lib.aimnet2_engine_last_timing.argtypes = [vp, c_float_p, ci]
     lib.aimnet2_gemm_nt.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.aimnet2_gemm_set_trace.argtypes = [vp]
     for name in EXPORTS:
         if name != "aimnet2_last_error":
             getattr(lib, name).restype = ci

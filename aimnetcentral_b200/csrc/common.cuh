@@ -133,6 +133,24 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return r;
 }
 __device__ __forceinline__ float2 ffma2s(float a, float2 b, float2 c) { return ffma2(make_float2(a, a), b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+    return r;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+    return r;
+}
 
 // exact-erf GELU and its derivative (nn.GELU() default, aimnet/modules/core.py:11-46), library form
 __device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
@@ -161,6 +179,32 @@ __device__ __forceinline__ void gelu_pair(float z, float& y, float& gp) {
     const float Phi = z > 0.f ? fmaf(-0.5f, e, 1.0f) : 0.5f * e;
     y = z * Phi;
     gp = fmaf(z * 0.3989422804014327f, E, Phi);
+}
+
+// gelu_pair for two values at once: the polynomial, the products and the final combinations run as packed FFMA2 /
+// FMUL2 (about 15 issued instructions per value instead of 26); same formulas, same error bounds.
+__device__ __forceinline__ void gelu_pair2(float2 z, float2& y, float2& gp) {
+    const float2 ax = make_float2(fabsf(z.x) * 0.70710678118654752f, fabsf(z.y) * 0.70710678118654752f);
+    const float2 den = ffma2s(0.47f, ax, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+    float2 P = make_float2(-0.019820483937064207f, -0.019820483937064207f);
+    P = ffma2(P, t, make_float2(0.14386611213498762f, 0.14386611213498762f));
+    P = ffma2(P, t, make_float2(-0.3281399463335257f, -0.3281399463335257f));
+    P = ffma2(P, t, make_float2(0.22202211138586878f, 0.22202211138586878f));
+    P = ffma2(P, t, make_float2(0.025256349473553902f, 0.025256349473553902f));
+    P = ffma2(P, t, make_float2(0.19197703572753022f, 0.19197703572753022f));
+    P = ffma2(P, t, make_float2(0.23444773423159065f, 0.23444773423159065f));
+    P = ffma2(P, t, make_float2(0.2652225546919865f, 0.2652225546919865f));
+    P = ffma2(P, t, make_float2(0.26516877756878143f, 0.26516877756878143f));
+    // E = exp(-z^2/2) = 2^(-0.5 log2(e) z^2)
+    const float2 arg = fmul2(fmul2(z, z), make_float2(-0.72134752044448170f, -0.72134752044448170f));
+    float2 E;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.x) : "f"(arg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.y) : "f"(arg.y));
+    const float2 h = fmul2(fmul2(t, P), fmul2(E, make_float2(0.5f, 0.5f)));   // erfc(|z|/sqrt 2) / 2
+    const float2 Phi = make_float2(z.x > 0.f ? 1.0f - h.x : h.x, z.y > 0.f ? 1.0f - h.y : h.y);
+    y = fmul2(z, Phi);
+    gp = ffma2(fmul2(z, make_float2(0.3989422804014327f, 0.3989422804014327f)), E, Phi);
 }
 
 // r_ij = x_j + s @ cell - x_i   (aimnet/ops.py:37-66)

@@ -147,6 +147,14 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
 
 }  // namespace aimnet
 
+// Debug: per-stage SM-clock stamps of CTA 0 of every following backend-2 launch (8 events x 2048 stages, device buffer
+// of 16384 uint64), nullptr to switch off.  Used by tools/gemm_trace.py only.
+namespace aimnet { void gemm_tc16_set_trace(unsigned long long* buf); }
+extern "C" int aimnet2_gemm_set_trace(void* device_buf) {
+    aimnet::gemm_tc16_set_trace(reinterpret_cast<unsigned long long*>(device_buf));
+    return AIMNET_OK;
+}
+
 // Operator seam for tests / tools: fp32 weights in, split on the device for the tensor-core backends.
 extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                                float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {

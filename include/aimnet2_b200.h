@@ -182,6 +182,10 @@ int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, int n);
 int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                     float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream);
 
+/* debug aid for the 3xFP16 GEMM (backend 2): when device_buf is non-NULL (16384 uint64 of device memory), CTA 0 of
+ * every following launch records SM-clock stamps per pipeline stage (8 events x 2048 stages); NULL switches it off. */
+int aimnet2_gemm_set_trace(void* device_buf);
+
 #ifdef __cplusplus
 }
 #endif
