@@ -71,6 +71,15 @@ struct CellView {
 };
 
 
+// an activation matrix in the pre-split form the 3xFP16 GEMM consumes and produces (gemm_tc16.cu): fp16 hi and lo of
+// s * x with one power-of-two scale per (row, 32-column chunk); inv holds 1 / s
+struct SplitMat {
+    void* hi;     // (rows, ld) __half
+    void* lo;     // (rows, ld) __half
+    float* inv;   // (rows, ldinv) fp32, ldinv >= cols / 32
+    int ld, ldinv;
+};
+
 // one Linear's weight matrix (N, ldw) in the forms the GEMM backends consume
 struct WeightView {
     const float* W;            // fp32 (SIMT backend 0)

@@ -30,6 +30,9 @@ int launch_conv_bwd(int, int, const NbView&, const float*, const CellView&, cons
                     const float*, float*, float*, float*, float*, float*, double*, int, int, cudaStream_t);
 int gemm_nt(const float*, int, const WeightView&, const float*, float*, int, float*, int, int, int, int, int, int,
             cudaStream_t);
+int gemm_nt_split(const SplitMat&, const WeightView&, const float*, float*, int, const SplitMat*, float*, int, int, int, int,
+                  int, cudaStream_t);
+int presplit_f32(const float*, int, int, int, const SplitMat&, cudaStream_t);
 int split_tf32(const float*, float*, float*, size_t, cudaStream_t);
 bool gemm_tc_available();
 void gemm_tc_set_deterministic(bool);
@@ -241,7 +244,19 @@ struct Buffers {
     float *dzA, *dzB, *dx, *dS_a, *dS_q, *grad_a, *grad_q, *da_tot, *dq, *dq_base;
     double* virial_atom;
     float* forces_tmp;
+    // pre-split activations of the 3xFP16 GEMM backend.  h16 / aim16 / h1_16 / d16 live in the memory of hA,hB / aim /
+    // h1 / dzA,dzB (fp16 hi + fp16 lo = the bytes of the fp32 matrix they replace); only x16, dz32 and the scales are extra.
+    SplitMat x16, h16[2], aim16, h1_16, d16[2];
+    float* dz32;
 };
+
+static SplitMat alias_split(float* base, size_t n, int width, float* inv) {
+    return SplitMat{base, reinterpret_cast<char*>(base) + n * width * 2, inv, width, width / 32};
+}
+static SplitMat with_ld(SplitMat m, int ld) {
+    m.ld = ld;
+    return m;
+}
 
 static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_cap, int lr_cap, bool pbc,
                   bool need_lr, int ldx) {
@@ -299,6 +314,14 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.dq_base = bp.take<float>(n * C);
     b.virial_atom = bp.take<double>(n * 9);
     b.forces_tmp = bp.take<float>(n * 3);
+    b.x16 = SplitMat{bp.take<__half>(n * ldx), bp.take<__half>(n * ldx), bp.take<float>(n * (ldx / 32)), ldx, ldx / 32};
+    b.h16[0] = alias_split(b.hA, n, 512, bp.take<float>(n * 16));
+    b.h16[1] = alias_split(b.hB, n, 512, bp.take<float>(n * 16));
+    b.aim16 = alias_split(b.aim, n, 256, bp.take<float>(n * 8));
+    b.h1_16 = alias_split(b.h1, n, 128, bp.take<float>(n * 4));
+    b.d16[0] = alias_split(b.dzA, n, 512, bp.take<float>(n * 16));
+    b.d16[1] = alias_split(b.dzB, n, 512, bp.take<float>(n * 16));
+    b.dz32 = bp.take<float>(n * 288);
 }
 
 static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
@@ -324,6 +347,30 @@ static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float
     gemm_mark(e, st);
     int rc = gemm_nt(dZ, L.out_pad, L.bwd(), nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
                      gp_prev ? 3 : 0, e->gemm_backend, st);
+    gemm_mark(e, st);
+    return rc;
+}
+
+// 3xFP16 backend: activations pre-split; out16 != nullptr writes the output pre-split for the next GEMM
+static int linear_fwd16(aimnet2_engine* e, const Linear& L, const SplitMat& X, float* Y32, const SplitMat* Y16, float* gp,
+                        bool act, int M, cudaStream_t st) {
+    gemm_mark(e, st);
+    int rc = gemm_nt_split(X, L.fwd(), L.b, Y32, L.out_pad, Y16, gp, L.out_pad, M, L.out_pad, L.in_pad, act ? 2 : 1, st);
+    gemm_mark(e, st);
+    return rc;
+}
+static int linear_bwd16(aimnet2_engine* e, const Linear& L, const SplitMat& dZ, float* dX32, int lddx, const SplitMat* dX16,
+                        const float* gp_prev, int ldgp, int M, cudaStream_t st) {
+    gemm_mark(e, st);
+    int rc = gemm_nt_split(dZ, L.bwd(), nullptr, dX32, lddx, dX16, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
+                           gp_prev ? 3 : 0, st);
+    gemm_mark(e, st);
+    return rc;
+}
+// fp32 -> pre-split (counted with the GEMM time: it is overhead of the precision scheme)
+static int presplit(aimnet2_engine* e, const float* X, int ldx, int M, int K, const SplitMat& out, cudaStream_t st) {
+    gemm_mark(e, st);
+    int rc = presplit_f32(X, ldx, M, K, out, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -378,6 +425,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     e->gemm_ev_used = 0;
     const bool pbc = sys->cell != nullptr;
     const bool backward = want_f || want_s;
+    const bool tc16 = e->gemm_backend == 2;
     const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
     const bool need_lr_terms = (o.coulomb_method == AIMNET_COULOMB_SIMPLE || o.coulomb_method == AIMNET_COULOMB_DSF ||
                                 ewald || o.dispersion);
@@ -463,16 +511,30 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         const float* qin = (p == 0) ? nullptr : b.q[p - 1];
         AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
                                 b.T_a[p], b.T_q[p], p > 0, st));
-        const float* in = b.x;
-        int ldin = ldx;
-        float* bufs[2] = {b.hA, b.hB};
-        for (int l = 0; l < nl; ++l) {
-            bool last = (l == nl - 1);
-            bool act = !last || p > 0;   // last_linear only for pass 0 (aimnet2.py:56,65,75)
-            float* out = last ? (p < 2 ? b.y[p] : b.aim) : bufs[l & 1];
-            AIM_TRY(linear_fwd(e, L[l], in, ldin, L[l].in_pad, out, act ? b.gp[p][l] : nullptr, act, N, st));
-            in = out;
-            ldin = L[l].out_pad;
+        if (tc16) {
+            AIM_TRY(presplit(e, b.x, ldx, N, L[0].in_pad, b.x16, st));
+            SplitMat in = with_ld(b.x16, ldx);
+            for (int l = 0; l < nl; ++l) {
+                bool last = (l == nl - 1);
+                bool act = !last || p > 0;   // last_linear only for pass 0 (aimnet2.py:56,65,75)
+                SplitMat out16 = with_ld(last ? b.aim16 : b.h16[l & 1], L[l].out_pad);
+                bool split_out = !last || p == 2;   // y of passes 0/1 feeds the charge equilibration in fp32
+                AIM_TRY(linear_fwd16(e, L[l], in, split_out ? nullptr : b.y[p], split_out ? &out16 : nullptr,
+                                     act ? b.gp[p][l] : nullptr, act, N, st));
+                in = out16;
+            }
+        } else {
+            const float* in = b.x;
+            int ldin = ldx;
+            float* bufs[2] = {b.hA, b.hB};
+            for (int l = 0; l < nl; ++l) {
+                bool last = (l == nl - 1);
+                bool act = !last || p > 0;   // last_linear only for pass 0 (aimnet2.py:56,65,75)
+                float* out = last ? (p < 2 ? b.y[p] : b.aim) : bufs[l & 1];
+                AIM_TRY(linear_fwd(e, L[l], in, ldin, L[l].in_pad, out, act ? b.gp[p][l] : nullptr, act, N, st));
+                in = out;
+                ldin = L[l].out_pad;
+            }
         }
         if (p < 2) {
             AIM_TRY(launch_nse_fwd(C, N, B, sys->mol_idx, b.mol_ptr, sys->charge, sys->mult, b.y[p], 288, qin,
@@ -480,9 +542,14 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         }
     }
     // energy head (aimnet/modules/core.py:114-132) + SAE (core.py:71-97)
-    AIM_TRY(linear_fwd(e, e->head[0], b.aim, 256, 256, b.h1, b.gp_h1, true, N, st));
-    AIM_TRY(linear_fwd(e, e->head[1], b.h1, 128, 128, b.h2, b.gp_h2, true, N, st));
-    AIM_TRY(launch_head_tail(N, b.h2, 128, b.gp_h2, e->w3, e->b3, sys->numbers, e->sae, b.e_nn, b.dzA, st));
+    if (tc16) {
+        AIM_TRY(linear_fwd16(e, e->head[0], b.aim16, nullptr, &b.h1_16, b.gp_h1, true, N, st));
+        AIM_TRY(linear_fwd16(e, e->head[1], b.h1_16, b.h2, nullptr, b.gp_h2, true, N, st));
+    } else {
+        AIM_TRY(linear_fwd(e, e->head[0], b.aim, 256, 256, b.h1, b.gp_h1, true, N, st));
+        AIM_TRY(linear_fwd(e, e->head[1], b.h1, 128, 128, b.h2, b.gp_h2, true, N, st));
+    }
+    AIM_TRY(launch_head_tail(N, b.h2, 128, b.gp_h2, e->w3, e->b3, sys->numbers, e->sae, b.e_nn, tc16 ? b.dz32 : b.dzA, st));
     AIM_TRY(launch_charges_out(C, N, b.q[1], res->charges, res->spin_charges, st));
     if (e->timing) cudaEventRecord(e->ev[2], st);
 
@@ -544,16 +611,33 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
 
     // ---------------- analytic reverse pass ----------------
     if (backward && N > 0) {
-        // head: dzA holds dz2 = w3 * gelu'(z2)
-        AIM_TRY(linear_bwd(e, e->head[1], b.dzA, b.dzB, 128, b.gp_h1, 128, N, st));
-        AIM_TRY(linear_bwd(e, e->head[0], b.dzB, b.dzA, 256, b.gp[2][e->mlp[2].size() - 1], 256, N, st));
+        // head: dzA (dz32 for the pre-split backend) holds dz2 = w3 * gelu'(z2)
         float* cur = b.dzA;   // gradient w.r.t. pre-activation of the last Linear of pass 2
         float* other = b.dzB;
+        int c16 = 0;          // pre-split backend: index of the d16 buffer holding that gradient
+        if (tc16) {
+            AIM_TRY(presplit(e, b.dz32, 128, N, 128, with_ld(b.d16[0], 128), st));
+            SplitMat o1 = with_ld(b.d16[1], 128), o0 = with_ld(b.d16[0], 256);
+            AIM_TRY(linear_bwd16(e, e->head[1], with_ld(b.d16[0], 128), nullptr, 0, &o1, b.gp_h1, 128, N, st));
+            AIM_TRY(linear_bwd16(e, e->head[0], o1, nullptr, 0, &o0, b.gp[2][e->mlp[2].size() - 1], 256, N, st));
+        } else {
+            AIM_TRY(linear_bwd(e, e->head[1], b.dzA, b.dzB, 128, b.gp_h1, 128, N, st));
+            AIM_TRY(linear_bwd(e, e->head[0], b.dzB, b.dzA, 256, b.gp[2][e->mlp[2].size() - 1], 256, N, st));
+        }
         for (int p = 2; p >= 0; --p) {
             const std::vector<Linear>& L = e->mlp[p];
             const int nl = (int)L.size();
             for (int l = nl - 1; l >= 0; --l) {
-                if (l > 0) {
+                if (tc16) {
+                    SplitMat dz = with_ld(b.d16[c16], L[l].out_pad);
+                    if (l > 0) {
+                        SplitMat o = with_ld(b.d16[c16 ^ 1], L[l].in_pad);
+                        AIM_TRY(linear_bwd16(e, L[l], dz, nullptr, 0, &o, b.gp[p][l - 1], L[l - 1].out_pad, N, st));
+                        c16 ^= 1;
+                    } else {
+                        AIM_TRY(linear_bwd16(e, L[0], dz, b.dx, ldx, nullptr, nullptr, 0, N, st));
+                    }
+                } else if (l > 0) {
                     AIM_TRY(linear_bwd(e, L[l], cur, other, L[l].in_pad, b.gp[p][l - 1], L[l - 1].out_pad, N, st));
                     std::swap(cur, other);
                 } else {
@@ -571,13 +655,15 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 AIM_TRY(launch_accum_grads(C, N, b.dx, ldx, b.grad_a, b.grad_q, b.dq_base, C, b.da_tot, 1, b.dq, st));
             // NSE backward of pass p-1 -> dz of the last Linear of pass p-1
             int pp = p - 1;
-            const float* qprev = (pp == 0) ? nullptr : b.q[pp - 1];
-            (void)qprev;
-            cur = b.dzA;
+            cur = tc16 ? b.dz32 : b.dzA;
             other = b.dzB;
             AIM_TRY(launch_nse_bwd(C, N, B, sys->mol_idx, b.mol_ptr, sys->charge, sys->mult, b.y[pp], 288, b.dq,
                                    b.sumq[pp], b.sumf[pp], b.s1, b.da_tot, pp > 0 ? b.gp[pp][e->mlp[pp].size() - 1] : nullptr,
                                    288, cur, 288, pp > 0 ? b.dq_base : nullptr, st));
+            if (tc16) {
+                AIM_TRY(presplit(e, b.dz32, 288, N, 288, with_ld(b.d16[0], 288), st));
+                c16 = 0;
+            }
         }
         if (want_s)
             AIM_TRY(launch_stress_reduce(b.mol_ptr, sys->n_cells, N, b.virial_atom, sys->cell, res->stress, st));

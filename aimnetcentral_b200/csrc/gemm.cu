@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
 
 int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int ldw, const float* bias, float* Y, int ldy,
                float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
-int gemm_nt_tc16(const float* A, int lda, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw,
-                 const float* bias, float* Y, int ldy, float* aux, int ldaux, int M, int N, int K, int mode,
+int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw, const float* bias,
+                 float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N, int K, int mode,
                  cudaStream_t st);                                                        // gemm_tc16.cu
+int presplit_f32(const float* X, int ldx, int M, int K, const SplitMat& out, cudaStream_t st);
+int unsplit_f32(const SplitMat& in, int M, int N, float* Y, int ldy, cudaStream_t st);
 int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st);
 int split_fp16_device(const float* w, void* hi, void* lo, float* inv_scale, unsigned int* scratch, size_t n, cudaStream_t st);
 bool gemm_tc_available();
@@ -123,10 +125,7 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
     AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
     AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
     if (M == 0) return AIMNET_OK;
-    if (backend == 2) {
-        AIM_REQUIRE(w.Wh16 != nullptr && w.Wl16 != nullptr, "gemm: 3xFP16 backend needs the fp16 split weights");
-        return gemm_nt_tc16(A, lda, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
-    }
+    AIM_REQUIRE(backend != 2, "gemm: the 3xFP16 backend takes pre-split activations (gemm_nt_split)");
     if (backend == 1) {
         AIM_REQUIRE(w.Whi != nullptr && w.Wlo != nullptr, "gemm: 3xTF32 backend needs the tf32 split weights");
         return gemm_nt_tc(A, lda, w.Whi, w.Wlo, w.ldw, bias, Y, ldy, aux, ldaux, M, N, K, mode, st);
@@ -145,6 +144,18 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
     return AIMNET_OK;
 }
 
+// 3xFP16 backend: A pre-split; output fp32 (Ysplit == nullptr) or pre-split for a consuming GEMM
+int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, float* Y, int ldy, const SplitMat* Ysplit,
+                  float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st) {
+    AIM_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes");
+    AIM_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad epilogue mode");
+    AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
+    AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
+    AIM_REQUIRE(w.Wh16 != nullptr && w.Wl16 != nullptr, "gemm: 3xFP16 backend needs the fp16 split weights");
+    if (M == 0) return AIMNET_OK;
+    return gemm_nt_tc16(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
+}
+
 }  // namespace aimnet
 
 // Debug: per-stage SM-clock stamps of CTA 0 of every following backend-2 launch (8 events x 2048 stages, device buffer
@@ -155,33 +166,51 @@ extern "C" int aimnet2_gemm_set_trace(void* device_buf) {
     return AIMNET_OK;
 }
 
-// Operator seam for tests / tools: fp32 weights in, split on the device for the tensor-core backends.
+// Operator seam for tests / tools: fp32 operands in; weights (and, for backend 2, activations) are split on the device.
+// Backend 2 only: mode | 16 makes the kernel write its output pre-split (the GEMM -> GEMM path of the engine), which is
+// then expanded back to fp32 into Y so that the caller can check it.
 extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                                float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {
     using namespace aimnet;
     cudaStream_t st = (cudaStream_t)stream;
     AIM_REQUIRE(backend >= 0 && backend <= 2, "gemm: backend must be 0 (SIMT), 1 (3xTF32) or 2 (3xFP16)");
+    const bool split_out = (mode & 16) != 0;
+    mode &= 15;
+    AIM_REQUIRE(!split_out || backend == 2, "gemm: pre-split output exists only for backend 2");
     WeightView wv{W, nullptr, nullptr, nullptr, nullptr, nullptr, ldw};
     if (backend == 0) return gemm_nt(A, lda, wv, bias, Y, ldy, aux, ldaux, M, N, K, mode, 0, st);
     AIM_REQUIRE(gemm_tc_available(), "gemm: tcgen05 backends not available");
-    AIM_REQUIRE(N > 0 && ldw > 0, "gemm: bad sizes");
+    AIM_REQUIRE(N > 0 && ldw > 0 && M >= 0 && K > 0, "gemm: bad sizes");
     size_t n = (size_t)N * ldw;
-    float* buf = nullptr;
-    AIM_CUDA_CHECK(cudaMallocAsync(&buf, sizeof(float) * (n * 2 + 64), st));
-    int rc;
     if (backend == 1) {
+        float* buf = nullptr;
+        AIM_CUDA_CHECK(cudaMallocAsync(&buf, sizeof(float) * n * 2, st));
         wv.Whi = buf;
         wv.Wlo = buf + n;
-        rc = split_tf32(W, buf, buf + n, n, st);
-    } else {
-        // [hi halfs | lo halfs | inv_scale | absmax scratch]
-        wv.Wh16 = buf;
-        wv.Wl16 = reinterpret_cast<char*>(buf) + n * 2;
-        float* inv = buf + n;
-        wv.inv_scale16 = inv;
-        rc = split_fp16_device(W, buf, reinterpret_cast<char*>(buf) + n * 2, inv, reinterpret_cast<unsigned int*>(inv + 16), n, st);
+        int rc = split_tf32(W, buf, buf + n, n, st);
+        if (rc == AIMNET_OK) rc = gemm_nt(A, lda, wv, bias, Y, ldy, aux, ldaux, M, N, K, mode, 1, st);
+        cudaFreeAsync(buf, st);
+        return rc;
     }
-    if (rc == AIMNET_OK) rc = gemm_nt(A, lda, wv, bias, Y, ldy, aux, ldaux, M, N, K, mode, backend, st);
+    AIM_REQUIRE(K % 32 == 0 && N % 32 == 0, "gemm: backend 2 needs K and N to be multiples of 32");
+    // one allocation: [W hi | W lo | scale, scratch | A hi | A lo | A inv | Y hi | Y lo | Y inv]
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t rows = (size_t)(M > 0 ? M : 1);
+    size_t o_wh = 0, o_wl = o_wh + up(n * 2), o_sc = o_wl + up(n * 2), o_ah = o_sc + 256, o_al = o_ah + up(rows * K * 2),
+           o_ai = o_al + up(rows * K * 2), o_yh = o_ai + up(rows * (K / 32) * 4), o_yl = o_yh + up(rows * N * 2),
+           o_yi = o_yl + up(rows * N * 2), total = o_yi + up(rows * (N / 32) * 4);
+    char* buf = nullptr;
+    AIM_CUDA_CHECK(cudaMallocAsync(&buf, total, st));
+    wv.Wh16 = buf + o_wh;
+    wv.Wl16 = buf + o_wl;
+    float* inv = reinterpret_cast<float*>(buf + o_sc);
+    wv.inv_scale16 = inv;
+    SplitMat As{buf + o_ah, buf + o_al, reinterpret_cast<float*>(buf + o_ai), K, K / 32};
+    SplitMat Ys{buf + o_yh, buf + o_yl, reinterpret_cast<float*>(buf + o_yi), N, N / 32};
+    int rc = split_fp16_device(W, buf + o_wh, buf + o_wl, inv, reinterpret_cast<unsigned int*>(inv + 16), n, st);
+    if (rc == AIMNET_OK) rc = presplit_f32(A, lda, M, K, As, st);
+    if (rc == AIMNET_OK) rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, st);
+    if (rc == AIMNET_OK && split_out) rc = unsplit_f32(Ys, M, N, Y, ldy, st);
     cudaFreeAsync(buf, st);
     return rc;
 }

@@ -1,8 +1,8 @@
 """Pipeline timeline of the 3xFP16 GEMM (CTA 0): where each warp role waits, per K=32 stage.
 
     python tools/gemm_trace.py [N] [K] [mode] [M]
-Events: 0 TMA got empty slot, 1 MMA got free TMEM buffer, 2 MMA got split stage, 3 splitter got TMA data,
-4 splitter done, 5 epilogue got chunk, 6 epilogue drained chunk, 7 tile epilogue done."""
+Events: 0 TMA got empty slot, 1 MMA got free TMEM buffer, 2 MMA got operands, 5 epilogue got chunk,
+6 epilogue drained chunk, 7 tile epilogue done."""
 import ctypes as C, sys
 import numpy as np
 import torch
@@ -39,8 +39,7 @@ def lag(a_, b_, sa=0, sb=0):
     x = t[b_, lo + sb:hi + sb] - t[a_, lo + sa:hi + sa]
     x = x[(t[b_, lo + sb:hi + sb] > 0) & (t[a_, lo + sa:hi + sa] > 0)]
     return x.mean(), np.percentile(x, 10), np.percentile(x, 90)
-for name, (a_, b_) in {"TMA issue -> splitter has data": (0, 3), "splitter has data -> split done": (3, 4),
-                        "split done -> MMA sees it (MMA got split stage)": (4, 2), "MMA got TMEM -> MMA got split (MMA waits for operands)": (1, 2),
+for name, (a_, b_) in {"TMA issue -> MMA has operands": (0, 2), "MMA got TMEM -> MMA got operands (MMA waits for TMA)": (1, 2),
                         "MMA issue -> epilogue got chunk": (2, 5), "epilogue got chunk -> drained": (5, 6)}.items():
     m, p10, p90 = lag(a_, b_)
     print(f"  {name:58s} mean {m:7.0f}  p10 {p10:7.0f}  p90 {p90:7.0f} clk")
