@@ -193,9 +193,11 @@ __device__ __forceinline__ void gelu_pair(float z, float& y, float& gp) {
 // gelu_pair for two values at once: the polynomial, the products and the final combinations run as packed FFMA2 /
 // FMUL2 (about 15 issued instructions per value instead of 26); same formulas, same error bounds.
 __device__ __forceinline__ void gelu_pair2(float2 z, float2& y, float2& gp) {
-    const float2 ax = make_float2(fabsf(z.x) * 0.70710678118654752f, fabsf(z.y) * 0.70710678118654752f);
-    const float2 den = ffma2s(0.47f, ax, make_float2(1.0f, 1.0f));
-    const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+    const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+    const float2 den = ffma2s(0.47f * 0.70710678118654752f, az, make_float2(1.0f, 1.0f));
+    float2 t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
     float2 P = make_float2(-0.019820483937064207f, -0.019820483937064207f);
     P = ffma2(P, t, make_float2(0.14386611213498762f, 0.14386611213498762f));
     P = ffma2(P, t, make_float2(-0.3281399463335257f, -0.3281399463335257f));
@@ -210,8 +212,10 @@ __device__ __forceinline__ void gelu_pair2(float2 z, float2& y, float2& gp) {
     float2 E;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.x) : "f"(arg.x));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.y) : "f"(arg.y));
-    const float2 h = fmul2(fmul2(t, P), fmul2(E, make_float2(0.5f, 0.5f)));   // erfc(|z|/sqrt 2) / 2
-    const float2 Phi = make_float2(z.x > 0.f ? 1.0f - h.x : h.x, z.y > 0.f ? 1.0f - h.y : h.y);
+    // h = erfc(|z|/sqrt 2) / 2;  Phi = 1/2 + sign(z) (1/2 - h)   (branch-free form of z > 0 ? 1 - h : h)
+    const float2 d = ffma2(fmul2(t, P), fmul2(E, make_float2(-0.5f, -0.5f)), make_float2(0.5f, 0.5f));
+    const float2 sd = make_float2(copysignf(d.x, z.x), copysignf(d.y, z.y));
+    const float2 Phi = fadd2(sd, make_float2(0.5f, 0.5f));
     y = fmul2(z, Phi);
     gp = ffma2(fmul2(z, make_float2(0.3989422804014327f, 0.3989422804014327f)), E, Phi);
 }

@@ -29,6 +29,32 @@ namespace aimnet {
 constexpr int kAtomsPerCta = 8;     // one warp per atom
 constexpr int kSlotsPerTile = 32;   // neighbour slots staged per tile and atom (one per lane)
 constexpr int kHalfA = 8;           // feature channels per thread (two half-warps split the 16 channels)
+// shared-memory layouts of the forward epilogue (bank-conflict-free for the access patterns described there)
+constexpr int kAghRow = 20;                       // agh^T row: 16 g + 4 pad -> 8 consecutive rows cover all 32 banks once
+constexpr int kSvRow = 52;                        // Sv of one channel: 3 k x 16 g + 4 pad
+constexpr int kSvAtom = kA * kSvRow + 16;         // + 16 between channels 7 and 8 (the two half-warps write different banks)
+constexpr int kFwdSmemBytes = 256 * 32 + (kA + 2) * kH * kAghRow * 4 + kAtomsPerCta * (kSvAtom + 2 * kSvRow) * 4 + 64;
+__device__ __forceinline__ int sv_off(int a) { return a * kSvRow + ((a >> 3) << 4); }
+// t[k] = sum_g w[g] * s[k][g], w: 16 floats, s: 3 rows of 16 floats (16-byte aligned)
+__device__ __forceinline__ void mix16(const float* __restrict__ w, const float* __restrict__ s, float* t) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4* s4 = reinterpret_cast<const float4*>(s + k * kG);
+        const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
+        float2 acc = make_float2(0.f, 0.f);
+        acc = ffma2(make_float2(w0.x, w0.y), make_float2(s0.x, s0.y), acc);
+        acc = ffma2(make_float2(w0.z, w0.w), make_float2(s0.z, s0.w), acc);
+        acc = ffma2(make_float2(w1.x, w1.y), make_float2(s1.x, s1.y), acc);
+        acc = ffma2(make_float2(w1.z, w1.w), make_float2(s1.z, s1.w), acc);
+        acc = ffma2(make_float2(w2.x, w2.y), make_float2(s2.x, s2.y), acc);
+        acc = ffma2(make_float2(w2.z, w2.w), make_float2(s2.z, s2.w), acc);
+        acc = ffma2(make_float2(w3.x, w3.y), make_float2(s3.x, s3.y), acc);
+        acc = ffma2(make_float2(w3.z, w3.w), make_float2(s3.z, s3.w), acc);
+        t[k] = acc.x + acc.y;
+    }
+}
 
 struct PairEntry {
     float ux, uy, uz, d;
@@ -101,10 +127,14 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
                                                           const float* __restrict__ agh_q, float* __restrict__ x,
                                                           int ldx, float* __restrict__ T_a, float* __restrict__ T_q,
                                                           int with_q) {
-    __shared__ PairEntry tile[256];                      // 8 atoms x 32 slots
-    __shared__ float sv[kAtomsPerCta][kAG * 3];          // vector part of S^a per atom: [a][g][3]
-    __shared__ float svq[kAtomsPerCta][2 * kG * 3];      // vector part of S^q per atom: [c][g][3]
-    __shared__ int scratch[8];
+    // dynamic shared memory (kFwdSmemBytes): pair tile | agh^T tables | per-atom vector parts
+    extern __shared__ __align__(16) unsigned char fwd_smem[];
+    PairEntry* tile = reinterpret_cast<PairEntry*>(fwd_smem);                        // 8 atoms x 32 slots
+    float* aghT_a = reinterpret_cast<float*>(fwd_smem + sizeof(PairEntry) * 256);    // [a][h][g], row stride kAghRow
+    float* aghT_q = aghT_a + kA * kH * kAghRow;                                      // [c][h][g]
+    float* sv_all = aghT_q + 2 * kH * kAghRow;                                       // [atom][a][k][g], see sv_off()
+    float* svq_all = sv_all + kAtomsPerCta * kSvAtom;                                // [atom][c][k][g]
+    int* scratch = reinterpret_cast<int*>(svq_all + kAtomsPerCta * 2 * kSvRow);
     const int tid = threadIdx.x;
     const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
     const int i = blockIdx.x * kAtomsPerCta + al;
@@ -114,6 +144,17 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
     const int len = atom_ok ? row_length(nb, i) : 0;
     const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
+    // agh (a,g,h) -> shared memory transposed to (a,h,g): the mixing epilogue reads 16 contiguous g per (a,h).  Made
+    // visible by the first __syncthreads of the pair loop (or the one before the epilogue when the loop is empty).
+    for (int e = tid; e < kA * kG * kH; e += 256) {
+        int a = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
+        aghT_a[(a * kH + hh) * kAghRow + gg] = agh_a[e];
+    }
+    if (with_q)
+        for (int e = tid; e < C * kG * kH; e += 256) {
+            int c = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
+            aghT_q[(c * kH + hh) * kAghRow + gg] = agh_q[e];
+        }
     // accumulators as (scalar, x) / (y, z) register pairs: the 8x4 outer-product update is 16 packed FFMA2 per pair
     float2 S01[kHalfA], S23[kHalfA];
 #pragma unroll
@@ -151,21 +192,22 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
         }
     }
     // ---- epilogue: scalar part straight to x, vector part through shared memory for the agh mixing ----
-    float* svl = sv[al];
+    __syncthreads();   // agh tables staged (covers maxlen == 0); nobody reads the pair tile any more
+    float* svl = sv_all + al * kSvAtom;
 #pragma unroll
     for (int a = 0; a < kHalfA; ++a) {
-        int aa = kHalfA * h + a;
-        svl[(aa * kG + g) * 3 + 0] = S01[a].y;
-        svl[(aa * kG + g) * 3 + 1] = S23[a].x;
-        svl[(aa * kG + g) * 3 + 2] = S23[a].y;
+        const int o = sv_off(kHalfA * h + a) + g;
+        svl[o] = S01[a].y;
+        svl[o + kG] = S23[a].x;
+        svl[o + 2 * kG] = S23[a].y;
     }
-    float* svql = svq[al];
+    float* svql = svq_all + al * 2 * kSvRow;
     if (with_q && h == 0) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            svql[(c * kG + g) * 3 + 0] = Sq01[c].y;
-            svql[(c * kG + g) * 3 + 1] = Sq23[c].x;
-            svql[(c * kG + g) * 3 + 2] = Sq23[c].y;
+            svql[c * kSvRow + g] = Sq01[c].y;
+            svql[c * kSvRow + kG + g] = Sq23[c].x;
+            svql[c * kSvRow + 2 * kG + g] = Sq23[c].y;
         }
     }
     if (atom_ok) {
@@ -191,45 +233,32 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
         for (int c = base + lane; c < ldx; c += 32) xr[c] = 0.f;
     }
     __syncwarp();
-    // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); each lane handles 6 (a,h) pairs
+    // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); each lane handles 6 (a,h) pairs: the 16
+    // weights and the three 16-vectors of Sv come in as 16-byte shared loads, the dot products run as packed FFMA2
     if (atom_ok) {
         float* xr = x + (size_t)i * ldx;
-#pragma unroll 1
+#pragma unroll 2
         for (int e = lane; e < kAH; e += 32) {
-            int a = e / kH, hh = e % kH;
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int gg = 0; gg < kG; ++gg) {
-                float w = agh_a[(a * kG + gg) * kH + hh];
-                const float* p = svl + (a * kG + gg) * 3;
-                t0 = fmaf(w, p[0], t0);
-                t1 = fmaf(w, p[1], t1);
-                t2 = fmaf(w, p[2], t2);
-            }
+            const int a = e / kH;
+            float t[3];
+            mix16(aghT_a + e * kAghRow, svl + sv_off(a), t);
             float* To = T_a + (size_t)i * kTA + e * 3;
-            To[0] = t0;
-            To[1] = t1;
-            To[2] = t2;
-            xr[2 * kAG + e] = t0 * t0 + t1 * t1 + t2 * t2;
+            To[0] = t[0];
+            To[1] = t[1];
+            To[2] = t[2];
+            xr[2 * kAG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
         }
         if (with_q) {
             int base = 2 * kAG + kAH;
             for (int e = lane; e < C * kH; e += 32) {
-                int c = e / kH, hh = e % kH;
-                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll
-                for (int gg = 0; gg < kG; ++gg) {
-                    float w = agh_q[(c * kG + gg) * kH + hh];
-                    const float* p = svql + (c * kG + gg) * 3;
-                    t0 = fmaf(w, p[0], t0);
-                    t1 = fmaf(w, p[1], t1);
-                    t2 = fmaf(w, p[2], t2);
-                }
+                const int c = e / kH;
+                float t[3];
+                mix16(aghT_q + e * kAghRow, svql + c * kSvRow, t);
                 float* To = T_q + (size_t)i * (C * kH * 3) + e * 3;
-                To[0] = t0;
-                To[1] = t1;
-                To[2] = t2;
-                xr[base + C + C * kG + e] = t0 * t0 + t1 * t1 + t2 * t2;
+                To[0] = t[0];
+                To[1] = t[1];
+                To[2] = t[2];
+                xr[base + C + C * kG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
             }
         }
     }
@@ -247,39 +276,57 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
                                                             const float* __restrict__ agh_a,
                                                             const float* __restrict__ agh_q, float* __restrict__ dS_a,
                                                             float* __restrict__ dS_q, int with_q) {
-    // one warp per atom, 8 atoms per block
-    __shared__ float dT_s[kAtomsPerCta][kTA];
-    __shared__ float dTq_s[kAtomsPerCta][2 * kH * 3];
+    // one warp per atom, 8 atoms per block.  agh is staged once per block in its natural (a,g,h) layout: a lane reads
+    // the 12 weights of its (a,g) as three 16-byte loads (row stride 12 words: 8 consecutive rows cover all banks);
+    // dT[a] (36 floats, row stride 36) comes in as nine 16-byte broadcast loads.
+    __shared__ __align__(16) float agh_s[kA * kG * kH];          // 12 KB
+    __shared__ __align__(16) float aghq_s[2 * kG * kH];
+    __shared__ __align__(16) float dT_s[kAtomsPerCta][kTA];
+    __shared__ __align__(16) float dTq_s[kAtomsPerCta][2 * kH * 3];
+    for (int e = threadIdx.x; e < kA * kG * kH / 4; e += 256)
+        reinterpret_cast<float4*>(agh_s)[e] = reinterpret_cast<const float4*>(agh_a)[e];
+    if (with_q)
+        for (int e = threadIdx.x; e < C * kG * kH; e += 256) aghq_s[e] = agh_q[e];
     const int al = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * kAtomsPerCta + al;
-    if (i >= n_atoms) return;
+    const bool atom_ok = i < n_atoms;
     float* dT = dT_s[al];
     float* dTq = dTq_s[al];
-    const float* dxr = dx + (size_t)i * ldx;
-    for (int e = lane; e < kTA; e += 32) dT[e] = 2.0f * T_a[(size_t)i * kTA + e] * dxr[2 * kAG + e / 3];
+    const float* dxr = dx + (size_t)(atom_ok ? i : 0) * ldx;
     const int base = 2 * kAG + kAH;
-    if (with_q)
-        for (int e = lane; e < C * kH * 3; e += 32)
-            dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
-    __syncwarp();
+    if (atom_ok) {
+        for (int e = lane; e < kTA; e += 32) dT[e] = 2.0f * T_a[(size_t)i * kTA + e] * dxr[2 * kAG + e / 3];
+        if (with_q)
+            for (int e = lane; e < C * kH * 3; e += 32)
+                dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
+    }
+    __syncthreads();
+    if (!atom_ok) return;
 #pragma unroll 2
     for (int k = 0; k < kAG / 32; ++k) {
-        int e = lane + 32 * k;
-        int aa = e >> 4, g = e & 15;
-        float4 o;
-        o.x = dxr[kAG + e];
+        const int e = lane + 32 * k;
+        const int aa = e >> 4;
+        const float4* w4 = reinterpret_cast<const float4*>(agh_s + e * kH);
+        const float4* t4 = reinterpret_cast<const float4*>(dT + aa * (kH * 3));
+        const float4 wa = w4[0], wb = w4[1], wc = w4[2];
+        const float w[kH] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+        float tv[kH * 3];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const float4 v = t4[j];
+            tv[4 * j + 0] = v.x;
+            tv[4 * j + 1] = v.y;
+            tv[4 * j + 2] = v.z;
+            tv[4 * j + 3] = v.w;
+        }
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
-            float w = agh_a[(aa * kG + g) * kH + h];
-            s0 = fmaf(w, dT[(aa * kH + h) * 3 + 0], s0);
-            s1 = fmaf(w, dT[(aa * kH + h) * 3 + 1], s1);
-            s2 = fmaf(w, dT[(aa * kH + h) * 3 + 2], s2);
+            s0 = fmaf(w[h], tv[3 * h + 0], s0);
+            s1 = fmaf(w[h], tv[3 * h + 1], s1);
+            s2 = fmaf(w[h], tv[3 * h + 2], s2);
         }
-        o.y = s0;
-        o.z = s1;
-        o.w = s2;
-        reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + e] = o;
+        reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + e] = make_float4(dxr[kAG + e], s0, s1, s2);
     }
     if (with_q && lane < C * kG) {
         int cc = lane >> 4, gq = lane & 15;
@@ -288,7 +335,7 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
         float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
-            float w = agh_q[(cc * kG + gq) * kH + h];
+            float w = aghq_s[(cc * kG + gq) * kH + h];
             q0 = fmaf(w, dTq[(cc * kH + h) * 3 + 0], q0);
             q1 = fmaf(w, dTq[(cc * kH + h) * 3 + 1], q1);
             q2 = fmaf(w, dTq[(cc * kH + h) * 3 + 2], q2);
@@ -560,8 +607,13 @@ static int conv_fwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q,
                            int with_q, cudaStream_t st) {
     int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    conv_fwd_kernel<C><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q,
-                                            with_q);
+    static bool configured = false;
+    if (!configured) {
+        AIM_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+        configured = true;
+    }
+    conv_fwd_kernel<C><<<grid, 256, kFwdSmemBytes, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx,
+                                                        T_a, T_q, with_q);
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }

@@ -142,7 +142,7 @@ struct Params {
     const float* a_inv;         // (M, lda_inv): 1 / s_a per row-chunk of A
     const float* aux;
     float* out_inv;             // split output: (M, ld_out_inv) inverse scales per row-chunk of Y
-    int lda_inv, ld_out_inv;
+    int lda_inv, ld_out_inv, ldaux;
     int M, N, K, mode;
     int bn;      // N-tile width (multiple of 32, <= 256): N is cut into equal tiles so that no CTA gets a sliver
     unsigned long long* trace;   // debug: per-stage SM-clock stamps of CTA 0 (8 events x kTraceLen), or nullptr
@@ -165,7 +165,8 @@ __device__ __forceinline__ void split_pair(float2 v, float sc, uint32_t& hi, uin
     const float2 sv = fmul2(v, make_float2(sc, sc));
     const __half2 h = __floats2half2_rn(sv.x, sv.y);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(sv.x - hf.x, sv.y - hf.y);
+    const float2 df = ffma2(hf, make_float2(-1.0f, -1.0f), sv);   // exact: hf is sv rounded to 11 bits
+    const __half2 l = __floats2half2_rn(df.x, df.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -296,10 +297,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         const int ch = warp >> 2;           // column half of the 256-wide accumulator
         const float w_inv = *p.w_inv_scale;
         int cit = 0;
-        uint32_t epi_phase = 0;
         unsigned char* box0 = epi_buf + warp * 2 * EPI_BOX;
         unsigned char* box1 = box0 + EPI_BOX;
-        uint64_t* ebar = &epi_bar[warp];
         const int rsw = (lane >> 1) & 3;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * p.bn;
@@ -359,8 +358,37 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             }
             // ---- tile epilogue.  Each thread holds one output row (lane) x 128 columns; a pair of 32-column groups is
             // one row-chunk (K=64) of the GEMM that consumes this output.  Rows are 1-3 KB apart in global memory, so
-            // everything goes through two 64B-swizzled 32-row shared-memory boxes per warp and leaves (or, for the aux
-            // operand of mode 3, arrives) as TMA bulk tensor copies: full 64-byte row segments, no LSU work.
+            // outputs go through 64B-swizzled 32-row shared-memory boxes and leave as TMA bulk tensor stores: full
+            // 64-byte row segments, no LSU work.  The two boxes of a warp form a ring: a box is rewritten only after the
+            // store issued from it two steps earlier has read it (wait_group.read 1), so the math of one 16-column step
+            // overlaps the store of the previous one.  The aux operand of mode 3 is prefetched into registers one
+            // 32-column group ahead with plain 16-byte loads (a thread reads 128 contiguous bytes of its own row).
+            int box_i = 0;
+            auto box_acquire = [&]() -> unsigned char* {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                unsigned char* bx = box_i ? box1 : box0;
+                box_i ^= 1;
+                return bx;
+            };
+            auto box_store = [&](const CUtensorMap* map, const unsigned char* bx, int c0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(map, bx, c0, row_base);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            };
+            float4 ax[8];   // mode 3: aux values of the current 32-column group
+            auto load_aux = [&](int g) {
+                const int col0 = ch * 128 + g * 32;
+                if (MODE == 3 && g < 4 && col0 < n_tile) {
+                    const float4* src = reinterpret_cast<const float4*>(p.aux + (size_t)min(row, p.M - 1) * p.ldaux + n0 + col0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ax[k] = __ldg(src + k);
+                }
+            };
+            load_aux(0);
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2) {
                 if (ch * 128 + c2 * 64 < n_tile) {
@@ -371,26 +399,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                             const int col = n0 + col0;
                             float2* v = &acc[c2 * 32 + hc * 16];
                             if (MODE == 3) {
-                                // aux block -> smem (the previous bulk stores must have finished reading the boxes)
-                                if (lane == 0) {
-                                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                                    mbar_expect_tx(ebar, 2 * EPI_BOX);
-                                    tma_load_2d(box0, &tmAux, ebar, col, row_base);
-                                    tma_load_2d(box1, &tmAux, ebar, col + 16, row_base);
-                                }
-                                mbar_wait(ebar, epi_phase);
-                                epi_phase ^= 1;
 #pragma unroll
-                                for (int hb = 0; hb < 2; ++hb) {
-                                    const unsigned char* bx = hb ? box1 : box0;
-#pragma unroll
-                                    for (int v4 = 0; v4 < 4; ++v4) {
-                                        float4 g = *reinterpret_cast<const float4*>(bx + lane * 64 + ((v4 ^ rsw) << 4));
-                                        v[hb * 8 + 2 * v4 + 0] = fmul2(v[hb * 8 + 2 * v4 + 0], make_float2(g.x, g.y));
-                                        v[hb * 8 + 2 * v4 + 1] = fmul2(v[hb * 8 + 2 * v4 + 1], make_float2(g.z, g.w));
-                                    }
+                                for (int k = 0; k < 8; ++k) {
+                                    v[2 * k + 0] = fmul2(v[2 * k + 0], make_float2(ax[k].x, ax[k].y));
+                                    v[2 * k + 1] = fmul2(v[2 * k + 1], make_float2(ax[k].z, ax[k].w));
                                 }
-                                __syncwarp();
+                                load_aux(c2 * 2 + hc + 1);
                             } else if (MODE == 1 || MODE == 2) {
 #pragma unroll
                                 for (int v4 = 0; v4 < 8; ++v4) {
@@ -401,47 +415,31 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                             }
                             if (MODE == 2) {
                                 // y = gelu(z) stays in the accumulator registers, gelu'(z) leaves as fp32 through the boxes
-                                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                                __syncwarp();
 #pragma unroll
                                 for (int hb = 0; hb < 2; ++hb) {
-                                    unsigned char* bx = hb ? box1 : box0;
+                                    float2 g[8];
 #pragma unroll
-                                    for (int v4 = 0; v4 < 4; ++v4) {
-                                        float2 g0, g1;
-                                        gelu_pair2(v[hb * 8 + 2 * v4 + 0], v[hb * 8 + 2 * v4 + 0], g0);
-                                        gelu_pair2(v[hb * 8 + 2 * v4 + 1], v[hb * 8 + 2 * v4 + 1], g1);
-                                        *reinterpret_cast<float4*>(bx + lane * 64 + ((v4 ^ rsw) << 4)) = make_float4(g0.x, g0.y, g1.x, g1.y);
-                                    }
-                                }
-                                if (p.aux != nullptr) {
-                                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                    __syncwarp();
-                                    if (lane == 0) {
-                                        tma_store_2d(&tmAux, box0, col, row_base);
-                                        tma_store_2d(&tmAux, box1, col + 16, row_base);
-                                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                    for (int k = 0; k < 8; ++k) gelu_pair2(v[hb * 8 + k], v[hb * 8 + k], g[k]);
+                                    if (p.aux != nullptr) {
+                                        unsigned char* bx = box_acquire();
+#pragma unroll
+                                        for (int v4 = 0; v4 < 4; ++v4)
+                                            *reinterpret_cast<float4*>(bx + lane * 64 + ((v4 ^ rsw) << 4)) =
+                                                make_float4(g[2 * v4].x, g[2 * v4].y, g[2 * v4 + 1].x, g[2 * v4 + 1].y);
+                                        box_store(&tmAux, bx, col + 16 * hb);
                                     }
                                 }
                             }
                             if (!SPLIT_OUT) {
-                                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                                __syncwarp();
 #pragma unroll
                                 for (int hb = 0; hb < 2; ++hb) {
-                                    unsigned char* bx = hb ? box1 : box0;
+                                    unsigned char* bx = box_acquire();
 #pragma unroll
                                     for (int v4 = 0; v4 < 4; ++v4) {
                                         const float2 z0 = v[hb * 8 + 2 * v4 + 0], z1 = v[hb * 8 + 2 * v4 + 1];
                                         *reinterpret_cast<float4*>(bx + lane * 64 + ((v4 ^ rsw) << 4)) = make_float4(z0.x, z0.y, z1.x, z1.y);
                                     }
-                                }
-                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                __syncwarp();
-                                if (lane == 0) {
-                                    tma_store_2d(&tmY, box0, col, row_base);
-                                    tma_store_2d(&tmY, box1, col + 16, row_base);
-                                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                    box_store(&tmY, bx, col + 16 * hb);
                                 }
                             }
                         }
@@ -463,21 +461,18 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                                 uint32_t hi[16], lo[16];
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) split_pair(v[hc * 16 + k], sc, hi[k], lo[k]);
-                                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                                __syncwarp();
+                                unsigned char* bh = box_acquire();
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int off = lane * 64 + ((j ^ rsw) << 4);
-                                    *reinterpret_cast<uint4*>(box0 + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                                    *reinterpret_cast<uint4*>(box1 + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                                }
-                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                __syncwarp();
-                                if (lane == 0) {
-                                    tma_store_2d(&tmY, box0, colp + hc * 32, row_base);
-                                    tma_store_2d(&tmY2, box1, colp + hc * 32, row_base);
-                                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                                }
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<uint4*>(bh + lane * 64 + ((j ^ rsw) << 4)) =
+                                        make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                box_store(&tmY, bh, colp + hc * 32);
+                                unsigned char* bl = box_acquire();
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<uint4*>(bl + lane * 64 + ((j ^ rsw) << 4)) =
+                                        make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                                box_store(&tmY2, bl, colp + hc * 32);
                             }
                         }
                     }
@@ -689,7 +684,7 @@ int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const floa
     } else {
         tmAux = tmY;
     }
-    Params p{bias, w_inv_scale, A.inv, aux, Ysplit ? Ysplit->inv : nullptr, A.ldinv, Ysplit ? Ysplit->ldinv : 0, M, N, K, mode, bn,
+    Params p{bias, w_inv_scale, A.inv, aux, Ysplit ? Ysplit->inv : nullptr, A.ldinv, Ysplit ? Ysplit->ldinv : 0, ldaux, M, N, K, mode, bn,
              g_trace};
     int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
