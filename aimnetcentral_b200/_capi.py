@@ -48,7 +48,6 @@ class System(C.Structure):
         ("coord", C.c_void_p), ("numbers", C.c_void_p), ("mol_idx", C.c_void_p), ("charge", C.c_void_p),
         ("mult", C.c_void_p), ("cell", C.c_void_p), ("host_cell", C.c_void_p), ("n_cells", C.c_int),
         ("pbc_host", C.c_void_p), ("nbmat", C.c_void_p), ("shifts", C.c_void_p), ("nb_width", C.c_int),
-        ("max_mol_atoms", C.c_int),
     ]
 
 
@@ -64,7 +63,7 @@ _LIB = None
 EXPORTS = [
     "aimnet2_last_error", "aimnet2_abi_version", "aimnet2_neighbor_matrix", "aimnet2_wrap_positions",
     "aimnet2_conv_sv_2d_sp_fwd", "aimnet2_conv_sv_2d_sp_bwd", "aimnet2_engine_create", "aimnet2_engine_destroy",
-    "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_deterministic", "aimnet2_engine_set_dense_conv", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
+    "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
     "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_enable_timing",
     "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace",
 ]
@@ -97,7 +96,6 @@ def load():
     lib.aimnet2_engine_set_options.argtypes = [vp, C.POINTER(Options)]
     lib.aimnet2_engine_set_gemm_backend.argtypes = [vp, ci]
     lib.aimnet2_engine_set_deterministic.argtypes = [vp, ci]
-    lib.aimnet2_engine_set_dense_conv.argtypes = [vp, ci]
     lib.aimnet2_engine_eval.argtypes = [vp, C.POINTER(System), C.POINTER(Result), ci, vp]
     lib.aimnet2_engine_eval_host.argtypes = [vp, C.POINTER(System), C.POINTER(Result), ci]
     lib.aimnet2_engine_last_launches.argtypes = [vp]

@@ -235,17 +235,6 @@ class AIMNet2Calculator:
                           UserWarning, stacklevel=3)
 
     # ---- evaluation ------------------------------------------------------------------------------------------
-    def _max_mol_size(self, mol_idx: Tensor) -> int:
-        """Atoms in the largest molecule of a flat batch (one small device reduction + read-back, cached per mol_idx
-        tensor): the counterpart of the reference's _max_mol_size bookkeeping (calculator.py:1495-1509)."""
-        key = (mol_idx.data_ptr(), tuple(mol_idx.shape), int(mol_idx._version))
-        cached = getattr(self, "_max_mol_cache", None)
-        if cached is not None and cached[0] == key:
-            return cached[1]
-        n = int(torch.bincount(mol_idx.to(torch.int64)).max()) if mol_idx.numel() else 0
-        self._max_mol_cache = (key, n)
-        return n
-
     def __call__(self, *args, **kwargs) -> dict[str, Any]:
         return self.eval(*args, **kwargs)
 
@@ -291,12 +280,10 @@ class AIMNet2Calculator:
         # ---- flatten (mol_flatten, calculator.py:1475-1511): the engine always runs the sparse layout ----
         batch_shape = None
         keep = None
-        max_mol = 0   # hint for the engine: molecules of <= 64 atoms take the dense-molecule conv kernels
         mult = d.get("mult")
         if coord.ndim == 3:
             Bn, Nn = coord.shape[:2]
             batch_shape = (Bn, Nn)
-            max_mol = int(Nn)
             numbers2 = numbers.reshape(Bn, Nn)
             real = numbers2 > 0
             mol_idx = torch.arange(Bn, device=self.device, dtype=torch.int32).unsqueeze(1).expand(Bn, Nn)
@@ -314,10 +301,6 @@ class AIMNet2Calculator:
             mol_f = d.get("mol_idx")
             if mol_f is None and charge.shape[0] != 1:
                 raise ValueError("mol_idx is required when charge has more than one entry")
-            if mol_f is None:
-                max_mol = int(coord.shape[0])
-            elif cell is None:
-                max_mol = self._max_mol_size(mol_f)
         coord_f = coord_f.contiguous()
         numbers_f = numbers_f.to(torch.int32).contiguous()
         mol_f = None if mol_f is None else mol_f.to(torch.int32).contiguous()
@@ -338,8 +321,7 @@ class AIMNet2Calculator:
             self._push_options(coulomb_override=method)
         try:
             out = self.engine.eval(coord_f, numbers_f, charge, mol_idx=mol_f, mult=mult, cell=cell, pbc=d.get("pbc"),
-                                   nbmat=nbmat, shifts=shifts, forces=bool(forces), stress=bool(stress),
-                                   max_mol_atoms=max_mol)
+                                   nbmat=nbmat, shifts=shifts, forces=bool(forces), stress=bool(stress))
         finally:
             if method != self._coulomb_method:
                 self._push_options()

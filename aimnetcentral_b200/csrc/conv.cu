@@ -22,6 +22,8 @@
 // Layout of one MLP input row x (ld = ldx, zero padded):
 //   [0,256)   a[i] flat (a*16+g)            [256,512) S_s[a,g]          [512,704) avf_v[a,h]
 //   pass>0:   [704,704+C) q[i,c]            [704+C, 704+17C) Sq_s[c,g]  [704+17C, 704+29C) avfq_v[c,h]
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace aimnet {
@@ -105,17 +107,6 @@ __device__ __forceinline__ int row_length(const NbView& nb, int i) {
     return nb.count ? min(nb.count[i], nb.width) : nb.width;
 }
 
-__device__ __forceinline__ int block_max_int(int v, int* scratch) {
-    // value is warp-uniform (one atom per warp)
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int r = scratch[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) r = max(r, scratch[k]);
-    __syncthreads();
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
@@ -134,7 +125,6 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
     float* aghT_q = aghT_a + kA * kH * kAghRow;                                      // [c][h][g]
     float* sv_all = aghT_q + 2 * kH * kAghRow;                                       // [atom][a][k][g], see sv_off()
     float* svq_all = sv_all + kAtomsPerCta * kSvAtom;                                // [atom][c][k][g]
-    int* scratch = reinterpret_cast<int*>(svq_all + kAtomsPerCta * 2 * kSvRow);
     const int tid = threadIdx.x;
     const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
     const int i = blockIdx.x * kAtomsPerCta + al;
@@ -142,10 +132,9 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
     const int ic = atom_ok ? i : 0;
     const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
     const int len = atom_ok ? row_length(nb, i) : 0;
-    const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
     // agh (a,g,h) -> shared memory transposed to (a,h,g): the mixing epilogue reads 16 contiguous g per (a,h).  Made
-    // visible by the first __syncthreads of the pair loop (or the one before the epilogue when the loop is empty).
+    // visible by the __syncthreads before the epilogue.
     for (int e = tid; e < kA * kG * kH; e += 256) {
         int a = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
         aghT_a[(a * kH + hh) * kAghRow + gg] = agh_a[e];
@@ -162,10 +151,11 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
     float2 Sq01[C], Sq23[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) Sq01[c] = Sq23[c] = make_float2(0.f, 0.f);
-    for (int m0 = 0; m0 < maxlen; m0 += kSlotsPerTile) {
-        __syncthreads();
+    // every warp stages the 32 slots of its own atom (thread = slot) and reads only those: warp-level sync is enough
+    for (int m0 = 0; m0 < len; m0 += kSlotsPerTile) {
+        __syncwarp();
         stage_pairs<false>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
-        __syncthreads();
+        __syncwarp();
         int lim = min(kSlotsPerTile, len - m0);
 #pragma unroll 2
         for (int s = 0; s < lim; ++s) {
@@ -192,7 +182,7 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
         }
     }
     // ---- epilogue: scalar part straight to x, vector part through shared memory for the agh mixing ----
-    __syncthreads();   // agh tables staged (covers maxlen == 0); nobody reads the pair tile any more
+    __syncthreads();   // agh tables staged
     float* svl = sv_all + al * kSvAtom;
 #pragma unroll
     for (int a = 0; a < kHalfA; ++a) {
@@ -359,7 +349,6 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
                                                           float* __restrict__ grad_q, float* __restrict__ forces,
                                                           double* __restrict__ virial_atom, int with_q) {
     __shared__ PairEntry tile[256];
-    __shared__ int scratch[8];
     const int tid = threadIdx.x;
     const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
     const int i = blockIdx.x * kAtomsPerCta + al;
@@ -367,7 +356,6 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
     const int ic = atom_ok ? i : 0;
     const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
     const int len = atom_ok ? row_length(nb, i) : 0;
-    const int maxlen = block_max_int(len, scratch);
     const float shift_g = aev.shifts[g];
     // own atom: dS_i[a][g][d] (as (scalar,x) / (y,z) register pairs) and a_i[a][g] for this thread's 8 channels
     float2 dSi01[kHalfA], dSi23[kHalfA];
@@ -409,10 +397,10 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
 #pragma unroll
     for (int k = 0; k < 9; ++k) vir[k] = 0.f;
 
-    for (int m0 = 0; m0 < maxlen; m0 += kSlotsPerTile) {
-        __syncthreads();
+    for (int m0 = 0; m0 < len; m0 += kSlotsPerTile) {   // per-warp staging: see conv_fwd_kernel
+        __syncwarp();
         stage_pairs<true>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
-        __syncthreads();
+        __syncwarp();
         int lim = min(kSlotsPerTile, len - m0);
         for (int s = 0; s < lim; ++s) {
             const PairEntry e = tile[al * 32 + s];
@@ -530,396 +518,6 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Dense-molecule variants (isolated molecules of at most kDenseMaxMol atoms, the analogue of the reference's dense
-// mode 0 for small molecules, aimnet/calculators/calculator.py:1495-1509 / aimnet/nbops.py:61-75).
-//
-// The gather kernels above are bound by L1 wavefronts: every (i, j) pair pulls a[j] (1 KB) and, in the backward pass,
-// dS[j] (4 KB) through the L1 data stage.  Atoms of one small molecule all see (nearly) the same neighbours, so here a
-// warp owns TWO centre atoms and walks the molecule's atom segment j = mol_ptr[m] .. mol_ptr[m+1] instead of a list
-// row: every lane keeps the accumulators of both atoms for its (half of the channels, g), so one gathered a[j] / dS[j]
-// register tile feeds two pairs: half the L1 wavefronts and load instructions per pair.  (Sharing the load between the
-// two half-warps instead does nothing: a 16-byte warp load is four quarter-warp wavefronts whatever the addresses are
-// -- measured, profiles/README.md.)  Pairs beyond the
-// cutoff, j == i and atoms of another molecule (a warp may straddle a molecule boundary) get fc = 0, which zeroes every
-// contribution exactly as the reference's masks do; slots where both atoms have fc = 0 are skipped by a warp vote.
-// Pair staging is per warp (__syncwarp only), CTAs are persistent and stage the agh tables once.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kDenseAtomsPerCta = 16;
-constexpr int kDenseFwdSmemBytes = 8 * 2 * 32 * 32 + (kA + 2) * kH * kAghRow * 4 + kDenseAtomsPerCta * (kSvAtom + 2 * kSvRow) * 4;
-
-template <bool kWithDeriv>
-__device__ __forceinline__ PairEntry dense_entry(const float* __restrict__ coord, int i, int j, bool ok, const AevParams& aev) {
-    float rx = 1.f, ry = 1.f, rz = 1.f;
-    if (ok) pair_vector(coord, i, j, nullptr, nullptr, rx, ry, rz);
-    float d = sqrtf(rx * rx + ry * ry + rz * rz);
-    float inv = 1.0f / d;
-    float dc = fminf(fmaxf(d, 1e-6f), aev.rc);
-    float sn, cs;
-    sincosf(dc * (kPi / aev.rc), &sn, &cs);
-    PairEntry e;
-    e.ux = rx * inv;
-    e.uy = ry * inv;
-    e.uz = rz * inv;
-    e.d = d;
-    e.fc = (ok && d < aev.rc) ? 0.5f * (cs + 1.0f) : 0.f;
-    e.dfc = (kWithDeriv && ok && d > 1e-6f && d < aev.rc) ? -0.5f * (kPi / aev.rc) * sn : 0.f;
-    e.j = j;
-    e.inv = inv;
-    return e;
-}
-
-// stage slots [m0, m0+32) of the warp's j range for both of its atoms
-template <bool kWithDeriv>
-__device__ __forceinline__ void dense_stage(PairEntry* wtile, const float* __restrict__ coord, int n_atoms, int i0, int m0,
-                                            int je, const int* mb, const int* me, const AevParams& aev) {
-    const int lane = threadIdx.x & 31;
-    const int j = m0 + lane;
-#pragma unroll
-    for (int a2 = 0; a2 < 2; ++a2) {
-        const int ia = i0 + a2;
-        const bool ok = ia < n_atoms && j < je && j >= mb[a2] && j < me[a2] && j != ia;
-        wtile[a2 * 32 + lane] = dense_entry<kWithDeriv>(coord, ia < n_atoms ? ia : 0, ok ? j : 0, ok, aev);
-    }
-}
-
-template <int C>
-__global__ void __launch_bounds__(256, 2) conv_fwd_dense_kernel(int n_atoms, int n_groups, const float* __restrict__ coord,
-                                                                const int32_t* __restrict__ mol_idx,
-                                                                const int32_t* __restrict__ mol_ptr, AevParams aev,
-                                                                const float* __restrict__ aT, const float* __restrict__ q,
-                                                                const float* __restrict__ agh_a,
-                                                                const float* __restrict__ agh_q, float* __restrict__ x,
-                                                                int ldx, float* __restrict__ T_a, float* __restrict__ T_q,
-                                                                int with_q) {
-    extern __shared__ __align__(16) unsigned char fwd_smem[];
-    PairEntry* tile = reinterpret_cast<PairEntry*>(fwd_smem);                            // [warp][atom][slot]
-    float* aghT_a = reinterpret_cast<float*>(fwd_smem + sizeof(PairEntry) * 8 * 64);     // [a][h][g], row stride kAghRow
-    float* aghT_q = aghT_a + kA * kH * kAghRow;
-    float* sv_all = aghT_q + 2 * kH * kAghRow;                                           // [atom][a][k][g]
-    float* svq_all = sv_all + kDenseAtomsPerCta * kSvAtom;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
-    for (int e = tid; e < kA * kG * kH; e += 256) {
-        int a = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
-        aghT_a[(a * kH + hh) * kAghRow + gg] = agh_a[e];
-    }
-    if (with_q)
-        for (int e = tid; e < C * kG * kH; e += 256) {
-            int c = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
-            aghT_q[(c * kH + hh) * kAghRow + gg] = agh_q[e];
-        }
-    __syncthreads();
-    PairEntry* wtile = tile + warp * 64;
-    const float shift_g = aev.shifts[g];
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int i0 = grp * kDenseAtomsPerCta + 2 * warp;
-        if (i0 >= n_atoms) continue;
-        int mb[2], me[2];
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-            const int ia = min(i0 + a2, n_atoms - 1);
-            const int m = mol_idx ? mol_idx[ia] : 0;
-            mb[a2] = mol_ptr[m];
-            me[a2] = mol_ptr[m + 1];
-        }
-        const int jb = mb[0], je = me[1];
-        // [atom][channel] accumulators as (scalar, x) / (y, z) register pairs
-        float2 S01[2][kHalfA], S23[2][kHalfA];
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2)
-#pragma unroll
-            for (int a = 0; a < kHalfA; ++a) S01[a2][a] = S23[a2][a] = make_float2(0.f, 0.f);
-        float2 Sq01[2][C], Sq23[2][C];
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2)
-#pragma unroll
-            for (int c = 0; c < C; ++c) Sq01[a2][c] = Sq23[a2][c] = make_float2(0.f, 0.f);
-        for (int m0 = jb; m0 < je; m0 += 32) {
-            __syncwarp();
-            dense_stage<false>(wtile, coord, n_atoms, i0, m0, je, mb, me, aev);
-            __syncwarp();
-            const int lim = min(32, je - m0);
-#pragma unroll 2
-            for (int s = 0; s < lim; ++s) {
-                const PairEntry e0 = wtile[s], e1 = wtile[32 + s];
-                if (e0.fc == 0.f && e1.fc == 0.f) continue;   // warp-uniform: the entries are broadcast reads
-                const int j = m0 + s;
-                const float4* row = reinterpret_cast<const float4*>(aT + (size_t)j * kAG) + g + 32 * h;
-                const float4 v0 = row[0], v1 = row[16];
-                const float av[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                float qj[C];
-                if (with_q) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) qj[c] = q[(size_t)j * C + c];
-                }
-#pragma unroll
-                for (int a2 = 0; a2 < 2; ++a2) {
-                    const PairEntry& e = a2 ? e1 : e0;
-                    float xg = e.d - shift_g;
-                    float w0 = aev_exp(-aev.eta * xg * xg) * e.fc;
-                    const float2 w01 = make_float2(w0, w0 * e.ux), w23 = make_float2(w0 * e.uy, w0 * e.uz);
-#pragma unroll
-                    for (int a = 0; a < kHalfA; ++a) {
-                        S01[a2][a] = ffma2s(av[a], w01, S01[a2][a]);
-                        S23[a2][a] = ffma2s(av[a], w23, S23[a2][a]);
-                    }
-                    if (with_q) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            Sq01[a2][c] = ffma2s(qj[c], w01, Sq01[a2][c]);
-                            Sq23[a2][c] = ffma2s(qj[c], w23, Sq23[a2][c]);
-                        }
-                    }
-                }
-            }
-        }
-        // ---- epilogue (warp-local): scalar part straight to x, vector part through shared memory for the agh mixing
-        float* svw = sv_all + (2 * warp) * kSvAtom;      // this warp's two atoms
-        float* svqw = svq_all + (2 * warp) * 2 * kSvRow;
-        __syncwarp();
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-            float* svl = svw + a2 * kSvAtom;
-#pragma unroll
-            for (int a = 0; a < kHalfA; ++a) {
-                const int o = sv_off(kHalfA * h + a) + g;
-                svl[o] = S01[a2][a].y;
-                svl[o + kG] = S23[a2][a].x;
-                svl[o + 2 * kG] = S23[a2][a].y;
-            }
-            if (with_q && h == 0) {
-                float* svql = svqw + a2 * 2 * kSvRow;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    svql[c * kSvRow + g] = Sq01[a2][c].y;
-                    svql[c * kSvRow + kG + g] = Sq23[a2][c].x;
-                    svql[c * kSvRow + 2 * kG + g] = Sq23[a2][c].y;
-                }
-            }
-            const int i = i0 + a2;
-            if (i < n_atoms) {
-                float* xr = x + (size_t)i * ldx;
-                const float4* own = reinterpret_cast<const float4*>(aT + (size_t)i * kAG) + g + 32 * h;
-                const float4 o0 = own[0], o1 = own[16];
-                const float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-                for (int a = 0; a < kHalfA; ++a) {
-                    const int aa = kHalfA * h + a;
-                    xr[aa * kG + g] = ov[a];
-                    xr[kAG + aa * kG + g] = S01[a2][a].x;
-                }
-                int base = 2 * kAG + kAH;
-                if (with_q) {
-                    if (lane < C) xr[base + lane] = q[(size_t)i * C + lane];
-                    if (h == 0) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq01[a2][c].x;
-                    }
-                    base += C * (1 + kG + kH);
-                }
-                for (int c = base + lane; c < ldx; c += 32) xr[c] = 0.f;
-            }
-        }
-        __syncwarp();
-        // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]: all 32 lanes work on atom 0's 192 (a,h) pairs, then on atom 1's
-#pragma unroll 1
-        for (int a2 = 0; a2 < 2; ++a2) {
-            const int ia = i0 + a2;
-            if (ia >= n_atoms) break;
-            float* xr = x + (size_t)ia * ldx;
-            const float* svl = svw + a2 * kSvAtom;
-#pragma unroll 2
-            for (int e = lane; e < kAH; e += 32) {
-                float t[3];
-                mix16(aghT_a + e * kAghRow, svl + sv_off(e / kH), t);
-                float* To = T_a + (size_t)ia * kTA + e * 3;
-                To[0] = t[0];
-                To[1] = t[1];
-                To[2] = t[2];
-                xr[2 * kAG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
-            }
-            if (with_q) {
-                const int base = 2 * kAG + kAH;
-                const float* svql = svqw + a2 * 2 * kSvRow;
-                for (int e = lane; e < C * kH; e += 32) {
-                    float t[3];
-                    mix16(aghT_q + e * kAghRow, svql + (e / kH) * kSvRow, t);
-                    float* To = T_q + (size_t)ia * (C * kH * 3) + e * 3;
-                    To[0] = t[0];
-                    To[1] = t[1];
-                    To[2] = t[2];
-                    xr[base + C + C * kG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
-                }
-            }
-        }
-    }
-}
-
-template <int C, bool kGradA>
-__global__ void __launch_bounds__(256, 1) conv_bwd_dense_kernel(int n_atoms, int n_groups, const float* __restrict__ coord,
-                                                                const int32_t* __restrict__ mol_idx,
-                                                                const int32_t* __restrict__ mol_ptr, AevParams aev,
-                                                                const float* __restrict__ aT, const float* __restrict__ q,
-                                                                const float* __restrict__ dS_a,
-                                                                const float* __restrict__ dS_q, float* __restrict__ grad_a,
-                                                                float* __restrict__ grad_q, float* __restrict__ forces,
-                                                                int with_q) {
-    __shared__ PairEntry tile[8 * 64];   // [warp][atom][slot]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
-    PairEntry* wtile = tile + warp * 64;
-    const float shift_g = aev.shifts[g];
-    const float4* dS4 = reinterpret_cast<const float4*>(dS_a);
-    const float4* dSq4 = reinterpret_cast<const float4*>(dS_q);
-    const bool qhalf = with_q && h == 0;   // the charge channels are handled by the h == 0 half only
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int i0 = grp * kDenseAtomsPerCta + 2 * warp;
-        if (i0 >= n_atoms) continue;
-        int mb[2], me[2];
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-            const int ia = min(i0 + a2, n_atoms - 1);
-            const int m = mol_idx ? mol_idx[ia] : 0;
-            mb[a2] = mol_ptr[m];
-            me[a2] = mol_ptr[m + 1];
-        }
-        const int jb = mb[0], je = me[1];
-        // own atoms: dS_i[a][g][d] as (scalar,x) / (y,z) register pairs and a_i[a][g] for this thread's 8 channels
-        float2 dSi01[2][kHalfA], dSi23[2][kHalfA];
-        float ai[2][kHalfA];
-        float2 dSqi01[2][C], dSqi23[2][C];
-        float qi[2][C];
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-            const int ic = min(i0 + a2, n_atoms - 1);
-            const float4* p = dS4 + (size_t)ic * kAG + (kHalfA * h) * kG + g;
-#pragma unroll
-            for (int a = 0; a < kHalfA; ++a) {
-                const float4 v = p[a * kG];
-                dSi01[a2][a] = make_float2(v.x, v.y);
-                dSi23[a2][a] = make_float2(v.z, v.w);
-            }
-            const float4* r = reinterpret_cast<const float4*>(aT + (size_t)ic * kAG) + g + 32 * h;
-            const float4 o0 = r[0], o1 = r[16];
-            const float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-            for (int a = 0; a < kHalfA; ++a) ai[a2][a] = ov[a];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float4 v = qhalf ? dSq4[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
-                dSqi01[a2][c] = make_float2(v.x, v.y);
-                dSqi23[a2][c] = make_float2(v.z, v.w);
-                qi[a2][c] = qhalf ? q[(size_t)ic * C + c] : 0.f;
-            }
-        }
-        float2 ga2[2][kHalfA];
-        float2 gq2[2][C];
-        float fx[2] = {0.f, 0.f}, fy[2] = {0.f, 0.f}, fz[2] = {0.f, 0.f};
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-#pragma unroll
-            for (int a = 0; a < kHalfA; ++a) ga2[a2][a] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < C; ++c) gq2[a2][c] = make_float2(0.f, 0.f);
-        }
-        for (int m0 = jb; m0 < je; m0 += 32) {
-            __syncwarp();
-            dense_stage<true>(wtile, coord, n_atoms, i0, m0, je, mb, me, aev);
-            __syncwarp();
-            const int lim = min(32, je - m0);
-            for (int s = 0; s < lim; ++s) {
-                const PairEntry e0 = wtile[s], e1 = wtile[32 + s];
-                if (e0.fc == 0.f && e1.fc == 0.f) continue;   // warp-uniform: the entries are broadcast reads
-                const int j = m0 + s;
-                const float4* arow = reinterpret_cast<const float4*>(aT + (size_t)j * kAG) + g + 32 * h;
-                const float4* drow = dS4 + (size_t)j * kAG + (kHalfA * h) * kG + g;
-                const float4 v0 = arow[0], v1 = arow[16];
-                const float aj[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                float4 dj[kHalfA];
-#pragma unroll
-                for (int a = 0; a < kHalfA; ++a) dj[a] = drow[a * kG];
-                float qj[C];
-                float4 dqj[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    qj[c] = qhalf ? q[(size_t)j * C + c] : 0.f;
-                    dqj[c] = qhalf ? dSq4[(size_t)j * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int a2 = 0; a2 < 2; ++a2) {
-                    const PairEntry& e = a2 ? e1 : e0;
-                    float xg = e.d - shift_g;
-                    float ex = aev_exp(-aev.eta * xg * xg);
-                    float gs = ex * e.fc;
-                    float dgs = ex * (e.dfc - 2.0f * aev.eta * xg * e.fc);
-                    const float2 G01 = make_float2(gs, -gs * e.ux), G23 = make_float2(-gs * e.uy, -gs * e.uz);
-                    float2 p01 = make_float2(0.f, 0.f), p23 = p01, r01 = p01, r23 = p01;
-#pragma unroll
-                    for (int a = 0; a < kHalfA; ++a) {
-                        const float2 dj01 = make_float2(dj[a].x, dj[a].y), dj23 = make_float2(dj[a].z, dj[a].w);
-                        if (kGradA) {
-                            ga2[a2][a] = ffma2(dj01, G01, ga2[a2][a]);
-                            ga2[a2][a] = ffma2(dj23, G23, ga2[a2][a]);
-                        }
-                        p01 = ffma2s(aj[a], dSi01[a2][a], p01);
-                        p23 = ffma2s(aj[a], dSi23[a2][a], p23);
-                        r01 = ffma2s(ai[a2][a], dj01, r01);
-                        r23 = ffma2s(ai[a2][a], dj23, r23);
-                    }
-                    if (qhalf) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float2 dq01 = make_float2(dqj[c].x, dqj[c].y), dq23 = make_float2(dqj[c].z, dqj[c].w);
-                            if (kGradA) {
-                                gq2[a2][c] = ffma2(dq01, G01, gq2[a2][c]);
-                                gq2[a2][c] = ffma2(dq23, G23, gq2[a2][c]);
-                            }
-                            p01 = ffma2s(qj[c], dSqi01[a2][c], p01);
-                            p23 = ffma2s(qj[c], dSqi23[a2][c], p23);
-                            r01 = ffma2s(qi[a2][c], dq01, r01);
-                            r23 = ffma2s(qi[a2][c], dq23, r23);
-                        }
-                    }
-                    const float gsi = gs * e.inv;
-                    float pu = p01.y * e.ux + p23.x * e.uy + p23.y * e.uz;
-                    float sc = (p01.x + pu) * dgs - pu * gsi;
-                    float ru = r01.y * e.ux + r23.x * e.uy + r23.y * e.uz;
-                    float scr = (ru - r01.x) * dgs - ru * gsi;
-                    float ds = sc - scr;
-                    fx[a2] += fmaf(e.ux, ds, (p01.y - r01.y) * gsi);
-                    fy[a2] += fmaf(e.uy, ds, (p23.x - r23.x) * gsi);
-                    fz[a2] += fmaf(e.uz, ds, (p23.y - r23.y) * gsi);
-                }
-            }
-        }
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-            const int i = i0 + a2;
-            float sx = warp_sum(fx[a2]), sy = warp_sum(fy[a2]), sz = warp_sum(fz[a2]);
-            float gq[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) gq[c] = (kGradA && with_q) ? warp_sum(gq2[a2][c].x + gq2[a2][c].y) : 0.f;
-            if (i < n_atoms) {
-                if (kGradA) {
-#pragma unroll
-                    for (int a = 0; a < kHalfA; ++a)
-                        grad_a[(size_t)i * kAG + (kHalfA * h + a) * kG + g] = ga2[a2][a].x + ga2[a2][a].y;
-                    if (with_q && lane < C) {
-                        float v = gq[0];
-#pragma unroll
-                        for (int c = 1; c < C; ++c) v = (lane == c) ? gq[c] : v;
-                        grad_q[(size_t)i * C + lane] = v;
-                    }
-                }
-                if (lane == 0) {
-                    forces[3 * i + 0] += sx;
-                    forces[3 * i + 1] += sy;
-                    forces[3 * i + 2] += sz;
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // operator seam: conv_sv_2d_sp with an explicit g tensor (aimnet/kernels/conv_sv_2d_sp_wp.py:90-164)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void conv_op_fwd_kernel(const float* __restrict__ a, const int32_t* __restrict__ idx,
@@ -1008,43 +606,10 @@ static int conv_fwd_launch(int n_atoms, const NbView& nb, const float* coord, co
     return AIMNET_OK;
 }
 
-static int dense_grid(int n_groups, int ctas_per_sm) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            num_sms = 148;
-    }
-    return n_groups < num_sms * ctas_per_sm ? n_groups : num_sms * ctas_per_sm;
-}
-
-template <int C>
-static int conv_fwd_dense_launch(int n_atoms, const float* coord, const int32_t* mol_idx, const int32_t* mol_ptr,
-                                 const AevParams& aev, const float* aT, const float* q, const float* agh_a,
-                                 const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        AIM_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_dense_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseFwdSmemBytes));
-        configured = true;
-    }
-    int n_groups = (n_atoms + kDenseAtomsPerCta - 1) / kDenseAtomsPerCta;
-    conv_fwd_dense_kernel<C><<<dense_grid(n_groups, 2), 256, kDenseFwdSmemBytes, st>>>(n_atoms, n_groups, coord, mol_idx, mol_ptr, aev, aT, q,
-                                                                                       agh_a, agh_q, x, ldx, T_a, T_q, with_q);
-    AIM_LAUNCH_CHECK();
-    return AIMNET_OK;
-}
-
-// dense != 0: isolated molecules of at most kDenseMaxMol atoms, walk the molecule segment (mol_ptr) instead of nb rows
 int launch_conv_fwd(int C, int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
                     const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q, const float* agh_a,
-                    const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q, const int32_t* mol_ptr,
-                    int dense, cudaStream_t st) {
+                    const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q, cudaStream_t st) {
     if (n_atoms == 0) return AIMNET_OK;
-    if (dense) {
-        if (C == 1)
-            return conv_fwd_dense_launch<1>(n_atoms, coord, mol_idx, mol_ptr, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q, with_q, st);
-        return conv_fwd_dense_launch<2>(n_atoms, coord, mol_idx, mol_ptr, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q, with_q, st);
-    }
     if (C == 1)
         return conv_fwd_launch<1>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q, with_q, st);
     return conv_fwd_launch<2>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx, T_a, T_q, with_q, st);
@@ -1055,23 +620,10 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
                            const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                            const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
-                           double* virial_atom, int with_q, int want_grad_a, const int32_t* mol_ptr, int dense,
-                           cudaStream_t st) {
+                           double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
     conv_bwd_prep_kernel<C><<<(n_atoms + kAtomsPerCta - 1) / kAtomsPerCta, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a,
                                                                                           agh_q, dS_a, dS_q, with_q);
     AIM_LAUNCH_CHECK();
-    if (dense) {
-        int n_groups = (n_atoms + kDenseAtomsPerCta - 1) / kDenseAtomsPerCta;
-        int grid = dense_grid(n_groups, 1);
-        if (want_grad_a)
-            conv_bwd_dense_kernel<C, true><<<grid, 256, 0, st>>>(n_atoms, n_groups, coord, mol_idx, mol_ptr, aev, aT, q, dS_a, dS_q,
-                                                                grad_a, grad_q, forces, with_q);
-        else
-            conv_bwd_dense_kernel<C, false><<<grid, 256, 0, st>>>(n_atoms, n_groups, coord, mol_idx, mol_ptr, aev, aT, q, dS_a, dS_q,
-                                                                 grad_a, grad_q, forces, with_q);
-        AIM_LAUNCH_CHECK();
-        return AIMNET_OK;
-    }
     int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
 #define AIM_CONV_BWD(GA, VIR)                                                                                       \
     conv_bwd_kernel<C, GA, VIR><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a, \
@@ -1091,13 +643,13 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
                     const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q, const float* dx,
                     int ldx, const float* T_a, const float* T_q, const float* agh_a, const float* agh_q, float* dS_a,
                     float* dS_q, float* grad_a, float* grad_q, float* forces, double* virial_atom, int with_q,
-                    int want_grad_a, const int32_t* mol_ptr, int dense, cudaStream_t st) {
+                    int want_grad_a, cudaStream_t st) {
     if (n_atoms == 0) return AIMNET_OK;
     if (C == 1)
         return conv_bwd_launch<1>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q,
-                                  grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, mol_ptr, dense, st);
+                                  grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, st);
     return conv_bwd_launch<2>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q,
-                              grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, mol_ptr, dense, st);
+                              grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, st);
 }
 
 }  // namespace aimnet

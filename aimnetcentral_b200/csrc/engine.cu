@@ -24,11 +24,10 @@ int neighbor_matrix_impl(const float*, int, float, const float*, const float*, c
 int wrap_positions_impl(const float*, float*, int, const float*, int, const uint8_t*, const int32_t*, cudaStream_t);
 int launch_conv_fwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
                     const float*, const float*, const float*, const float*, float*, int, float*, float*, int,
-                    const int32_t*, int, cudaStream_t);
+                    cudaStream_t);
 int launch_conv_bwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
                     const float*, const float*, const float*, int, const float*, const float*, const float*,
-                    const float*, float*, float*, float*, float*, float*, double*, int, int, const int32_t*, int,
-                    cudaStream_t);
+                    const float*, float*, float*, float*, float*, float*, double*, int, int, cudaStream_t);
 int gemm_nt(const float*, int, const WeightView&, const float*, float*, int, float*, int, int, int, int, int, int,
             cudaStream_t);
 int gemm_nt_split(const SplitMat&, const WeightView&, const float*, float*, int, const SplitMat*, float*, int, int, int, int,
@@ -73,7 +72,6 @@ int ewald_prepare(EwaldPlan&, const float*, int, double, double, cudaStream_t);
 void ewald_release(EwaldPlan&);
 int launch_ewald_recip(const EwaldPlan&, int, const float*, const float*, double*, float*, float*, double*, cudaStream_t);
 
-constexpr int kDenseMaxMol = 64;   // largest molecule handled by the dense-molecule conv kernels
 static inline int pad32(int x) { return (x + 31) / 32 * 32; }
 static inline int round16(int x) { return (x + 15) / 16 * 16; }
 
@@ -109,7 +107,6 @@ struct aimnet2_engine {
     float *d3_c6ref = nullptr, *d3_cnref = nullptr, *d3_rcov = nullptr, *d3_r4r2 = nullptr;
     aimnet2_options_t opt{};
     int gemm_backend = 0;
-    int dense_conv = 1;   // use the dense-molecule conv kernels when the input qualifies
     // workspace (grow-only)
     char* ws = nullptr;
     size_t ws_bytes = 0;
@@ -443,10 +440,6 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         lr_cut = std::max(lr_cut, (float)e->ewald.rc);
     }
     const bool own_sr = sys->nbmat == nullptr;
-    // dense-molecule message passing (conv.cu): isolated molecules no larger than kDenseMaxMol walk their own atom
-    // segment, two centre atoms per warp, instead of neighbour-matrix rows.  B == 1 needs no hint.
-    const int max_mol = sys->max_mol_atoms > 0 ? sys->max_mol_atoms : (B == 1 ? N : 0);
-    const int dense = (!pbc && own_sr && e->dense_conv && max_mol > 0 && max_mol <= kDenseMaxMol) ? 1 : 0;
     if (e->timing) cudaEventRecord(e->ev[0], st);
 
     Buffers b;
@@ -517,7 +510,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         const int nl = (int)L.size();
         const float* qin = (p == 0) ? nullptr : b.q[p - 1];
         AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
-                                b.T_a[p], b.T_q[p], p > 0, b.mol_ptr, dense, st));
+                                b.T_a[p], b.T_q[p], p > 0, st));
         if (tc16) {
             AIM_TRY(presplit(e, b.x, ldx, N, L[0].in_pad, b.x16, st));
             SplitMat in = with_ld(b.x16, ldx);
@@ -653,8 +646,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             }
             const float* qin = (p == 0) ? nullptr : b.q[p - 1];
             AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
-                                    e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, b.mol_ptr,
-                                    dense, st));
+                                    e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
             if (p == 0) break;
             // dE/da_p and dE/dq_{p-1}
             if (p == 2)
@@ -794,12 +786,6 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
     return AIMNET_OK;
 }
 
-extern "C" int aimnet2_engine_set_dense_conv(aimnet2_engine_t* e, int on) {
-    AIM_REQUIRE(e, "set_dense_conv: null engine");
-    e->dense_conv = on != 0;
-    return AIMNET_OK;
-}
-
 extern "C" int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on) {
     AIM_REQUIRE(e, "set_deterministic: null engine");
     gemm_tc_set_deterministic(on != 0);   // process-wide switch of the GEMM chunking policy
@@ -850,15 +836,6 @@ extern "C" int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_syste
     aimnet2_system_t ds;
     aimnet2_result_t dr;
     carve_stage(probe, ds, dr);
-    int host_max_mol = sys->max_mol_atoms;
-    if (host_max_mol <= 0 && sys->mol_idx && N > 0) {   // mol_idx is host memory here: one cheap pass gives the hint
-        int run = 1;
-        host_max_mol = 1;
-        for (int k = 1; k < N; ++k) {
-            run = (sys->mol_idx[k] == sys->mol_idx[k - 1]) ? run + 1 : 1;
-            host_max_mol = std::max(host_max_mol, run);
-        }
-    }
     if (probe.off + 1024 > e->stage_bytes) {
         if (e->stage) AIM_CUDA_CHECK(cudaFree(e->stage));
         e->stage = nullptr;
@@ -867,7 +844,6 @@ extern "C" int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_syste
     }
     Bump bp{e->stage};
     carve_stage(bp, ds, dr);
-    ds.max_mol_atoms = host_max_mol;
 #define H2D(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st))
 #define D2H(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st))
     if (N > 0) {

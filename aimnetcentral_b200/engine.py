@@ -121,9 +121,6 @@ class Engine:
         o.d3_cutoff, o.d3_smoothing, o.sr_cutoff = d["d3_cutoff"], d["d3_smoothing"], d["sr_cutoff"]
         _capi.check(self._lib.aimnet2_engine_set_options(self._h, C.byref(o)), "set_options")
 
-    def set_dense_conv(self, on: bool):
-        _capi.check(self._lib.aimnet2_engine_set_dense_conv(self._h, int(bool(on))), "set_dense_conv")
-
     def set_gemm_backend(self, backend: int):
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
         self.gemm_backend = int(backend)
@@ -153,7 +150,7 @@ class Engine:
     def eval(self, coord: torch.Tensor, numbers: torch.Tensor, charge: torch.Tensor, mol_idx: torch.Tensor | None = None,
              mult: torch.Tensor | None = None, cell: torch.Tensor | None = None, pbc=None,
              nbmat: torch.Tensor | None = None, shifts: torch.Tensor | None = None, forces: bool = True,
-             stress: bool = False, return_nbmat: bool = False, max_mol_atoms: int = 0) -> dict:
+             stress: bool = False, return_nbmat: bool = False) -> dict:
         """Device-resident evaluation. coord (N,3) f32, numbers (N) i32, charge (B) f32, mol_idx (N) i32 sorted,
         cell (3,3)|(B,3,3) f32 — all on self.device, contiguous."""
         dev = self.device
@@ -189,7 +186,6 @@ class Engine:
                 pbc_arr = _pbc_bytes(pbc, n_cells)
                 sys_.pbc_host = pbc_arr.ctypes.data
         sys_.n_cells = n_cells
-        sys_.max_mol_atoms = int(max_mol_atoms)   # hint: <= 64 selects the dense-molecule conv kernels
         if nbmat is not None:
             sys_.nbmat, sys_.nb_width = nbmat.data_ptr(), int(nbmat.shape[1])
             sys_.shifts = _ptr(shifts)

@@ -197,7 +197,6 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--gemm-backend", type=int, default=None)
-    ap.add_argument("--no-dense-conv", action="store_true", help="always walk neighbor-matrix rows (A/B switch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -225,8 +224,6 @@ def main():
     eng = Engine(sd, spec.C, dev)
     if args.gemm_backend is not None:
         eng.set_gemm_backend(args.gemm_backend)
-    if args.no_dense_conv:
-        eng.set_dense_conv(False)
     pbc = w["cell"] is not None
     eng.set_options(coulomb_method=w.get("coulomb", "dsf" if pbc else "simple"), dispersion=True)
     N = len(w["numbers"])
@@ -250,12 +247,9 @@ def main():
         gather_e = torch.empty(world * B, dtype=torch.float64, device=dev)
         gather_f = torch.empty(world * N, 3, dtype=torch.float32, device=dev)
 
-    # largest molecule (host-side, once): molecules of <= 64 atoms take the dense-molecule conv kernels
-    max_mol = int(np.bincount(w["mol_idx"]).max()) if w["mol_idx"] is not None else (N if not pbc else 0)
-
     def step(i):
         out = eng.eval(coords_d[i], numbers_d, charge_d, mol_idx=mol_d, mult=mult_d, cell=cell_d, forces=True,
-                       stress=w["stress"], max_mol_atoms=max_mol)
+                       stress=w["stress"])
         if world > 1:  # result gather of the batch split (NCCL over NVLink)
             dist.all_gather_into_tensor(gather_e, out["energy"])
             dist.all_gather_into_tensor(gather_f, out["forces"])

@@ -138,10 +138,6 @@ typedef struct {
     const int32_t* nbmat;             /* (rows, nb_width) sentinel = n_atoms, or NULL = build it */
     const int32_t* shifts;            /* (rows, nb_width, 3) or NULL */
     int nb_width;
-    /* optional hint: atoms in the largest molecule (0 = unknown).  Isolated molecules of at most 64 atoms take the
-     * dense-molecule message-passing kernels (the counterpart of the reference's dense mode 0 for small molecules,
-     * aimnet/calculators/calculator.py:1495-1509); results are the same either way. */
-    int max_mol_atoms;
 } aimnet2_system_t;
 
 typedef struct {
@@ -165,9 +161,6 @@ int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
 /* 1 = bitwise run-to-run reproducible results (fixed K-chunking in the tcgen05 GEMM; every other kernel is atomics-free
  * already) — the counterpart of AIMNet2Calculator(deterministic=True), aimnet/calculators/calculator.py:76-84 */
 int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on);
-/* 1 (default) = inputs that qualify (no cell, engine-built neighbor list, largest molecule <= 64 atoms by the
- * max_mol_atoms hint) use the dense-molecule message-passing kernels; 0 = always walk neighbor-matrix rows */
-int aimnet2_engine_set_dense_conv(aimnet2_engine_t* e, int on);
 
 /* device-resident inputs/outputs; flags = AIMNET_WANT_* */
 int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
