@@ -111,7 +111,7 @@ __device__ __forceinline__ int row_length(const NbView& nb, int i) {
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb, const float* __restrict__ coord,
+__global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, int n_groups, NbView nb, const float* __restrict__ coord,
                                                           CellView cv, const int32_t* __restrict__ mol_idx,
                                                           AevParams aev, const float* __restrict__ aT,
                                                           const float* __restrict__ q, const float* __restrict__ agh_a,
@@ -127,14 +127,9 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
     float* svq_all = sv_all + kAtomsPerCta * kSvAtom;                                // [atom][c][k][g]
     const int tid = threadIdx.x;
     const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
-    const int i = blockIdx.x * kAtomsPerCta + al;
-    const bool atom_ok = i < n_atoms;
-    const int ic = atom_ok ? i : 0;
-    const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
-    const int len = atom_ok ? row_length(nb, i) : 0;
     const float shift_g = aev.shifts[g];
-    // agh (a,g,h) -> shared memory transposed to (a,h,g): the mixing epilogue reads 16 contiguous g per (a,h).  Made
-    // visible by the __syncthreads before the epilogue.
+    // agh (a,g,h) -> shared memory transposed to (a,h,g): the mixing epilogue reads 16 contiguous g per (a,h).  Staged
+    // once: the CTA is persistent and walks groups of 8 atoms; after this barrier the warps run independently.
     for (int e = tid; e < kA * kG * kH; e += 256) {
         int a = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
         aghT_a[(a * kH + hh) * kAghRow + gg] = agh_a[e];
@@ -144,111 +139,119 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
             int c = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
             aghT_q[(c * kH + hh) * kAghRow + gg] = agh_q[e];
         }
-    // accumulators as (scalar, x) / (y, z) register pairs: the 8x4 outer-product update is 16 packed FFMA2 per pair
-    float2 S01[kHalfA], S23[kHalfA];
+    __syncthreads();
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int i = grp * kAtomsPerCta + al;
+        const bool atom_ok = i < n_atoms;
+        const int ic = atom_ok ? i : 0;
+        const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
+        const int len = atom_ok ? row_length(nb, i) : 0;
+        // accumulators as (scalar, x) / (y, z) register pairs: the 8x4 outer-product update is 16 packed FFMA2 per pair
+        float2 S01[kHalfA], S23[kHalfA];
 #pragma unroll
-    for (int a = 0; a < kHalfA; ++a) S01[a] = S23[a] = make_float2(0.f, 0.f);
-    float2 Sq01[C], Sq23[C];
+        for (int a = 0; a < kHalfA; ++a) S01[a] = S23[a] = make_float2(0.f, 0.f);
+        float2 Sq01[C], Sq23[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) Sq01[c] = Sq23[c] = make_float2(0.f, 0.f);
-    // every warp stages the 32 slots of its own atom (thread = slot) and reads only those: warp-level sync is enough
-    for (int m0 = 0; m0 < len; m0 += kSlotsPerTile) {
-        __syncwarp();
-        stage_pairs<false>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
-        __syncwarp();
-        int lim = min(kSlotsPerTile, len - m0);
+        for (int c = 0; c < C; ++c) Sq01[c] = Sq23[c] = make_float2(0.f, 0.f);
+        // every warp stages the 32 slots of its own atom (thread = slot) and reads only those: warp-level sync is enough
+        for (int m0 = 0; m0 < len; m0 += kSlotsPerTile) {
+            __syncwarp();
+            stage_pairs<false>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
+            __syncwarp();
+            int lim = min(kSlotsPerTile, len - m0);
 #pragma unroll 2
-        for (int s = 0; s < lim; ++s) {
-            const PairEntry e = tile[al * 32 + s];
-            const float4* row = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g + 32 * h;
-            float4 v0 = row[0], v1 = row[16];
-            float xg = e.d - shift_g;
-            float w0 = aev_exp(-aev.eta * xg * xg) * e.fc;
-            const float2 w01 = make_float2(w0, w0 * e.ux), w23 = make_float2(w0 * e.uy, w0 * e.uz);
-            float av[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            for (int s = 0; s < lim; ++s) {
+                const PairEntry e = tile[al * 32 + s];
+                const float4* row = reinterpret_cast<const float4*>(aT + (size_t)e.j * kAG) + g + 32 * h;
+                float4 v0 = row[0], v1 = row[16];
+                float xg = e.d - shift_g;
+                float w0 = aev_exp(-aev.eta * xg * xg) * e.fc;
+                const float2 w01 = make_float2(w0, w0 * e.ux), w23 = make_float2(w0 * e.uy, w0 * e.uz);
+                float av[kHalfA] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int a = 0; a < kHalfA; ++a) {
-                S01[a] = ffma2s(av[a], w01, S01[a]);
-                S23[a] = ffma2s(av[a], w23, S23[a]);
-            }
-            if (with_q) {
+                for (int a = 0; a < kHalfA; ++a) {
+                    S01[a] = ffma2s(av[a], w01, S01[a]);
+                    S23[a] = ffma2s(av[a], w23, S23[a]);
+                }
+                if (with_q) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    float qj = q[(size_t)e.j * C + c];
-                    Sq01[c] = ffma2s(qj, w01, Sq01[c]);
-                    Sq23[c] = ffma2s(qj, w23, Sq23[c]);
+                    for (int c = 0; c < C; ++c) {
+                        float qj = q[(size_t)e.j * C + c];
+                        Sq01[c] = ffma2s(qj, w01, Sq01[c]);
+                        Sq23[c] = ffma2s(qj, w23, Sq23[c]);
+                    }
                 }
             }
         }
-    }
-    // ---- epilogue: scalar part straight to x, vector part through shared memory for the agh mixing ----
-    __syncthreads();   // agh tables staged
-    float* svl = sv_all + al * kSvAtom;
-#pragma unroll
-    for (int a = 0; a < kHalfA; ++a) {
-        const int o = sv_off(kHalfA * h + a) + g;
-        svl[o] = S01[a].y;
-        svl[o + kG] = S23[a].x;
-        svl[o + 2 * kG] = S23[a].y;
-    }
-    float* svql = svq_all + al * 2 * kSvRow;
-    if (with_q && h == 0) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            svql[c * kSvRow + g] = Sq01[c].y;
-            svql[c * kSvRow + kG + g] = Sq23[c].x;
-            svql[c * kSvRow + 2 * kG + g] = Sq23[c].y;
-        }
-    }
-    if (atom_ok) {
-        float* xr = x + (size_t)i * ldx;
-        const float4* own = reinterpret_cast<const float4*>(aT + (size_t)i * kAG) + g + 32 * h;
-        float4 o0 = own[0], o1 = own[16];
-        float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        // ---- epilogue: scalar part straight to x, vector part through shared memory for the agh mixing ----
+        __syncwarp();      // the previous atom's mixing is done with this warp's Sv scratch
+        float* svl = sv_all + al * kSvAtom;
 #pragma unroll
         for (int a = 0; a < kHalfA; ++a) {
-            int aa = kHalfA * h + a;
-            xr[aa * kG + g] = ov[a];
-            xr[kAG + aa * kG + g] = S01[a].x;
+            const int o = sv_off(kHalfA * h + a) + g;
+            svl[o] = S01[a].y;
+            svl[o + kG] = S23[a].x;
+            svl[o + 2 * kG] = S23[a].y;
         }
-        int base = 2 * kAG + kAH;
-        if (with_q) {
-            if (lane < C) xr[base + lane] = q[(size_t)i * C + lane];
-            if (h == 0) {
+        float* svql = svq_all + al * 2 * kSvRow;
+        if (with_q && h == 0) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq01[c].x;
+            for (int c = 0; c < C; ++c) {
+                svql[c * kSvRow + g] = Sq01[c].y;
+                svql[c * kSvRow + kG + g] = Sq23[c].x;
+                svql[c * kSvRow + 2 * kG + g] = Sq23[c].y;
             }
-            base += C * (1 + kG + kH);
         }
-        for (int c = base + lane; c < ldx; c += 32) xr[c] = 0.f;
-    }
-    __syncwarp();
-    // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); each lane handles 6 (a,h) pairs: the 16
-    // weights and the three 16-vectors of Sv come in as 16-byte shared loads, the dot products run as packed FFMA2
-    if (atom_ok) {
-        float* xr = x + (size_t)i * ldx;
-#pragma unroll 2
-        for (int e = lane; e < kAH; e += 32) {
-            const int a = e / kH;
-            float t[3];
-            mix16(aghT_a + e * kAghRow, svl + sv_off(a), t);
-            float* To = T_a + (size_t)i * kTA + e * 3;
-            To[0] = t[0];
-            To[1] = t[1];
-            To[2] = t[2];
-            xr[2 * kAG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
-        }
-        if (with_q) {
+        if (atom_ok) {
+            float* xr = x + (size_t)i * ldx;
+            const float4* own = reinterpret_cast<const float4*>(aT + (size_t)i * kAG) + g + 32 * h;
+            float4 o0 = own[0], o1 = own[16];
+            float ov[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+            for (int a = 0; a < kHalfA; ++a) {
+                int aa = kHalfA * h + a;
+                xr[aa * kG + g] = ov[a];
+                xr[kAG + aa * kG + g] = S01[a].x;
+            }
             int base = 2 * kAG + kAH;
-            for (int e = lane; e < C * kH; e += 32) {
-                const int c = e / kH;
+            if (with_q) {
+                if (lane < C) xr[base + lane] = q[(size_t)i * C + lane];
+                if (h == 0) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xr[base + C + c * kG + g] = Sq01[c].x;
+                }
+                base += C * (1 + kG + kH);
+            }
+            for (int c = base + lane; c < ldx; c += 32) xr[c] = 0.f;
+        }
+        __syncwarp();
+        // T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188); each lane handles 6 (a,h) pairs: the 16
+        // weights and the three 16-vectors of Sv come in as 16-byte shared loads, the dot products run as packed FFMA2
+        if (atom_ok) {
+            float* xr = x + (size_t)i * ldx;
+#pragma unroll 2
+            for (int e = lane; e < kAH; e += 32) {
+                const int a = e / kH;
                 float t[3];
-                mix16(aghT_q + e * kAghRow, svql + c * kSvRow, t);
-                float* To = T_q + (size_t)i * (C * kH * 3) + e * 3;
+                mix16(aghT_a + e * kAghRow, svl + sv_off(a), t);
+                float* To = T_a + (size_t)i * kTA + e * 3;
                 To[0] = t[0];
                 To[1] = t[1];
                 To[2] = t[2];
-                xr[base + C + C * kG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+                xr[2 * kAG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+            }
+            if (with_q) {
+                int base = 2 * kAG + kAH;
+                for (int e = lane; e < C * kH; e += 32) {
+                    const int c = e / kH;
+                    float t[3];
+                    mix16(aghT_q + e * kAghRow, svql + c * kSvRow, t);
+                    float* To = T_q + (size_t)i * (C * kH * 3) + e * 3;
+                    To[0] = t[0];
+                    To[1] = t[1];
+                    To[2] = t[2];
+                    xr[base + C + C * kG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+                }
             }
         }
     }
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(256, 3) conv_fwd_kernel(int n_atoms, NbView nb
 //   d avf_v[a,h] -> dT[a,h,d] = 2 T[a,h,d] * d avf_v[a,h] -> dSv[a,g,d] = sum_h agh[a,g,h] dT[a,h,d]
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const float* __restrict__ dx, int ldx,
+__global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, int n_groups, const float* __restrict__ dx, int ldx,
                                                             const float* __restrict__ T_a,
                                                             const float* __restrict__ T_q,
                                                             const float* __restrict__ agh_a,
@@ -278,20 +281,20 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
     if (with_q)
         for (int e = threadIdx.x; e < C * kG * kH; e += 256) aghq_s[e] = agh_q[e];
     const int al = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * kAtomsPerCta + al;
-    const bool atom_ok = i < n_atoms;
     float* dT = dT_s[al];
     float* dTq = dTq_s[al];
-    const float* dxr = dx + (size_t)(atom_ok ? i : 0) * ldx;
     const int base = 2 * kAG + kAH;
-    if (atom_ok) {
-        for (int e = lane; e < kTA; e += 32) dT[e] = 2.0f * T_a[(size_t)i * kTA + e] * dxr[2 * kAG + e / 3];
-        if (with_q)
-            for (int e = lane; e < C * kH * 3; e += 32)
-                dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
-    }
-    __syncthreads();
-    if (!atom_ok) return;
+    __syncthreads();   // agh staged; from here on the warps of this persistent CTA run independently
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int i = grp * kAtomsPerCta + al;
+    if (i >= n_atoms) continue;
+    const float* dxr = dx + (size_t)i * ldx;
+    __syncwarp();
+    for (int e = lane; e < kTA; e += 32) dT[e] = 2.0f * T_a[(size_t)i * kTA + e] * dxr[2 * kAG + e / 3];
+    if (with_q)
+        for (int e = lane; e < C * kH * 3; e += 32)
+            dTq[e] = 2.0f * T_q[(size_t)i * (C * kH * 3) + e] * dxr[base + C + C * kG + e / 3];
+    __syncwarp();
 #pragma unroll 2
     for (int k = 0; k < kAG / 32; ++k) {
         const int e = lane + 32 * k;
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, const f
         oq.z = q1;
         oq.w = q2;
         reinterpret_cast<float4*>(dS_q)[(size_t)i * (C * kG) + lane] = oq;
+    }
     }
 }
 
@@ -594,14 +598,22 @@ static int conv_fwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
                            const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q,
                            int with_q, cudaStream_t st) {
-    int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
     static bool configured = false;
+    static int max_ctas = 148 * 3;
     if (!configured) {
         AIM_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+        int dev = 0, sms = 148, per_sm = 3;
+        AIM_CUDA_CHECK(cudaGetDevice(&dev));
+        AIM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        AIM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_fwd_kernel<C>, 256, kFwdSmemBytes));
+        max_ctas = sms * (per_sm > 0 ? per_sm : 1);
         configured = true;
     }
-    conv_fwd_kernel<C><<<grid, 256, kFwdSmemBytes, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q, x, ldx,
-                                                        T_a, T_q, with_q);
+    // persistent CTAs (one resident wave): the agh tables are staged once per CTA, not once per 8 atoms
+    const int grid = n_groups < max_ctas ? n_groups : max_ctas;
+    conv_fwd_kernel<C><<<grid, 256, kFwdSmemBytes, st>>>(n_atoms, n_groups, nb, coord, cv, mol_idx, aev, aT, q, agh_a, agh_q,
+                                                        x, ldx, T_a, T_q, with_q);
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }
@@ -621,10 +633,19 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                            const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
                            double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
-    conv_bwd_prep_kernel<C><<<(n_atoms + kAtomsPerCta - 1) / kAtomsPerCta, 256, 0, st>>>(n_atoms, dx, ldx, T_a, T_q, agh_a,
-                                                                                          agh_q, dS_a, dS_q, with_q);
+    const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    static int prep_ctas = 0;
+    if (prep_ctas == 0) {
+        int dev = 0, sms = 148, per_sm = 4;
+        AIM_CUDA_CHECK(cudaGetDevice(&dev));
+        AIM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        AIM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_bwd_prep_kernel<C>, 256, 0));
+        prep_ctas = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    conv_bwd_prep_kernel<C><<<n_groups < prep_ctas ? n_groups : prep_ctas, 256, 0, st>>>(n_atoms, n_groups, dx, ldx, T_a, T_q,
+                                                                                          agh_a, agh_q, dS_a, dS_q, with_q);
     AIM_LAUNCH_CHECK();
-    int grid = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    int grid = n_groups;
 #define AIM_CONV_BWD(GA, VIR)                                                                                       \
     conv_bwd_kernel<C, GA, VIR><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a, \
                                                       grad_q, forces, virial_atom, with_q)

@@ -366,3 +366,25 @@ def test_user_supplied_neighbor_matrix():
     out = {k: v.cpu().numpy() for k, v in calc(dict(inputs, nbmat=nb), forces=True).items()}
     assert np.abs(out["forces"] - ref["forces"]).max() < FORCE_ATOL
     assert abs(out["energy"][0] - ref["energy"][0]) < ENERGY_ATOL
+
+
+@pytest.mark.gpu
+def test_repeated_evaluations_are_bitwise_identical():
+    """Every kernel is atomics-free with fixed reduction orders, so repeating an evaluation must reproduce it bit for
+    bit in the default mode too; any difference is a race (tools/race_check.py is the longer version)."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import allose_supercell, random_molecules
+
+    spec = ModelSpec()
+    calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+    coord, numbers = random_molecules(300, 50, seed=3)
+    z, x, cell = allose_supercell((2, 1, 1), jitter=0.02, seed=1)
+    cases = [({"coord": coord, "numbers": numbers, "charge": np.zeros(300, np.float32)}, dict(forces=True), "simple"),
+             ({"coord": x, "numbers": z, "charge": np.zeros(1, np.float32), "cell": cell}, dict(forces=True, stress=True), "dsf")]
+    for inp, kw, method in cases:
+        calc.set_lrcoulomb_method(method)
+        ref = {k: v.clone() for k, v in calc(dict(inp), **kw).items()}
+        for _ in range(20):
+            out = calc(dict(inp), **kw)
+            for k in ref:
+                assert torch.equal(ref[k], out[k]), k
