@@ -4,6 +4,7 @@ import warnings
 
 import numpy as np
 import pytest
+import torch
 
 from conftest import CHARGE_ATOL, ENERGY_ATOL, FORCE_ATOL, golden_state_dict, load_golden
 
