@@ -9,12 +9,15 @@ namespace aimnet {
 __device__ __forceinline__ int gather_slot_to_canonical(int t) { return (((t >> 6) << 2) + (t & 3)) * kG + ((t >> 2) & 15); }
 
 // a0[i] = afv[Z_i]   (aimnet/models/aimnet2.py:144-147), stored in the gather layout
-__global__ void embed_kernel(int n, const int32_t* __restrict__ numbers, const float* __restrict__ afv,
-                             float* __restrict__ aT0) {
-    int i = blockIdx.x, t = threadIdx.x;
+// 64 threads per atom (one float4 of the gather layout each), 4 atoms per block
+__global__ void __launch_bounds__(256) embed_kernel(int n, const int32_t* __restrict__ numbers, const float* __restrict__ afv,
+                                                    float* __restrict__ aT0) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 6), u = threadIdx.x & 63;
+    if (i >= n) return;
     int z = numbers[i];
     z = (z < 0 || z > 63) ? 0 : z;
-    aT0[(size_t)i * kAG + t] = afv[(size_t)z * kAG + gather_slot_to_canonical(t)];
+    const float* src = afv + (size_t)z * kAG + ((u >> 4) << 2) * kG + (u & 15);   // canonical (4 aq + k) * 16 + g
+    reinterpret_cast<float4*>(aT0)[(size_t)i * (kAG / 4) + u] = make_float4(src[0], src[kG], src[2 * kG], src[3 * kG]);
 }
 
 // molecule segment pointers from sorted mol_idx (nullptr = one molecule)
@@ -88,8 +91,18 @@ __global__ void __launch_bounds__(256) nse_apply_fwd_kernel(int C, int n, const 
                                                             const float* __restrict__ sumf,
                                                             const float* __restrict__ a_old, float* __restrict__ a_new,
                                                             float* __restrict__ q_new) {
-    int i = blockIdx.x, t = threadIdx.x;   // features live in the gather layout
-    a_new[(size_t)i * kAG + t] = a_old[(size_t)i * kAG + t] + y[(size_t)i * ldy + 2 * C + gather_slot_to_canonical(t)];
+    // features live in the gather layout: 64 threads per atom (one float4 = channels 4 aq .. 4 aq + 3 of one g), 4 atoms per block
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 6), t = threadIdx.x & 63;
+    if (i >= n) return;
+    {
+        const float* yr = y + (size_t)i * ldy + 2 * C + ((t >> 4) << 2) * kG + (t & 15);
+        float4 a = reinterpret_cast<const float4*>(a_old)[(size_t)i * (kAG / 4) + t];
+        a.x += yr[0];
+        a.y += yr[kG];
+        a.z += yr[2 * kG];
+        a.w += yr[3 * kG];
+        reinterpret_cast<float4*>(a_new)[(size_t)i * (kAG / 4) + t] = a;
+    }
     if (t < C) {
         int m = mol_idx ? mol_idx[i] : 0;
         float qu = (q_prev ? q_prev[(size_t)i * C + t] : 0.f) + y[(size_t)i * ldy + t];
@@ -135,26 +148,38 @@ __global__ void __launch_bounds__(288) nse_apply_bwd_kernel(int C, int n, const 
                                                             const float* __restrict__ gp_last, int ldgp,
                                                             float* __restrict__ dz, int lddz,
                                                             float* __restrict__ dq_prev) {
-    int i = blockIdx.x, t = threadIdx.x;
-    if (t >= lddz) return;
-    float v = 0.f;
-    int m = mol_idx ? mol_idx[i] : 0;
-    if (t < 2 * C) {
-        int c = (t < C) ? t : t - C;
-        float G = sumf[m * C + c] + 1.0e-6f;
-        float h = gq[(size_t)i * C + c] - s1[m * C + c] / G;
-        if (t < C) {
-            v = h;
-            if (dq_prev) dq_prev[(size_t)i * C + c] = h;
-        } else {
-            float D = target_charge(C, c, charge, mult, m) - sumq[m * C + c];
-            v = 2.0f * y[(size_t)i * ldy + C + c] * (D / G) * h;
+    // 72 threads per atom, four consecutive columns each (float4 stores / gelu' loads), 4 atoms per block
+    const int i = blockIdx.x * 4 + threadIdx.x / 72, u = threadIdx.x % 72;
+    if (i >= n || 4 * u >= lddz) return;
+    const int m = mol_idx ? mol_idx[i] : 0;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int t = 4 * u + k;
+        v[k] = 0.f;
+        if (t < 2 * C) {
+            int c = (t < C) ? t : t - C;
+            float G = sumf[m * C + c] + 1.0e-6f;
+            float h = gq[(size_t)i * C + c] - s1[m * C + c] / G;
+            if (t < C) {
+                v[k] = h;
+                if (dq_prev) dq_prev[(size_t)i * C + c] = h;
+            } else {
+                float D = target_charge(C, c, charge, mult, m) - sumq[m * C + c];
+                v[k] = 2.0f * y[(size_t)i * ldy + C + c] * (D / G) * h;
+            }
+        } else if (t < 2 * C + kAG) {
+            v[k] = da_tot[(size_t)i * kAG + (t - 2 * C)];
         }
-    } else if (t < 2 * C + kAG) {
-        v = da_tot[(size_t)i * kAG + (t - 2 * C)];
     }
-    if (gp_last != nullptr && t < 2 * C + kAG) v *= gp_last[(size_t)i * ldgp + t];
-    dz[(size_t)i * lddz + t] = v;
+    if (gp_last != nullptr) {   // columns past 2C + 256 hold v = 0 (and gelu' = gelu'(0) there)
+        const float4 g = *reinterpret_cast<const float4*>(gp_last + (size_t)i * ldgp + 4 * u);
+        v[0] *= g.x;
+        v[1] *= g.y;
+        v[2] *= g.z;
+        v[3] *= g.w;
+    }
+    *reinterpret_cast<float4*>(dz + (size_t)i * lddz + 4 * u) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // da_tot (+)= dx[:, :256] + grad_a ;  dq = base_q + dx[:, 704+c] + grad_q
@@ -164,10 +189,16 @@ __global__ void __launch_bounds__(256) accum_grads_kernel(int C, int n, const fl
                                                           const float* __restrict__ base_q, int base_q_stride,
                                                           float* __restrict__ da_tot, int accumulate,
                                                           float* __restrict__ dq) {
-    int i = blockIdx.x, t = threadIdx.x;
-    float v = dx[(size_t)i * ldx + t] + grad_a[(size_t)i * kAG + t];
-    if (accumulate) v += da_tot[(size_t)i * kAG + t];
-    da_tot[(size_t)i * kAG + t] = v;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 6), t = threadIdx.x & 63;   // 64 threads (float4) per atom, 4 atoms per block
+    if (i >= n) return;
+    const float4 d = *reinterpret_cast<const float4*>(dx + (size_t)i * ldx + 4 * t);
+    const float4 ga = reinterpret_cast<const float4*>(grad_a)[(size_t)i * (kAG / 4) + t];
+    float4 v = make_float4(d.x + ga.x, d.y + ga.y, d.z + ga.z, d.w + ga.w);
+    if (accumulate) {
+        const float4 o = reinterpret_cast<const float4*>(da_tot)[(size_t)i * (kAG / 4) + t];
+        v = make_float4(v.x + o.x, v.y + o.y, v.z + o.z, v.w + o.w);
+    }
+    reinterpret_cast<float4*>(da_tot)[(size_t)i * (kAG / 4) + t] = v;
     if (t < C) {
         float b = base_q[(size_t)i * base_q_stride + (base_q_stride == 1 ? 0 : t)];
         dq[(size_t)i * C + t] = b + dx[(size_t)i * ldx + (2 * kAG + kAH) + t] + grad_q[(size_t)i * C + t];
@@ -264,7 +295,7 @@ __global__ void charges_out_kernel(int C, int n, const float* __restrict__ q, fl
     } while (0)
 
 int launch_embed(int n, const int32_t* numbers, const float* afv, float* a0, cudaStream_t st) {
-    if (n) AIM_K(embed_kernel<<<n, 256, 0, st>>>(n, numbers, afv, a0));
+    if (n) AIM_K(embed_kernel<<<(n + 3) / 4, 256, 0, st>>>(n, numbers, afv, a0));
     return AIMNET_OK;
 }
 int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, cudaStream_t st) {
@@ -276,7 +307,7 @@ int launch_nse_fwd(int C, int n, int n_mol, const int32_t* mol_idx, const int32_
                    const float* a_old, float* a_new, float* q_new, cudaStream_t st) {
     if (!n) return AIMNET_OK;
     AIM_K(nse_reduce_fwd_kernel<<<n_mol, 256, 0, st>>>(C, mol_ptr, y, ldy, q_prev, sumq, sumf));
-    AIM_K(nse_apply_fwd_kernel<<<n, 256, 0, st>>>(C, n, mol_idx, charge, mult, y, ldy, q_prev, sumq, sumf, a_old, a_new,
+    AIM_K(nse_apply_fwd_kernel<<<(n + 3) / 4, 256, 0, st>>>(C, n, mol_idx, charge, mult, y, ldy, q_prev, sumq, sumf, a_old, a_new,
                                                  q_new));
     return AIMNET_OK;
 }
@@ -285,19 +316,19 @@ int launch_nse_bwd(int C, int n, int n_mol, const int32_t* mol_idx, const int32_
                    float* s1, const float* da_tot, const float* gp_last, int ldgp, float* dz, int lddz, float* dq_prev,
                    cudaStream_t st) {
     if (!n) return AIMNET_OK;
-    if (lddz > 288) {
-        set_error("nse_bwd: lddz > 288");
+    if (lddz > 288 || lddz % 4 != 0 || (gp_last != nullptr && ldgp % 4 != 0)) {
+        set_error("nse_bwd: lddz must be a multiple of 4 and at most 288");
         return AIMNET_EINVAL;
     }
     AIM_K(nse_reduce_bwd_kernel<<<n_mol, 256, 0, st>>>(C, mol_ptr, y, ldy, gq, s1));
-    AIM_K(nse_apply_bwd_kernel<<<n, 288, 0, st>>>(C, n, mol_idx, charge, mult, y, ldy, gq, sumq, sumf, s1, da_tot,
+    AIM_K(nse_apply_bwd_kernel<<<(n + 3) / 4, 288, 0, st>>>(C, n, mol_idx, charge, mult, y, ldy, gq, sumq, sumf, s1, da_tot,
                                                  gp_last, ldgp, dz, lddz, dq_prev));
     return AIMNET_OK;
 }
 int launch_accum_grads(int C, int n, const float* dx, int ldx, const float* grad_a, const float* grad_q,
                        const float* base_q, int base_q_stride, float* da_tot, int accumulate, float* dq,
                        cudaStream_t st) {
-    if (n) AIM_K(accum_grads_kernel<<<n, 256, 0, st>>>(C, n, dx, ldx, grad_a, grad_q, base_q, base_q_stride, da_tot,
+    if (n) AIM_K(accum_grads_kernel<<<(n + 3) / 4, 256, 0, st>>>(C, n, dx, ldx, grad_a, grad_q, base_q, base_q_stride, da_tot,
                                                       accumulate, dq));
     return AIMNET_OK;
 }
