@@ -190,6 +190,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     float* sbias = reinterpret_cast<float*>(smem + OFF_BARS + 256);                // [256]
     unsigned char* epi_buf = smem + OFF_EPI;                                       // 8 x 2 x 2 KB, 1 KB aligned
 
+    // Mode 3 runs three operand stages and uses the fourth stage's 48 KB as a ring of 2 KB boxes (three per epilogue
+    // warp) into which TMA prefetches the aux operand 16 columns at a time; the other modes keep four stages.
+    constexpr int kStages = (MODE == 3) ? STAGES - 1 : STAGES;
+    unsigned char* aux_buf = smem + (STAGES - 1) * STAGE_BYTES;                      // mode 3 only: 24 x 2 KB
+    uint64_t* aux_bar = reinterpret_cast<uint64_t*>(smem + OFF_BARS + 1280);         // [8 warps][3]
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + p.bn - 1) / p.bn;
     const uint32_t tx_bytes = (uint32_t)(2 * A_HALF + 2 * p.bn * BK * 2);
@@ -206,6 +212,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             mbar_init(&tmem_empty[b], 8);
         }
         for (int w = 0; w < 8; ++w) mbar_init(&epi_bar[w], 1);
+        for (int w = 0; w < 24; ++w) mbar_init(&aux_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpAlloc) {
@@ -237,7 +244,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                     tma_load_2d(sp + A_HALF, &tmAl, &full[s], ks * BK, m0);
                     tma_load_2d(sp + 2 * A_HALF, &tmBh, &full[s], ks * BK, n0);
                     tma_load_2d(sp + 2 * A_HALF + B_BYTES, &tmBl, &full[s], ks * BK, n0);
-                    if (++s == STAGES) {
+                    if (++s == kStages) {
                         s = 0;
                         ph ^= 1;
                     }
@@ -277,7 +284,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                             tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
                         }
                         tc_commit(&empty[s]);   // frees the stage once these MMAs have read it
-                        if (++s == STAGES) {
+                        if (++s == kStages) {
                             s = 0;
                             ph ^= 1;
                         }
@@ -299,6 +306,9 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         int cit = 0;
         unsigned char* box0 = epi_buf + warp * 2 * EPI_BOX;
         unsigned char* box1 = box0 + EPI_BOX;
+        unsigned char* abox = aux_buf + warp * 3 * EPI_BOX;   // mode 3: this warp's aux ring
+        uint64_t* abar = aux_bar + warp * 3;
+        int ag = 0;                                           // running aux step -> ring slot ag % 3, phase (ag / 3) & 1
         const int rsw = (lane >> 1) & 3;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * p.bn;
@@ -309,6 +319,17 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             float2 acc[64];   // one output row x 128 columns, as register pairs for the packed FFMA2 / FMUL2 / FADD2
 #pragma unroll
             for (int k = 0; k < 64; ++k) acc[k] = make_float2(0.f, 0.f);
+            // mode 3: number of 16-column aux steps of this warp in this tile; the first three are requested now and
+            // arrive while the tile's MMAs run
+            const int aux_steps = (MODE == 3) ? max(0, min(n_tile - ch * 128, 128)) / 16 : 0;
+            auto aux_request = [&](int step, int slot) {   // lane 0 only
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&abar[slot], EPI_BOX);
+                tma_load_2d(abox + slot * EPI_BOX, &tmAux, &abar[slot], n0 + ch * 128 + 16 * step, row_base);
+            };
+            if (MODE == 3 && lane == 0) {
+                for (int k = 0; k < 3 && k < aux_steps; ++k) aux_request(k, (ag + k) % 3);
+            }
             if (MODE == 1 || MODE == 2) {
                 // bias of this tile's columns -> shared memory (read back as warp-wide broadcasts in the epilogue)
                 asm volatile("bar.sync 1, 256;");   // previous tile's readers are done
@@ -379,16 +400,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             };
-            float4 ax[8];   // mode 3: aux values of the current 32-column group
-            auto load_aux = [&](int g) {
-                const int col0 = ch * 128 + g * 32;
-                if (MODE == 3 && g < 4 && col0 < n_tile) {
-                    const float4* src = reinterpret_cast<const float4*>(p.aux + (size_t)min(row, p.M - 1) * p.ldaux + n0 + col0);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) ax[k] = __ldg(src + k);
-                }
-            };
-            load_aux(0);
+            int aux_step = 0;   // mode 3: 16-column steps consumed in this tile
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2) {
                 if (ch * 128 + c2 * 64 < n_tile) {
@@ -400,11 +412,21 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                             float2* v = &acc[c2 * 32 + hc * 16];
                             if (MODE == 3) {
 #pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    v[2 * k + 0] = fmul2(v[2 * k + 0], make_float2(ax[k].x, ax[k].y));
-                                    v[2 * k + 1] = fmul2(v[2 * k + 1], make_float2(ax[k].z, ax[k].w));
+                                for (int hb = 0; hb < 2; ++hb) {
+                                    const int slot = ag % 3;
+                                    mbar_wait(&abar[slot], (uint32_t)(ag / 3) & 1);
+                                    const unsigned char* bx = abox + slot * EPI_BOX;
+#pragma unroll
+                                    for (int v4 = 0; v4 < 4; ++v4) {
+                                        const float4 g = *reinterpret_cast<const float4*>(bx + lane * 64 + ((v4 ^ rsw) << 4));
+                                        v[hb * 8 + 2 * v4 + 0] = fmul2(v[hb * 8 + 2 * v4 + 0], make_float2(g.x, g.y));
+                                        v[hb * 8 + 2 * v4 + 1] = fmul2(v[hb * 8 + 2 * v4 + 1], make_float2(g.z, g.w));
+                                    }
+                                    __syncwarp();   // every lane has read the box: refill it three steps ahead
+                                    if (lane == 0 && aux_step + 3 < aux_steps) aux_request(aux_step + 3, slot);
+                                    ++ag;
+                                    ++aux_step;
                                 }
-                                load_aux(c2 * 2 + hc + 1);
                             } else if (MODE == 1 || MODE == 2) {
 #pragma unroll
                                 for (int v4 = 0; v4 < 8; ++v4) {
