@@ -106,8 +106,9 @@ struct CoulombParams {
     double factor;    // signed prefactor c (eV*A): -k for the embedded SR term, +k for the external term
 };
 
+constexpr int kC6Row = 28;   // c6ref rows (25 values) padded to a multiple of four floats for 16-byte loads
 struct D3Params {
-    const float* c6ref;   // (95,95,5,5)
+    const float* c6ref;   // (95,95,28): (95,95,5,5) with every 25-value row padded to kC6Row
     const float* cnref;   // (95,5)
     const float* rcov;    // (95)
     const float* r4r2;    // (95)

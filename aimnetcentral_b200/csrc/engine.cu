@@ -728,7 +728,12 @@ extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weigh
     e->sr_rc = w->sr_rc;
     e->sr_envelope = w->sr_envelope;
     if (w->d3_c6ref) {
-        if ((rc = upload(e, &e->d3_c6ref, w->d3_c6ref, (size_t)95 * 95 * 25))) return rc;
+        {   // rows padded to kC6Row floats so that the pair kernels read them with 16-byte loads
+            std::vector<float> padded((size_t)95 * 95 * kC6Row, 0.f);
+            for (size_t r = 0; r < (size_t)95 * 95; ++r)
+                for (int k = 0; k < 25; ++k) padded[r * kC6Row + k] = w->d3_c6ref[r * 25 + k];
+            if ((rc = upload(e, &e->d3_c6ref, padded.data(), padded.size()))) return rc;
+        }
         if ((rc = upload(e, &e->d3_cnref, w->d3_cnref, (size_t)95 * 5))) return rc;
         if ((rc = upload(e, &e->d3_rcov, w->d3_rcov, 95))) return rc;
         if ((rc = upload(e, &e->d3_r4r2, w->d3_r4r2, 95))) return rc;

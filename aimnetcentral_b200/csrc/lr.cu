@@ -229,17 +229,30 @@ __global__ void d3_weights_kernel(int n, const int32_t* __restrict__ numbers, D3
     o[15] = 0.f;
 }
 
+// c6ref rows are padded to 28 floats (kC6Row) at upload and the weight table rows are 16 floats, so a pair reads its
+// 25 reference values and the neighbour's 10 weights as ten 16-byte loads instead of 35 scalar ones.
 __device__ __forceinline__ void d3_c6(const D3Params& p, int zi, int zj, const float* __restrict__ wi,
                                       const float* __restrict__ wj, float& c6, float& dc6_dcni) {
-    const float* cr = p.c6ref + ((size_t)zi * 95 + zj) * 25;
-    float si[5], ei[5], di[5], sj[5], ej[5];
+    const float4* cr4 = reinterpret_cast<const float4*>(p.c6ref + ((size_t)zi * 95 + zj) * kC6Row);
+    float cr[28];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const float4 v = __ldg(cr4 + k);
+        cr[4 * k + 0] = v.x;
+        cr[4 * k + 1] = v.y;
+        cr[4 * k + 2] = v.z;
+        cr[4 * k + 3] = v.w;
+    }
+    const float4* wj4 = reinterpret_cast<const float4*>(wj);
+    const float4 j0 = wj4[0], j1 = wj4[1], j2 = wj4[2];
+    const float sj[5] = {j0.x, j0.y, j0.z, j0.w, j1.x};
+    const float ej[5] = {j1.y, j1.z, j1.w, j2.x, j2.y};
+    float si[5], ei[5], di[5];
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
         si[a] = wi[a];
         ei[a] = wi[5 + a];
         di[a] = wi[10 + a];
-        sj[a] = wj[a];
-        ej[a] = wj[5 + a];
     }
     float wsum = 0.f, csum = 0.f, dwsum = 0.f, dcsum = 0.f;
 #pragma unroll
