@@ -80,6 +80,10 @@ struct SplitMat {
     int ld, ldinv;
 };
 
+// at or below this many rows (atoms) the per-atom MLPs run on the small-M fp32 SIMT kernel: the tensor-core pipelines are
+// latency-bound there (gemm.cu)
+constexpr int kSmallM = 512;
+
 // one Linear's weight matrix (N, ldw) in the forms the GEMM backends consume
 struct WeightView {
     const float* W;            // fp32 (SIMT backend 0)

@@ -107,6 +107,8 @@ struct aimnet2_engine {
     float *d3_c6ref = nullptr, *d3_cnref = nullptr, *d3_rcov = nullptr, *d3_r4r2 = nullptr;
     aimnet2_options_t opt{};
     int gemm_backend = 0;
+    int small_m_rows = kSmallM;   // at or below this many atoms the MLPs run on the small-M fp32 SIMT kernel (0 = never)
+    int backend_now = 0;    // backend of the evaluation in flight (gemm_backend or 0 for small systems)
     // workspace (grow-only)
     char* ws = nullptr;
     size_t ws_bytes = 0;
@@ -337,7 +339,7 @@ static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
 static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ldx, int K, float* Y, float* gp, bool act,
                       int M, cudaStream_t st) {
     gemm_mark(e, st);
-    int rc = gemm_nt(X, ldx, L.fwd(), L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1, e->gemm_backend, st);
+    int rc = gemm_nt(X, ldx, L.fwd(), L.b, Y, L.out_pad, gp, L.out_pad, M, L.out_pad, K, act ? 2 : 1, e->backend_now, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -346,7 +348,7 @@ static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float
                       int ldgp, int M, cudaStream_t st) {
     gemm_mark(e, st);
     int rc = gemm_nt(dZ, L.out_pad, L.bwd(), nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
-                     gp_prev ? 3 : 0, e->gemm_backend, st);
+                     gp_prev ? 3 : 0, e->backend_now, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -425,7 +427,10 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     e->gemm_ev_used = 0;
     const bool pbc = sys->cell != nullptr;
     const bool backward = want_f || want_s;
-    const bool tc16 = e->gemm_backend == 2;
+    // small systems: the tensor-core pipelines are latency-bound below a few hundred rows, the fp32 SIMT small-M kernel wins
+    const int backend_eff = (e->gemm_backend != 0 && N <= e->small_m_rows) ? 0 : e->gemm_backend;
+    const bool tc16 = backend_eff == 2;
+    e->backend_now = backend_eff;
     const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
     const bool need_lr_terms = (o.coulomb_method == AIMNET_COULOMB_SIMPLE || o.coulomb_method == AIMNET_COULOMB_DSF ||
                                 ewald || o.dispersion);
@@ -788,6 +793,13 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
     AIM_REQUIRE(backend >= 0 && backend <= 2, "set_gemm_backend: backend must be 0 (SIMT), 1 (3xTF32) or 2 (3xFP16)");
     AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backends not available in this build");
     e->gemm_backend = backend;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows) {
+    AIM_REQUIRE(e, "set_small_m_rows: null engine");
+    AIM_REQUIRE(rows >= 0 && rows <= kSmallM, "set_small_m_rows: rows must be in [0, 512]");
+    e->small_m_rows = rows;
     return AIMNET_OK;
 }
 

@@ -105,6 +105,90 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
     }
 }
 
+// Small-M variant of the fp32 SIMT kernel: 16 x 16 output tiles, 64 threads (one row x four columns each), K in chunks
+// of 32 with register prefetch.  For a single molecule (M = number of atoms, ~100) the tensor-core kernels are
+// latency-bound (TMEM allocation, 22 dependent TMA stages, one or two CTAs busy): ~17 us per layer.  This kernel spreads
+// the same layer over (M/16) x (N/16) small CTAs (256 for 113 x 512) so that every SM works on it; it is what the
+// engine uses at or below kSmallM rows.
+constexpr int SBM = 16, SBN = 16, SBK = 32;
+
+template <int MODE>
+__global__ void __launch_bounds__(64) gemm_nt_small_kernel(const float* __restrict__ A, int lda,
+                                                           const float* __restrict__ W, int ldw,
+                                                           const float* __restrict__ bias, float* __restrict__ Y,
+                                                           int ldy, float* __restrict__ aux, int ldaux, int M, int N,
+                                                           int K) {
+    __shared__ float As[2][SBK][SBM + 1];
+    __shared__ __align__(16) float Ws[2][SBK][SBN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 3, ty = tid >> 2;          // output: row ty, columns 4 tx .. 4 tx + 3
+    const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+    // loads: tile rows lr and lr + 8, k offset lk (two float4 of A and of W per thread)
+    const int lr = tid >> 3, lk = (tid & 7) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 ra[2], rw[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = m0 + lr + 8 * u, n = n0 + lr + 8 * u;
+            ra[u] = (r < M) ? *reinterpret_cast<const float4*>(A + (size_t)r * lda + k0 + lk) : make_float4(0, 0, 0, 0);
+            rw[u] = (n < N) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k0 + lk) : make_float4(0, 0, 0, 0);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = lr + 8 * u;
+            As[buf][lk + 0][r] = ra[u].x;
+            As[buf][lk + 1][r] = ra[u].y;
+            As[buf][lk + 2][r] = ra[u].z;
+            As[buf][lk + 3][r] = ra[u].w;
+            Ws[buf][lk + 0][r] = rw[u].x;
+            Ws[buf][lk + 1][r] = rw[u].y;
+            Ws[buf][lk + 2][r] = rw[u].z;
+            Ws[buf][lk + 3][r] = rw[u].w;
+        }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    const int nk = K / SBK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * SBK);
+#pragma unroll
+        for (int k = 0; k < SBK; ++k) {
+            const float a = As[buf][k][ty];
+            const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+            acc[0] = fmaf(a, b.x, acc[0]);
+            acc[1] = fmaf(a, b.y, acc[1]);
+            acc[2] = fmaf(a, b.z, acc[2]);
+            acc[3] = fmaf(a, b.w, acc[3]);
+        }
+        if (kt + 1 < nk) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    const int row = m0 + ty, col = n0 + tx * 4;
+    if (row >= M || col >= N) return;
+    float4 bz = make_float4(0, 0, 0, 0);
+    if (MODE == 1 || MODE == 2) bz = *reinterpret_cast<const float4*>(bias + col);
+    float4 z = make_float4(acc[0] + bz.x, acc[1] + bz.y, acc[2] + bz.z, acc[3] + bz.w);
+    if (MODE == 2) {
+        float4 gp;
+        gelu_pair(z.x, z.x, gp.x);
+        gelu_pair(z.y, z.y, gp.y);
+        gelu_pair(z.z, z.z, gp.z);
+        gelu_pair(z.w, z.w, gp.w);
+        if (aux != nullptr) *reinterpret_cast<float4*>(aux + (size_t)row * ldaux + col) = gp;
+    } else if (MODE == 3) {
+        const float4 gp = *reinterpret_cast<const float4*>(aux + (size_t)row * ldaux + col);
+        z = make_float4(z.x * gp.x, z.y * gp.y, z.z * gp.z, z.w * gp.w);
+    }
+    *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = z;
+}
+
 int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int ldw, const float* bias, float* Y, int ldy,
                float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
 int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw, const float* bias,
@@ -133,6 +217,17 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
     AIM_REQUIRE(w.W != nullptr, "gemm: SIMT backend needs the fp32 weights");
     const float* W = w.W;
     const int ldw = w.ldw;
+    if (M <= kSmallM && K % SBK == 0) {
+        dim3 sgrid((N + SBN - 1) / SBN, (M + SBM - 1) / SBM);
+        switch (mode) {
+            case 0: gemm_nt_small_kernel<0><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            case 1: gemm_nt_small_kernel<1><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            case 2: gemm_nt_small_kernel<2><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            default: gemm_nt_small_kernel<3><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+        }
+        AIM_LAUNCH_CHECK();
+        return AIMNET_OK;
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     switch (mode) {
         case 0: gemm_nt_simt_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;

@@ -121,6 +121,10 @@ class Engine:
         o.d3_cutoff, o.d3_smoothing, o.sr_cutoff = d["d3_cutoff"], d["d3_smoothing"], d["sr_cutoff"]
         _capi.check(self._lib.aimnet2_engine_set_options(self._h, C.byref(o)), "set_options")
 
+    def set_small_m_rows(self, rows: int):
+        """Evaluations with at most `rows` atoms use the small-M fp32 SIMT GEMM (default 512, 0 = never)."""
+        _capi.check(self._lib.aimnet2_engine_set_small_m_rows(self._h, int(rows)), "set_small_m_rows")
+
     def set_gemm_backend(self, backend: int):
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
         self.gemm_backend = int(backend)

@@ -158,6 +158,9 @@ int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt
 /* GEMM backend for the per-atom MLPs: 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 3xFP16 with row-chunk scaling
  * (default when available) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
+/* Evaluations with at most `rows` atoms run the MLPs on the small-M fp32 SIMT kernel whatever the backend (the
+ * tensor-core pipelines are latency-bound for a single molecule); default 512, 0 = never. */
+int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows);
 /* 1 = bitwise run-to-run reproducible results (fixed K-chunking in the tcgen05 GEMM; every other kernel is atomics-free
  * already) — the counterpart of AIMNet2Calculator(deterministic=True), aimnet/calculators/calculator.py:76-84 */
 int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on);

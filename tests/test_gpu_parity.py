@@ -45,13 +45,20 @@ def _report(name, out, ref, n):
     return de, df, dq
 
 
+@pytest.mark.parametrize("mlp", ["tensor-core", "small-m-simt"])
 @pytest.mark.parametrize("name,kw", CASES, ids=[c[0] for c in CASES])
-def test_calculator_matches_reference_golden(name, kw):
+def test_calculator_matches_reference_golden(name, kw, mlp):
+    """Every fixture through both MLP paths: the tcgen05 3xFP16 GEMMs (forced by switching the small-system shortcut
+    off) and the small-M fp32 SIMT kernel that systems of <= 512 atoms take by default."""
     inputs, ref, meta = load_golden(name)
     calc = get_calc(meta)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        res = calc(dict(inputs), forces=True, stress=bool(kw.get("stress")))
+    calc.engine.set_small_m_rows(0 if mlp == "tensor-core" else 512)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = calc(dict(inputs), forces=True, stress=bool(kw.get("stress")))
+    finally:
+        calc.engine.set_small_m_rows(512)
     out = {k: v.detach().cpu().numpy() for k, v in res.items()}
     assert out["energy"].dtype == np.float64 and out["forces"].dtype == np.float32
     de, df, dq = _report(name, out, ref, len(inputs["numbers"]))
