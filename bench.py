@@ -336,7 +336,11 @@ def main():
     peak_tf = bf16 / 3.0 if eng.gemm_backend == 2 else bf16 / 2.0 / 3.0
     achieved = flops / (gms * 1e-3) / 1e12
     roofline = {"kernel": "gemm_nt (per-atom MLP stacks, %d launches/step)" % n_gemm, "bound": "tensor",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                # DRAM bytes of the largest GEMM launch (51 200 x 512 x 704, GELU + pre-split output) from the committed
+                # `ncu --set full` capture profiles/r1_prof_gemm_tc16_summary.csv: 159 MB read + 163 MB written, against
+                # 144 MB (A hi+lo) + 210 MB (y hi+lo, gelu') algorithmic -- no re-reads; null for the other workloads
+                "traffic": 321.8e6 if (args.workload == "cfg2" and eng.gemm_backend == 2) else None,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained") +
                                (" / 3 (3xFP16 split on the kind::f16 pipe)" if eng.gemm_backend == 2 else
                                 " / 2 (tf32) / 3 (3xTF32 split)"),
