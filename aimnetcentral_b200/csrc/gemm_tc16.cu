@@ -186,7 +186,6 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     volatile int* chunk_last = reinterpret_cast<volatile int*>(bars + 2 * STAGES + 5);   // [2] last chunk of its tile?
-    uint64_t* epi_bar = bars + 20;                                                  // [8] one per epilogue warp
     float* sbias = reinterpret_cast<float*>(smem + OFF_BARS + 256);                // [256]
     unsigned char* epi_buf = smem + OFF_EPI;                                       // 8 x 2 x 2 KB, 1 KB aligned
 
@@ -211,7 +210,6 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], 8);
         }
-        for (int w = 0; w < 8; ++w) mbar_init(&epi_bar[w], 1);
         for (int w = 0; w < 24; ++w) mbar_init(&aux_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
