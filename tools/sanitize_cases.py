@@ -1,0 +1,38 @@
+"""Small evaluations covering every kernel family, meant to run under compute-sanitizer:
+    compute-sanitizer --tool memcheck   python tools/sanitize_cases.py
+    compute-sanitizer --tool initcheck  python tools/sanitize_cases.py
+    compute-sanitizer --tool racecheck  python tools/sanitize_cases.py
+"simt" as argument restricts the run to the small-M SIMT MLP path: initcheck does not see TMA bulk stores as writes, so
+the tensor-core path floods it with false positives (everything downstream of a TMA-stored activation).
+"""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+from aimnetcentral_b200.structures import allose_supercell, random_molecules
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+spec = ModelSpec()
+calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+coord, numbers = random_molecules(6, 23, seed=5)
+mol = {"coord": coord, "numbers": numbers, "charge": np.zeros(6, np.float32)}
+z, x, cell = allose_supercell((1, 1, 1), jitter=0.02, seed=1)
+pbc = {"coord": x, "numbers": z, "charge": np.zeros(1, np.float32), "cell": cell}
+for tc in ((False,) if which == "simt" else (True, False)):
+    calc.engine.set_small_m_rows(0 if tc else 512)   # tensor-core GEMMs / small-M SIMT GEMMs
+    calc.set_lrcoulomb_method("simple")
+    out = calc(dict(mol), forces=True)
+    calc.set_lrcoulomb_method("dsf")
+    out2 = calc(dict(pbc), forces=True, stress=True)
+    if which in ("all", "simt"):
+        calc.set_lrcoulomb_method("ewald")
+        out3 = calc(dict(pbc), forces=True, stress=True)
+    torch.cuda.synchronize()
+    print("tensor-core" if tc else "small-m", float(out["energy"].sum()), float(out2["energy"].sum()))
+spec2 = ModelSpec(num_charge_channels=2)
+calc2 = AIMNet2Calculator((random_state_dict(1, spec2), spec2), device="cuda:0")
+calc2.engine.set_small_m_rows(512 if which == "simt" else 0)
+out4 = calc2({**mol, "mult": np.ones(6, np.float32)}, forces=True)
+torch.cuda.synchronize()
+print("nse", float(out4["energy"].sum()))
