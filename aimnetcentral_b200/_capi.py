@@ -39,6 +39,7 @@ class Options(C.Structure):
         ("coulomb_method", C.c_int), ("dsf_alpha", C.c_float), ("dsf_rc", C.c_float), ("ewald_accuracy", C.c_float),
         ("dispersion", C.c_int), ("d3_s6", C.c_float), ("d3_s8", C.c_float), ("d3_a1", C.c_float),
         ("d3_a2", C.c_float), ("d3_cutoff", C.c_float), ("d3_smoothing", C.c_float), ("sr_cutoff", C.c_float),
+        ("neighbor_skin", C.c_float),
     ]
 
 
@@ -64,7 +65,7 @@ EXPORTS = [
     "aimnet2_last_error", "aimnet2_abi_version", "aimnet2_neighbor_matrix", "aimnet2_wrap_positions",
     "aimnet2_conv_sv_2d_sp_fwd", "aimnet2_conv_sv_2d_sp_bwd", "aimnet2_engine_create", "aimnet2_engine_destroy",
     "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_small_m_rows", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
-    "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_enable_timing",
+    "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_skin_stats", "aimnet2_engine_enable_timing",
     "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace",
 ]
 
@@ -101,6 +102,7 @@ def load():
     lib.aimnet2_engine_eval_host.argtypes = [vp, C.POINTER(System), C.POINTER(Result), ci]
     lib.aimnet2_engine_last_launches.argtypes = [vp]
     lib.aimnet2_engine_info.argtypes = [vp, c_int_p, c_int_p, C.POINTER(C.c_int64)]
+    lib.aimnet2_engine_skin_stats.argtypes = [vp, c_int_p, c_int_p]
     lib.aimnet2_engine_enable_timing.argtypes = [vp, ci]
     lib.aimnet2_engine_last_timing.argtypes = [vp, c_float_p, ci]
     lib.aimnet2_gemm_nt.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, vp]

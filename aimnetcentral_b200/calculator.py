@@ -80,7 +80,8 @@ class AIMNet2Calculator:
                  needs_dispersion: bool | None = None, device: str | None = None, compile_model: bool = False,
                  compile_kwargs: dict | None = None, cache_static: bool = False, train: bool = False,
                  deterministic: bool = False, ensemble_member: int = 0, revision: str | None = None,
-                 token: str | None = None, *, model_import_paths=None, model_import_mode: str = "extend"):
+                 token: str | None = None, *, model_import_paths=None, model_import_mode: str = "extend",
+                 neighbor_skin: float = 0.0):
         if device is None:
             device = "cuda"
         dev = torch.device(device)
@@ -127,6 +128,8 @@ class AIMNet2Calculator:
         self.cutoff_lr = float("inf") if self._has_coulomb else (self._dftd3_cutoff if self._has_dftd3 else None)
         self._mult_ignored_checked = False
         self._batch: int | None = None
+        # extension over the reference API: Verlet skin (A) for neighbor-list reuse across MD steps; 0 = rebuild every call
+        self._neighbor_skin = float(neighbor_skin)
         self.engine = Engine(sd, C, self.device, sr_rc=float(sr_rc), sr_envelope=sr_env, load_d3=self._has_dftd3)
         # duck-typed `model` handle for the adapters that read `base_calc.model._metadata` / `.num_charge_channels`
         # (aimnet/calculators/aimnet2ase.py:69, aimnet2torchsim.py:78-125)
@@ -172,7 +175,7 @@ class AIMNet2Calculator:
             dsf_rc=float(self._dsf_rc), ewald_accuracy=float(self._ewald_accuracy), dispersion=self._has_dftd3,
             d3_s6=float(d3.get("s6", 1.0)), d3_s8=float(d3.get("s8", 0.0)), d3_a1=float(d3.get("a1", 0.0)),
             d3_a2=float(d3.get("a2", 0.0)), d3_cutoff=float(self._dftd3_cutoff), d3_smoothing=float(self._dftd3_smoothing),
-            sr_cutoff=float(self.cutoff))
+            sr_cutoff=float(self.cutoff), neighbor_skin=float(getattr(self, "_neighbor_skin", 0.0)))
 
     def set_lrcoulomb_method(self, method: str, cutoff: float = 15.0, dsf_alpha: float = 0.2, ewald_accuracy: float = 1e-6):
         if method not in ("simple", "dsf", "ewald", "pme"):

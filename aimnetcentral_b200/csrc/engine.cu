@@ -51,6 +51,9 @@ int launch_energy_reduce(int, const int32_t*, const double*, const double*, cons
                          cudaStream_t);
 int launch_stress_reduce(const int32_t*, int, int, const double*, const float*, float*, cudaStream_t);
 int launch_charges_out(int, int, const float*, float*, float*, cudaStream_t);
+int launch_skin_check(int, const float*, const float*, float, int32_t*, cudaStream_t);
+int launch_skin_save(int, const float*, const float*, float*, float*, cudaStream_t);
+int launch_skin_apply(int, const float*, const float*, float*, cudaStream_t);
 
 int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, const float*, const CoulombParams&,
                    double*, float*, float*, double*, int, cudaStream_t);
@@ -130,6 +133,18 @@ struct aimnet2_engine {
     float last_gemm_ms = 0.f;
     int last_gemm_launches = 0;
     EwaldPlan ewald;
+    // Verlet-skin reuse of the neighbor lists (options.neighbor_skin > 0): what the lists in the workspace were built for
+    struct {
+        bool valid = false;
+        int N = 0, B = 0, n_cells = 0, sr_cap = 0, lr_cap = 0;
+        bool need_lr = false;
+        float sr_cut = 0.f, lr_cut = 0.f, skin = 0.f;
+        const char* ws = nullptr;
+        const int32_t* mol_idx = nullptr;
+        std::vector<float> cell;
+        std::vector<uint8_t> pbc;
+        int builds = 0, reuses = 0;
+    } skin;
     std::vector<void*> owned;
 };
 
@@ -250,6 +265,8 @@ struct Buffers {
     // h1 / dzA,dzB (fp16 hi + fp16 lo = the bytes of the fp32 matrix they replace); only x16, dz32 and the scales are extra.
     SplitMat x16, h16[2], aim16, h1_16, d16[2];
     float* dz32;
+    float *coord_ref, *wrap_off;   // Verlet skin: positions at list-build time, lattice offset applied by the wrap
+    int32_t* skin_flag;
 };
 
 static SplitMat alias_split(float* base, size_t n, int width, float* inv) {
@@ -324,6 +341,9 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.d16[0] = alias_split(b.dzA, n, 512, bp.take<float>(n * 16));
     b.d16[1] = alias_split(b.dzB, n, 512, bp.take<float>(n * 16));
     b.dz32 = bp.take<float>(n * 288);
+    b.coord_ref = bp.take<float>(n * 3);
+    b.wrap_off = bp.take<float>(n * 3);
+    b.skin_flag = bp.take<int32_t>(4);
 }
 
 static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
@@ -448,6 +468,19 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     if (e->timing) cudaEventRecord(e->ev[0], st);
 
     Buffers b;
+    const float skin = own_sr ? std::max(0.f, o.neighbor_skin) : 0.f;
+    auto skin_matches = [&]() {
+        auto& k = e->skin;
+        if (!k.valid || k.N != N || k.B != B || k.n_cells != sys->n_cells || k.sr_cap != e->sr_cap || k.lr_cap != e->lr_cap ||
+            k.need_lr != need_lr_list || k.sr_cut != o.sr_cutoff || k.lr_cut != lr_cut || k.skin != skin || k.ws != e->ws ||
+            k.mol_idx != sys->mol_idx)
+            return false;
+        for (int c = 0; c < 9 * sys->n_cells; ++c)
+            if (k.cell[c] != sys->host_cell[c]) return false;
+        for (int c = 0; c < 3 * sys->n_cells; ++c)
+            if (k.pbc[c] != (sys->pbc_host ? sys->pbc_host[c] : (uint8_t)1)) return false;
+        return true;
+    };
     for (int attempt = 0;; ++attempt) {
         AIM_REQUIRE(attempt < 8, "engine_eval: neighbor buffers failed to converge");
         Bump probe{nullptr};
@@ -457,6 +490,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             AIM_CUDA_CHECK(cudaStreamSynchronize(st));
             if (e->ws) AIM_CUDA_CHECK(cudaFree(e->ws));
             e->ws = nullptr;
+            e->skin.valid = false;
             size_t want = need + need / 8;
             AIM_CUDA_CHECK(cudaMalloc((void**)&e->ws, want));
             e->ws_bytes = want;
@@ -464,6 +498,19 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         Bump bp{e->ws};
         carve(e, bp, b, N, B, e->sr_cap, e->lr_cap, pbc, need_lr_list, ldx);
         if (N == 0) break;
+        if (skin > 0.f && attempt == 0 && skin_matches()) {
+            // lists built at cutoff + skin are still complete if no atom has moved by more than skin / 2 since the build
+            AIM_TRY(launch_skin_check(N, sys->coord, b.coord_ref, 0.25f * skin * skin, b.skin_flag, st));
+            AIM_CUDA_CHECK(cudaMemcpyAsync(e->pinned_int + 8, b.skin_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (e->pinned_int[8] == 0) {
+                // same lattice offsets as at build time: the stored shifts refer to those images
+                if (pbc) AIM_TRY(launch_skin_apply(N, sys->coord, b.wrap_off, b.coord_w, st));
+                e->skin.reuses++;
+                break;
+            }
+        }
+        e->skin.valid = false;
         const float* coord = sys->coord;
         if (pbc) {
             AIM_TRY(wrap_positions_impl(sys->coord, b.coord_w, N, sys->cell, sys->n_cells, sys->pbc_host, sys->mol_idx, st));
@@ -472,7 +519,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         bool retry = false;
         if (own_sr) {
             int maxc = 0;
-            int rc = build_list(e, coord, N, o.sr_cutoff, sys, sys->mol_idx, 1, e->sr_cap, b.nb_sr, b.sh_sr, b.cnt_sr,
+            int rc = build_list(e, coord, N, o.sr_cutoff + skin, sys, sys->mol_idx, 1, e->sr_cap, b.nb_sr, b.sh_sr, b.cnt_sr,
                                 &maxc, b.nb_scratch, st);
             if (rc == AIMNET_NEIGHBOR_OVERFLOW) {
                 e->sr_cap = round16(maxc + maxc / 4 + 1);
@@ -483,7 +530,8 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         }
         if (!retry && need_lr_list) {
             int maxc = 0;
-            int rc = build_list(e, coord, N, lr_cut, sys, sys->mol_idx, 0, e->lr_cap, b.nb_lr, b.sh_lr, b.cnt_lr, &maxc, b.nb_scratch, st);
+            int rc = build_list(e, coord, N, lr_cut + skin, sys, sys->mol_idx, 0, e->lr_cap, b.nb_lr, b.sh_lr, b.cnt_lr, &maxc,
+                                b.nb_scratch, st);
             if (rc == AIMNET_NEIGHBOR_OVERFLOW) {
                 e->lr_cap = round16(maxc + maxc / 8 + 1);
                 retry = true;
@@ -491,7 +539,21 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 return rc;
             e->last_lr_width = std::max(1, maxc);
         }
-        if (!retry) break;
+        if (!retry) {
+            if (skin > 0.f) {
+                AIM_TRY(launch_skin_save(N, sys->coord, pbc ? b.coord_w : nullptr, b.coord_ref, b.wrap_off, st));
+                auto& k = e->skin;
+                k.N = N, k.B = B, k.n_cells = sys->n_cells, k.sr_cap = e->sr_cap, k.lr_cap = e->lr_cap;
+                k.need_lr = need_lr_list, k.sr_cut = o.sr_cutoff, k.lr_cut = lr_cut, k.skin = skin;
+                k.ws = e->ws, k.mol_idx = sys->mol_idx;
+                k.cell.assign(sys->host_cell ? sys->host_cell : nullptr, sys->host_cell ? sys->host_cell + 9 * sys->n_cells : nullptr);
+                k.pbc.assign((size_t)3 * sys->n_cells, (uint8_t)1);
+                if (sys->pbc_host) k.pbc.assign(sys->pbc_host, sys->pbc_host + 3 * sys->n_cells);
+                k.valid = true;
+                k.builds++;
+            }
+            break;
+        }
     }
     if (e->timing) cudaEventRecord(e->ev[1], st);
     const float* coord = pbc ? b.coord_w : sys->coord;
@@ -894,6 +956,13 @@ extern "C" int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int
     if (sr_width) *sr_width = e->last_sr_width;
     if (lr_width) *lr_width = e->last_lr_width;
     if (workspace_bytes) *workspace_bytes = (int64_t)e->ws_bytes;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_skin_stats(const aimnet2_engine_t* e, int* builds, int* reuses) {
+    AIM_REQUIRE(e, "skin_stats: null engine");
+    if (builds) *builds = e->skin.builds;
+    if (reuses) *reuses = e->skin.reuses;
     return AIMNET_OK;
 }
 

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(256) d3_cn_kernel(int n, PairSource ps, const 
         float rx, ry, rz;
         if (!slot_geometry(ps, coord, cell, i, m, j, rx, ry, rz)) continue;
         float db = fmaxf(sqrtf(rx * rx + ry * ry + rz * rz), 1e-12f) * (float)(1.0 / kBohr);
+        if (db >= p.r_off) continue;   // the list may reach further (other long-range term, Verlet skin)
         float arg = 16.0f * ((rci + p.rcov[clampz(numbers[j])]) / db - 1.0f);
         acc += 1.0f / (1.0f + expf(-arg));
     }
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(256) d3_cn_force_kernel(int n, PairSource ps, 
         if (!slot_geometry(ps, coord, cell, i, m, j, rx, ry, rz)) continue;
         float dA = fmaxf(sqrtf(rx * rx + ry * ry + rz * rz), 1e-12f);
         float d = dA * ib;
+        if (d >= p.r_off) continue;
         float R = rci + p.rcov[clampz(numbers[j])];
         float s = 1.0f / (1.0f + expf(-16.0f * (R / d - 1.0f)));
         float dcn = s * (1.0f - s) * 16.0f * (-R / (d * d)) * ib;   // d cn / d d_Angstrom

@@ -288,6 +288,31 @@ __global__ void charges_out_kernel(int C, int n, const float* __restrict__ q, fl
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// ---- Verlet-skin bookkeeping (engine.cu): has any atom moved by more than skin/2 since the lists were built? ----
+__global__ void skin_check_kernel(int n, const float* __restrict__ x, const float* __restrict__ ref, float thr2,
+                                  int32_t* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool moved = false;
+    if (i < n) {
+        float dx = x[3 * i] - ref[3 * i], dy = x[3 * i + 1] - ref[3 * i + 1], dz = x[3 * i + 2] - ref[3 * i + 2];
+        float d2 = dx * dx + dy * dy + dz * dz;
+        moved = !(d2 <= thr2);   // NaN counts as moved
+    }
+    if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+// ref = x; off = wrapped - x (the lattice vector the wrap added), or 0 without a cell
+__global__ void skin_save_kernel(int n, const float* __restrict__ x, const float* __restrict__ wrapped,
+                                 float* __restrict__ ref, float* __restrict__ off) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * n) return;
+    ref[i] = x[i];
+    off[i] = wrapped ? wrapped[i] - x[i] : 0.f;
+}
+__global__ void skin_apply_kernel(int n, const float* __restrict__ x, const float* __restrict__ off, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n) out[i] = x[i] + off[i];
+}
+
 #define AIM_K(...)          \
     do {                    \
         __VA_ARGS__;        \
@@ -345,6 +370,19 @@ int launch_energy_reduce(int n_mol, const int32_t* mol_ptr, const double* e0, co
 int launch_stress_reduce(const int32_t* mol_ptr, int n_cells, int n, const double* virial_atom, const float* cell,
                          float* stress, cudaStream_t st) {
     AIM_K(stress_reduce_kernel<<<n_cells, 256, 0, st>>>(mol_ptr, n_cells, n, virial_atom, cell, stress));
+    return AIMNET_OK;
+}
+int launch_skin_check(int n, const float* x, const float* ref, float thr2, int32_t* flag, cudaStream_t st) {
+    AIM_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    if (n) AIM_K(skin_check_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, x, ref, thr2, flag));
+    return AIMNET_OK;
+}
+int launch_skin_save(int n, const float* x, const float* wrapped, float* ref, float* off, cudaStream_t st) {
+    if (n) AIM_K(skin_save_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, x, wrapped, ref, off));
+    return AIMNET_OK;
+}
+int launch_skin_apply(int n, const float* x, const float* off, float* out, cudaStream_t st) {
+    if (n) AIM_K(skin_apply_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, x, off, out));
     return AIMNET_OK;
 }
 int launch_charges_out(int C, int n, const float* q, float* charges, float* spin, cudaStream_t st) {

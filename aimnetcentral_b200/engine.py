@@ -96,7 +96,7 @@ class Engine:
         self.gemm_backend = 2 if self._lib.aimnet2_engine_set_gemm_backend(h, 2) == 0 else 0
         self.options = dict(coulomb_method="simple", dsf_alpha=0.2, dsf_rc=15.0, ewald_accuracy=1e-6, dispersion=False,
                             d3_s6=1.0, d3_s8=0.3908, d3_a1=0.566, d3_a2=3.128, d3_cutoff=15.0, d3_smoothing=0.2,
-                            sr_cutoff=5.0)
+                            sr_cutoff=5.0, neighbor_skin=0.0)
 
     # ------------------------------------------------------------------------------------------------------
     def close(self):
@@ -119,6 +119,7 @@ class Engine:
         o.dispersion = 1 if d["dispersion"] else 0
         o.d3_s6, o.d3_s8, o.d3_a1, o.d3_a2 = d["d3_s6"], d["d3_s8"], d["d3_a1"], d["d3_a2"]
         o.d3_cutoff, o.d3_smoothing, o.sr_cutoff = d["d3_cutoff"], d["d3_smoothing"], d["sr_cutoff"]
+        o.neighbor_skin = float(d.get("neighbor_skin", 0.0))
         _capi.check(self._lib.aimnet2_engine_set_options(self._h, C.byref(o)), "set_options")
 
     def set_small_m_rows(self, rows: int):
@@ -144,6 +145,12 @@ class Engine:
 
     def last_launches(self) -> int:
         return int(self._lib.aimnet2_engine_last_launches(self._h))
+
+    def skin_stats(self) -> tuple[int, int]:
+        """(list builds, list reuses) since the engine was created; only counted with neighbor_skin > 0."""
+        a, b = C.c_int(), C.c_int()
+        self._lib.aimnet2_engine_skin_stats(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def info(self) -> dict:
         a, b, c = C.c_int(), C.c_int(), C.c_int64()

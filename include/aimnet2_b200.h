@@ -119,6 +119,11 @@ typedef struct {
     float d3_s6, d3_s8, d3_a1, d3_a2;
     float d3_cutoff, d3_smoothing;    /* 15.0, 0.2 */
     float sr_cutoff;                  /* 5.0 */
+    /* Verlet skin in Angstrom (0 = rebuild the neighbor lists on every evaluation, the reference's behaviour).  With a
+     * skin the engine builds its lists at cutoff + skin and keeps them until an atom has moved by more than skin / 2
+     * since the build (same atoms, cell and options); every pair kernel applies its own cutoff, so results do not
+     * depend on the skin.  Ignored when the caller supplies nbmat. */
+    float neighbor_skin;
 } aimnet2_options_t;
 
 /* One evaluation.  Flat (mode-1) layout, real atoms only (the engine adds no padding atom; sentinel = n_atoms).
@@ -174,6 +179,8 @@ int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_system_t* sys, c
 /* introspection: kernels launched by the last eval, last short-range / long-range list widths, workspace bytes */
 int aimnet2_engine_last_launches(const aimnet2_engine_t* e);
 int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int* lr_width, int64_t* workspace_bytes);
+/* Verlet skin bookkeeping: evaluations that built the lists / reused them (options.neighbor_skin > 0) */
+int aimnet2_engine_skin_stats(const aimnet2_engine_t* e, int* builds, int* reuses);
 /* per-phase device times (ms) of the last eval when timing was enabled (level 1: phase events, level 2: also one
  * event pair around every GEMM launch); slots: 0 neighbors, 1 forward,
  * 2 long-range, 3 backward, 4 total; returns number of phases written */

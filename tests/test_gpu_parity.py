@@ -396,3 +396,47 @@ def test_repeated_evaluations_are_bitwise_identical():
             out = calc(dict(inp), **kw)
             for k in ref:
                 assert torch.equal(ref[k], out[k]), k
+
+
+def test_verlet_skin_reuse_matches_rebuild():
+    """neighbor_skin > 0: lists built at cutoff + skin are reused while no atom has moved by more than skin / 2, with the
+    lattice offsets of the build; the results must equal those of a calculator that rebuilds every call (every pair
+    kernel applies its own cutoff, extra listed pairs contribute exactly zero)."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import allose_supercell, random_molecules
+
+    spec = ModelSpec()
+    sd = random_state_dict(0, spec)
+    ref_calc = AIMNet2Calculator((sd, spec), device="cuda:0")
+    skin_calc = AIMNet2Calculator((sd, spec), device="cuda:0", neighbor_skin=1.0)
+    rng = np.random.default_rng(7)
+    z, x0, cell = allose_supercell((2, 1, 1), jitter=0.02, seed=1)
+    x0 = x0.astype(np.float32)
+    # put one atom right at a cell face so that the trajectory carries it across the periodic boundary
+    frac = x0 @ np.linalg.inv(cell)
+    frac[0, 0] = 0.999
+    x0 = (frac @ cell).astype(np.float32)
+    for calc in (ref_calc, skin_calc):
+        calc.set_lrcoulomb_method("dsf")
+    x = x0.copy()
+    for step in range(6):
+        inp = {"coord": x, "numbers": z, "charge": np.zeros(1, np.float32), "cell": cell}
+        a = ref_calc(dict(inp), forces=True, stress=True)
+        b = skin_calc(dict(inp), forces=True, stress=True)
+        assert abs(float(a["energy"] - b["energy"])) < 1e-6, step
+        assert float((a["forces"] - b["forces"]).abs().max()) < 1e-6, step
+        assert float((a["stress"] - b["stress"]).abs().max()) < 1e-8, step
+        x = x + rng.normal(0, 0.04, x.shape).astype(np.float32)   # ~0.1 A per step: crosses skin / 2 after a few steps
+        x[0, 0] += 0.05
+    builds, reuses = skin_calc.engine.skin_stats()
+    assert reuses >= 2 and builds >= 2, (builds, reuses)
+    # isolated molecules: only the short-range list exists
+    coord, numbers = random_molecules(8, 40, seed=2)
+    ref_calc.set_lrcoulomb_method("simple")
+    skin_calc.set_lrcoulomb_method("simple")
+    for step in range(3):
+        inp = {"coord": coord, "numbers": numbers, "charge": np.zeros(8, np.float32)}
+        a = ref_calc(dict(inp), forces=True)
+        b = skin_calc(dict(inp), forces=True)
+        assert float((a["forces"] - b["forces"]).abs().max()) < 1e-6
+        coord = coord + rng.normal(0, 0.02, coord.shape).astype(np.float32)
