@@ -130,6 +130,11 @@ class AIMNet2Calculator:
         self._batch: int | None = None
         # extension over the reference API: Verlet skin (A) for neighbor-list reuse across MD steps; 0 = rebuild every call
         self._neighbor_skin = float(neighbor_skin)
+        if self.cache_static and self._neighbor_skin <= 0.0:
+            # cache_static (calculator.py:1091-1238 of the reference: reuse the neighbor matrices while the caller keeps
+            # passing the same, unmodified coordinates) maps onto the engine's list reuse with a vanishing skin: the
+            # device-side displacement check replaces the reference's tensor-identity bookkeeping
+            self._neighbor_skin = 1.0e-3
         self.engine = Engine(sd, C, self.device, sr_rc=float(sr_rc), sr_envelope=sr_env, load_d3=self._has_dftd3)
         # duck-typed `model` handle for the adapters that read `base_calc.model._metadata` / `.num_charge_channels`
         # (aimnet/calculators/aimnet2ase.py:69, aimnet2torchsim.py:78-125)

@@ -51,8 +51,8 @@ int launch_energy_reduce(int, const int32_t*, const double*, const double*, cons
                          cudaStream_t);
 int launch_stress_reduce(const int32_t*, int, int, const double*, const float*, float*, cudaStream_t);
 int launch_charges_out(int, int, const float*, float*, float*, cudaStream_t);
-int launch_skin_check(int, const float*, const float*, float, int32_t*, cudaStream_t);
-int launch_skin_save(int, const float*, const float*, float*, float*, cudaStream_t);
+int launch_skin_check(int, const float*, const float*, float, const int32_t*, const int32_t*, int32_t*, cudaStream_t);
+int launch_skin_save(int, const float*, const float*, float*, float*, const int32_t*, int32_t*, cudaStream_t);
 int launch_skin_apply(int, const float*, const float*, float*, cudaStream_t);
 
 int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, const float*, const CoulombParams&,
@@ -140,7 +140,7 @@ struct aimnet2_engine {
         bool need_lr = false;
         float sr_cut = 0.f, lr_cut = 0.f, skin = 0.f;
         const char* ws = nullptr;
-        const int32_t* mol_idx = nullptr;
+        bool has_mol = false;
         std::vector<float> cell;
         std::vector<uint8_t> pbc;
         int builds = 0, reuses = 0;
@@ -266,7 +266,7 @@ struct Buffers {
     SplitMat x16, h16[2], aim16, h1_16, d16[2];
     float* dz32;
     float *coord_ref, *wrap_off;   // Verlet skin: positions at list-build time, lattice offset applied by the wrap
-    int32_t* skin_flag;
+    int32_t *skin_flag, *mol_ref;
 };
 
 static SplitMat alias_split(float* base, size_t n, int width, float* inv) {
@@ -344,6 +344,7 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.coord_ref = bp.take<float>(n * 3);
     b.wrap_off = bp.take<float>(n * 3);
     b.skin_flag = bp.take<int32_t>(4);
+    b.mol_ref = bp.take<int32_t>(n);
 }
 
 static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
@@ -473,7 +474,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         auto& k = e->skin;
         if (!k.valid || k.N != N || k.B != B || k.n_cells != sys->n_cells || k.sr_cap != e->sr_cap || k.lr_cap != e->lr_cap ||
             k.need_lr != need_lr_list || k.sr_cut != o.sr_cutoff || k.lr_cut != lr_cut || k.skin != skin || k.ws != e->ws ||
-            k.mol_idx != sys->mol_idx)
+            k.has_mol != (sys->mol_idx != nullptr))
             return false;
         for (int c = 0; c < 9 * sys->n_cells; ++c)
             if (k.cell[c] != sys->host_cell[c]) return false;
@@ -500,7 +501,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         if (N == 0) break;
         if (skin > 0.f && attempt == 0 && skin_matches()) {
             // lists built at cutoff + skin are still complete if no atom has moved by more than skin / 2 since the build
-            AIM_TRY(launch_skin_check(N, sys->coord, b.coord_ref, 0.25f * skin * skin, b.skin_flag, st));
+            AIM_TRY(launch_skin_check(N, sys->coord, b.coord_ref, 0.25f * skin * skin, sys->mol_idx, b.mol_ref, b.skin_flag, st));
             AIM_CUDA_CHECK(cudaMemcpyAsync(e->pinned_int + 8, b.skin_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             AIM_CUDA_CHECK(cudaStreamSynchronize(st));
             if (e->pinned_int[8] == 0) {
@@ -541,11 +542,11 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         }
         if (!retry) {
             if (skin > 0.f) {
-                AIM_TRY(launch_skin_save(N, sys->coord, pbc ? b.coord_w : nullptr, b.coord_ref, b.wrap_off, st));
+                AIM_TRY(launch_skin_save(N, sys->coord, pbc ? b.coord_w : nullptr, b.coord_ref, b.wrap_off, sys->mol_idx, b.mol_ref, st));
                 auto& k = e->skin;
                 k.N = N, k.B = B, k.n_cells = sys->n_cells, k.sr_cap = e->sr_cap, k.lr_cap = e->lr_cap;
                 k.need_lr = need_lr_list, k.sr_cut = o.sr_cutoff, k.lr_cut = lr_cut, k.skin = skin;
-                k.ws = e->ws, k.mol_idx = sys->mol_idx;
+                k.ws = e->ws, k.has_mol = sys->mol_idx != nullptr;
                 k.cell.assign(sys->host_cell ? sys->host_cell : nullptr, sys->host_cell ? sys->host_cell + 9 * sys->n_cells : nullptr);
                 k.pbc.assign((size_t)3 * sys->n_cells, (uint8_t)1);
                 if (sys->pbc_host) k.pbc.assign(sys->pbc_host, sys->pbc_host + 3 * sys->n_cells);

@@ -290,20 +290,24 @@ __global__ void charges_out_kernel(int C, int n, const float* __restrict__ q, fl
 // ------------------------------------------------------------------------------------------------------------
 // ---- Verlet-skin bookkeeping (engine.cu): has any atom moved by more than skin/2 since the lists were built? ----
 __global__ void skin_check_kernel(int n, const float* __restrict__ x, const float* __restrict__ ref, float thr2,
+                                  const int32_t* __restrict__ mol, const int32_t* __restrict__ mol_ref,
                                   int32_t* __restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool moved = false;
     if (i < n) {
         float dx = x[3 * i] - ref[3 * i], dy = x[3 * i + 1] - ref[3 * i + 1], dz = x[3 * i + 2] - ref[3 * i + 2];
         float d2 = dx * dx + dy * dy + dz * dz;
-        moved = !(d2 <= thr2);   // NaN counts as moved
+        moved = !(d2 <= thr2);                             // NaN counts as moved
+        if (mol != nullptr) moved |= mol[i] != mol_ref[i];  // same atoms, another partition into molecules
     }
     if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
-// ref = x; off = wrapped - x (the lattice vector the wrap added), or 0 without a cell
+// ref = x; off = wrapped - x (the lattice vector the wrap added), or 0 without a cell; mol_ref = mol
 __global__ void skin_save_kernel(int n, const float* __restrict__ x, const float* __restrict__ wrapped,
-                                 float* __restrict__ ref, float* __restrict__ off) {
+                                 float* __restrict__ ref, float* __restrict__ off, const int32_t* __restrict__ mol,
+                                 int32_t* __restrict__ mol_ref) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && mol != nullptr) mol_ref[i] = mol[i];
     if (i >= 3 * n) return;
     ref[i] = x[i];
     off[i] = wrapped ? wrapped[i] - x[i] : 0.f;
@@ -372,13 +376,15 @@ int launch_stress_reduce(const int32_t* mol_ptr, int n_cells, int n, const doubl
     AIM_K(stress_reduce_kernel<<<n_cells, 256, 0, st>>>(mol_ptr, n_cells, n, virial_atom, cell, stress));
     return AIMNET_OK;
 }
-int launch_skin_check(int n, const float* x, const float* ref, float thr2, int32_t* flag, cudaStream_t st) {
+int launch_skin_check(int n, const float* x, const float* ref, float thr2, const int32_t* mol, const int32_t* mol_ref,
+                      int32_t* flag, cudaStream_t st) {
     AIM_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
-    if (n) AIM_K(skin_check_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, x, ref, thr2, flag));
+    if (n) AIM_K(skin_check_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, x, ref, thr2, mol, mol_ref, flag));
     return AIMNET_OK;
 }
-int launch_skin_save(int n, const float* x, const float* wrapped, float* ref, float* off, cudaStream_t st) {
-    if (n) AIM_K(skin_save_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, x, wrapped, ref, off));
+int launch_skin_save(int n, const float* x, const float* wrapped, float* ref, float* off, const int32_t* mol,
+                     int32_t* mol_ref, cudaStream_t st) {
+    if (n) AIM_K(skin_save_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, x, wrapped, ref, off, mol, mol_ref));
     return AIMNET_OK;
 }
 int launch_skin_apply(int n, const float* x, const float* off, float* out, cudaStream_t st) {

@@ -454,3 +454,28 @@ def test_verlet_skin_reuse_matches_rebuild():
         b = skin_calc(dict(inp), forces=True)
         assert float((a["forces"] - b["forces"]).abs().max()) < 2e-5
         coord = coord + rng.normal(0, 0.02, coord.shape).astype(np.float32)
+    assert skin_calc.engine.skin_stats()[1] >= reuses + 2   # the molecule batch reused its list too
+
+
+def test_cache_static_reuses_lists_for_unchanged_geometry():
+    """cache_static=True (reference: calculator.py:1091-1238): repeated evaluation of an unchanged geometry reuses the
+    neighbor matrices; a changed geometry rebuilds them; results are those of a plain calculator."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import random_molecules
+
+    spec = ModelSpec()
+    sd = random_state_dict(0, spec)
+    plain = AIMNet2Calculator((sd, spec), device="cuda:0")
+    cached = AIMNet2Calculator((sd, spec), device="cuda:0", cache_static=True)
+    coord, numbers = random_molecules(4, 30, seed=21)
+    inp = {"coord": coord, "numbers": numbers, "charge": np.zeros(4, np.float32)}
+    ref = plain(dict(inp), forces=True)
+    for _ in range(3):
+        out = cached(dict(inp), forces=True)
+        assert float((out["forces"] - ref["forces"]).abs().max()) < 1e-6
+    builds, reuses = cached.engine.skin_stats()
+    assert (builds, reuses) == (1, 2)
+    moved = dict(inp, coord=coord + 0.05)
+    out = cached(moved, forces=True)
+    assert float((out["forces"] - plain(moved, forces=True)["forces"]).abs().max()) < 1e-6
+    assert cached.engine.skin_stats()[0] == 2
