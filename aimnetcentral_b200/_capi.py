@@ -60,9 +60,10 @@ class Result(C.Structure):
 
 
 _LIB = None
+ABI_VERSION = 2   # include/aimnet2_b200.h AIMNET2_ABI_VERSION
 
 EXPORTS = [
-    "aimnet2_last_error", "aimnet2_abi_version", "aimnet2_neighbor_matrix", "aimnet2_wrap_positions",
+    "aimnet2_last_error", "aimnet2_abi_version", "aimnet2_abi_struct_sizes", "aimnet2_neighbor_matrix", "aimnet2_wrap_positions",
     "aimnet2_conv_sv_2d_sp_fwd", "aimnet2_conv_sv_2d_sp_bwd", "aimnet2_engine_create", "aimnet2_engine_destroy",
     "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_small_m_rows", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
     "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_skin_stats", "aimnet2_engine_enable_timing",
@@ -110,6 +111,14 @@ def load():
     for name in EXPORTS:
         if name != "aimnet2_last_error":
             getattr(lib, name).restype = ci
+    lib.aimnet2_abi_struct_sizes.argtypes = [c_int_p, c_int_p, c_int_p, c_int_p]
+    # the ctypes mirrors above must describe the structs this library was compiled with
+    sizes = [C.c_int() for _ in range(4)]
+    lib.aimnet2_abi_struct_sizes(*[C.byref(x) for x in sizes])
+    mine = [C.sizeof(Weights), C.sizeof(Options), C.sizeof(System), C.sizeof(Result)]
+    if lib.aimnet2_abi_version() != ABI_VERSION or [x.value for x in sizes] != mine:
+        raise RuntimeError(f"{path}: ABI mismatch (library version {lib.aimnet2_abi_version()}, struct sizes "
+                           f"{[x.value for x in sizes]}; binding version {ABI_VERSION}, sizes {mine}) - rebuild the library")
     _LIB = lib
     return lib
 

@@ -757,7 +757,14 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
 
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" const char* aimnet2_last_error(void) { return aimnet::g_error.c_str(); }
-extern "C" int aimnet2_abi_version(void) { return 1; }
+extern "C" int aimnet2_abi_version(void) { return AIMNET2_ABI_VERSION; }
+extern "C" int aimnet2_abi_struct_sizes(int* weights, int* options, int* system, int* result) {
+    if (weights) *weights = (int)sizeof(aimnet2_weights_t);
+    if (options) *options = (int)sizeof(aimnet2_options_t);
+    if (system) *system = (int)sizeof(aimnet2_system_t);
+    if (result) *result = (int)sizeof(aimnet2_result_t);
+    return AIMNET_OK;
+}
 
 extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weights_t* w, int device) {
     AIM_REQUIRE(out && w, "engine_create: null argument");

@@ -48,7 +48,11 @@ extern "C" {
 #define AIMNET_WANT_STRESS 2
 
 const char* aimnet2_last_error(void);
+/* Bumped whenever a struct below changes (2: aimnet2_options_t.neighbor_skin).  A binding checks it, and the sizes of the
+ * four structs as this library was compiled, against its own declarations before the first call. */
+#define AIMNET2_ABI_VERSION 2
 int aimnet2_abi_version(void);
+int aimnet2_abi_struct_sizes(int* weights, int* options, int* system, int* result);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Neighbor matrix (full list, both directions).  Canonical form: `d2 < cutoff^2` in float32, rows sorted by

@@ -23,7 +23,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_capi.EXPORTS) == declared
     lib.aimnet2_abi_version.restype = ctypes.c_int
-    assert lib.aimnet2_abi_version() == 1
+    assert lib.aimnet2_abi_version() == _capi.ABI_VERSION == 2
+    # struct layouts of the ctypes binding == the compiled header (checked inside _capi.load(), repeated here)
+    sizes = [ctypes.c_int() for _ in range(4)]
+    lib.aimnet2_abi_struct_sizes(*[ctypes.byref(x) for x in sizes])
+    assert [x.value for x in sizes] == [ctypes.sizeof(t) for t in (_capi.Weights, _capi.Options, _capi.System, _capi.Result)]
 
 
 def test_calculator_refuses_cpu():
