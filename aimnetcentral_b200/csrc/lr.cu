@@ -17,6 +17,11 @@
 
 namespace aimnet {
 
+// The pair walkers divide a lot (1/d, damping denominators, switches).  IEEE division costs ~12 instructions plus a slow
+// path per site; MUFU.RCP based division is within 2 ulp, three orders of magnitude inside the parity budget.
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float frcp(float b) { return __fdividef(1.0f, b); }
+
 __device__ __forceinline__ void row_range(const PairSource& ps, int i, int& begin, int& end) {
     if (ps.nb.nbmat) {
         begin = 0;
@@ -47,19 +52,19 @@ __device__ __forceinline__ bool slot_geometry(const PairSource& ps, const float*
 }
 
 template <int MODE>
-__device__ __forceinline__ void pair_phi(float d, const CoulombParams& p, float& phi, float& dphi) {
-    float inv = 1.0f / d;
+__device__ __forceinline__ void pair_phi(float d, const CoulombParams& p, float& phi, float& dphi, float& inv) {
+    inv = frcp(d);
     if (MODE == PAIR_SIMPLE) {
         phi = inv;
         dphi = -inv * inv;
     } else if (MODE == PAIR_SR_EXP) {
         // exp_cutoff, aimnet/ops.py:88-90
-        float t = d / p.rc;
+        float t = fdiv(d, p.rc);
         bool clamped = t >= 1.0f - 1e-6f;
         t = fminf(fmaxf(t, 0.f), 1.0f - 1e-6f);
         float om = 1.0f - t * t;
-        float fc = expf(-1.0f / om) / 0.36787944117144233f;
-        float dfc = clamped ? 0.f : -fc * 2.0f * t / (om * om) / p.rc;
+        float fc = expf(-frcp(om)) * 2.718281828459045f;
+        float dfc = clamped ? 0.f : fdiv(-fc * 2.0f * t, om * om * p.rc);
         phi = fc * inv;
         dphi = dfc * inv - fc * inv * inv;
     } else if (MODE == PAIR_SR_COS) {
@@ -116,12 +121,12 @@ __global__ void __launch_bounds__(256) coulomb_pair_kernel(int n, PairSource ps,
         float rx, ry, rz;
         if (!slot_geometry(ps, coord, cell, i, m, j, rx, ry, rz)) continue;
         float d = sqrtf(rx * rx + ry * ry + rz * rz);
-        float phi, dphi;
-        pair_phi<MODE>(d, p, phi, dphi);
+        float phi, dphi, inv;
+        pair_phi<MODE>(d, p, phi, dphi, inv);
         float qj = q[j];
         esum += (double)(qi * qj * phi);
         gsum += qj * phi;
-        float w = qi * qj * dphi / d;   // e'(d) / d  -> times r gives e' u
+        float w = qi * qj * dphi * inv;   // e'(d) / d  -> times r gives e' u
         fx += w * rx;
         fy += w * ry;
         fz += w * rz;
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(256) d3_cn_kernel(int n, PairSource ps, const 
         if (!slot_geometry(ps, coord, cell, i, m, j, rx, ry, rz)) continue;
         float db = fmaxf(sqrtf(rx * rx + ry * ry + rz * rz), 1e-12f) * (float)(1.0 / kBohr);
         if (db >= p.r_off) continue;   // the list may reach further (other long-range term, Verlet skin)
-        float arg = 16.0f * ((rci + p.rcov[clampz(numbers[j])]) / db - 1.0f);
-        acc += 1.0f / (1.0f + expf(-arg));
+        float arg = 16.0f * (fdiv(rci + p.rcov[clampz(numbers[j])], db) - 1.0f);
+        acc += frcp(1.0f + expf(-arg));
     }
     acc = warp_sum(acc);
     if (lane == 0) cn[i] = acc;
@@ -269,7 +274,7 @@ __device__ __forceinline__ void d3_c6(const D3Params& p, int zi, int zj, const f
             dcsum = fmaf(c, dw, dcsum);
         }
     if (wsum > 1e-12f) {
-        float inv = 1.0f / fmaxf(wsum, 1e-12f);
+        float inv = frcp(fmaxf(wsum, 1e-12f));
         c6 = csum * inv;
         dc6_dcni = (dcsum - c6 * dwsum) * inv;
     } else {
@@ -310,10 +315,11 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
         // switch (lr.py:1580-1593)
         float sw = 1.f, dsw = 0.f;
         if (d > p.r_on) {
-            float t = fminf(fmaxf((d - p.r_on) / (p.r_off - p.r_on), 0.f), 1.f);
+            const float iw = frcp(p.r_off - p.r_on);
+            float t = fminf(fmaxf((d - p.r_on) * iw, 0.f), 1.f);
             float t2 = t * t;
             sw = 1.0f - t2 * t * (10.0f - 15.0f * t + 6.0f * t2);
-            dsw = (t < 1.f) ? -30.0f * t2 * (1.0f - t) * (1.0f - t) / (p.r_off - p.r_on) : 0.f;
+            dsw = (t < 1.f) ? -30.0f * t2 * (1.0f - t) * (1.0f - t) * iw : 0.f;
         }
         if (sw == 0.f && dsw == 0.f) continue;
         int zj = clampz(numbers[j]);
@@ -323,14 +329,14 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
         float r0 = p.a1 * sqrtf(rr) + p.a2;
         float d2 = d * d, d4 = d2 * d2, d6 = d4 * d2, d8 = d4 * d4;
         float r02 = r0 * r0, r04 = r02 * r02, r06 = r04 * r02, r08 = r04 * r04;
-        float i6 = 1.0f / (d6 + r06), i8 = 1.0f / (d8 + r08);
+        float i6 = frcp(d6 + r06), i8 = frcp(d8 + r08);
         float damp = p.s6 * i6 + p.s8 * rr * i8;
         float ddamp = -(p.s6 * 6.0f * d4 * d * i6 * i6 + p.s8 * rr * 8.0f * d6 * d * i8 * i8);
         float eij = -c6 * damp * sw;
         esum += (double)eij;
         gsum += -dc6 * damp * sw;
         float de = -c6 * (ddamp * sw + damp * dsw) * ib;   // d e / d d_Angstrom
-        float w = de / dA;
+        float w = fdiv(de, dA);
         fx += w * rx;
         fy += w * ry;
         fz += w * rz;
@@ -397,14 +403,15 @@ __global__ void __launch_bounds__(256) d3_cn_force_kernel(int n, PairSource ps, 
         float d = dA * ib;
         if (d >= p.r_off) continue;
         float R = rci + p.rcov[clampz(numbers[j])];
-        float s = 1.0f / (1.0f + expf(-16.0f * (R / d - 1.0f)));
+        float s = frcp(1.0f + expf(-16.0f * (fdiv(R, d) - 1.0f)));
         float dcn = s * (1.0f - s) * 16.0f * (-R / (d * d)) * ib;   // d cn / d d_Angstrom
-        float w = (gi + dEdCN[j]) * dcn / dA;
+        const float idA = frcp(dA);
+        float w = (gi + dEdCN[j]) * dcn * idA;
         fx += w * rx;
         fy += w * ry;
         fz += w * rz;
         if (virial_atom) {
-            float wv = gi * dcn / dA;
+            float wv = gi * dcn * idA;
             vir[0] += (double)(wv * rx * rx);
             vir[1] += (double)(wv * rx * ry);
             vir[2] += (double)(wv * rx * rz);
