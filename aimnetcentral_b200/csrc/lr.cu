@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(256) coulomb_pair_kernel(int n, PairSource ps,
     float qi = q[i];
     double esum = 0.0;
     float gsum = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
-    double vir[9];
+    float vir[9];   // per-lane fp32 partial sums (a lane sees 1/32 of the row), reduced and accumulated in fp64 below
 #pragma unroll
-    for (int k = 0; k < 9; ++k) vir[k] = 0.0;
+    for (int k = 0; k < 9; ++k) vir[k] = 0.f;
     for (int m = b + lane; m < e; m += 32) {
         int j;
         float rx, ry, rz;
@@ -131,15 +131,15 @@ __global__ void __launch_bounds__(256) coulomb_pair_kernel(int n, PairSource ps,
         fy += w * ry;
         fz += w * rz;
         if (virial_atom) {
-            vir[0] += (double)(w * rx * rx);
-            vir[1] += (double)(w * rx * ry);
-            vir[2] += (double)(w * rx * rz);
-            vir[3] += (double)(w * ry * rx);
-            vir[4] += (double)(w * ry * ry);
-            vir[5] += (double)(w * ry * rz);
-            vir[6] += (double)(w * rz * rx);
-            vir[7] += (double)(w * rz * ry);
-            vir[8] += (double)(w * rz * rz);
+            vir[0] += w * rx * rx;
+            vir[1] += w * rx * ry;
+            vir[2] += w * rx * rz;
+            vir[3] += w * ry * rx;
+            vir[4] += w * ry * ry;
+            vir[5] += w * ry * rz;
+            vir[6] += w * rz * rx;
+            vir[7] += w * rz * ry;
+            vir[8] += w * rz * rz;
         }
     }
     esum = warp_sum(esum);
@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(256) coulomb_pair_kernel(int n, PairSource ps,
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
+    double dvir[9];
     if (virial_atom)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vir[k] = warp_sum(vir[k]);
+        for (int k = 0; k < 9; ++k) dvir[k] = warp_sum((double)vir[k]);
     if (lane == 0) {
         double c = p.factor;
         double ei = c * esum;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256) coulomb_pair_kernel(int n, PairSource ps,
         }
         if (virial_atom)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += c * vir[k];
+            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += c * dvir[k];
     }
 }
 
@@ -260,19 +261,25 @@ __device__ __forceinline__ void d3_c6(const D3Params& p, int zi, int zj, const f
         ei[a] = wi[5 + a];
         di[a] = wi[10 + a];
     }
+    // sum_ab c_ab w_a w_b [s_a + s_b >= -12] with the b sums hoisted: four instructions per (a, b) instead of eight
+    float tj[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) tj[b] = -12.0f - sj[b];
     float wsum = 0.f, csum = 0.f, dwsum = 0.f, dcsum = 0.f;
 #pragma unroll
-    for (int a = 0; a < 5; ++a)
+    for (int a = 0; a < 5; ++a) {
+        float kb = 0.f, kc = 0.f;
 #pragma unroll
         for (int b = 0; b < 5; ++b) {
-            float keep = (si[a] + sj[b] >= -12.0f) ? ej[b] : 0.f;   // invalid references carry w = 0 and s = -1e30
-            float c = cr[a * 5 + b];
-            float w = ei[a] * keep, dw = di[a] * keep;
-            wsum += w;
-            csum = fmaf(c, w, csum);
-            dwsum += dw;
-            dcsum = fmaf(c, dw, dcsum);
+            float keep = (si[a] >= tj[b]) ? ej[b] : 0.f;   // invalid references carry w = 0 and s = -1e30
+            kb += keep;
+            kc = fmaf(cr[a * 5 + b], keep, kc);
         }
+        wsum = fmaf(ei[a], kb, wsum);
+        csum = fmaf(ei[a], kc, csum);
+        dwsum = fmaf(di[a], kb, dwsum);
+        dcsum = fmaf(di[a], kc, dcsum);
+    }
     if (wsum > 1e-12f) {
         float inv = frcp(fmaxf(wsum, 1e-12f));
         c6 = csum * inv;
@@ -303,9 +310,9 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
     const float ib = (float)(1.0 / kBohr);
     double esum = 0.0;
     float gsum = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
-    double vir[9];
+    float vir[9];   // per-lane fp32 partial sums (a lane sees 1/32 of the row), reduced and accumulated in fp64 below
 #pragma unroll
-    for (int k = 0; k < 9; ++k) vir[k] = 0.0;
+    for (int k = 0; k < 9; ++k) vir[k] = 0.f;
     for (int m = b + lane; m < e; m += 32) {
         int j;
         float rx, ry, rz;
@@ -341,15 +348,15 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
         fy += w * ry;
         fz += w * rz;
         if (virial_atom) {
-            vir[0] += (double)(w * rx * rx);
-            vir[1] += (double)(w * rx * ry);
-            vir[2] += (double)(w * rx * rz);
-            vir[3] += (double)(w * ry * rx);
-            vir[4] += (double)(w * ry * ry);
-            vir[5] += (double)(w * ry * rz);
-            vir[6] += (double)(w * rz * rx);
-            vir[7] += (double)(w * rz * ry);
-            vir[8] += (double)(w * rz * rz);
+            vir[0] += w * rx * rx;
+            vir[1] += w * rx * ry;
+            vir[2] += w * rx * rz;
+            vir[3] += w * ry * rx;
+            vir[4] += w * ry * ry;
+            vir[5] += w * ry * rz;
+            vir[6] += w * rz * rx;
+            vir[7] += w * rz * ry;
+            vir[8] += w * rz * rz;
         }
     }
     esum = warp_sum(esum);
@@ -357,9 +364,10 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
+    double dvir[9];
     if (virial_atom)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vir[k] = warp_sum(vir[k]);
+        for (int k = 0; k < 9; ++k) dvir[k] = warp_sum((double)vir[k]);
     if (lane == 0) {
         const double c = 0.5 * kHartree;
         e_atom[i] = c * esum;
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(256) d3_energy_kernel(int n, PairSource ps, co
         }
         if (virial_atom)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += c * vir[k];
+            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += c * dvir[k];
     }
 }
 
@@ -392,9 +400,9 @@ __global__ void __launch_bounds__(256) d3_cn_force_kernel(int n, PairSource ps, 
     float gi = dEdCN[i];
     const float ib = (float)(1.0 / kBohr);
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    double vir[9];
+    float vir[9];   // per-lane fp32 partial sums (a lane sees 1/32 of the row), reduced and accumulated in fp64 below
 #pragma unroll
-    for (int k = 0; k < 9; ++k) vir[k] = 0.0;
+    for (int k = 0; k < 9; ++k) vir[k] = 0.f;
     for (int m = b + lane; m < e; m += 32) {
         int j;
         float rx, ry, rz;
@@ -412,30 +420,31 @@ __global__ void __launch_bounds__(256) d3_cn_force_kernel(int n, PairSource ps, 
         fz += w * rz;
         if (virial_atom) {
             float wv = gi * dcn * idA;
-            vir[0] += (double)(wv * rx * rx);
-            vir[1] += (double)(wv * rx * ry);
-            vir[2] += (double)(wv * rx * rz);
-            vir[3] += (double)(wv * ry * rx);
-            vir[4] += (double)(wv * ry * ry);
-            vir[5] += (double)(wv * ry * rz);
-            vir[6] += (double)(wv * rz * rx);
-            vir[7] += (double)(wv * rz * ry);
-            vir[8] += (double)(wv * rz * rz);
+            vir[0] += wv * rx * rx;
+            vir[1] += wv * rx * ry;
+            vir[2] += wv * rx * rz;
+            vir[3] += wv * ry * rx;
+            vir[4] += wv * ry * ry;
+            vir[5] += wv * ry * rz;
+            vir[6] += wv * rz * rx;
+            vir[7] += wv * rz * ry;
+            vir[8] += wv * rz * rz;
         }
     }
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
+    double dvir[9];
     if (virial_atom)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vir[k] = warp_sum(vir[k]);
+        for (int k = 0; k < 9; ++k) dvir[k] = warp_sum((double)vir[k]);
     if (lane == 0) {
         forces[3 * i + 0] += fx;
         forces[3 * i + 1] += fy;
         forces[3 * i + 2] += fz;
         if (virial_atom)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += vir[k];
+            for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += dvir[k];
     }
 }
 
