@@ -70,6 +70,10 @@ struct EwaldPlan {
     double* d_ck = nullptr;
     double* d_S = nullptr;
     int cap = 0;
+    int32_t* d_hkl = nullptr;    // keep in sync with ewald.cu
+    uint32_t* d_frac = nullptr;
+    int frac_cap = 0;
+    double inv[9] = {0};
 };
 int ewald_prepare(EwaldPlan&, const float*, int, double, double, cudaStream_t);
 void ewald_release(EwaldPlan&);

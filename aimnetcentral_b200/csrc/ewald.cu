@@ -14,7 +14,11 @@
 //   F_i     = k_e (8 pi q_i / V) sum c_k k (Re S sin(k.r_i) - Im S cos(k.r_i))
 //   dE/deps_ab = k_e (4 pi / V) sum c_k |S|^2 [ -delta_ab + 2 k_a k_b (1/(4 alpha^2) + 1/k^2) ]
 //   E_self = -k_e alpha/sqrt(pi) sum q_i^2 ,  E_bg = -k_e pi Q^2 / (2 V alpha^2)
-// Phases are formed in fp64 and reduced to one period before the fp32 sincos (|k.r| reaches a few hundred radians).
+// Phases: k.r = 2 pi (h f1 + k f2 + l f3) with f the fractional coordinates.  f is quantised once per evaluation to
+// 32-bit fixed point (2^32 per period, 1.5e-9 rad), the integer combination h F1 + k F2 + l F3 wraps modulo one period
+// by construction, and the fp32 sincospi sees an argument in [-1, 1): exact range reduction with three integer
+// multiply-adds instead of an fp64 dot product + rint per (atom, k) pair.  Sums run in fp32 per lane and are flushed into
+// fp64 every 16 terms.
 #include <cmath>
 #include <vector>
 
@@ -22,31 +26,51 @@
 
 namespace aimnet {
 
-__device__ __forceinline__ void phase_sincos(double kx, double ky, double kz, const float* __restrict__ r, float& s,
-                                             float& c) {
-    double ph = kx * (double)r[0] + ky * (double)r[1] + kz * (double)r[2];
-    double t = ph * 0.15915494309189535;   // / 2 pi
-    t -= rint(t);
-    sincospif((float)(2.0 * t), &s, &c);
+__device__ __forceinline__ void phase_sincos(int h, int k, int l, const uint32_t* __restrict__ F, float& s, float& c) {
+    const uint32_t ph = (uint32_t)h * F[0] + (uint32_t)k * F[1] + (uint32_t)l * F[2];   // modulo 2^32 = one period
+    sincospif((float)(int32_t)ph * 4.656612873077393e-10f, &s, &c);                     // pi * ph / 2^31
+}
+
+// fractional coordinates in 32-bit fixed point: F_j = frac(sum_c r_c inv[3c + j]) * 2^32
+__global__ void __launch_bounds__(256) ewald_frac_kernel(int n, const float* __restrict__ coord, double i0, double i1,
+                                                         double i2, double i3, double i4, double i5, double i6,
+                                                         double i7, double i8, uint32_t* __restrict__ F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = coord[3 * i], y = coord[3 * i + 1], z = coord[3 * i + 2];
+    const double f[3] = {x * i0 + y * i3 + z * i6, x * i1 + y * i4 + z * i7, x * i2 + y * i5 + z * i8};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double t = f[j] - floor(f[j]);
+        F[3 * i + j] = (uint32_t)(unsigned long long)llrint(t * 4294967296.0);   // 2^32 wraps to 0: the same phase
+    }
 }
 
 // one warp per k vector: S(k) = sum_i q_i exp(i k.r_i)
-__global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const float* __restrict__ coord,
-                                                       const float* __restrict__ q, const double* __restrict__ kvec,
+__global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint32_t* __restrict__ F,
+                                                       const float* __restrict__ q, const int32_t* __restrict__ hkl,
                                                        double* __restrict__ S) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nk) return;
-    double kx = kvec[3 * w], ky = kvec[3 * w + 1], kz = kvec[3 * w + 2];
+    const int h = hkl[3 * w], k = hkl[3 * w + 1], l = hkl[3 * w + 2];
     double re = 0.0, im = 0.0;
+    float pre = 0.f, pim = 0.f;
+    int cnt = 0;
     for (int i = lane; i < n; i += 32) {
         float s, c;
-        phase_sincos(kx, ky, kz, coord + 3 * i, s, c);
-        float qi = q[i];
-        re += (double)(qi * c);
-        im += (double)(qi * s);
+        phase_sincos(h, k, l, F + 3 * i, s, c);
+        const float qi = q[i];
+        pre = fmaf(qi, c, pre);
+        pim = fmaf(qi, s, pim);
+        if (++cnt == 16) {
+            re += (double)pre;
+            im += (double)pim;
+            pre = pim = 0.f;
+            cnt = 0;
+        }
     }
-    re = warp_sum(re);
-    im = warp_sum(im);
+    re = warp_sum(re + (double)pre);
+    im = warp_sum(im + (double)pim);
     if (lane == 0) {
         S[2 * w] = re;
         S[2 * w + 1] = im;
@@ -69,8 +93,9 @@ __global__ void __launch_bounds__(256) ewald_qsum_kernel(int n, const float* __r
 }
 
 // one warp per atom: dE/dq_i and F_i
-__global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const float* __restrict__ coord,
-                                                         const float* __restrict__ q, const double* __restrict__ kvec,
+__global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const uint32_t* __restrict__ F,
+                                                         const float* __restrict__ q, const int32_t* __restrict__ hkl,
+                                                         const double* __restrict__ kvec,
                                                          const double* __restrict__ ck, const double* __restrict__ S,
                                                          double pref, double self_coeff, double bg_unit,
                                                          const double* __restrict__ qsum,
@@ -79,23 +104,32 @@ __global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const fl
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
     int i = w;
-    const float* r = coord + 3 * i;
+    const uint32_t Fi[3] = {F[3 * i], F[3 * i + 1], F[3 * i + 2]};
     double g = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+    float pg = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    int cnt = 0;
     for (int k = lane; k < nk; k += 32) {
-        double kx = kvec[3 * k], ky = kvec[3 * k + 1], kz = kvec[3 * k + 2];
         float s, c;
-        phase_sincos(kx, ky, kz, r, s, c);
-        double re = S[2 * k], im = S[2 * k + 1], cc = ck[k];
-        g += cc * (re * c + im * s);
-        double t = cc * (re * s - im * c);
-        fx += t * kx;
-        fy += t * ky;
-        fz += t * kz;
+        phase_sincos(hkl[3 * k], hkl[3 * k + 1], hkl[3 * k + 2], Fi, s, c);
+        const float re = (float)S[2 * k], im = (float)S[2 * k + 1], cc = (float)ck[k];
+        pg = fmaf(cc, re * c + im * s, pg);
+        const float t = cc * (re * s - im * c);
+        px = fmaf(t, (float)kvec[3 * k], px);
+        py = fmaf(t, (float)kvec[3 * k + 1], py);
+        pz = fmaf(t, (float)kvec[3 * k + 2], pz);
+        if (++cnt == 16) {
+            g += (double)pg;
+            fx += (double)px;
+            fy += (double)py;
+            fz += (double)pz;
+            pg = px = py = pz = 0.f;
+            cnt = 0;
+        }
     }
-    g = warp_sum(g);
-    fx = warp_sum(fx);
-    fy = warp_sum(fy);
-    fz = warp_sum(fz);
+    g = warp_sum(g + (double)pg);
+    fx = warp_sum(fx + (double)px);
+    fy = warp_sum(fy + (double)py);
+    fz = warp_sum(fz + (double)pz);
     if (lane == 0) {
         double qi = (double)q[i];
         // 2*pref = k_e 8 pi / V ; self: E = self_coeff q^2 ; background: dE/dq = bg_coeff (already times Q)
@@ -165,6 +199,10 @@ struct EwaldPlan {
     double* d_ck = nullptr;
     double* d_S = nullptr;
     int cap = 0;
+    int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors
+    uint32_t* d_frac = nullptr;  // (frac_cap, 3) fixed-point fractional coordinates of the current positions
+    int frac_cap = 0;
+    double inv[9] = {0};         // inverse cell
 };
 
 void ewald_parameters(const float* host_cell, int n_atoms, double accuracy, double rc_cap, double& alpha, double& rc,
@@ -213,7 +251,9 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
         double an = std::sqrt(a[3 * j] * a[3 * j] + a[3 * j + 1] * a[3 * j + 1] + a[3 * j + 2] * a[3 * j + 2]);
         nmax[j] = (int)std::ceil(pl.kc * an / (2.0 * M_PI));
     }
+    for (int c = 0; c < 9; ++c) pl.inv[c] = inv[c];
     std::vector<double> kv, ck;
+    std::vector<int32_t> hk;
     double kc2 = pl.kc * pl.kc, inv4a2 = 1.0 / (4.0 * pl.alpha * pl.alpha);
     for (int h = 0; h <= nmax[0]; ++h)
         for (int k = (h == 0 ? 0 : -nmax[1]); k <= nmax[1]; ++k)
@@ -227,18 +267,29 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
                 kv.push_back(ky);
                 kv.push_back(kz);
                 ck.push_back(std::exp(-k2 * inv4a2) / k2);
+                hk.push_back(h);
+                hk.push_back(k);
+                hk.push_back(l);
             }
     pl.nk = (int)ck.size();
     if (pl.nk > pl.cap) {
         if (pl.d_kvec) cudaFree(pl.d_kvec);
+        if (pl.d_hkl) cudaFree(pl.d_hkl);
         pl.cap = pl.nk + pl.nk / 4 + 64;
         AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_kvec, sizeof(double) * (6 * pl.cap + 2)));
+        AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_hkl, sizeof(int32_t) * 3 * pl.cap));
         pl.d_ck = pl.d_kvec + 3 * pl.cap;
         pl.d_S = pl.d_ck + pl.cap;
+    }
+    if (n_atoms > pl.frac_cap) {
+        if (pl.d_frac) cudaFree(pl.d_frac);
+        pl.frac_cap = n_atoms + n_atoms / 8 + 64;
+        AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_frac, sizeof(uint32_t) * 3 * pl.frac_cap));
     }
     if (pl.nk > 0) {
         AIM_CUDA_CHECK(cudaMemcpyAsync(pl.d_kvec, kv.data(), sizeof(double) * 3 * pl.nk, cudaMemcpyHostToDevice, st));
         AIM_CUDA_CHECK(cudaMemcpyAsync(pl.d_ck, ck.data(), sizeof(double) * pl.nk, cudaMemcpyHostToDevice, st));
+        AIM_CUDA_CHECK(cudaMemcpyAsync(pl.d_hkl, hk.data(), sizeof(int32_t) * 3 * pl.nk, cudaMemcpyHostToDevice, st));
         AIM_CUDA_CHECK(cudaStreamSynchronize(st));   // kv / ck are stack-scoped host vectors
     }
     return AIMNET_OK;
@@ -246,8 +297,12 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
 
 void ewald_release(EwaldPlan& pl) {
     if (pl.d_kvec) cudaFree(pl.d_kvec);
+    if (pl.d_hkl) cudaFree(pl.d_hkl);
+    if (pl.d_frac) cudaFree(pl.d_frac);
     pl.d_kvec = pl.d_ck = pl.d_S = nullptr;
-    pl.cap = pl.nk = 0;
+    pl.d_hkl = nullptr;
+    pl.d_frac = nullptr;
+    pl.cap = pl.nk = pl.frac_cap = 0;
 }
 
 // adds the reciprocal, self and background terms to e_atom / gq / forces / virial_atom
@@ -261,12 +316,17 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
     double* d_q = pl.d_S + 2 * (size_t)pl.cap - 0;   // one spare double behind S (see ewald_prepare)
     ewald_qsum_kernel<<<1, 256, 0, st>>>(n, q, d_q);
     AIM_LAUNCH_CHECK();
+    AIM_REQUIRE(n <= pl.frac_cap, "ewald: plan prepared for fewer atoms");
+    const double* iv = pl.inv;
+    ewald_frac_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, coord, iv[0], iv[1], iv[2], iv[3], iv[4], iv[5], iv[6], iv[7], iv[8],
+                                                       pl.d_frac);
+    AIM_LAUNCH_CHECK();
     if (pl.nk > 0) {
-        ewald_sf_kernel<<<(pl.nk + 7) / 8, 256, 0, st>>>(n, pl.nk, coord, q, pl.d_kvec, pl.d_S);
+        ewald_sf_kernel<<<(pl.nk + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, pl.d_hkl, pl.d_S);
         AIM_LAUNCH_CHECK();
     }
-    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, coord, q, pl.d_kvec, pl.d_ck, pl.d_S, pref, self_coeff,
-                                                  bg_unit, d_q, e_atom, gq, forces);
+    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, pl.d_hkl, pl.d_kvec, pl.d_ck, pl.d_S, pref,
+                                                  self_coeff, bg_unit, d_q, e_atom, gq, forces);
     AIM_LAUNCH_CHECK();
     ewald_energy_kernel<<<1, 256, 0, st>>>(pl.nk, pl.d_kvec, pl.d_ck, pl.d_S, pref, 1.0 / (4.0 * pl.alpha * pl.alpha), bg_unit,
                                            d_q, e_atom, virial_atom);
