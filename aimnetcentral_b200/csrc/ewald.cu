@@ -94,11 +94,22 @@ __global__ void __launch_bounds__(256) ewald_qsum_kernel(int n, const float* __r
     }
 }
 
+// per k vector, after S(k) is known: one 32-byte record (c_k Re S, c_k Im S, k_x, k_y | k_z, h, k, l) so that the atom
+// kernel reads two 16-byte words per (atom, k) pair instead of 60 bytes of fp64 / int arrays
+__global__ void __launch_bounds__(256) ewald_pack_kernel(int nk, const int32_t* __restrict__ hkl,
+                                                         const double* __restrict__ kvec, const double* __restrict__ ck,
+                                                         const double* __restrict__ S, float4* __restrict__ rec) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    const double c = ck[k];
+    rec[2 * k] = make_float4((float)(c * S[2 * k]), (float)(c * S[2 * k + 1]), (float)kvec[3 * k], (float)kvec[3 * k + 1]);
+    rec[2 * k + 1] = make_float4((float)kvec[3 * k + 2], __int_as_float(hkl[3 * k]), __int_as_float(hkl[3 * k + 1]),
+                                 __int_as_float(hkl[3 * k + 2]));
+}
+
 // one warp per atom: dE/dq_i and F_i
 __global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const uint32_t* __restrict__ F,
-                                                         const float* __restrict__ q, const int32_t* __restrict__ hkl,
-                                                         const double* __restrict__ kvec,
-                                                         const double* __restrict__ ck, const double* __restrict__ S,
+                                                         const float* __restrict__ q, const float4* __restrict__ rec,
                                                          double pref, double self_coeff, double bg_unit,
                                                          const double* __restrict__ qsum,
                                                          double* __restrict__ e_atom, float* __restrict__ gq,
@@ -111,14 +122,14 @@ __global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const ui
     float pg = 0.f, px = 0.f, py = 0.f, pz = 0.f;
     int cnt = 0;
     for (int k = lane; k < nk; k += 32) {
+        const float4 r0 = __ldg(rec + 2 * k), r1 = __ldg(rec + 2 * k + 1);
         float s, c;
-        phase_sincos(hkl[3 * k], hkl[3 * k + 1], hkl[3 * k + 2], Fi, s, c);
-        const float re = (float)S[2 * k], im = (float)S[2 * k + 1], cc = (float)ck[k];
-        pg = fmaf(cc, re * c + im * s, pg);
-        const float t = cc * (re * s - im * c);
-        px = fmaf(t, (float)kvec[3 * k], px);
-        py = fmaf(t, (float)kvec[3 * k + 1], py);
-        pz = fmaf(t, (float)kvec[3 * k + 2], pz);
+        phase_sincos(__float_as_int(r1.y), __float_as_int(r1.z), __float_as_int(r1.w), Fi, s, c);
+        pg += r0.x * c + r0.y * s;
+        const float t = r0.x * s - r0.y * c;
+        px = fmaf(t, r0.z, px);
+        py = fmaf(t, r0.w, py);
+        pz = fmaf(t, r1.x, pz);
         if (++cnt == 16) {
             g += (double)pg;
             fx += (double)px;
@@ -201,7 +212,7 @@ struct EwaldPlan {
     double* d_ck = nullptr;
     double* d_S = nullptr;
     int cap = 0;
-    int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors
+    int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors, then (cap, 8) fp32 records
     uint32_t* d_frac = nullptr;  // (frac_cap, 3) fixed-point fractional coordinates of the current positions
     int frac_cap = 0;
     double inv[9] = {0};         // inverse cell
@@ -279,7 +290,7 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
         if (pl.d_hkl) cudaFree(pl.d_hkl);
         pl.cap = pl.nk + pl.nk / 4 + 64;
         AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_kvec, sizeof(double) * (6 * pl.cap + 2)));
-        AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_hkl, sizeof(int32_t) * 3 * pl.cap));
+        AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_hkl, sizeof(int32_t) * (4 + 8) * pl.cap));   // hkl (padded to 4) | records
         pl.d_ck = pl.d_kvec + 3 * pl.cap;
         pl.d_S = pl.d_ck + pl.cap;
     }
@@ -327,8 +338,13 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
         ewald_sf_kernel<<<(pl.nk + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, pl.d_hkl, pl.d_S);
         AIM_LAUNCH_CHECK();
     }
-    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, pl.d_hkl, pl.d_kvec, pl.d_ck, pl.d_S, pref,
-                                                  self_coeff, bg_unit, d_q, e_atom, gq, forces);
+    float4* rec = reinterpret_cast<float4*>(pl.d_hkl + 4 * (size_t)pl.cap);   // 16-byte aligned: cap * 16 bytes in
+    if (pl.nk > 0) {
+        ewald_pack_kernel<<<(pl.nk + 255) / 256, 256, 0, st>>>(pl.nk, pl.d_hkl, pl.d_kvec, pl.d_ck, pl.d_S, rec);
+        AIM_LAUNCH_CHECK();
+    }
+    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, rec, pref, self_coeff, bg_unit, d_q, e_atom, gq,
+                                                  forces);
     AIM_LAUNCH_CHECK();
     ewald_energy_kernel<<<1, 256, 0, st>>>(pl.nk, pl.d_kvec, pl.d_ck, pl.d_S, pref, 1.0 / (4.0 * pl.alpha * pl.alpha), bg_unit,
                                            d_q, e_atom, virial_atom);
