@@ -33,25 +33,27 @@ __device__ __forceinline__ void phase_sincos(int h, int k, int l, const uint32_t
     __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &s, &c);                     // pi * ph / 2^31
 }
 
-// fractional coordinates in 32-bit fixed point: F_j = frac(sum_c r_c inv[3c + j]) * 2^32
-__global__ void __launch_bounds__(256) ewald_frac_kernel(int n, const float* __restrict__ coord, double i0, double i1,
-                                                         double i2, double i3, double i4, double i5, double i6,
-                                                         double i7, double i8, uint32_t* __restrict__ F) {
+// per atom: fractional coordinates in 32-bit fixed point, F_j = frac(sum_c r_c inv[3c + j]) * 2^32, and the charge,
+// packed into one 16-byte word (the structure-factor kernel reads one word per (k, atom) pair)
+__global__ void __launch_bounds__(256) ewald_frac_kernel(int n, const float* __restrict__ coord, const float* __restrict__ q,
+                                                         double i0, double i1, double i2, double i3, double i4, double i5,
+                                                         double i6, double i7, double i8, uint4* __restrict__ F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = coord[3 * i], y = coord[3 * i + 1], z = coord[3 * i + 2];
     const double f[3] = {x * i0 + y * i3 + z * i6, x * i1 + y * i4 + z * i7, x * i2 + y * i5 + z * i8};
+    uint32_t o[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         double t = f[j] - floor(f[j]);
-        F[3 * i + j] = (uint32_t)(unsigned long long)llrint(t * 4294967296.0);   // 2^32 wraps to 0: the same phase
+        o[j] = (uint32_t)(unsigned long long)llrint(t * 4294967296.0);   // 2^32 wraps to 0: the same phase
     }
+    F[i] = make_uint4(o[0], o[1], o[2], __float_as_uint(q[i]));
 }
 
 // one warp per k vector: S(k) = sum_i q_i exp(i k.r_i)
-__global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint32_t* __restrict__ F,
-                                                       const float* __restrict__ q, const int32_t* __restrict__ hkl,
-                                                       double* __restrict__ S) {
+__global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint4* __restrict__ F,
+                                                       const int32_t* __restrict__ hkl, double* __restrict__ S) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nk) return;
     const int h = hkl[3 * w], k = hkl[3 * w + 1], l = hkl[3 * w + 2];
@@ -59,9 +61,11 @@ __global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint
     float pre = 0.f, pim = 0.f;
     int cnt = 0;
     for (int i = lane; i < n; i += 32) {
+        const uint4 a = __ldg(F + i);
+        const uint32_t Fi[3] = {a.x, a.y, a.z};
         float s, c;
-        phase_sincos(h, k, l, F + 3 * i, s, c);
-        const float qi = q[i];
+        phase_sincos(h, k, l, Fi, s, c);
+        const float qi = __uint_as_float(a.w);
         pre = fmaf(qi, c, pre);
         pim = fmaf(qi, s, pim);
         if (++cnt == 16) {
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) ewald_pack_kernel(int nk, const int32_t* 
 }
 
 // one warp per atom: dE/dq_i and F_i
-__global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const uint32_t* __restrict__ F,
+__global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const uint4* __restrict__ F,
                                                          const float* __restrict__ q, const float4* __restrict__ rec,
                                                          double pref, double self_coeff, double bg_unit,
                                                          const double* __restrict__ qsum,
@@ -117,7 +121,8 @@ __global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const ui
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
     int i = w;
-    const uint32_t Fi[3] = {F[3 * i], F[3 * i + 1], F[3 * i + 2]};
+    const uint4 fa = F[i];
+    const uint32_t Fi[3] = {fa.x, fa.y, fa.z};
     double g = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     float pg = 0.f, px = 0.f, py = 0.f, pz = 0.f;
     int cnt = 0;
@@ -213,7 +218,7 @@ struct EwaldPlan {
     double* d_S = nullptr;
     int cap = 0;
     int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors, then (cap, 8) fp32 records
-    uint32_t* d_frac = nullptr;  // (frac_cap, 3) fixed-point fractional coordinates of the current positions
+    uint32_t* d_frac = nullptr;  // (frac_cap, 4) fixed-point fractional coordinates of the current positions + charge bits
     int frac_cap = 0;
     double inv[9] = {0};         // inverse cell
 };
@@ -297,7 +302,7 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
     if (n_atoms > pl.frac_cap) {
         if (pl.d_frac) cudaFree(pl.d_frac);
         pl.frac_cap = n_atoms + n_atoms / 8 + 64;
-        AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_frac, sizeof(uint32_t) * 3 * pl.frac_cap));
+        AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_frac, sizeof(uint32_t) * 4 * pl.frac_cap));
     }
     if (pl.nk > 0) {
         AIM_CUDA_CHECK(cudaMemcpyAsync(pl.d_kvec, kv.data(), sizeof(double) * 3 * pl.nk, cudaMemcpyHostToDevice, st));
@@ -331,11 +336,12 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
     AIM_LAUNCH_CHECK();
     AIM_REQUIRE(n <= pl.frac_cap, "ewald: plan prepared for fewer atoms");
     const double* iv = pl.inv;
-    ewald_frac_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, coord, iv[0], iv[1], iv[2], iv[3], iv[4], iv[5], iv[6], iv[7], iv[8],
-                                                       pl.d_frac);
+    uint4* fq = reinterpret_cast<uint4*>(pl.d_frac);
+    ewald_frac_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, coord, q, iv[0], iv[1], iv[2], iv[3], iv[4], iv[5], iv[6], iv[7],
+                                                       iv[8], fq);
     AIM_LAUNCH_CHECK();
     if (pl.nk > 0) {
-        ewald_sf_kernel<<<(pl.nk + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, pl.d_hkl, pl.d_S);
+        ewald_sf_kernel<<<(pl.nk + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, pl.d_hkl, pl.d_S);
         AIM_LAUNCH_CHECK();
     }
     float4* rec = reinterpret_cast<float4*>(pl.d_hkl + 4 * (size_t)pl.cap);   // 16-byte aligned: cap * 16 bytes in
@@ -343,7 +349,7 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
         ewald_pack_kernel<<<(pl.nk + 255) / 256, 256, 0, st>>>(pl.nk, pl.d_hkl, pl.d_kvec, pl.d_ck, pl.d_S, rec);
         AIM_LAUNCH_CHECK();
     }
-    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, pl.d_frac, q, rec, pref, self_coeff, bg_unit, d_q, e_atom, gq,
+    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, q, rec, pref, self_coeff, bg_unit, d_q, e_atom, gq,
                                                   forces);
     AIM_LAUNCH_CHECK();
     ewald_energy_kernel<<<1, 256, 0, st>>>(pl.nk, pl.d_kvec, pl.d_ck, pl.d_S, pref, 1.0 / (4.0 * pl.alpha * pl.alpha), bg_unit,
