@@ -114,6 +114,7 @@ struct aimnet2_engine {
     float *d3_c6ref = nullptr, *d3_cnref = nullptr, *d3_rcov = nullptr, *d3_r4r2 = nullptr;
     aimnet2_options_t opt{};
     int gemm_backend = 0;
+    int poison = -1;              // test seam: byte written over the workspace before every evaluation (-1 = off)
     int small_m_rows = kSmallM;   // at or below this many atoms the MLPs run on the small-M fp32 SIMT kernel (0 = never)
     int backend_now = 0;    // backend of the evaluation in flight (gemm_backend or 0 for small systems)
     // workspace (grow-only)
@@ -503,6 +504,10 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         Bump bp{e->ws};
         carve(e, bp, b, N, B, e->sr_cap, e->lr_cap, pbc, need_lr_list, ldx);
         if (N == 0) break;
+        if (e->poison >= 0) {
+            AIM_CUDA_CHECK(cudaMemsetAsync(e->ws, e->poison, e->ws_bytes, st));
+            e->skin.valid = false;
+        }
         if (skin > 0.f && attempt == 0 && skin_matches()) {
             // lists built at cutoff + skin are still complete if no atom has moved by more than skin / 2 since the build
             AIM_TRY(launch_skin_check(N, sys->coord, b.coord_ref, 0.25f * skin * skin, sys->mol_idx, b.mol_ref, b.skin_flag, st));
@@ -874,6 +879,13 @@ extern "C" int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows) {
     AIM_REQUIRE(e, "set_small_m_rows: null engine");
     AIM_REQUIRE(rows >= 0 && rows <= kSmallM, "set_small_m_rows: rows must be in [0, 512]");
     e->small_m_rows = rows;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_debug_poison(aimnet2_engine_t* e, int byte) {
+    AIM_REQUIRE(e, "debug_poison: null engine");
+    AIM_REQUIRE(byte >= -1 && byte <= 255, "debug_poison: byte must be -1 (off) or 0..255");
+    e->poison = byte;
     return AIMNET_OK;
 }
 

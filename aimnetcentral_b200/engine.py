@@ -126,6 +126,10 @@ class Engine:
         """Evaluations with at most `rows` atoms use the small-M fp32 SIMT GEMM (default 512, 0 = never)."""
         _capi.check(self._lib.aimnet2_engine_set_small_m_rows(self._h, int(rows)), "set_small_m_rows")
 
+    def debug_poison(self, byte: int):
+        """Test seam: fill the device workspace with `byte` before every evaluation (-1 = off)."""
+        _capi.check(self._lib.aimnet2_engine_debug_poison(self._h, int(byte)), "debug_poison")
+
     def set_gemm_backend(self, backend: int):
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
         self.gemm_backend = int(backend)

@@ -170,6 +170,9 @@ int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
 /* Evaluations with at most `rows` atoms run the MLPs on the small-M fp32 SIMT kernel whatever the backend (the
  * tensor-core pipelines are latency-bound for a single molecule); default 512, 0 = never. */
 int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows);
+/* Test seam: fill the engine's device workspace with `byte` (0..255) before every evaluation, so that a kernel reading
+ * scratch memory it has not written shows up in the results (0xFF = NaN patterns); -1 switches it off (default). */
+int aimnet2_engine_debug_poison(aimnet2_engine_t* e, int byte);
 /* 1 = bitwise run-to-run reproducible results (fixed K-chunking in the tcgen05 GEMM; every other kernel is atomics-free
  * already) — the counterpart of AIMNet2Calculator(deterministic=True), aimnet/calculators/calculator.py:76-84 */
 int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on);

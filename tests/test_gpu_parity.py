@@ -149,6 +149,15 @@ def test_oracle_parity_random_batch():
         print(f"[parity] molecules off: {np.nonzero(dE > 1e-5)[0].tolist()}  atoms with dq > 1e-5: {np.nonzero(dQ > 1e-5)[0].tolist()[:40]}"
               f" (n={int((dQ > 1e-5).sum())})  atoms with dF > 5e-5: n={int((dF > 5e-5).sum())} first {np.nonzero(dF > 5e-5)[0].tolist()[:20]}"
               f"  second evaluation differs from the first by {again:.3e}")
+        # which side moved?  arbitrate with the oracle in float64 and a second run of the float32 oracle
+        import platform
+        ref2 = oracle_calculate(sd, inp)
+        ref64 = oracle_calculate(sd, inp, dtype=torch.float64)
+        print(f"[parity] fp32 oracle rerun differs by {np.abs(ref2['energy'] - ref['energy']).max():.3e};"
+              f" vs fp64 oracle: cuda max|dE|={np.abs(res['energy'].cpu().numpy() - ref64['energy']).max():.3e},"
+              f" fp32 oracle max|dE|={np.abs(ref['energy'] - ref64['energy']).max():.3e};"
+              f" host {platform.processor() or platform.machine()}, torch threads {torch.get_num_threads()},"
+              f" device {torch.cuda.get_device_name(0)}")
     assert de < ENERGY_ATOL and df < FORCE_ATOL and dq < CHARGE_ATOL
 
 
