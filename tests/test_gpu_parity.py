@@ -37,6 +37,15 @@ CASES = [
 ]
 
 
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return next(line.split(":", 1)[1].strip() for line in f if line.startswith("model name"))
+    except Exception:
+        import platform
+        return platform.processor() or platform.machine()
+
+
 def _report(name, out, ref, n):
     de = np.abs(out["energy"] - ref["energy"]).max()
     df = np.abs(out["forces"] - ref["forces"]).max()
@@ -150,13 +159,12 @@ def test_oracle_parity_random_batch():
               f" (n={int((dQ > 1e-5).sum())})  atoms with dF > 5e-5: n={int((dF > 5e-5).sum())} first {np.nonzero(dF > 5e-5)[0].tolist()[:20]}"
               f"  second evaluation differs from the first by {again:.3e}")
         # which side moved?  arbitrate with the oracle in float64 and a second run of the float32 oracle
-        import platform
         ref2 = oracle_calculate(sd, inp)
         ref64 = oracle_calculate(sd, inp, dtype=torch.float64)
         print(f"[parity] fp32 oracle rerun differs by {np.abs(ref2['energy'] - ref['energy']).max():.3e};"
               f" vs fp64 oracle: cuda max|dE|={np.abs(res['energy'].cpu().numpy() - ref64['energy']).max():.3e},"
               f" fp32 oracle max|dE|={np.abs(ref['energy'] - ref64['energy']).max():.3e};"
-              f" host {platform.processor() or platform.machine()}, torch threads {torch.get_num_threads()},"
+              f" host {_cpu_model()}, torch threads {torch.get_num_threads()},"
               f" device {torch.cuda.get_device_name(0)}")
     assert de < ENERGY_ATOL and df < FORCE_ATOL and dq < CHARGE_ATOL
 
@@ -414,6 +422,34 @@ def test_repeated_evaluations_are_bitwise_identical():
             out = calc(dict(inp), **kw)
             for k in ref:
                 assert torch.equal(ref[k], out[k]), k
+
+
+def test_poisoned_workspace_does_not_change_results():
+    """No kernel may read scratch memory it has not written in the same evaluation: with the device workspace filled
+    with 0xFF (NaN as fp32 and as fp16, -1 as an index) or 0x7B (huge finite values, which would wreck the row-chunk
+    scales of the 3xFP16 GEMM) before the evaluation, results stay bit-identical (tools/poison_probe.py is the longer
+    version; compute-sanitizer's initcheck cannot do this for the tensor-core path, it does not see TMA stores)."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import allose_supercell, random_molecules
+
+    spec = ModelSpec()
+    calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+    coord, numbers = random_molecules(20, 40, seed=11)
+    z, x, cell = allose_supercell((1, 1, 1), jitter=0.02, seed=1)
+    cases = [({"coord": coord, "numbers": numbers, "charge": np.zeros(20, np.float32)}, dict(forces=True), "simple"),
+             ({"coord": x, "numbers": z, "charge": np.zeros(1, np.float32), "cell": cell}, dict(forces=True, stress=True), "ewald")]
+    for rows in (0, 512):
+        calc.engine.set_small_m_rows(rows)
+        for inp, kw, method in cases:
+            calc.set_lrcoulomb_method(method)
+            calc.engine.debug_poison(-1)
+            ref = {k: v.clone() for k, v in calc(dict(inp), **kw).items() if torch.is_tensor(v)}
+            for byte in (0xFF, 0x7B):
+                calc.engine.debug_poison(byte)
+                out = calc(dict(inp), **kw)
+                for k in ref:
+                    assert torch.equal(ref[k], out[k]), (rows, method, hex(byte), k)
+    calc.engine.debug_poison(-1)
 
 
 def test_verlet_skin_reuse_matches_rebuild():

@@ -50,3 +50,27 @@ for name, spec, coulomb, inp, kw in cases():
                       " ".join(f"{k}: {d[0]:.3e}{' NaN' if d[1] else ''}" for k, d in diffs.items()))
     print(f"{name}: done", flush=True)
 print(f"poison probe: {bad} evaluations differ from the clean run")
+
+# ---- stress: many poisoned evaluations of the tensor-core path (a consumer that races ahead of its producer reads the
+# poison instead of last evaluation's identical values, which is what hides such a race in repeat-evaluation tests)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
+spec = ModelSpec()
+calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+calc.engine.set_small_m_rows(0)
+for nmol, nat, seed in ((64, 50, 99), (100, 37, 5), (13, 50, 8)):
+    coord, numbers = random_molecules(nmol, nat, seed=seed)
+    inp = {"coord": torch.as_tensor(coord, device="cuda:0"), "numbers": torch.as_tensor(numbers, device="cuda:0"),
+           "charge": torch.zeros(nmol, device="cuda:0")}
+    calc.engine.debug_poison(-1)
+    ref = {k: v.clone() for k, v in calc(dict(inp), forces=True).items() if torch.is_tensor(v)}
+    nbad = 0
+    for r in range(reps):
+        calc.engine.debug_poison(0xFF if r % 2 == 0 else 0x00)
+        out = calc(dict(inp), forces=True)
+        if not all(torch.equal(ref[k], out[k]) for k in ref):
+            nbad += 1
+            if nbad <= 5:
+                print(f"stress {nmol}x{nat} rep {r}: " + " ".join(
+                    f"{k}: max diff {float((out[k].double() - ref[k].double()).abs().nan_to_num(nan=1e30).max()):.3e} nan={bool(out[k].isnan().any())}"
+                    for k in ref), flush=True)
+    print(f"stress {nmol}x{nat}: {reps} poisoned evaluations, {nbad} differ", flush=True)
