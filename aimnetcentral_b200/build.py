@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         with open(os.path.join(OUT_DIR, src.replace(".cu", ".ptxas.txt")), "w") as fh:
-            fh.write(r.stderr)
+            fh.write("".join(ln for ln in r.stderr.splitlines(True) if "Compile time" not in ln))   # keep the log diff-stable
         if verbose:
             print(r.stderr)
         return obj

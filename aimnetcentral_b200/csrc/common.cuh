@@ -80,6 +80,27 @@ struct SplitMat {
     int ld, ldinv;
 };
 
+// Ewald reciprocal-space plan of one periodic system (ewald.cu): k vectors and coefficients for the current cell, device
+// scratch for the structure factors and the per-atom fixed-point phases.  Owned by the engine, rebuilt when the cell, the
+// atom count or the accuracy changes.
+struct EwaldPlan {
+    double cell[9] = {0};
+    double accuracy = 0, rc_cap = 0;
+    int n_atoms = 0;
+    double alpha = 0, rc = 0, kc = 0, volume = 0;
+    int nk = 0;
+    double* d_kvec = nullptr;
+    double* d_ck = nullptr;
+    double* d_S = nullptr;
+    int cap = 0;
+    int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors, then (cap, 8) fp32 records
+    uint32_t* d_frac = nullptr;  // (frac_cap, 4) fixed-point fractional coordinates of the current positions + charge bits
+    int frac_cap = 0;
+    double inv[9] = {0};         // inverse cell
+};
+int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double accuracy, double rc_cap, cudaStream_t st);
+void ewald_release(EwaldPlan& pl);
+
 // at or below this many rows (atoms) the per-atom MLPs run on the small-M fp32 SIMT kernel: the tensor-core pipelines are
 // latency-bound there (gemm.cu)
 constexpr int kSmallM = 512;

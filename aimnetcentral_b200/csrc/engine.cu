@@ -60,23 +60,6 @@ int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, c
 int launch_d3(int, const PairSource&, const float*, const CellView&, const int32_t*, const D3Params&, float*, float*,
               float*, double*, float*, double*, cudaStream_t);
 
-struct EwaldPlan {
-    double cell[9] = {0};
-    double accuracy = 0, rc_cap = 0;
-    int n_atoms = 0;
-    double alpha = 0, rc = 0, kc = 0, volume = 0;
-    int nk = 0;
-    double* d_kvec = nullptr;
-    double* d_ck = nullptr;
-    double* d_S = nullptr;
-    int cap = 0;
-    int32_t* d_hkl = nullptr;    // keep in sync with ewald.cu
-    uint32_t* d_frac = nullptr;
-    int frac_cap = 0;
-    double inv[9] = {0};
-};
-int ewald_prepare(EwaldPlan&, const float*, int, double, double, cudaStream_t);
-void ewald_release(EwaldPlan&);
 int launch_ewald_recip(const EwaldPlan&, int, const float*, const float*, double*, float*, float*, double*, cudaStream_t);
 
 static inline int pad32(int x) { return (x + 31) / 32 * 32; }

@@ -207,21 +207,6 @@ __global__ void __launch_bounds__(256) ewald_energy_kernel(int nk, const double*
     }
 }
 
-struct EwaldPlan {
-    double cell[9] = {0};
-    double accuracy = 0, rc_cap = 0;
-    int n_atoms = 0;
-    double alpha = 0, rc = 0, kc = 0, volume = 0;
-    int nk = 0;
-    double* d_kvec = nullptr;
-    double* d_ck = nullptr;
-    double* d_S = nullptr;
-    int cap = 0;
-    int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors, then (cap, 8) fp32 records
-    uint32_t* d_frac = nullptr;  // (frac_cap, 4) fixed-point fractional coordinates of the current positions + charge bits
-    int frac_cap = 0;
-    double inv[9] = {0};         // inverse cell
-};
 
 void ewald_parameters(const float* host_cell, int n_atoms, double accuracy, double rc_cap, double& alpha, double& rc,
                       double& kc, double& volume) {
