@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 

@@ -11,56 +11,13 @@
 #include <vector>
 
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 
 static thread_local std::string g_error;
 thread_local int g_launch_count = 0;
 void set_error(const std::string& msg) { g_error = msg; }
-
-// ---- declarations of the launchers living in the other translation units -----------------------------------
-int neighbor_matrix_impl(const float*, int, float, const float*, const float*, const uint8_t*, int, const int32_t*, int,
-                         int, int, int, int32_t*, int32_t*, int32_t*, int*, cudaStream_t, bool, int32_t*, int32_t*);
-int wrap_positions_impl(const float*, float*, int, const float*, int, const uint8_t*, const int32_t*, cudaStream_t);
-int launch_conv_fwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
-                    const float*, const float*, const float*, const float*, float*, int, float*, float*, int,
-                    cudaStream_t);
-int launch_conv_bwd(int, int, const NbView&, const float*, const CellView&, const int32_t*, const AevParams&,
-                    const float*, const float*, const float*, int, const float*, const float*, const float*,
-                    const float*, float*, float*, float*, float*, float*, double*, int, int, cudaStream_t);
-int gemm_nt(const float*, int, const WeightView&, const float*, float*, int, float*, int, int, int, int, int, int,
-            cudaStream_t);
-int gemm_nt_split(const SplitMat&, const WeightView&, const float*, float*, int, const SplitMat*, float*, int, int, int, int,
-                  int, cudaStream_t);
-int presplit_f32(const float*, int, int, int, const SplitMat&, cudaStream_t);
-int split_tf32(const float*, float*, float*, size_t, cudaStream_t);
-bool gemm_tc_available();
-void gemm_tc_set_deterministic(bool);
-int launch_embed(int, const int32_t*, const float*, float*, cudaStream_t);
-int launch_mol_ptr(const int32_t*, int, int, int32_t*, cudaStream_t);
-int launch_nse_fwd(int, int, int, const int32_t*, const int32_t*, const float*, const float*, const float*, int,
-                   const float*, float*, float*, const float*, float*, float*, cudaStream_t);
-int launch_nse_bwd(int, int, int, const int32_t*, const int32_t*, const float*, const float*, const float*, int,
-                   const float*, const float*, const float*, float*, const float*, const float*, int, float*, int,
-                   float*, cudaStream_t);
-int launch_accum_grads(int, int, const float*, int, const float*, const float*, const float*, int, float*, int, float*,
-                       cudaStream_t);
-int launch_head_tail(int, const float*, int, const float*, const float*, float, const int32_t*, const double*, double*,
-                     float*, cudaStream_t);
-int launch_energy_reduce(int, const int32_t*, const double*, const double*, const double*, const double*, double*,
-                         cudaStream_t);
-int launch_stress_reduce(const int32_t*, int, int, const double*, const float*, float*, cudaStream_t);
-int launch_charges_out(int, int, const float*, float*, float*, cudaStream_t);
-int launch_skin_check(int, const float*, const float*, float, const int32_t*, const int32_t*, int32_t*, cudaStream_t);
-int launch_skin_save(int, const float*, const float*, float*, float*, const int32_t*, int32_t*, cudaStream_t);
-int launch_skin_apply(int, const float*, const float*, float*, cudaStream_t);
-
-int launch_coulomb(int, int, const PairSource&, const float*, const CellView&, const float*, const CoulombParams&,
-                   double*, float*, float*, double*, int, cudaStream_t);
-int launch_d3(int, const PairSource&, const float*, const CellView&, const int32_t*, const D3Params&, float*, float*,
-              float*, double*, float*, double*, cudaStream_t);
-
-int launch_ewald_recip(const EwaldPlan&, int, const float*, const float*, double*, float*, float*, double*, cudaStream_t);
 
 static inline int pad32(int x) { return (x + 31) / 32 * 32; }
 static inline int round16(int x) { return (x + 15) / 16 * 16; }

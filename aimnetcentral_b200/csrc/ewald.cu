@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 

@@ -11,6 +11,7 @@
 // Backend 1 (gemm_tc.cu): tcgen05 3xTF32 with TMEM accumulators.
 // Backend 2 (gemm_tc16.cu): tcgen05 3xFP16 with per-(row, K-chunk) power-of-two scaling — the default.
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 
@@ -189,16 +190,6 @@ __global__ void __launch_bounds__(64) gemm_nt_small_kernel(const float* __restri
     *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = z;
 }
 
-int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int ldw, const float* bias, float* Y, int ldy,
-               float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);   // gemm_tc.cu
-int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw, const float* bias,
-                 float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N, int K, int mode,
-                 cudaStream_t st);                                                        // gemm_tc16.cu
-int presplit_f32(const float* X, int ldx, int M, int K, const SplitMat& out, cudaStream_t st);
-int unsplit_f32(const SplitMat& in, int M, int N, float* Y, int ldy, cudaStream_t st);
-int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st);
-int split_fp16_device(const float* w, void* hi, void* lo, float* inv_scale, unsigned int* scratch, size_t n, cudaStream_t st);
-bool gemm_tc_available();
 
 int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, float* Y, int ldy, float* aux, int ldaux, int M,
             int N, int K, int mode, int backend, cudaStream_t st) {
@@ -255,7 +246,6 @@ int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, flo
 
 // Debug: per-stage SM-clock stamps of CTA 0 of every following backend-2 launch (8 events x 2048 stages, device buffer
 // of 16384 uint64), nullptr to switch off.  Used by tools/gemm_trace.py only.
-namespace aimnet { void gemm_tc16_set_trace(unsigned long long* buf); }
 extern "C" int aimnet2_gemm_set_trace(void* device_buf) {
     aimnet::gemm_tc16_set_trace(reinterpret_cast<unsigned long long*>(device_buf));
     return AIMNET_OK;

@@ -39,6 +39,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 

@@ -14,6 +14,7 @@
 // all-pairs "simple" Coulomb (calculator.py:1635-1636 asks for max_neighbors = N there), the molecule's own atom
 // segment [mol_ptr[m], mol_ptr[m+1]) — the N x N list is never materialised.
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 
@@ -415,8 +416,8 @@ static bool make_grid(const float* hc, const uint8_t* pbc, float cutoff, int n_a
 int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, const float* cell, const float* host_cell,
                          const uint8_t* pbc_host, int n_cells, const int32_t* batch_idx, int n_systems, int max_nb,
                          int fill_value, int sorted, int32_t* nbmat, int32_t* shifts, int32_t* nnb,
-                         int* max_count_host, cudaStream_t st, bool prefer_cells, int32_t* scratch = nullptr,
-                         int32_t* pinned_host = nullptr) {
+                         int* max_count_host, cudaStream_t st, bool prefer_cells, int32_t* scratch,
+                         int32_t* pinned_host) {
     // scratch (optional, device): >= n_systems + 3*n_cells + 8 ints owned by the caller, avoids the stream-ordered
     // allocations below; pinned_host (optional): page-locked int for the overflow read-back
     AIM_REQUIRE(n_atoms >= 0 && max_nb >= 1, "neighbor_matrix: bad sizes");

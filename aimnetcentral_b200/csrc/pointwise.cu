@@ -1,6 +1,7 @@
 // Small per-atom / per-molecule kernels around the GEMMs: embedding, charge equilibration (NSE) forward and
 // backward, energy head tail, fp64 per-molecule reductions.
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace aimnet {
 
