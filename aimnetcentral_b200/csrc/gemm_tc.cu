@@ -545,18 +545,9 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     CUtensorMap tmY, tmAux;
     if ((rc = make_map(&tmY, Y, M, N, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_map(&tmAux, aux ? aux : Y, M, N, aux ? ldaux : ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    static int chunk = 0;
-    if (chunk == 0) {
-        const char* env = getenv("AIMNET_TC_CHUNK");
-        chunk = env ? atoi(env) : CHUNK;
-        if (chunk < 1) chunk = 1;
-    }
-    static int chunk_max = 0;
-    if (chunk_max == 0) {
-        const char* env = getenv("AIMNET_TC_CHUNK_MAX");
-        chunk_max = env ? atoi(env) : chunk;   // elastic growth is experimental and off by default
-        if (chunk_max < chunk) chunk_max = chunk;
-    }
+    // fixed K-chunking: TMEM accumulates CHUNK stages before the fp32 register add (the elastic variant stayed an
+    // experiment: results must be run-to-run reproducible)
+    const int chunk = CHUNK, chunk_max = CHUNK;
     Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, g_tc_deterministic ? chunk : chunk_max, bn};
     int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
