@@ -42,6 +42,13 @@ extern thread_local int g_launch_count;
         }                                                                                           \
     } while (0)
 
+// propagate a non-zero status of a launcher
+#define AIM_TRY(expr)                      \
+    do {                                   \
+        int _rc = (expr);                  \
+        if (_rc != AIMNET_OK) return _rc;  \
+    } while (0)
+
 #define AIM_REQUIRE(cond, msg)                                                                      \
     do {                                                                                            \
         if (!(cond)) {                                                                              \
@@ -99,6 +106,10 @@ struct EwaldPlan {
     double inv[9] = {0};         // inverse cell
 };
 int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double accuracy, double rc_cap, cudaStream_t st);
+// Kolafa-Perram style parameters for a target accuracy (aimnet/calculators/calculator.py:663-666): eta from V and N,
+// r_c = sqrt(-2 ln eps) eta (capped by rc_cap when > 0), k_c = sqrt(-2 ln eps) / eta, alpha = 1 / (sqrt(2) eta)
+void ewald_parameters(const float* host_cell, int n_atoms, double accuracy, double rc_cap, double& alpha, double& rc,
+                      double& kc, double& volume);
 void ewald_release(EwaldPlan& pl);
 
 // at or below this many rows (atoms) the per-atom MLPs run on the small-M fp32 SIMT kernel: the tensor-core pipelines are

@@ -355,12 +355,6 @@ static void collect_timing(aimnet2_engine* e) {
     }
 }
 
-#define AIM_TRY(expr)                      \
-    do {                                   \
-        int _rc = (expr);                  \
-        if (_rc != AIMNET_OK) return _rc;  \
-    } while (0)
-
 static int build_list(aimnet2_engine* e, const float* coord, int N, float cutoff, const aimnet2_system_t* sys,
                       const int32_t* mol_idx, int sorted, int cap, int32_t* nb, int32_t* sh, int32_t* cnt, int* maxc,
                       int32_t* scratch, cudaStream_t st) {

@@ -194,6 +194,46 @@ int aimnet2_engine_skin_stats(const aimnet2_engine_t* e, int* builds, int* reuse
 int aimnet2_engine_enable_timing(aimnet2_engine_t* e, int on);
 int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, int n);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pair-term operator seams: the external long-range kernels behind entry points shaped like the third-party calls of
+ * the reference (SURVEY.md section 8b, B3 iii).  Common arguments:
+ *   positions (n_atoms,3) f32 device, Angstrom      cell (n_cells,3,3) f32 device or NULL, n_cells in {0, 1, n_systems}
+ *   batch_idx (n_atoms) i32 device, sorted, or NULL (one system)
+ *   nbmat (n_atoms, nb_width) i32 device, full list (both directions), unused slots = fill_value
+ *   shifts (n_atoms, nb_width, 3) i32 device integer lattice vectors (required with a cell)
+ *   energy (n_systems) f64 device out              forces (n_atoms,3) f32 device out or NULL
+ *   virial (n_systems,3,3) f64 device out or NULL: W = -dE/d(strain), the convention of
+ *   aimnet/calculators/derivatives.py:128-131
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Damped-shifted-force Coulomb; replaces nvalchemiops...dsf_coulomb as called at aimnet/modules/lr.py:526-540 (closed
+ * form: lr.py:594-611).  Energies in e^2/Angstrom, forces in e^2/Angstrom^2: the caller multiplies by Hartree*Bohr
+ * (lr.py:542-547).  charge_grad (n_atoms) f32 out or NULL: dE/dq_i at fixed geometry (what autograd supplies through the
+ * graph-attached charges in the reference). */
+int aimnet2_dsf_coulomb(const float* positions, const float* charges, int n_atoms, float cutoff, float alpha,
+                        const float* cell, int n_cells, const int32_t* batch_idx, int n_systems, const int32_t* nbmat,
+                        const int32_t* shifts, int nb_width, int fill_value, double* energy, float* forces,
+                        float* charge_grad, double* virial, void* stream);
+
+/* DFT-D3(BJ) two-body dispersion with the quintic 5th-order switch; replaces nvalchemiops...dftd3 as called at
+ * aimnet/modules/lr.py:1204-1228 (closed form: lr.py:1580-1657).  Positions in Angstrom, energies in eV, forces in
+ * eV/Angstrom (the Python wrapper converts from / to the Bohr / Hartree units of that call site); r_on / r_off in Bohr.
+ * Tables in the packed form of this library: c6ref (95,95,28) f32 = the (95,95,5,5) reference C6 with every 25-value
+ * row padded to 28 (16-byte aligned), cnref (95,5) f32 = reference CN of element z's a-th reference system, -1 where
+ * that reference does not exist; rcov, r4r2 (95) f32.  coord_num (n_atoms) f32 out or NULL. */
+int aimnet2_dftd3(const float* positions, const int32_t* numbers, int n_atoms, float s6, float s8, float a1, float a2,
+                  float r_on_bohr, float r_off_bohr, const float* c6ref, const float* cnref, const float* rcov,
+                  const float* r4r2, const float* cell, int n_cells, const int32_t* batch_idx, int n_systems,
+                  const int32_t* nbmat, const int32_t* shifts, int nb_width, int fill_value, double* energy,
+                  float* forces, float* coord_num, double* virial, void* stream);
+
+/* Ewald splitting parameters for a target accuracy (host arithmetic only); replaces
+ * nvalchemiops...estimate_ewald_parameters as used at aimnet/calculators/calculator.py:1566-1587, formulas
+ * calculator.py:663-666: eta = (V^2/N)^(1/6)/sqrt(2 pi), r_c = sqrt(-2 ln eps) eta, k_c = sqrt(-2 ln eps)/eta,
+ * alpha = 1/(sqrt(2) eta).  host_cell: 9 floats in host memory; outputs may be NULL. */
+int aimnet2_estimate_ewald_parameters(const float* host_cell, int n_atoms, double accuracy, double* alpha,
+                                      double* real_space_cutoff, double* reciprocal_space_cutoff);
+
 /* standalone NT GEMM with fused epilogue (test seam for the MLP kernels):
  * Y[M,N] = act(A[M,K] @ W[N,K]^T + bias); mode 0 none, 1 bias, 2 bias+GELU (also writes gelu'(z) to aux when non-NULL),
  * 3 multiply by aux[M,N].  lda/ldw/ldy in elements. */

@@ -118,3 +118,26 @@ def test_model_sources_v2_artifact_and_module(tmp_path):
         _load_model_source("aimnet2")  # registry names need a download: outside scope, reported clearly
     with pytest.raises(TypeError):
         _load_model_source(42)
+
+
+def test_estimate_ewald_parameters_seam_matches_oracle():
+    """Host-only operator seam (no GPU work): splitting parameters as the reference reads them from
+    estimate_ewald_parameters (aimnet/calculators/calculator.py:1566-1587, formulas :663-666), per system."""
+    import math
+
+    import torch
+
+    from aimnetcentral_b200 import ops
+    from oracle.aimnet2_oracle import ewald_parameters
+
+    cells = torch.tensor([[[10.0, 0, 0], [1.0, 12.0, 0], [0.5, 0.3, 9.0]], [[20.0, 0, 0], [0, 21.0, 0], [0, 0, 19.0]]])
+    batch_idx = torch.tensor([0] * 57 + [1] * 300, dtype=torch.int32)
+    p = ops.estimate_ewald_parameters(torch.zeros(357, 3), cells, batch_idx=batch_idx, accuracy=1e-6)
+    for s, n in enumerate((57, 300)):
+        vol = abs(np.linalg.det(cells[s].numpy().astype(np.float64)))
+        eta, rc, kc = ewald_parameters(vol, n, 1e-6)
+        assert p.real_space_cutoff[s].item() == pytest.approx(rc, rel=1e-6)
+        assert p.reciprocal_space_cutoff[s].item() == pytest.approx(kc, rel=1e-6)
+        assert p.alpha[s].item() == pytest.approx(1.0 / (math.sqrt(2.0) * eta), rel=1e-6)
+    with pytest.raises(ValueError):
+        ops.estimate_ewald_parameters(torch.zeros(3, 3), torch.zeros(3, 3), accuracy=1e-6)   # singular cell
