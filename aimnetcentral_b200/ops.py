@@ -262,9 +262,11 @@ def dsf_coulomb(positions: Tensor, charges: Tensor, cutoff: float, alpha: float,
     gq = torch.empty(n, dtype=torch.float32, device=dev)
     virial = torch.empty(S, 3, 3, dtype=torch.float64, device=dev) if compute_virial else None
     p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
-    rc = lib.aimnet2_dsf_coulomb(pos.data_ptr(), q.data_ptr(), n, float(cutoff), float(alpha), p(cell_t), n_cells, p(bidx),
-                                 S, nb.data_ptr(), p(sh), nb.shape[1], int(n if fill_value is None else fill_value),
-                                 energy.data_ptr(), p(forces), gq.data_ptr(), p(virial), _stream(dev))
+    with torch.cuda.device(dev):
+        rc = lib.aimnet2_dsf_coulomb(pos.data_ptr(), q.data_ptr(), n, float(cutoff), float(alpha), p(cell_t), n_cells,
+                                     p(bidx), S, nb.data_ptr(), p(sh), nb.shape[1],
+                                     int(n if fill_value is None else fill_value), energy.data_ptr(), p(forces),
+                                     gq.data_ptr(), p(virial), _stream(dev))
     _capi.check(rc, "dsf_coulomb")
     if charges.requires_grad:
         full_gq = gq if charges.reshape(-1).shape[0] == n else torch.cat([gq, gq.new_zeros(charges.numel() - n)])
@@ -339,10 +341,11 @@ def dftd3(positions: Tensor, numbers: Tensor, a1: float, a2: float, s8: float, s
     if not r_on < r_off:     # no smoothing window requested: a hard cutoff far outside any list
         r_on, r_off = 0.999e10, 1e10
     p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
-    rc = lib.aimnet2_dftd3(pos.data_ptr(), z.data_ptr(), n, float(s6), float(s8), float(a1), float(a2), r_on, r_off,
-                           c6p.data_ptr(), cnref.data_ptr(), rcov.data_ptr(), rr.data_ptr(), p(cell_t), n_cells, p(bidx), S,
-                           nb.data_ptr(), p(sh), nb.shape[1], int(n if fill_value is None else fill_value),
-                           energy.data_ptr(), forces.data_ptr(), cn.data_ptr(), p(virial), _stream(dev))
+    with torch.cuda.device(dev):
+        rc = lib.aimnet2_dftd3(pos.data_ptr(), z.data_ptr(), n, float(s6), float(s8), float(a1), float(a2), r_on, r_off,
+                               c6p.data_ptr(), cnref.data_ptr(), rcov.data_ptr(), rr.data_ptr(), p(cell_t), n_cells, p(bidx),
+                               S, nb.data_ptr(), p(sh), nb.shape[1], int(n if fill_value is None else fill_value),
+                               energy.data_ptr(), forces.data_ptr(), cn.data_ptr(), p(virial), _stream(dev))
     _capi.check(rc, "dftd3")
     out = [energy / HARTREE, forces * (BOHR / HARTREE), cn]
     if compute_virial:
