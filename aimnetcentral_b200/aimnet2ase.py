@@ -1,7 +1,14 @@
-"""ASE adapter with the reference's surface (aimnet/calculators/aimnet2ase.py:35-274): pure host marshalling around
-`AIMNet2Calculator.__call__`.  Non-periodic Atoms go in as a `(1, N, 3)` batch, periodic ones as flat `(N, 3)` +
-`cell` + `pbc`; charge / multiplicity come from `atoms.info` first, then from the calculator.  Hessians are outside
-the engine's hot path and raise.
+"""ASE front end for the engine: an `ase.calculators.calculator.Calculator` whose `calculate()` is one call of
+`AIMNet2Calculator` (the surface of aimnet/calculators/aimnet2ase.py:35-274: constructor arguments, `set_atoms`,
+`set_charge`, `set_mult`, `update_tensors`, `get_dipole_moment`, `get_spin_charges`, `get_hessian`, the result keys).
+
+How a structure is handed over:
+  * isolated system  -> a batch of one, `coord (1, N, 3)`, `numbers (1, N)`, `charge (1,)`, `mult (1,)`;
+  * periodic system  -> flat `coord (N, 3)` plus `cell (3, 3)` and `pbc (3,)`.
+Total charge and multiplicity are taken from `atoms.info` ("charge", "mult" or "spin") when present, otherwise from the
+values given to the constructor / setters.  The small per-system inputs (species, charge, multiplicity) live on the
+device between steps and are re-uploaded only when their host values change, so an MD or optimizer loop pays for the
+coordinates only.  Second derivatives are outside the engine's hot path and raise.
 """
 from __future__ import annotations
 
@@ -12,114 +19,141 @@ import torch
 
 try:
     from ase.calculators.calculator import Calculator, PropertyNotImplementedError, all_changes  # type: ignore
-except ImportError as exc:  # same behaviour as the reference: importable without ASE, unusable until it is installed
-    _ASE_IMPORT_ERROR: ImportError | None = exc
+    _ASE_MISSING: ImportError | None = None
+except ImportError as _exc:   # importable without ASE (like the reference); constructing the adapter then fails
+    _ASE_MISSING = _exc
+    all_changes = []  # type: ignore[assignment]
+
+    class PropertyNotImplementedError(RuntimeError):  # type: ignore[no-redef]
+        """Stand-in raised for properties the model cannot provide."""
 
     class Calculator:  # type: ignore[no-redef]
-        def __init__(self, *args, **kwargs):
+        """Just enough of ASE's base class for this module to import."""
+
+        def __init__(self, *_, **__):
             self.results = {}
 
         def reset(self):
             self.results = {}
 
-        def check_state(self, *args, **kwargs):
+        def check_state(self, *_, **__):
             return []
 
-        def calculate(self, *args, **kwargs):
+        def calculate(self, *_, **__):
             return None
-
-    class PropertyNotImplementedError(RuntimeError):  # type: ignore[no-redef]
-        pass
-
-    all_changes = []  # type: ignore[assignment]
-else:
-    _ASE_IMPORT_ERROR = None
 
 from .calculator import AIMNet2Calculator
 
+_BASE_PROPERTIES = ("energy", "forces", "free_energy", "charges", "stress", "dipole_moment")
+
+
+def _info_of(atoms) -> dict:
+    return getattr(atoms, "info", None) or {}
+
+
+def _multiplicity_in(info: dict):
+    return info.get("mult", info.get("spin"))
+
+
+def _lattice(atoms):
+    """(cell (3,3) float array, pbc (3,) bool array) of a periodic structure, or (None, None)."""
+    cell = getattr(atoms, "cell", None)
+    if cell is None or not np.asarray(atoms.pbc).any():
+        return None, None
+    return np.asarray(getattr(cell, "array", cell)), np.asarray(atoms.pbc)
+
+
+class _DeviceScalars:
+    """Species / charge / multiplicity tensors kept on the device; each is re-uploaded only when the host value it was
+    made from has changed (so ASE's per-step `reset()` costs nothing here)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.numbers = self.charge = self.mult = None
+        self._host = {}
+
+    def species(self, numbers) -> torch.Tensor:
+        host = np.asarray(numbers)
+        last = self._host.get("numbers")
+        if last is None or host.shape != last.shape or (host != last).any():
+            self._host["numbers"] = host.copy()
+            self.numbers = torch.as_tensor(host, dtype=torch.int32, device=self.device)
+        return self.numbers
+
+    def scalar(self, which: str, value) -> torch.Tensor:
+        if which not in self._host or self._host[which] != value:
+            self._host[which] = value
+            setattr(self, which, torch.tensor(value, dtype=torch.float32, device=self.device))
+        return getattr(self, which)
+
 
 class AIMNet2ASE(Calculator):
-    implemented_properties: ClassVar[list[str]] = ["energy", "forces", "free_energy", "charges", "stress", "dipole_moment"]
+    implemented_properties: ClassVar[list[str]] = list(_BASE_PROPERTIES)
 
     def __init__(self, base_calc: AIMNet2Calculator | str = "aimnet2", charge=0, mult=1, validate_species: bool = True):
-        if _ASE_IMPORT_ERROR is not None:
-            raise ImportError("AIMNet2ASE requires ASE.") from _ASE_IMPORT_ERROR
+        if _ASE_MISSING is not None:
+            raise ImportError("AIMNet2ASE requires ASE.") from _ASE_MISSING
         super().__init__()
-        if isinstance(base_calc, str):
-            base_calc = AIMNet2Calculator(base_calc)
-        self.base_calc = base_calc
+        self.base_calc = AIMNet2Calculator(base_calc) if isinstance(base_calc, str) else base_calc
         self.validate_species = validate_species
-        if self.base_calc.is_nse:
-            self.__dict__["implemented_properties"] = [*self.__class__.implemented_properties, "spin_charges"]
-        self.reset()
-        self.charge = charge
-        self.mult = mult
+        self.charge, self.mult = charge, mult
+        if self.base_calc.is_nse:   # open-shell models also report per-atom spin populations
+            self.__dict__["implemented_properties"] = [*_BASE_PROPERTIES, "spin_charges"]
+        known = (self.base_calc.metadata or {}).get("implemented_species")
+        self.implemented_species = np.array(known, dtype=np.int64) if known else None
+        self._dev = _DeviceScalars(self.base_calc.device)
         self.update_tensors()
-        meta = self.base_calc.metadata
-        species = meta.get("implemented_species") if meta is not None else None
-        self.implemented_species = np.array(species, dtype=np.int64) if species else None
 
-    def reset(self):
-        super().reset()
-        self._t_numbers = None
-        self._t_charge = None
-        self._t_mult = None
-
+    # ---- state ------------------------------------------------------------------------------------------------
     def set_atoms(self, atoms):
-        if self.implemented_species is not None and not np.isin(atoms.numbers, self.implemented_species).all():
+        allowed = self.implemented_species
+        if allowed is not None and not np.isin(atoms.numbers, allowed).all():
             raise ValueError("Some species are not implemented in the AIMNet2Calculator")
         self.reset()
         self.atoms = atoms
 
     def check_state(self, atoms, tol=1e-15):
-        state = super().check_state(atoms, tol=tol)
-        if (not state) and getattr(self, "atoms", None) is not None:
-            old, new = getattr(self.atoms, "info", {}), getattr(atoms, "info", {})
-            if old.get("charge") != new.get("charge"):
-                state.append("info")
-            elif self.base_calc.is_nse and old.get("spin", old.get("mult")) != new.get("spin", new.get("mult")):
-                state.append("info")
-        return state
+        """ASE's comparison does not look at `atoms.info`; a changed charge (or multiplicity for an open-shell model)
+        there must invalidate cached results too."""
+        changed = super().check_state(atoms, tol=tol)
+        mine = getattr(self, "atoms", None)
+        if changed or mine is None:
+            return changed
+        before, now = _info_of(mine), _info_of(atoms)
+        differs = before.get("charge") != now.get("charge")
+        if not differs and self.base_calc.is_nse:
+            differs = _multiplicity_in(before) != _multiplicity_in(now)
+        return ["info"] if differs else changed
 
     def set_charge(self, charge):
         self.charge = charge
-        self._t_charge = None
         self.update_tensors()
 
     def set_mult(self, mult):
         self.mult = mult
-        self._t_mult = None
         self.update_tensors()
 
-    def _update_charge_spin_from_info(self, atoms=None):
-        atoms = atoms if atoms is not None else getattr(self, "atoms", None)
-        if atoms is None:
-            return
-        info = getattr(atoms, "info", {})
-        charge = info.get("charge")
-        if charge is not None and charge != self.charge:
-            self.charge = charge
-            self._t_charge = None
-        if self.base_calc.is_nse:
-            mult = info.get("mult", info.get("spin"))
-            if mult is not None and mult != self.mult:
-                self.mult = mult
-                self._t_mult = None
+    def _adopt_info(self, atoms):
+        """`atoms.info` wins over the values set on the calculator."""
+        info = _info_of(atoms)
+        q = info.get("charge")
+        if q is not None:
+            self.charge = q
+        m = _multiplicity_in(info) if self.base_calc.is_nse else None
+        if m is not None:
+            self.mult = m
 
     def update_tensors(self, atoms=None):
+        """Bring the device-resident species / charge / multiplicity up to date with the host values."""
         atoms = atoms if atoms is not None else getattr(self, "atoms", None)
-        dev = self.base_calc.device
         if atoms is not None:
-            new = torch.as_tensor(np.asarray(atoms.numbers), dtype=torch.int32, device=dev)
-            if self._t_numbers is None or self._t_numbers.shape != new.shape or not torch.equal(self._t_numbers, new):
-                self._t_numbers = new
-        if self._t_charge is None:
-            self._t_charge = torch.tensor(self.charge, dtype=torch.float32, device=dev)
-        if self._t_mult is None:
-            self._t_mult = torch.tensor(self.mult, dtype=torch.float32, device=dev)
+            self._dev.species(atoms.numbers)
+        self._dev.scalar("charge", self.charge)
+        self._dev.scalar("mult", self.mult)
 
+    # ---- derived properties -----------------------------------------------------------------------------------
     def get_dipole_moment(self, atoms):
-        return np.sum(self.get_charges()[:, np.newaxis] * atoms.get_positions(), axis=0)
+        return (self.get_charges()[:, None] * atoms.get_positions()).sum(axis=0)
 
     def get_spin_charges(self, atoms=None):
         if "spin_charges" not in self.results:
@@ -129,38 +163,32 @@ class AIMNet2ASE(Calculator):
     def get_hessian(self, atoms=None):
         raise PropertyNotImplementedError("Hessians are outside the B200 engine's hot path (SURVEY.md §8f f4)")
 
+    # ---- the step ---------------------------------------------------------------------------------------------
+    def _inputs_for(self, atoms) -> tuple[dict, bool]:
+        """The calculator's input dict for `atoms` and whether it was wrapped into a batch of one."""
+        device = self.base_calc.device
+        system = {"coord": torch.tensor(np.asarray(atoms.positions), dtype=torch.float32, device=device),
+                  "numbers": self._dev.numbers, "charge": self._dev.charge, "mult": self._dev.mult}
+        cell, pbc = _lattice(atoms)
+        if cell is None:
+            return {key: t.unsqueeze(0) for key, t in system.items()}, True
+        system["cell"], system["pbc"] = cell, pbc
+        return system, False
+
     def calculate(self, atoms=None, properties=None, system_changes=all_changes):
-        if properties is None:
-            properties = ["energy"]
-        super().calculate(atoms, properties, system_changes)
-        self._update_charge_spin_from_info()
+        wanted = ["energy"] if properties is None else properties
+        super().calculate(atoms, wanted, system_changes)
+        self._adopt_info(self.atoms)
         self.update_tensors()
-        periodic = self.atoms.cell is not None and np.asarray(self.atoms.pbc).any()
-        cell = np.asarray(self.atoms.cell.array if hasattr(self.atoms.cell, "array") else self.atoms.cell) if periodic else None
-        dev = self.base_calc.device
-        _in = {"coord": torch.tensor(np.asarray(self.atoms.positions), dtype=torch.float32, device=dev),
-               "numbers": self._t_numbers, "charge": self._t_charge, "mult": self._t_mult}
-        unsqueezed = False
-        if cell is not None:
-            _in["cell"] = cell
-            _in["pbc"] = np.asarray(self.atoms.pbc)
-        else:
-            _in = {k: v.unsqueeze(0) for k, v in _in.items()}
-            unsqueezed = True
-        results = self.base_calc(_in, forces="forces" in properties, stress="stress" in properties,
-                                 validate_species=self.validate_species)
-        out = {}
-        for k, v in results.items():
-            if unsqueezed and k != "energy":
-                v = v.squeeze(0)
-            out[k] = v.detach().cpu().numpy()
-        self.results["energy"] = out["energy"].item()
-        self.results["free_energy"] = self.results["energy"]
-        self.results["charges"] = out["charges"]
-        self.results["dipole_moment"] = np.sum(out["charges"][:, None] * np.asarray(self.atoms.positions), axis=0)
-        if "forces" in properties:
-            self.results["forces"] = out["forces"]
-        if "stress" in properties:
-            self.results["stress"] = out["stress"]
-        if "spin_charges" in out:
-            self.results["spin_charges"] = out["spin_charges"]
+        system, batched = self._inputs_for(self.atoms)
+        raw = self.base_calc(system, forces="forces" in wanted, stress="stress" in wanted,
+                             validate_species=self.validate_species)
+        host = {key: (t.squeeze(0) if batched and key != "energy" else t).detach().cpu().numpy() for key, t in raw.items()}
+        energy = host["energy"].item()
+        self.results.update(energy=energy, free_energy=energy, charges=host["charges"],
+                            dipole_moment=(host["charges"][:, None] * np.asarray(self.atoms.positions)).sum(axis=0))
+        for key in ("forces", "stress"):
+            if key in wanted:
+                self.results[key] = host[key]
+        if "spin_charges" in host:
+            self.results["spin_charges"] = host["spin_charges"]

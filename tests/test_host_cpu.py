@@ -141,3 +141,117 @@ def test_estimate_ewald_parameters_seam_matches_oracle():
         assert p.alpha[s].item() == pytest.approx(1.0 / (math.sqrt(2.0) * eta), rel=1e-6)
     with pytest.raises(ValueError):
         ops.estimate_ewald_parameters(torch.zeros(3, 3), torch.zeros(3, 3), accuracy=1e-6)   # singular cell
+
+
+def test_ase_adapter_host_logic(monkeypatch):
+    """AIMNet2ASE is pure host marshalling around `calc(dict, forces=, stress=, validate_species=)`: with a stand-in for
+    ASE's Calculator base class and a recording stand-in for the calculator (CPU tensors) every branch of it runs here —
+    batch-of-one for isolated systems, flat + cell + pbc for periodic ones, atoms.info over constructor values, result
+    keys and shapes, residency of the per-system inputs, the error paths (surface of aimnet/calculators/aimnet2ase.py:35-274)."""
+    import sys
+    import types
+
+    import torch
+
+    class _Base:
+        def __init__(self, *a, **k):
+            self.results, self.atoms = {}, None
+
+        def reset(self):
+            self.results = {}
+
+        def check_state(self, atoms, tol=1e-15):
+            return []
+
+        def calculate(self, atoms=None, properties=None, system_changes=None):
+            if atoms is not None:
+                self.atoms = atoms
+
+        def get_charges(self):
+            return self.results["charges"]
+
+    mod = types.ModuleType("ase.calculators.calculator")
+    mod.Calculator, mod.PropertyNotImplementedError, mod.all_changes = _Base, RuntimeError, ["positions"]
+    for name, m in (("ase", types.ModuleType("ase")), ("ase.calculators", types.ModuleType("ase.calculators")),
+                    ("ase.calculators.calculator", mod)):
+        monkeypatch.setitem(sys.modules, name, m)
+    monkeypatch.delitem(sys.modules, "aimnetcentral_b200.aimnet2ase", raising=False)
+    from aimnetcentral_b200.aimnet2ase import AIMNet2ASE
+
+    class FakeCalc:
+        device, metadata = torch.device("cpu"), {"implemented_species": [1, 6, 7, 8]}
+
+        def __init__(self, nse=False):
+            self.is_nse, self.calls = nse, []
+
+        def __call__(self, data, forces=False, stress=False, validate_species=True):
+            self.calls.append((data, forces, stress, validate_species))
+            batched = data["coord"].ndim == 3
+            n = data["coord"].shape[-2]
+            lead = (1,) if batched else ()
+            out = {"energy": torch.tensor([-7.25], dtype=torch.float64), "charges": torch.arange(n, dtype=torch.float32).reshape(*lead, n)}
+            if forces:
+                out["forces"] = torch.ones(*lead, n, 3)
+            if stress:
+                out["stress"] = torch.eye(3)
+            if self.is_nse:
+                out["spin_charges"] = torch.zeros(*lead, n)
+            return out
+
+    class Atoms:
+        def __init__(self, numbers, positions, cell=None, pbc=False, info=None):
+            self.numbers, self.positions = np.asarray(numbers), np.asarray(positions, dtype=np.float64)
+            self.cell = None if cell is None else np.asarray(cell, dtype=np.float64)
+            self.pbc = np.array([pbc] * 3) if np.isscalar(pbc) else np.asarray(pbc)
+            self.info = info or {}
+
+        def get_positions(self):
+            return self.positions
+
+    pos = np.arange(12, dtype=np.float64).reshape(4, 3)
+    fake = FakeCalc()
+    ase_calc = AIMNet2ASE(fake, charge=0, mult=1, validate_species=False)
+    assert "spin_charges" not in ase_calc.implemented_properties and list(ase_calc.implemented_species) == [1, 6, 7, 8]
+    # isolated system: a batch of one, atoms.info["charge"] wins, numbers/charge/mult are device tensors
+    ase_calc.calculate(Atoms([6, 1, 1, 8], pos, info={"charge": 1}), properties=["energy", "forces"])
+    data, forces, stress, validate = fake.calls[-1]
+    assert data["coord"].shape == (1, 4, 3) and data["coord"].dtype == torch.float32
+    assert data["numbers"].shape == (1, 4) and data["numbers"].dtype == torch.int32
+    assert data["charge"].shape == (1,) and data["charge"].item() == 1.0 and data["mult"].item() == 1.0
+    assert forces and not stress and validate is False and "cell" not in data
+    r = ase_calc.results
+    assert r["energy"] == -7.25 and r["free_energy"] == -7.25 and r["charges"].shape == (4,) and r["forces"].shape == (4, 3)
+    assert np.allclose(r["dipole_moment"], (np.arange(4)[:, None] * pos).sum(axis=0)) and "stress" not in r
+    assert np.allclose(ase_calc.get_dipole_moment(ase_calc.atoms), r["dipole_moment"])
+    # the species tensor stays resident while the numbers do not change, and follows them when they do
+    first = data["numbers"]
+    ase_calc.calculate(Atoms([6, 1, 1, 8], pos + 0.1, info={"charge": 1}), properties=["energy"])
+    assert fake.calls[-1][0]["numbers"].data_ptr() == first.data_ptr()
+    ase_calc.calculate(Atoms([6, 1, 1, 7], pos, info={"charge": 1}), properties=["energy"])
+    assert fake.calls[-1][0]["numbers"].flatten().tolist() == [6, 1, 1, 7]
+    # periodic system: flat coordinates + cell + pbc, stress through
+    cell = np.diag([9.0, 10.0, 11.0])
+    ase_calc.calculate(Atoms([6, 1, 1, 8], pos, cell=cell, pbc=True), properties=["energy", "forces", "stress"])
+    data, forces, stress, _ = fake.calls[-1]
+    assert data["coord"].shape == (4, 3) and np.allclose(data["cell"], cell) and data["pbc"].all() and forces and stress
+    assert ase_calc.results["stress"].shape == (3, 3) and ase_calc.results["charges"].shape == (4,)
+    # setters, info-driven invalidation, error paths
+    ase_calc.set_charge(-1)
+    ase_calc.calculate(Atoms([6, 1, 1, 8], pos), properties=["energy"])
+    assert fake.calls[-1][0]["charge"].item() == -1.0
+    a0, a1 = Atoms([6], pos[:1], info={"charge": 0}), Atoms([6], pos[:1], info={"charge": 1})
+    ase_calc.atoms = a0
+    assert ase_calc.check_state(a1) == ["info"] and ase_calc.check_state(a0) == []
+    with pytest.raises(ValueError):
+        ase_calc.set_atoms(Atoms([6, 26], pos[:2]))
+    with pytest.raises(RuntimeError):
+        ase_calc.get_spin_charges()
+    with pytest.raises(RuntimeError):
+        ase_calc.get_hessian()
+    # open-shell model: multiplicity from atoms.info ("mult" or "spin"), spin populations in the results
+    nse = AIMNet2ASE(FakeCalc(nse=True), charge=0, mult=1)
+    assert "spin_charges" in nse.implemented_properties
+    nse.calculate(Atoms([6, 1, 1, 8], pos, info={"spin": 3}), properties=["energy"])
+    assert nse.base_calc.calls[-1][0]["mult"].item() == 3.0 and nse.get_spin_charges().shape == (4,)
+    assert nse.check_state(Atoms([6, 1, 1, 8], pos, info={"spin": 1})) == ["info"]
+    monkeypatch.delitem(sys.modules, "aimnetcentral_b200.aimnet2ase", raising=False)
