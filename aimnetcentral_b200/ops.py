@@ -292,7 +292,7 @@ def _pack_d3_tables(c6_reference: Tensor, coord_num_ref: Tensor, dev):
     key = (c6_reference.data_ptr(), coord_num_ref.data_ptr(), str(dev))
     hit = _D3_PACKED.get(key)
     if hit is not None:
-        return hit
+        return hit[0], hit[1]
     c6 = c6_reference.detach().to(device=dev, dtype=torch.float32)
     cn = coord_num_ref.detach().to(device=dev, dtype=torch.float32)
     if c6.shape != (95, 95, 5, 5):
@@ -307,7 +307,8 @@ def _pack_d3_tables(c6_reference: Tensor, coord_num_ref: Tensor, dev):
         raise ValueError("coord_num_ref must have shape (95, 95, 5, 5) or (95, 5)")
     c6p = torch.nn.functional.pad(c6.reshape(95, 95, 25), (0, 3)).contiguous()
     _D3_PACKED.clear()   # one entry: the tables are process-wide constants in practice
-    _D3_PACKED[key] = (c6p, cnref)
+    # the entry keeps the source tensors alive, so a matching data_ptr cannot be a recycled allocation
+    _D3_PACKED[key] = (c6p, cnref, c6_reference, coord_num_ref)
     return c6p, cnref
 
 
