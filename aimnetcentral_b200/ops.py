@@ -8,7 +8,7 @@
 * `AdaptiveNeighborList` — the reference's auto-sizing wrapper (aimnet/calculators/neighbors.py:21-147) over our op.
 * `dsf_coulomb`, `dftd3`, `estimate_ewald_parameters` — the pair-term kernels with the keyword arguments and return
   tuples of the nvalchemiops calls at aimnet/modules/lr.py:526-540, :1204-1228 and
-  aimnet/calculators/calculator.py:1566-1587 (GPU parity tests pending: tests/test_gpu_seams_unverified.py).
+  aimnet/calculators/calculator.py:1566-1587 (GPU parity tests pending: tests/test_gpu_unverified.py).
 """
 from __future__ import annotations
 

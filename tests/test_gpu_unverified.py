@@ -1,9 +1,14 @@
-"""Pair-term operator seams (SURVEY.md section 8b, B3 iii): `ops.dsf_coulomb` and `ops.dftd3` against independent float64
-torch restatements of the reference's closed forms (aimnet/modules/lr.py:559-615 and :1580-1657) on the very neighbor
-matrices the seam receives.
+"""GPU tests that have NOT RUN YET: written after the GPU budget of round 1 was spent.  They carry the `gpu_unverified`
+marker instead of `gpu`, so that the `-m gpu` suite stays exactly what has passed on a B200; without CUDA they skip.
+Run them with `pytest -m gpu_unverified`, fix what they find, then move them to the `gpu` files.
 
-NOT YET RUN: written after the GPU budget of round 1 was spent.  They carry the `gpu_unverified` marker instead of `gpu`
-so that the `-m gpu` suite stays what has actually passed on a B200; on a machine without CUDA they skip."""
+* Pair-term operator seams (SURVEY.md section 8b, B3 iii): `ops.dsf_coulomb` and `ops.dftd3` against independent float64
+  torch restatements of the reference's closed forms (aimnet/modules/lr.py:559-615 and :1580-1657) on the very neighbor
+  matrices the seam receives.
+* The MLP GEMM with more output tiles than SMs: every accuracy test of the `gpu` suite fits one wave of CTAs (<= 75 tiles),
+  the multi-tile-per-CTA path of the persistent kernel is only covered by invariance / repeatability tests there."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -105,3 +110,41 @@ def test_dftd3_against_closed_form():
     assert (f_ev + gx).abs().max() < 2e-5
     assert (w_ev + geps).abs().max() < 1e-4
     assert cn.min() > 0
+
+
+@pytest.mark.parametrize("backend", [2, 18])   # 18 = backend 2 writing its output pre-split (mode | 16)
+@pytest.mark.parametrize("M,N,K,mode", [(20000, 512, 704, 2), (20000, 288, 384, 1), (20000, 704, 512, 3), (19999, 512, 512, 0)])
+def test_gemm_more_tiles_than_sms(M, N, K, mode, backend):
+    """157 row tiles x 2-3 column tiles = 314-471 tiles on 148 persistent CTAs: each CTA runs 2-4 tiles back to back
+    (TMEM / box-ring / aux-ring state carried across tiles), checked against float64 like tests/test_gpu_ops.py does for
+    the single-wave shapes."""
+    from aimnetcentral_b200 import _capi
+
+    lib = _capi.load()
+    dev = "cuda:0"
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    aux_in = torch.randn(M, N, generator=g).to(dev)
+    Y = torch.empty(M, N, device=dev)
+    aux = aux_in.clone() if mode == 3 else torch.empty(M, N, device=dev)
+    flag = 16 if backend == 18 else 0
+    rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K,
+                             mode | flag, 2, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.aimnet2_last_error()
+    z = A.double() @ W.double().T
+    if mode in (1, 2):
+        z = z + b.double()
+    if mode == 2:
+        ref = torch.nn.functional.gelu(z)
+        zz = z.clone().requires_grad_(True)
+        gp = torch.autograd.grad(torch.nn.functional.gelu(zz).sum(), zz)[0]
+        assert torch.allclose(aux.double(), gp, atol=2e-5, rtol=1e-5)
+    elif mode == 3:
+        ref = z * aux_in.double()
+    else:
+        ref = z
+    err = (Y.double() - ref).abs()
+    worst = int(err.max(dim=1).values.argmax())
+    assert torch.allclose(Y.double(), ref, atol=5e-5, rtol=1e-5), (float(err.max()), "row", worst, "row tile", worst // 128)
