@@ -255,3 +255,33 @@ def test_ase_adapter_host_logic(monkeypatch):
     assert nse.base_calc.calls[-1][0]["mult"].item() == 3.0 and nse.get_spin_charges().shape == (4,)
     assert nse.check_state(Atoms([6, 1, 1, 8], pos, info={"spin": 1})) == ["info"]
     monkeypatch.delitem(sys.modules, "aimnetcentral_b200.aimnet2ase", raising=False)
+
+
+def test_pair_term_seams_reject_bad_arguments_before_touching_the_gpu():
+    """Argument validation of the pair-term entry points happens before any CUDA call, so it can be exercised here:
+    status -1 (invalid argument, raised as ValueError by the Python layer) and a message in aimnet2_last_error()."""
+    from aimnetcentral_b200 import _capi
+
+    lib = _capi.load()
+    one = ctypes.c_void_p(1)   # never dereferenced: the calls below fail validation first
+    # no neighbor matrix
+    rc = lib.aimnet2_dsf_coulomb(one, one, 4, 9.0, 0.2, None, 0, None, 1, None, None, 0, 4, one, None, None, None, None)
+    assert rc == -1 and b"neighbor matrix" in lib.aimnet2_last_error()
+    # a cell without shifts
+    rc = lib.aimnet2_dsf_coulomb(one, one, 4, 9.0, 0.2, one, 1, None, 1, one, None, 8, 4, one, None, None, None, None)
+    assert rc == -1 and b"shifts" in lib.aimnet2_last_error()
+    # cell count that is neither 1 nor the number of systems
+    rc = lib.aimnet2_dsf_coulomb(one, one, 4, 9.0, 0.2, one, 2, None, 3, one, one, 8, 4, one, None, None, None, None)
+    assert rc == -1 and b"n_cells" in lib.aimnet2_last_error()
+    # non-positive cutoff
+    rc = lib.aimnet2_dsf_coulomb(one, one, 4, 0.0, 0.2, None, 0, None, 1, one, None, 8, 4, one, None, None, None, None)
+    assert rc == -1 and b"cutoff" in lib.aimnet2_last_error()
+    # D3: switching window upside down, missing tables
+    rc = lib.aimnet2_dftd3(one, one, 4, 1.0, 0.39, 0.57, 3.1, 30.0, 20.0, one, one, one, one, None, 0, None, 1, one, None, 8, 4,
+                           one, None, None, None, None)
+    assert rc == -1 and b"r_on" in lib.aimnet2_last_error()
+    rc = lib.aimnet2_dftd3(one, one, 4, 1.0, 0.39, 0.57, 3.1, 20.0, 30.0, None, one, one, one, None, 0, None, 1, one, None, 8, 4,
+                           one, None, None, None, None)
+    assert rc == -1 and b"null argument" in lib.aimnet2_last_error()
+    with pytest.raises(ValueError):
+        _capi.check(rc, "dftd3")
