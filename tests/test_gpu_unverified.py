@@ -148,3 +148,35 @@ def test_gemm_more_tiles_than_sms(M, N, K, mode, backend):
     err = (Y.double() - ref).abs()
     worst = int(err.max(dim=1).values.argmax())
     assert torch.allclose(Y.double(), ref, atol=5e-5, rtol=1e-5), (float(err.max()), "row", worst, "row tile", worst // 128)
+
+
+def test_rotation_invariance_molecules():
+    """Rigid rotation of every molecule of a batch (tests/test_calculator.py:976-1014 of the reference): energies and
+    charges unchanged, forces rotate with the frame.  The rotated coordinates are different fp32 numbers (~5e-7 A), so
+    the bounds are a few times the parity tolerance."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import random_molecules
+
+    spec = ModelSpec()
+    calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+    coord, numbers = random_molecules(96, 50, seed=17)
+    charge = np.zeros(96, np.float32)
+    charge[::5] = -1.0
+    rng = np.random.default_rng(2)
+    q = rng.normal(size=(96, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                  np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                  np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2)   # (96,3,3)
+    rotated = np.einsum("bij,bnj->bni", R, coord.astype(np.float64)).astype(np.float32)
+    for rows in (0, 512):
+        calc.engine.set_small_m_rows(rows)
+        r1 = {k: v.cpu().numpy() for k, v in calc({"coord": coord, "numbers": numbers, "charge": charge}, forces=True).items()}
+        r2 = {k: v.cpu().numpy() for k, v in calc({"coord": rotated, "numbers": numbers, "charge": charge}, forces=True).items()}
+        f1_rot = np.einsum("bij,bnj->bni", R, r1["forces"].astype(np.float64))
+        de = np.abs(r2["energy"] - r1["energy"]).max()
+        df = np.abs(r2["forces"] - f1_rot).max()
+        dq = np.abs(r2["charges"] - r1["charges"]).max()
+        print(f"[invariance] rotation (small_m_rows {rows}): dE {de:.2e} dF {df:.2e} dq {dq:.2e}")
+        assert de < 2e-4 and df < 5e-4 and dq < 1e-4
