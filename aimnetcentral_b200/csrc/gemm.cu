@@ -252,16 +252,18 @@ extern "C" int aimnet2_gemm_set_trace(void* device_buf) {
 }
 
 // Operator seam for tests / tools: fp32 operands in; weights (and, for backend 2, activations) are split on the device.
-// Backend 2 only: mode | 16 makes the kernel write its output pre-split (the GEMM -> GEMM path of the engine), which is
+// Backends 2 and 3 (3 = the experimental pipelined-epilogue kernel of gemm_tc16p.cu, not used by the engine): mode | 16
+// makes the kernel write its output pre-split (the GEMM -> GEMM path of the engine), which is
 // then expanded back to fp32 into Y so that the caller can check it.
 extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                                float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {
     using namespace aimnet;
     cudaStream_t st = (cudaStream_t)stream;
-    AIM_REQUIRE(backend >= 0 && backend <= 2, "gemm: backend must be 0 (SIMT), 1 (3xTF32) or 2 (3xFP16)");
+    AIM_REQUIRE(backend >= 0 && backend <= 3,
+                "gemm: backend must be 0 (SIMT), 1 (3xTF32), 2 (3xFP16) or 3 (3xFP16, pipelined epilogue: experimental)");
     const bool split_out = (mode & 16) != 0;
     mode &= 15;
-    AIM_REQUIRE(!split_out || backend == 2, "gemm: pre-split output exists only for backend 2");
+    AIM_REQUIRE(!split_out || backend >= 2, "gemm: pre-split output exists only for the 3xFP16 backends");
     WeightView wv{W, nullptr, nullptr, nullptr, nullptr, nullptr, ldw};
     if (backend == 0) return gemm_nt(A, lda, wv, bias, Y, ldy, aux, ldaux, M, N, K, mode, 0, st);
     AIM_REQUIRE(gemm_tc_available(), "gemm: tcgen05 backends not available");
@@ -294,7 +296,17 @@ extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw,
     SplitMat Ys{buf + o_yh, buf + o_yl, reinterpret_cast<float*>(buf + o_yi), N, N / 32};
     int rc = split_fp16_device(W, buf + o_wh, buf + o_wl, inv, reinterpret_cast<unsigned int*>(inv + 16), n, st);
     if (rc == AIMNET_OK) rc = presplit_f32(A, lda, M, K, As, st);
-    if (rc == AIMNET_OK) rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, st);
+    if (rc == AIMNET_OK && backend == 2)
+        rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, st);
+    if (rc == AIMNET_OK && backend == 3) {
+        if (mode < 0 || mode > 3 || (mode == 3 && aux == nullptr) || ((mode == 1 || mode == 2) && bias == nullptr)) {
+            set_error("invalid argument: gemm: bad epilogue mode / missing aux or bias");
+            rc = AIMNET_EINVAL;
+        } else {
+            rc = gemm_nt_tc16p(As, wv.Wh16, wv.Wl16, wv.inv_scale16, wv.ldw, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux,
+                               M, N, K, mode, st);
+        }
+    }
     if (rc == AIMNET_OK && split_out) rc = unsplit_f32(Ys, M, N, Y, ldy, st);
     cudaFreeAsync(buf, st);
     return rc;

@@ -47,6 +47,11 @@ int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const floa
                  const float* bias, float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N,
                  int K, int mode, cudaStream_t st);
 
+// ---- gemm_tc16p.cu: experimental backend 3 (software-pipelined tile epilogue); same contract as gemm_nt_tc16
+int gemm_nt_tc16p(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw,
+                  const float* bias, float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N,
+                  int K, int mode, cudaStream_t st);
+
 // ---- pointwise.cu: embedding, NSE charge equilibration, reductions, Verlet-skin bookkeeping
 int launch_embed(int n, const int32_t* numbers, const float* afv, float* a0, cudaStream_t st);
 int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, cudaStream_t st);

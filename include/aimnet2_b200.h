@@ -236,7 +236,9 @@ int aimnet2_estimate_ewald_parameters(const float* host_cell, int n_atoms, doubl
 
 /* standalone NT GEMM with fused epilogue (test seam for the MLP kernels):
  * Y[M,N] = act(A[M,K] @ W[N,K]^T + bias); mode 0 none, 1 bias, 2 bias+GELU (also writes gelu'(z) to aux when non-NULL),
- * 3 multiply by aux[M,N].  lda/ldw/ldy in elements. */
+ * 3 multiply by aux[M,N].  lda/ldw/ldy in elements.  backend: 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 (what the
+ * engine runs), 3 = experimental 3xFP16 kernel with the tile epilogue pipelined under the next tile's MMAs (not used by
+ * the engine, not yet validated on a GPU).  mode | 16 (backends 2, 3): the kernel writes its output pre-split. */
 int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                     float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream);
 

@@ -112,27 +112,57 @@ def test_dftd3_against_closed_form():
     assert cn.min() > 0
 
 
-@pytest.mark.parametrize("backend", [2, 18])   # 18 = backend 2 writing its output pre-split (mode | 16)
-@pytest.mark.parametrize("M,N,K,mode", [(20000, 512, 704, 2), (20000, 288, 384, 1), (20000, 704, 512, 3), (19999, 512, 512, 0)])
-def test_gemm_more_tiles_than_sms(M, N, K, mode, backend):
-    """157 row tiles x 2-3 column tiles = 314-471 tiles on 148 persistent CTAs: each CTA runs 2-4 tiles back to back
-    (TMEM / box-ring / aux-ring state carried across tiles), checked against float64 like tests/test_gpu_ops.py does for
-    the single-wave shapes."""
+def _gemm_seam(A, W, b, aux_in, mode, backend):
+    """Y, aux of aimnet2_gemm_nt; backend + 16 = the same backend writing its output pre-split (mode | 16)."""
     from aimnetcentral_b200 import _capi
 
     lib = _capi.load()
-    dev = "cuda:0"
-    g = torch.Generator(device="cpu").manual_seed(M + N + K)
-    A = torch.randn(M, K, generator=g).to(dev)
-    W = (torch.randn(N, K, generator=g) * 0.05).to(dev)
-    b = torch.randn(N, generator=g).to(dev)
-    aux_in = torch.randn(M, N, generator=g).to(dev)
-    Y = torch.empty(M, N, device=dev)
-    aux = aux_in.clone() if mode == 3 else torch.empty(M, N, device=dev)
-    flag = 16 if backend == 18 else 0
+    M, K = A.shape
+    N = W.shape[0]
+    Y = torch.empty(M, N, device=A.device)
+    aux = aux_in.clone() if mode == 3 else torch.empty(M, N, device=A.device)
+    flag = 16 if backend >= 16 else 0
     rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K,
-                             mode | flag, 2, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                             mode | flag, backend & 15, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.aimnet2_last_error()
+    torch.cuda.synchronize()
+    return Y, aux
+
+
+def _gemm_operands(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    aux_in = torch.randn(M, N, generator=g).cuda()
+    return A, W, b, aux_in
+
+
+@pytest.mark.parametrize("split_out", [0, 16])
+@pytest.mark.parametrize("M,N,K,mode", [(300, 512, 704, 2), (1000, 288, 384, 1), (77, 736, 512, 0), (513, 384, 512, 3),
+                                        (1, 128, 256, 2), (640, 128, 128, 2), (20000, 512, 704, 2), (20000, 704, 512, 3),
+                                        (20000, 288, 384, 1), (19999, 256, 512, 0)])
+def test_gemm_pipelined_epilogue_equals_backend2_bitwise(M, N, K, mode, split_out):
+    """Backend 3 (gemm_tc16p.cu: 128x128 tiles, two accumulator sets, the epilogue of tile t sliced under the K loop of
+    tile t+1) performs the same operations in the same order per output element as backend 2, so its results must be
+    bit-identical — including short K loops (fewer chunks than epilogue slices), ragged last tiles and CTAs that run
+    many tiles.  RUN UNDER `timeout`: the kernel has never executed."""
+    A, W, b, aux_in = _gemm_operands(M, N, K)
+    Y2, aux2 = _gemm_seam(A, W, b, aux_in, mode, 2 + split_out)
+    Y3, aux3 = _gemm_seam(A, W, b, aux_in, mode, 3 + split_out)
+    assert torch.equal(Y2, Y3), float((Y2 - Y3).abs().max())
+    if mode == 2:
+        assert torch.equal(aux2, aux3)
+
+
+@pytest.mark.parametrize("backend", [2, 18, 3, 19])   # +16 = the backend writing its output pre-split (mode | 16)
+@pytest.mark.parametrize("M,N,K,mode", [(20000, 512, 704, 2), (20000, 288, 384, 1), (20000, 704, 512, 3), (19999, 512, 512, 0)])
+def test_gemm_more_tiles_than_sms(M, N, K, mode, backend):
+    """157 row tiles x 2-6 column tiles = 314-942 tiles on 148 persistent CTAs: each CTA runs 2-7 tiles back to back
+    (TMEM / box-ring / aux-ring state carried across tiles), checked against float64 like tests/test_gpu_ops.py does for
+    the single-wave shapes."""
+    A, W, b, aux_in = _gemm_operands(M, N, K)
+    Y, aux = _gemm_seam(A, W, b, aux_in, mode, backend)
     z = A.double() @ W.double().T
     if mode in (1, 2):
         z = z + b.double()

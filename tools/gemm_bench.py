@@ -1,4 +1,7 @@
-"""Time the MLP GEMM shapes of cfg-2 (M=51200) per backend / epilogue mode; report TFLOP/s (1x flops)."""
+"""Time the MLP GEMM shapes of cfg-2 (M=51200) per backend / epilogue mode through the aimnet2_gemm_nt seam; report TFLOP/s
+(1x flops).  `python tools/gemm_bench.py 2,3,18,19` compares the engine's 3xFP16 kernel (2) with the experimental pipelined
+epilogue (3); +16 = pre-split output.  For backends >= 2 the seam also splits W and A on the device and (with +16) expands
+the result again, the same overhead for 2 and 3: use ncu on this script for kernel-only times."""
 import ctypes as C, sys, os
 import torch
 sys.path.insert(0, ".")
@@ -16,11 +19,12 @@ for N, K, mode in shapes:
     for be in backends:
         # pre-split weights are re-made inside aimnet2_gemm_nt for backend 1 (small, included in the timing)
         for _ in range(3):
-            lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode, be, st)
+            lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode | (be & 16), be & 15, st)
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
         for _ in range(10):
-            rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode, be, st)
+            rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode | (be & 16), be & 15, st)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"backend={be} chunk={os.environ.get('AIMNET_TC_CHUNK','8')} N={N:4d} K={K:4d} mode={mode} {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:7.1f} TFLOP/s")
+        assert rc == 0, lib.aimnet2_last_error()
+        print(f"backend={be:2d} N={N:4d} K={K:4d} mode={mode} {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:7.1f} TFLOP/s", flush=True)
