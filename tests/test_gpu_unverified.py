@@ -155,10 +155,20 @@ def test_gemm_pipelined_epilogue_equals_backend2_bitwise(M, N, K, mode, split_ou
         assert torch.equal(aux2, aux3)
 
 
-@pytest.mark.parametrize("backend", [2, 18, 3, 19])   # +16 = the backend writing its output pre-split (mode | 16)
-@pytest.mark.parametrize("M,N,K,mode", [(20000, 512, 704, 2), (20000, 288, 384, 1), (20000, 704, 512, 3), (19999, 512, 512, 0)])
+_MANY_TILES = [(20000, 512, 704, 2), (20000, 288, 384, 1), (20000, 704, 512, 3), (19999, 512, 512, 0)]
+
+
+@pytest.mark.parametrize("backend", [3, 19])
+@pytest.mark.parametrize("M,N,K,mode", _MANY_TILES)
+def test_gemm_more_tiles_than_sms_pipelined(M, N, K, mode, backend):
+    """The same check for the experimental backend 3 (942 tiles for the 704-wide layer: six or seven tiles per CTA)."""
+    test_gemm_more_tiles_than_sms(M, N, K, mode, backend)
+
+
+@pytest.mark.parametrize("backend", [2, 18])   # +16 = the backend writing its output pre-split (mode | 16)
+@pytest.mark.parametrize("M,N,K,mode", _MANY_TILES)
 def test_gemm_more_tiles_than_sms(M, N, K, mode, backend):
-    """157 row tiles x 2-6 column tiles = 314-942 tiles on 148 persistent CTAs: each CTA runs 2-7 tiles back to back
+    """157 row tiles x 2-3 column tiles = 314-471 tiles on 148 persistent CTAs: each CTA runs 2-4 tiles back to back
     (TMEM / box-ring / aux-ring state carried across tiles), checked against float64 like tests/test_gpu_ops.py does for
     the single-wave shapes."""
     A, W, b, aux_in = _gemm_operands(M, N, K)
