@@ -323,7 +323,8 @@ static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float
 static int linear_fwd16(aimnet2_engine* e, const Linear& L, const SplitMat& X, float* Y32, const SplitMat* Y16, float* gp,
                         bool act, int M, cudaStream_t st) {
     gemm_mark(e, st);
-    int rc = gemm_nt_split(X, L.fwd(), L.b, Y32, L.out_pad, Y16, gp, L.out_pad, M, L.out_pad, L.in_pad, act ? 2 : 1, st);
+    int rc = gemm_nt_split(X, L.fwd(), L.b, Y32, L.out_pad, Y16, gp, L.out_pad, M, L.out_pad, L.in_pad, act ? 2 : 1,
+                           e->backend_now == 3, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -331,7 +332,7 @@ static int linear_bwd16(aimnet2_engine* e, const Linear& L, const SplitMat& dZ, 
                         const float* gp_prev, int ldgp, int M, cudaStream_t st) {
     gemm_mark(e, st);
     int rc = gemm_nt_split(dZ, L.bwd(), nullptr, dX32, lddx, dX16, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
-                           gp_prev ? 3 : 0, st);
+                           gp_prev ? 3 : 0, e->backend_now == 3, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -389,7 +390,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     const bool backward = want_f || want_s;
     // small systems: the tensor-core pipelines are latency-bound below a few hundred rows, the fp32 SIMT small-M kernel wins
     const int backend_eff = (e->gemm_backend != 0 && N <= e->small_m_rows) ? 0 : e->gemm_backend;
-    const bool tc16 = backend_eff == 2;
+    const bool tc16 = backend_eff >= 2;   // 2 = 3xFP16 (default), 3 = the same with the experimental pipelined epilogue
     e->backend_now = backend_eff;
     const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
     const bool need_lr_terms = (o.coulomb_method == AIMNET_COULOMB_SIMPLE || o.coulomb_method == AIMNET_COULOMB_DSF ||
@@ -803,7 +804,8 @@ extern "C" int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_opt
 
 extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend) {
     AIM_REQUIRE(e, "set_gemm_backend: null engine");
-    AIM_REQUIRE(backend >= 0 && backend <= 2, "set_gemm_backend: backend must be 0 (SIMT), 1 (3xTF32) or 2 (3xFP16)");
+    AIM_REQUIRE(backend >= 0 && backend <= 3,
+                "set_gemm_backend: backend must be 0 (SIMT), 1 (3xTF32), 2 (3xFP16) or 3 (3xFP16 with the experimental pipelined epilogue)");
     AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backends not available in this build");
     e->gemm_backend = backend;
     return AIMNET_OK;

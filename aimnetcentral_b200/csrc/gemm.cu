@@ -232,13 +232,15 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
 
 // 3xFP16 backend: A pre-split; output fp32 (Ysplit == nullptr) or pre-split for a consuming GEMM
 int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, float* Y, int ldy, const SplitMat* Ysplit,
-                  float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st) {
+                  float* aux, int ldaux, int M, int N, int K, int mode, bool pipelined, cudaStream_t st) {
     AIM_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes");
     AIM_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad epilogue mode");
     AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
     AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
     AIM_REQUIRE(w.Wh16 != nullptr && w.Wl16 != nullptr, "gemm: 3xFP16 backend needs the fp16 split weights");
     if (M == 0) return AIMNET_OK;
+    if (pipelined)   // experimental backend 3 (gemm_tc16p.cu)
+        return gemm_nt_tc16p(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
     return gemm_nt_tc16(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
 }
 
@@ -296,17 +298,8 @@ extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw,
     SplitMat Ys{buf + o_yh, buf + o_yl, reinterpret_cast<float*>(buf + o_yi), N, N / 32};
     int rc = split_fp16_device(W, buf + o_wh, buf + o_wl, inv, reinterpret_cast<unsigned int*>(inv + 16), n, st);
     if (rc == AIMNET_OK) rc = presplit_f32(A, lda, M, K, As, st);
-    if (rc == AIMNET_OK && backend == 2)
-        rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, st);
-    if (rc == AIMNET_OK && backend == 3) {
-        if (mode < 0 || mode > 3 || (mode == 3 && aux == nullptr) || ((mode == 1 || mode == 2) && bias == nullptr)) {
-            set_error("invalid argument: gemm: bad epilogue mode / missing aux or bias");
-            rc = AIMNET_EINVAL;
-        } else {
-            rc = gemm_nt_tc16p(As, wv.Wh16, wv.Wl16, wv.inv_scale16, wv.ldw, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux,
-                               M, N, K, mode, st);
-        }
-    }
+    if (rc == AIMNET_OK)
+        rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, backend == 3, st);
     if (rc == AIMNET_OK && split_out) rc = unsplit_f32(Ys, M, N, Y, ldy, st);
     cudaFreeAsync(buf, st);
     return rc;

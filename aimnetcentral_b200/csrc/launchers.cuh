@@ -28,7 +28,8 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
 int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, float* Y, int ldy, float* aux, int ldaux,
             int M, int N, int K, int mode, int backend, cudaStream_t st);
 int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, float* Y, int ldy,
-                  const SplitMat* Ysplit, float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);
+                  const SplitMat* Ysplit, float* aux, int ldaux, int M, int N, int K, int mode, bool pipelined,
+                  cudaStream_t st);
 
 // ---- gemm_tc.cu: tcgen05 3xTF32 backend
 bool gemm_tc_available();

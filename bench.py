@@ -333,7 +333,7 @@ def main():
         pass
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
     # three error-compensating MMAs per product; kind::f16 runs at the bf16 rate, kind::tf32 at half of it
-    peak_tf = bf16 / 3.0 if eng.gemm_backend == 2 else bf16 / 2.0 / 3.0
+    peak_tf = bf16 / 3.0 if eng.gemm_backend in (2, 3) else bf16 / 2.0 / 3.0
     achieved = flops / (gms * 1e-3) / 1e12
     roofline = {"kernel": "gemm_nt (per-atom MLP stacks, %d launches/step)" % n_gemm, "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -342,7 +342,7 @@ def main():
                 # 144 MB (A hi+lo) + 210 MB (y hi+lo, gelu') algorithmic -- no re-reads; null for the other workloads
                 "traffic": 321.8e6 if (args.workload == "cfg2" and eng.gemm_backend == 2) else None,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained") +
-                               (" / 3 (3xFP16 split on the kind::f16 pipe)" if eng.gemm_backend == 2 else
+                               (" / 3 (3xFP16 split on the kind::f16 pipe)" if eng.gemm_backend in (2, 3) else
                                 " / 2 (tf32) / 3 (3xTF32 split)"),
                 "gemm_ms_per_step": gms, "gemm_share_of_step": gms / (ms_max / K),
                 "phase_ms": {k: float(np.median([p[k] for p in phases])) for k in
@@ -357,7 +357,8 @@ def main():
                        "weights": "seeded random, aimnet2 architecture (2.2M params)",
                        "l2": "per-step working set (activations + saved tensors, >1 GB) exceeds the 126 MB L2; "
                              "coordinates change every step",
-                       "gemm_backend": {2: "tcgen05-3xfp16-rowchunk-scaled", 1: "tcgen05-3xtf32"}.get(eng.gemm_backend, "simt-fp32"),
+                       "gemm_backend": {2: "tcgen05-3xfp16-rowchunk-scaled", 3: "tcgen05-3xfp16-rowchunk-scaled-pipelined-epilogue (experimental)",
+                                        1: "tcgen05-3xtf32"}.get(eng.gemm_backend, "simt-fp32"),
                        "multi_gpu": "independent batches per rank + all_gather of energy/forces (NCCL)" if world > 1 else "single"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),

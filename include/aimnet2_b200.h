@@ -165,7 +165,8 @@ int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weights_t* w, in
 int aimnet2_engine_destroy(aimnet2_engine_t* e);
 int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt);
 /* GEMM backend for the per-atom MLPs: 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 3xFP16 with row-chunk scaling
- * (default when available) */
+ * (default when available), 3 = backend 2's arithmetic with the experimental pipelined tile epilogue (gemm_tc16p.cu; not
+ * validated on a GPU yet) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
 /* Evaluations with at most `rows` atoms run the MLPs on the small-M fp32 SIMT kernel whatever the backend (the
  * tensor-core pipelines are latency-bound for a single molecule); default 512, 0 = never. */

@@ -220,3 +220,25 @@ def test_rotation_invariance_molecules():
         dq = np.abs(r2["charges"] - r1["charges"]).max()
         print(f"[invariance] rotation (small_m_rows {rows}): dE {de:.2e} dF {df:.2e} dq {dq:.2e}")
         assert de < 2e-4 and df < 5e-4 and dq < 1e-4
+
+
+def test_engine_with_pipelined_gemm_equals_backend2():
+    """The whole evaluation with the per-atom MLPs on the experimental backend 3: bit-identical to backend 2 (same
+    arithmetic per element), on a batch large enough for several tiles per CTA."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import random_molecules
+
+    spec = ModelSpec()
+    calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+    coord, numbers = random_molecules(600, 50, seed=21)
+    inp = {"coord": coord, "numbers": numbers, "charge": np.zeros(600, np.float32)}
+    calc.engine.set_gemm_backend(2)
+    ref = {k: v.clone() for k, v in calc(dict(inp), forces=True).items()}
+    calc.engine.set_gemm_backend(3)
+    try:
+        out = calc(dict(inp), forces=True)
+        torch.cuda.synchronize()
+    finally:
+        calc.engine.set_gemm_backend(2)
+    for k in ref:
+        assert torch.equal(ref[k], out[k]), (k, float((ref[k].double() - out[k].double()).abs().max()))
