@@ -57,6 +57,15 @@ extern thread_local int g_launch_count;
         }                                                                                           \
     } while (0)
 
+// Launch configuration caches are per device: cudaFuncSetAttribute and the SM count belong to a device, not to the
+// process (one process may own engines on several GPUs).  Entries are idempotent, so unsynchronised writers agree.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+
 struct AevParams {
     float shifts[kG];
     float eta;

@@ -600,16 +600,18 @@ static int conv_fwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q,
                            int with_q, cudaStream_t st) {
     const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    static bool configured = false;
-    static int max_ctas = 148 * 3;
-    if (!configured) {
+    static bool configured_dev[kMaxDevices] = {};
+    static int max_ctas_dev[kMaxDevices] = {};
+    const int dslot = current_device_slot();
+    int& max_ctas = max_ctas_dev[dslot];
+    if (!configured_dev[dslot]) {
         AIM_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
         int dev = 0, sms = 148, per_sm = 3;
         AIM_CUDA_CHECK(cudaGetDevice(&dev));
         AIM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         AIM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_fwd_kernel<C>, 256, kFwdSmemBytes));
         max_ctas = sms * (per_sm > 0 ? per_sm : 1);
-        configured = true;
+        configured_dev[dslot] = true;
     }
     // persistent CTAs (one resident wave): the agh tables are staged once per CTA, not once per 8 atoms
     const int grid = n_groups < max_ctas ? n_groups : max_ctas;
@@ -635,7 +637,8 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
                            double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
     const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    static int prep_ctas = 0;
+    static int prep_ctas_dev[kMaxDevices] = {};
+    int& prep_ctas = prep_ctas_dev[current_device_slot()];
     if (prep_ctas == 0) {
         int dev = 0, sms = 148, per_sm = 4;
         AIM_CUDA_CHECK(cudaGetDevice(&dev));

@@ -22,6 +22,11 @@ void set_error(const std::string& msg) { g_error = msg; }
 static inline int pad32(int x) { return (x + 31) / 32 * 32; }
 static inline int round16(int x) { return (x + 15) / 16 * 16; }
 
+struct Region {   // one carved workspace buffer (debug layout)
+    const char* name;
+    size_t off, bytes;
+};
+
 struct Linear {
     int in = 0, out = 0, in_pad = 0, out_pad = 0;
     float* W = nullptr;    // (out_pad, in_pad)
@@ -91,6 +96,8 @@ struct aimnet2_engine {
         int builds = 0, reuses = 0;
     } skin;
     std::vector<void*> owned;
+    std::vector<aimnet::Region> layout;   // names / offsets of the workspace buffers of the last evaluation (debug)
+    bool deterministic = false;           // recorded only: every kernel of the engine is run-to-run reproducible
 };
 
 namespace aimnet {
@@ -176,10 +183,12 @@ static int make_linear(aimnet2_engine* e, Linear& L, const float* w, const float
 struct Bump {
     char* base;
     size_t off = 0;
+    std::vector<Region>* map = nullptr;   // debug: names / offsets of the carved buffers (aimnet2_engine_debug_layout)
     template <typename T>
-    T* take(size_t count) {
+    T* take(size_t count, const char* name = nullptr) {
         off = (off + 255) & ~(size_t)255;
         T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        if (map && name) map->push_back(Region{name, off, sizeof(T) * count});
         off += sizeof(T) * count;
         return p;
     }
@@ -226,70 +235,76 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
                   bool need_lr, int ldx) {
     int C = e->C;
     size_t n = (size_t)std::max(N, 1);
-    b.coord_w = bp.take<float>(n * 3);
-    b.mol_ptr = bp.take<int32_t>(B + 2);
-    b.nb_scratch = bp.take<int32_t>((size_t)B * 4 + 16);
-    b.nb_sr = bp.take<int32_t>(n * sr_cap);
-    b.sh_sr = pbc ? bp.take<int32_t>(n * sr_cap * 3) : nullptr;
-    b.cnt_sr = bp.take<int32_t>(n);
-    b.nb_lr = need_lr ? bp.take<int32_t>(n * lr_cap) : nullptr;
-    b.sh_lr = need_lr ? bp.take<int32_t>(n * lr_cap * 3) : nullptr;
-    b.cnt_lr = bp.take<int32_t>(n);
-    for (int p = 0; p < 3; ++p) b.a[p] = bp.take<float>(n * kAG);
-    for (int p = 0; p < 2; ++p) b.q[p] = bp.take<float>(n * C);
-    b.x = bp.take<float>(n * ldx);
-    b.hA = bp.take<float>(n * 512);
-    b.hB = bp.take<float>(n * 512);
-    for (int p = 0; p < 2; ++p) b.y[p] = bp.take<float>(n * 288);
-    b.aim = bp.take<float>(n * 256);
+    b.coord_w = bp.take<float>(n * 3, "coord_w");
+    b.mol_ptr = bp.take<int32_t>(B + 2, "mol_ptr");
+    b.nb_scratch = bp.take<int32_t>((size_t)B * 4 + 16, "nb_scratch");
+    b.nb_sr = bp.take<int32_t>(n * sr_cap, "nb_sr");
+    b.sh_sr = pbc ? bp.take<int32_t>(n * sr_cap * 3, "sh_sr") : nullptr;
+    b.cnt_sr = bp.take<int32_t>(n, "cnt_sr");
+    b.nb_lr = need_lr ? bp.take<int32_t>(n * lr_cap, "nb_lr") : nullptr;
+    b.sh_lr = need_lr ? bp.take<int32_t>(n * lr_cap * 3, "sh_lr") : nullptr;
+    b.cnt_lr = bp.take<int32_t>(n, "cnt_lr");
+    static const char* const kNameA[3] = {"a0", "a1", "a2"};
+    static const char* const kNameQ[2] = {"q0", "q1"};
+    static const char* const kNameY[2] = {"y0", "y1"};
+    static const char* const kNameGp[3][4] = {{"gp00", "gp01", "gp02", "gp03"}, {"gp10", "gp11", "gp12", "gp13"}, {"gp20", "gp21", "gp22", "gp23"}};
+    static const char* const kNameTa[3] = {"T_a0", "T_a1", "T_a2"};
+    static const char* const kNameTq[3] = {"T_q0", "T_q1", "T_q2"};
+    for (int p = 0; p < 3; ++p) b.a[p] = bp.take<float>(n * kAG, kNameA[p]);
+    for (int p = 0; p < 2; ++p) b.q[p] = bp.take<float>(n * C, kNameQ[p]);
+    b.x = bp.take<float>(n * ldx, "x");
+    b.hA = bp.take<float>(n * 512, "hA");
+    b.hB = bp.take<float>(n * 512, "hB");
+    for (int p = 0; p < 2; ++p) b.y[p] = bp.take<float>(n * 288, kNameY[p]);
+    b.aim = bp.take<float>(n * 256, "aim");
     for (int p = 0; p < 3; ++p)
         for (int l = 0; l < 4; ++l)
-            b.gp[p][l] = (l < (int)e->mlp[p].size()) ? bp.take<float>(n * e->mlp[p][l].out_pad) : nullptr;
-    b.h1 = bp.take<float>(n * 128);
-    b.h2 = bp.take<float>(n * 128);
-    b.gp_h1 = bp.take<float>(n * 128);
-    b.gp_h2 = bp.take<float>(n * 128);
+            b.gp[p][l] = (l < (int)e->mlp[p].size()) ? bp.take<float>(n * e->mlp[p][l].out_pad, kNameGp[p][l]) : nullptr;
+    b.h1 = bp.take<float>(n * 128, "h1");
+    b.h2 = bp.take<float>(n * 128, "h2");
+    b.gp_h1 = bp.take<float>(n * 128, "gp_h1");
+    b.gp_h2 = bp.take<float>(n * 128, "gp_h2");
     for (int p = 0; p < 3; ++p) {
-        b.T_a[p] = bp.take<float>(n * kTA);
-        b.T_q[p] = bp.take<float>(n * C * kH * 3);
+        b.T_a[p] = bp.take<float>(n * kTA, kNameTa[p]);
+        b.T_q[p] = bp.take<float>(n * C * kH * 3, kNameTq[p]);
     }
     for (int p = 0; p < 2; ++p) {
-        b.sumq[p] = bp.take<float>((size_t)B * C);
-        b.sumf[p] = bp.take<float>((size_t)B * C);
+        b.sumq[p] = bp.take<float>((size_t)B * C, p ? "sumq1" : "sumq0");
+        b.sumf[p] = bp.take<float>((size_t)B * C, p ? "sumf1" : "sumf0");
     }
-    b.s1 = bp.take<float>((size_t)B * C);
-    b.e_nn = bp.take<double>(n);
-    b.e_sr = bp.take<double>(n);
-    b.e_lr = bp.take<double>(n);
-    b.e_d3 = bp.take<double>(n);
-    b.gq = bp.take<float>(n);
-    b.cn = bp.take<float>(n);
-    b.dEdCN = bp.take<float>(n);
-    b.d3w = bp.take<float>(n * 16);
-    b.dzA = bp.take<float>(n * 512);
-    b.dzB = bp.take<float>(n * 512);
-    b.dx = bp.take<float>(n * ldx);
-    b.dS_a = bp.take<float>(n * kAG * 4);
-    b.dS_q = bp.take<float>(n * C * kG * 4);
-    b.grad_a = bp.take<float>(n * kAG);
-    b.grad_q = bp.take<float>(n * C);
-    b.da_tot = bp.take<float>(n * kAG);
-    b.dq = bp.take<float>(n * C);
-    b.dq_base = bp.take<float>(n * C);
-    b.virial_atom = bp.take<double>(n * 9);
-    b.forces_tmp = bp.take<float>(n * 3);
-    b.x16 = SplitMat{bp.take<__half>(n * ldx), bp.take<__half>(n * ldx), bp.take<float>(n * (ldx / 32)), ldx, ldx / 32};
-    b.h16[0] = alias_split(b.hA, n, 512, bp.take<float>(n * 16));
-    b.h16[1] = alias_split(b.hB, n, 512, bp.take<float>(n * 16));
-    b.aim16 = alias_split(b.aim, n, 256, bp.take<float>(n * 8));
-    b.h1_16 = alias_split(b.h1, n, 128, bp.take<float>(n * 4));
-    b.d16[0] = alias_split(b.dzA, n, 512, bp.take<float>(n * 16));
-    b.d16[1] = alias_split(b.dzB, n, 512, bp.take<float>(n * 16));
-    b.dz32 = bp.take<float>(n * 288);
-    b.coord_ref = bp.take<float>(n * 3);
-    b.wrap_off = bp.take<float>(n * 3);
-    b.skin_flag = bp.take<int32_t>(4);
-    b.mol_ref = bp.take<int32_t>(n);
+    b.s1 = bp.take<float>((size_t)B * C, "s1");
+    b.e_nn = bp.take<double>(n, "e_nn");
+    b.e_sr = bp.take<double>(n, "e_sr");
+    b.e_lr = bp.take<double>(n, "e_lr");
+    b.e_d3 = bp.take<double>(n, "e_d3");
+    b.gq = bp.take<float>(n, "gq");
+    b.cn = bp.take<float>(n, "cn");
+    b.dEdCN = bp.take<float>(n, "dEdCN");
+    b.d3w = bp.take<float>(n * 16, "d3w");
+    b.dzA = bp.take<float>(n * 512, "dzA");
+    b.dzB = bp.take<float>(n * 512, "dzB");
+    b.dx = bp.take<float>(n * ldx, "dx");
+    b.dS_a = bp.take<float>(n * kAG * 4, "dS_a");
+    b.dS_q = bp.take<float>(n * C * kG * 4, "dS_q");
+    b.grad_a = bp.take<float>(n * kAG, "grad_a");
+    b.grad_q = bp.take<float>(n * C, "grad_q");
+    b.da_tot = bp.take<float>(n * kAG, "da_tot");
+    b.dq = bp.take<float>(n * C, "dq");
+    b.dq_base = bp.take<float>(n * C, "dq_base");
+    b.virial_atom = bp.take<double>(n * 9, "virial_atom");
+    b.forces_tmp = bp.take<float>(n * 3, "forces_tmp");
+    b.x16 = SplitMat{bp.take<__half>(n * ldx, "x16_hi"), bp.take<__half>(n * ldx, "x16_lo"), bp.take<float>(n * (ldx / 32), "x16_inv"), ldx, ldx / 32};
+    b.h16[0] = alias_split(b.hA, n, 512, bp.take<float>(n * 16, "hA_inv"));
+    b.h16[1] = alias_split(b.hB, n, 512, bp.take<float>(n * 16, "hB_inv"));
+    b.aim16 = alias_split(b.aim, n, 256, bp.take<float>(n * 8, "aim_inv"));
+    b.h1_16 = alias_split(b.h1, n, 128, bp.take<float>(n * 4, "h1_inv"));
+    b.d16[0] = alias_split(b.dzA, n, 512, bp.take<float>(n * 16, "dzA_inv"));
+    b.d16[1] = alias_split(b.dzB, n, 512, bp.take<float>(n * 16, "dzB_inv"));
+    b.dz32 = bp.take<float>(n * 288, "dz32");
+    b.coord_ref = bp.take<float>(n * 3, "coord_ref");
+    b.wrap_off = bp.take<float>(n * 3, "wrap_off");
+    b.skin_flag = bp.take<int32_t>(4, "skin_flag");
+    b.mol_ref = bp.take<int32_t>(n, "mol_ref");
 }
 
 static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
@@ -437,6 +452,8 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             e->ws_bytes = want;
         }
         Bump bp{e->ws};
+        e->layout.clear();
+        bp.map = &e->layout;
         carve(e, bp, b, N, B, e->sr_cap, e->lr_cap, pbc, need_lr_list, ldx);
         if (N == 0) break;
         if (e->poison >= 0) {
@@ -501,7 +518,11 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         }
     }
     if (e->timing) cudaEventRecord(e->ev[1], st);
-    const float* coord = pbc ? b.coord_w : sys->coord;
+    // The engine's own lists refer to the wrapped copy.  A caller-supplied nbmat / shifts pair refers to the caller's
+    // positions as given (the reference wraps only inside make_nbmat, which is skipped when 'nbmat' is in the data:
+    // calculator.py:1071, 1521-1529), so the short-range kernels then read sys->coord.
+    const float* coord_lr = pbc ? b.coord_w : sys->coord;
+    const float* coord = (pbc && own_sr) ? b.coord_w : sys->coord;
     AIM_TRY(launch_mol_ptr(sys->mol_idx, N, B, b.mol_ptr, st));
 
     NbView sr;
@@ -590,7 +611,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     bool have_lr = false, have_d3 = false;
     if (o.coulomb_method == AIMNET_COULOMB_SIMPLE) {
         CoulombParams cp{0.f, 0.f, 0.f, 0.f, 0.f, k};
-        AIM_TRY(launch_coulomb(PAIR_SIMPLE, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        AIM_TRY(launch_coulomb(PAIR_SIMPLE, N, lrs, coord_lr, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
         have_lr = true;
     } else if (o.coulomb_method == AIMNET_COULOMB_DSF) {
         double a = o.dsf_alpha, R = o.dsf_rc;
@@ -602,19 +623,19 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         cp.shift_slope = (float)(erfc_rc / (R * R) + 2.0 * a / std::sqrt(M_PI) * std::exp(-a * a * R * R) / R);
         cp.self_coeff = (float)(-(erfc_rc / R / 2.0 + a / std::sqrt(M_PI)));
         cp.factor = k;
-        AIM_TRY(launch_coulomb(PAIR_DSF, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        AIM_TRY(launch_coulomb(PAIR_DSF, N, lrs, coord_lr, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
         have_lr = true;
     }
     else if (ewald) {
         CoulombParams cp{(float)e->ewald.rc, (float)e->ewald.alpha, 0.f, 0.f, 0.f, k};
-        AIM_TRY(launch_coulomb(PAIR_EWALD, N, lrs, coord, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
-        AIM_TRY(launch_ewald_recip(e->ewald, N, coord, qfin, b.e_lr, b.gq, backward ? F : nullptr, vir, st));
+        AIM_TRY(launch_coulomb(PAIR_EWALD, N, lrs, coord_lr, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
+        AIM_TRY(launch_ewald_recip(e->ewald, N, coord_lr, qfin, b.e_lr, b.gq, backward ? F : nullptr, vir, st));
         have_lr = true;
     }
     if (o.dispersion) {
         D3Params dp{e->d3_c6ref, e->d3_cnref, e->d3_rcov, e->d3_r4r2, o.d3_s6, o.d3_s8, o.d3_a1, o.d3_a2,
                     (float)(o.d3_cutoff * (1.0 - o.d3_smoothing) / kBohr), (float)(o.d3_cutoff / kBohr)};
-        AIM_TRY(launch_d3(N, lrs, coord, cv, sys->numbers, dp, b.cn, b.d3w, b.dEdCN, b.e_d3, backward ? F : nullptr, vir, st));
+        AIM_TRY(launch_d3(N, lrs, coord_lr, cv, sys->numbers, dp, b.cn, b.d3w, b.dEdCN, b.e_d3, backward ? F : nullptr, vir, st));
         have_d3 = true;
     }
     AIM_TRY(launch_energy_reduce(B, b.mol_ptr, b.e_nn, b.e_sr, have_lr ? b.e_lr : nullptr, have_d3 ? b.e_d3 : nullptr,
@@ -773,6 +794,9 @@ extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weigh
     AIM_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     AIM_CUDA_CHECK(cudaMallocHost((void**)&e->pinned_int, 64));
     for (int k = 0; k < 6; ++k) AIM_CUDA_CHECK(cudaEventCreate(&e->ev[k]));
+    // the uploads above are cudaMemcpy calls from pageable memory: they return once the data is staged, the DMA may
+    // still be in flight, and own_stream / a caller's non-blocking stream is not ordered after the legacy stream
+    AIM_CUDA_CHECK(cudaDeviceSynchronize());
     *out = e;
     return AIMNET_OK;
 }
@@ -825,9 +849,27 @@ extern "C" int aimnet2_engine_debug_poison(aimnet2_engine_t* e, int byte) {
     return AIMNET_OK;
 }
 
+extern "C" int aimnet2_engine_debug_layout(const aimnet2_engine_t* e, char* buf, int buf_bytes) {
+    AIM_REQUIRE(e && buf && buf_bytes > 0, "debug_layout: null argument");
+    std::string s;
+    for (const Region& r : e->layout) s += std::string(r.name) + " " + std::to_string(r.off) + " " + std::to_string(r.bytes) + "\n";
+    AIM_REQUIRE((int)s.size() < buf_bytes, "debug_layout: buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_debug_read_workspace(aimnet2_engine_t* e, void* host_dst, int64_t offset, int64_t bytes) {
+    AIM_REQUIRE(e && host_dst && offset >= 0 && bytes >= 0, "debug_read_workspace: bad argument");
+    AIM_REQUIRE((size_t)(offset + bytes) <= e->ws_bytes, "debug_read_workspace: range outside the workspace");
+    AIM_CUDA_CHECK(cudaSetDevice(e->device));
+    AIM_CUDA_CHECK(cudaDeviceSynchronize());
+    AIM_CUDA_CHECK(cudaMemcpy(host_dst, e->ws + offset, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return AIMNET_OK;
+}
+
 extern "C" int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on) {
     AIM_REQUIRE(e, "set_deterministic: null engine");
-    gemm_tc_set_deterministic(on != 0);   // process-wide switch of the GEMM chunking policy
+    e->deterministic = on != 0;   // per engine; every kernel uses fixed chunking and no atomics, so both settings agree
     return AIMNET_OK;
 }
 

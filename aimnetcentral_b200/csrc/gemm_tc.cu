@@ -504,9 +504,6 @@ static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld
 
 bool gemm_tc_available() { return tc::get_encode() != nullptr; }
 
-static bool g_tc_deterministic = false;
-void gemm_tc_set_deterministic(bool on) { g_tc_deterministic = on; }
-
 int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st) {
     if (n == 0) return AIMNET_OK;
     tc::split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, hi, lo, n);
@@ -523,9 +520,11 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
                 "gemm_tc: outputs must be 16-byte aligned");
     AIM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Whi & 15) == 0 && ((uintptr_t)Wlo & 15) == 0 && lda % 4 == 0 && ldw % 4 == 0,
                 "gemm_tc: operands must be 16-byte aligned");
-    static bool configured = false;
-    static int num_sms = 148;
-    if (!configured) {
+    static bool configured_dev[kMaxDevices] = {};
+    static int num_sms_dev[kMaxDevices] = {};
+    const int dslot = current_device_slot();
+    int& num_sms = num_sms_dev[dslot];
+    if (!configured_dev[dslot]) {
         AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -533,7 +532,7 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
         int dev = 0;
         AIM_CUDA_CHECK(cudaGetDevice(&dev));
         AIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
+        configured_dev[dslot] = true;
     }
     CUtensorMap tmA, tmBh, tmBl;
     int rc;
@@ -548,7 +547,7 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
     // fixed K-chunking: TMEM accumulates CHUNK stages before the fp32 register add (the elastic variant stayed an
     // experiment: results must be run-to-run reproducible)
     const int chunk = CHUNK, chunk_max = CHUNK;
-    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, g_tc_deterministic ? chunk : chunk_max, bn};
+    Params p{bias, Y, aux, ldy, ldaux, M, N, K, mode, chunk, chunk_max, bn};
     int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int grid = tiles < num_sms ? tiles : num_sms;
     switch (mode) {

@@ -667,9 +667,11 @@ int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const floa
     }
     AIM_REQUIRE(aux == nullptr || (((uintptr_t)aux & 15) == 0 && ldaux % 4 == 0), "gemm_tc16: aux must be 16-byte aligned");
     AIM_REQUIRE(w_inv_scale != nullptr, "gemm_tc16: weight scale missing");
-    static bool configured = false;
-    static int num_sms = 148;
-    if (!configured) {
+    static bool configured_dev[kMaxDevices] = {};
+    static int num_sms_dev[kMaxDevices] = {};
+    const int dslot = current_device_slot();
+    int& num_sms = num_sms_dev[dslot];
+    if (!configured_dev[dslot]) {
 #define AIM_TC16_ATTR(MODE)                                                                                                     \
     AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc16_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
     AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc16_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -681,7 +683,7 @@ int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const floa
         int dev = 0;
         AIM_CUDA_CHECK(cudaGetDevice(&dev));
         AIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
+        configured_dev[dslot] = true;
     }
     CUtensorMap tmAh, tmAl, tmBh, tmBl, tmY, tmY2, tmAux;
     const CUtensorMapDataType F16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;

@@ -613,9 +613,11 @@ int gemm_nt_tc16p(const SplitMat& A, const void* Whi, const void* Wlo, const flo
     AIM_REQUIRE(bias == nullptr || ((uintptr_t)bias & 15) == 0, "gemm_tc16p: bias must be 16-byte aligned");
     AIM_REQUIRE(w_inv_scale != nullptr, "gemm_tc16p: weight scale missing");
     if (M == 0) return AIMNET_OK;
-    static bool configured = false;
-    static int num_sms = 148;
-    if (!configured) {
+    static bool configured_dev[kMaxDevices] = {};
+    static int num_sms_dev[kMaxDevices] = {};
+    const int dslot = current_device_slot();
+    int& num_sms = num_sms_dev[dslot];
+    if (!configured_dev[dslot]) {
 #define AIM_TC16P_ATTR(MODE)                                                                                                      \
     AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc16p_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
     AIM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc16p_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -627,7 +629,7 @@ int gemm_nt_tc16p(const SplitMat& A, const void* Whi, const void* Wlo, const flo
         int dev = 0;
         AIM_CUDA_CHECK(cudaGetDevice(&dev));
         AIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
+        configured_dev[dslot] = true;
     }
     CUtensorMap tmAh, tmAl, tmBh, tmBl, tmY, tmY2, tmAux;
     const CUtensorMapDataType F16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;

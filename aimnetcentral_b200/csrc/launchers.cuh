@@ -33,7 +33,6 @@ int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, flo
 
 // ---- gemm_tc.cu: tcgen05 3xTF32 backend
 bool gemm_tc_available();
-void gemm_tc_set_deterministic(bool on);
 int split_tf32(const float* w, float* hi, float* lo, size_t n, cudaStream_t st);
 int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int ldw, const float* bias, float* Y,
                int ldy, float* aux, int ldaux, int M, int N, int K, int mode, cudaStream_t st);

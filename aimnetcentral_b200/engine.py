@@ -130,6 +130,27 @@ class Engine:
         """Test seam: fill the device workspace with `byte` before every evaluation (-1 = off)."""
         _capi.check(self._lib.aimnet2_engine_debug_poison(self._h, int(byte)), "debug_poison")
 
+    def debug_layout(self) -> dict:
+        """Test seam: {buffer name: (byte offset, bytes)} of the workspace as carved for the last evaluation."""
+        buf = C.create_string_buffer(1 << 16)
+        _capi.check(self._lib.aimnet2_engine_debug_layout(self._h, buf, len(buf)), "debug_layout")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, off, nbytes = line.split()
+            out[name] = (int(off), int(nbytes))
+        return out
+
+    def debug_snapshot(self, names=None) -> dict:
+        """Test seam: host copies (uint8 arrays) of the named workspace buffers (all when None) after a device sync."""
+        snap = {}
+        for name, (off, nbytes) in self.debug_layout().items():
+            if names is not None and name not in names:
+                continue
+            arr = np.empty(nbytes, np.uint8)
+            _capi.check(self._lib.aimnet2_engine_debug_read_workspace(self._h, arr.ctypes.data, off, nbytes), "debug_read_workspace")
+            snap[name] = arr
+        return snap
+
     def set_gemm_backend(self, backend: int):
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
         self.gemm_backend = int(backend)

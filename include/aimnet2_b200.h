@@ -174,8 +174,13 @@ int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows);
 /* Test seam: fill the engine's device workspace with `byte` (0..255) before every evaluation, so that a kernel reading
  * scratch memory it has not written shows up in the results (0xFF = NaN patterns); -1 switches it off (default). */
 int aimnet2_engine_debug_poison(aimnet2_engine_t* e, int byte);
-/* 1 = bitwise run-to-run reproducible results (fixed K-chunking in the tcgen05 GEMM; every other kernel is atomics-free
- * already) — the counterpart of AIMNet2Calculator(deterministic=True), aimnet/calculators/calculator.py:76-84 */
+/* Debug seams for fault isolation (tools/first_touch.py): the names, byte offsets and sizes of the workspace buffers of the
+ * last evaluation as text lines "name offset bytes\n" (buf_bytes must hold them all), and a synchronous copy of a
+ * workspace range to host memory.  The layout is only meaningful until the next evaluation. */
+int aimnet2_engine_debug_layout(const aimnet2_engine_t* e, char* buf, int buf_bytes);
+int aimnet2_engine_debug_read_workspace(aimnet2_engine_t* e, void* host_dst, int64_t offset, int64_t bytes);
+/* 1 = bitwise run-to-run reproducible results (every kernel of the engine already uses fixed chunking and no atomics, so this
+ * only records the request; the flag is per engine) — the counterpart of AIMNet2Calculator(deterministic=True), aimnet/calculators/calculator.py:76-84 */
 int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on);
 
 /* device-resident inputs/outputs; flags = AIMNET_WANT_* */

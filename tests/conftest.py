@@ -19,9 +19,6 @@ CHARGE_ATOL = 1e-4
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_unverified: GPU tests written when no GPU time was left (end of round 1); they "
-                            "have never run and are therefore NOT part of `-m gpu` - run them with `-m gpu_unverified` and "
-                            "promote them to `gpu` once they pass on a B200")
 
 
 def load_golden(name):

@@ -486,6 +486,36 @@ def test_user_supplied_neighbor_matrix():
     assert abs(out["energy"][0] - ref["energy"][0]) < ENERGY_ATOL
 
 
+def test_user_supplied_periodic_neighbor_matrix_with_atoms_outside_the_cell():
+    """Caller-provided nbmat + shifts with a cell refer to the caller's positions AS GIVEN (the reference wraps only
+    inside make_nbmat, skipped when 'nbmat' is in the data: calculator.py:1071, 1521-1529).  Half of the atoms are moved
+    out of the cell by lattice vectors n_i and the shifts corrected to s' = s + n_i - n_j; results must not change."""
+    from aimnetcentral_b200 import ops
+
+    inputs, ref, meta = load_golden("pbc_box60_dsf")
+    calc = get_calc(meta)
+    N = len(inputs["numbers"])
+    cell = torch.as_tensor(inputs["cell"], dtype=torch.float32, device="cuda").reshape(3, 3)
+    xw = ops.wrap_positions(torch.as_tensor(inputs["coord"], dtype=torch.float32, device="cuda"), cell)
+    nb, cnt, sh = ops.neighbor_list(xw, 5.0, cell=cell.reshape(1, 3, 3), pbc=torch.ones(1, 3, dtype=torch.bool, device="cuda"),
+                                    max_neighbors=160)
+    w = int(cnt.max().item())
+    nb, sh = nb[:, :w].contiguous(), sh[:, :w].contiguous()
+    n_i = torch.as_tensor(np.random.default_rng(8).integers(-2, 3, (N, 3)), dtype=torch.int32, device="cuda")
+    n_i[::2] = 0
+    x_out = xw + n_i.to(torch.float32) @ cell
+    j = nb.clamp(max=N - 1).long()
+    sh_out = torch.where((nb < N).unsqueeze(-1), sh + n_i.unsqueeze(1) - n_i[j], torch.zeros_like(sh))
+    pad = lambda t, v: torch.cat([t, torch.full((1, *t.shape[1:]), v, dtype=t.dtype, device=t.device)])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = calc(dict(inputs, coord=x_out, nbmat=pad(nb, N), shifts=pad(sh_out, 0)), forces=True, stress=True)
+    out = {k: v.cpu().numpy() for k, v in res.items()}
+    de, df, dq = _report("pbc_box60 caller nbmat, atoms outside the cell", out, ref, N)
+    assert de < ENERGY_ATOL and df < FORCE_ATOL and dq < CHARGE_ATOL
+    assert np.abs(out["stress"] - ref["stress"]).max() < 1e-5
+
+
 @pytest.mark.gpu
 def test_repeated_evaluations_are_bitwise_identical():
     """Every kernel is atomics-free with fixed reduction orders, so repeating an evaluation must reproduce it bit for

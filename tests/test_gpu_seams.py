@@ -1,12 +1,11 @@
-"""GPU tests that have NOT RUN YET: written after the GPU budget of round 1 was spent.  They carry the `gpu_unverified`
-marker instead of `gpu`, so that the `-m gpu` suite stays exactly what has passed on a B200; without CUDA they skip.
-Run them with `pytest -m gpu_unverified`, fix what they find, then move them to the `gpu` files.
+"""GPU tests of the pair-term operator seams, the multi-tile GEMM path and backend 3 (first run on a B200 in round 2,
+all green: profiles/r2a_gpu_verify.txt).
 
 * Pair-term operator seams (SURVEY.md section 8b, B3 iii): `ops.dsf_coulomb` and `ops.dftd3` against independent float64
   torch restatements of the reference's closed forms (aimnet/modules/lr.py:559-615 and :1580-1657) on the very neighbor
   matrices the seam receives.
-* The MLP GEMM with more output tiles than SMs: every accuracy test of the `gpu` suite fits one wave of CTAs (<= 75 tiles),
-  the multi-tile-per-CTA path of the persistent kernel is only covered by invariance / repeatability tests there."""
+* The MLP GEMM with more output tiles than SMs (the persistent CTA runs several tiles back to back: all of cfg-2).
+* Backend 3 (pipelined tile epilogue) bitwise against backend 2."""
 import ctypes as C
 
 import numpy as np
@@ -15,7 +14,7 @@ import torch
 
 from conftest import load_golden
 
-pytestmark = [pytest.mark.gpu_unverified, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+pytestmark = pytest.mark.gpu
 
 HARTREE, BOHR = 27.211386024367243, 0.5291772105638411
 
