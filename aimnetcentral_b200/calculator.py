@@ -12,6 +12,7 @@ from __future__ import annotations
 import math
 import os
 import warnings
+import weakref
 from types import MappingProxyType, SimpleNamespace
 from typing import Any, ClassVar, Mapping
 
@@ -127,6 +128,9 @@ class AIMNet2Calculator:
         self._dftd3_smoothing = self._default_dftd3_smoothing
         self.cutoff_lr = float("inf") if self._has_coulomb else (self._dftd3_cutoff if self._has_dftd3 else None)
         self._mult_ignored_checked = False
+        self._species_validation_cache = None   # (key, weakref(numbers tensor), impl) — calculator.py:808-826
+        self._impl_lut = None
+        self._host_cell_cache = None            # (key, weakref(cell tensor), host copy)
         self._batch: int | None = None
         # extension over the reference API: Verlet skin (A) for neighbor-list reuse across MD steps; 0 = rebuild every call
         self._neighbor_skin = float(neighbor_skin)
@@ -218,19 +222,69 @@ class AIMNet2Calculator:
 
     # ---- validation (calculator.py:785-851) ------------------------------------------------------------------
     def _validate_species_and_charge(self, data: dict) -> None:
+        """calculator.py:785-851.  The species part is skipped when the same `numbers` tensor was validated before
+        (identity + `_version` cache, calculator.py:808-826); other inputs (numpy arrays, lists) are checked with one
+        vectorised table lookup instead of a Python set over every atom."""
         if "numbers" not in data:
             return
         impl = (self._metadata or {}).get("implemented_species") or []
         if impl:
-            seen = {int(z) for z in torch.as_tensor(data["numbers"]).flatten().tolist() if int(z) > 0}
-            unsupported = sorted(seen - set(int(z) for z in impl))
-            if unsupported:
-                raise ValueError(f"Atomic numbers {unsupported} are not in this model's implemented_species "
-                                 f"{sorted(impl)}. Pass validate_species=False to bypass.")
+            numbers = data["numbers"]
+            key = self._numbers_validation_key(numbers)
+            cached = self._species_validation_cache
+            hit = (key is not None and cached is not None and cached[0] == key and cached[1]() is numbers
+                   and cached[2] is impl)
+            if not hit:
+                self._validate_numbers(numbers, impl)
+                if key is not None:
+                    self._species_validation_cache = (key, weakref.ref(numbers), impl)
         if (self._metadata or {}).get("supports_charged_systems") is False:
             charge_t = torch.as_tensor(data.get("charge", 0.0))
             if charge_t.numel() > 0 and float(charge_t.abs().max().item()) > 1e-6:
                 raise ValueError("This model does not support net-charged systems. Pass validate_species=False to bypass.")
+
+    @staticmethod
+    def _numbers_validation_key(value):
+        """calculator.py:853-870: identity key of a tensor (`_version` guards in-place mutation); None for inputs whose
+        mutation cannot be detected (numpy arrays, lists) — those are re-validated every call."""
+        if isinstance(value, Tensor) and value.layout == torch.strided:
+            return (id(value), value.data_ptr(), value._version, tuple(value.shape), value.dtype, value.device)
+        return None
+
+    def _validate_numbers(self, numbers, impl) -> None:
+        lut = self._impl_lut
+        if lut is None or lut[0] is not impl:
+            ok = np.zeros(256, bool)
+            ok[[int(z) for z in impl if 0 <= int(z) < 256]] = True
+            lut = self._impl_lut = (impl, ok)
+        if isinstance(numbers, Tensor):
+            z = numbers.detach().flatten()
+            if z.is_cuda:
+                # one small D2H (the histogram) instead of every atom
+                z = torch.bincount(z.clamp(0, 255).to(torch.int64), minlength=256).cpu().numpy()
+                present = np.nonzero(z)[0]
+            else:
+                present = np.unique(z.numpy())
+        else:
+            present = np.unique(np.asarray(numbers))
+        present = present[present > 0]
+        bad = [int(v) for v in present if v > 255 or not lut[1][int(v)]]
+        if bad:
+            raise ValueError(f"Atomic numbers {sorted(bad)} are not in this model's implemented_species "
+                             f"{sorted(impl)}. Pass validate_species=False to bypass.")
+
+    def _host_cell(self, raw, cell_dev: Tensor) -> np.ndarray:
+        """Host copy of the cell for the engine's grid sizing without a per-call device sync: taken from the caller's
+        host data when there is one, else cached per CUDA tensor (identity + `_version`)."""
+        if not (isinstance(raw, Tensor) and raw.is_cuda):
+            return np.ascontiguousarray(np.asarray(raw.detach().numpy() if isinstance(raw, Tensor) else raw, dtype=np.float32))
+        key = (id(raw), raw.data_ptr(), raw._version, tuple(raw.shape))
+        c = self._host_cell_cache
+        if c is not None and c[0] == key and c[1]() is raw:
+            return c[2]
+        host = np.ascontiguousarray(cell_dev.detach().cpu().numpy().astype(np.float32))
+        self._host_cell_cache = (key, weakref.ref(raw), host)
+        return host
 
     def _maybe_warn_mult_ignored(self, data: dict) -> None:
         if self._mult_ignored_checked or self.is_nse or data.get("mult") is None:
@@ -319,8 +373,10 @@ class AIMNet2Calculator:
             mult = mult.to(torch.float32).expand(charge.shape[0]).contiguous()
         else:
             mult = None
+        host_cell = None
         if cell is not None:
             cell = cell.to(torch.float32).contiguous()
+            host_cell = self._host_cell(data["cell"], cell)
         nbmat, shifts = d.get("nbmat"), d.get("shifts")
         if nbmat is not None:
             nbmat = nbmat.to(torch.int32).contiguous()
@@ -329,7 +385,7 @@ class AIMNet2Calculator:
             self._push_options(coulomb_override=method)
         try:
             out = self.engine.eval(coord_f, numbers_f, charge, mol_idx=mol_f, mult=mult, cell=cell, pbc=d.get("pbc"),
-                                   nbmat=nbmat, shifts=shifts, forces=bool(forces), stress=bool(stress))
+                                   host_cell=host_cell, nbmat=nbmat, shifts=shifts, forces=bool(forces), stress=bool(stress))
         finally:
             if method != self._coulomb_method:
                 self._push_options()

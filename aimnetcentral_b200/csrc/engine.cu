@@ -77,11 +77,13 @@ struct aimnet2_engine {
     int timing = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
-    // per-GEMM events (timing level 2): pairs (begin, end) in launch order
+    // per-launch events of the two dominant kernel classes (timing level 2): pairs (begin, end) in launch order;
+    // class 0 = per-atom MLP GEMMs (+ presplit), class 1 = AEV / conv_sv forward and backward
     std::vector<cudaEvent_t> gemm_ev;
+    std::vector<int> gemm_ev_class;
     int gemm_ev_used = 0;
-    float last_gemm_ms = 0.f;
-    int last_gemm_launches = 0;
+    float last_gemm_ms = 0.f, last_conv_ms = 0.f;
+    int last_gemm_launches = 0, last_conv_launches = 0;
     EwaldPlan ewald;
     // Verlet-skin reuse of the neighbor lists (options.neighbor_skin > 0): what the lists in the workspace were built for
     struct {
@@ -307,15 +309,18 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.mol_ref = bp.take<int32_t>(n, "mol_ref");
 }
 
-static void gemm_mark(aimnet2_engine* e, cudaStream_t st) {
+static void class_mark(aimnet2_engine* e, int cls, cudaStream_t st) {
     if (e->timing < 2) return;
     if (e->gemm_ev_used == (int)e->gemm_ev.size()) {
         cudaEvent_t ev;
         cudaEventCreate(&ev);
         e->gemm_ev.push_back(ev);
+        e->gemm_ev_class.push_back(0);
     }
+    e->gemm_ev_class[e->gemm_ev_used] = cls;
     cudaEventRecord(e->gemm_ev[e->gemm_ev_used++], st);
 }
+static void gemm_mark(aimnet2_engine* e, cudaStream_t st) { class_mark(e, 0, st); }
 
 static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ldx, int K, float* Y, float* gp, bool act,
                       int M, cudaStream_t st) {
@@ -362,12 +367,18 @@ static int presplit(aimnet2_engine* e, const float* X, int ldx, int M, int K, co
 static void collect_timing(aimnet2_engine* e) {
     for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev[k], e->ev[k + 1]);
     cudaEventElapsedTime(&e->last_ms[4], e->ev[0], e->ev[4]);
-    e->last_gemm_ms = 0.f;
-    e->last_gemm_launches = e->gemm_ev_used / 2;
+    e->last_gemm_ms = e->last_conv_ms = 0.f;
+    e->last_gemm_launches = e->last_conv_launches = 0;
     for (int k = 0; k + 1 < e->gemm_ev_used; k += 2) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e->gemm_ev[k], e->gemm_ev[k + 1]);
-        e->last_gemm_ms += ms;
+        if (e->gemm_ev_class[k] == 0) {
+            e->last_gemm_ms += ms;
+            e->last_gemm_launches++;
+        } else {
+            e->last_conv_ms += ms;
+            e->last_conv_launches++;
+        }
     }
 }
 
@@ -542,8 +553,10 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         const std::vector<Linear>& L = e->mlp[p];
         const int nl = (int)L.size();
         const float* qin = (p == 0) ? nullptr : b.q[p - 1];
+        class_mark(e, 1, st);
         AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
                                 b.T_a[p], b.T_q[p], p > 0, st));
+        class_mark(e, 1, st);
         if (tc16) {
             AIM_TRY(presplit(e, b.x, ldx, N, L[0].in_pad, b.x16, st));
             SplitMat in = with_ld(b.x16, ldx);
@@ -678,8 +691,10 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 }
             }
             const float* qin = (p == 0) ? nullptr : b.q[p - 1];
+            class_mark(e, 1, st);
             AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
                                     e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
+            class_mark(e, 1, st);
             if (p == 0) break;
             // dE/da_p and dE/dq_{p-1}
             if (p == 2)
@@ -980,5 +995,7 @@ extern "C" int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, 
     for (; k < n && k < 5; ++k) ms[k] = e->last_ms[k];
     if (k < n) ms[k++] = e->last_gemm_ms;                    // summed GEMM device time (timing level 2)
     if (k < n) ms[k++] = (float)e->last_gemm_launches;
+    if (k < n) ms[k++] = e->last_conv_ms;                    // summed AEV / conv_sv device time (timing level 2)
+    if (k < n) ms[k++] = (float)e->last_conv_launches;       // event pairs (one per conv_fwd / conv_bwd call)
     return k;
 }

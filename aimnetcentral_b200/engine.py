@@ -163,10 +163,10 @@ class Engine:
         _capi.check(self._lib.aimnet2_engine_enable_timing(self._h, int(level)))
 
     def last_timing(self) -> dict:
-        buf = (C.c_float * 7)()
-        self._lib.aimnet2_engine_last_timing(self._h, buf, 7)
+        buf = (C.c_float * 9)()
+        self._lib.aimnet2_engine_last_timing(self._h, buf, 9)
         return dict(zip(("neighbors_ms", "forward_ms", "pair_terms_ms", "backward_ms", "total_ms", "gemm_ms",
-                         "gemm_launches"), list(buf)))
+                         "gemm_launches", "conv_ms", "conv_calls"), list(buf)))
 
     def last_launches(self) -> int:
         return int(self._lib.aimnet2_engine_last_launches(self._h))
@@ -186,7 +186,7 @@ class Engine:
     def eval(self, coord: torch.Tensor, numbers: torch.Tensor, charge: torch.Tensor, mol_idx: torch.Tensor | None = None,
              mult: torch.Tensor | None = None, cell: torch.Tensor | None = None, pbc=None,
              nbmat: torch.Tensor | None = None, shifts: torch.Tensor | None = None, forces: bool = True,
-             stress: bool = False, return_nbmat: bool = False) -> dict:
+             stress: bool = False, return_nbmat: bool = False, host_cell: np.ndarray | None = None) -> dict:
         """Device-resident evaluation. coord (N,3) f32, numbers (N) i32, charge (B) f32, mol_idx (N) i32 sorted,
         cell (3,3)|(B,3,3) f32 — all on self.device, contiguous."""
         dev = self.device
@@ -212,11 +212,13 @@ class Engine:
         sys_.coord, sys_.numbers, sys_.charge = coord.data_ptr(), numbers.data_ptr(), charge.data_ptr()
         sys_.mol_idx = _ptr(mol_idx)
         sys_.mult = _ptr(mult)
-        host_cell = pbc_arr = None
+        pbc_arr = None
         n_cells = 0
         if cell is not None:
             n_cells = 1 if cell.ndim == 2 else int(cell.shape[0])
-            host_cell = np.ascontiguousarray(cell.detach().cpu().numpy().reshape(n_cells, 3, 3).astype(np.float32))
+            if host_cell is None:   # device sync; callers that know the cell on the host pass it (calculator.py does)
+                host_cell = cell.detach().cpu().numpy()
+            host_cell = np.ascontiguousarray(np.asarray(host_cell, dtype=np.float32).reshape(n_cells, 3, 3))
             sys_.cell, sys_.host_cell = cell.data_ptr(), host_cell.ctypes.data
             if pbc is not None:
                 pbc_arr = _pbc_bytes(pbc, n_cells)

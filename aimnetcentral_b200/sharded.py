@@ -1,12 +1,19 @@
 """Multi-GPU batch split: independent molecules / periodic replicas are sharded across ranks with no
-data-path collective; the only communication is the rank-ordered result gather (NCCL over NVLink on GPUs, gloo in
-the CPU tests).  One process per GPU, launched with torchrun.
+data-path collective; the only communication is ONE rank-ordered result gather per evaluation (NCCL over NVLink on
+GPUs, gloo in the CPU tests).  One process per GPU, launched with torchrun.
 
 The reference has no multi-GPU inference path ("run independent processes per GPU", docs/tutorials/performance.md:
-275-288); this module is that advice with the bookkeeping done for the caller.
+275-288); this module is that advice with the bookkeeping done for the caller:
+
+* contiguous molecule ranges balanced by ATOM count (a rank's work is proportional to its atoms, not its molecules);
+* every output of a rank (energy f64, forces / charges / spin charges f32, stress f32) packed into one byte buffer and
+  exchanged with a single `all_gather_into_tensor` (payloads are ~1 MB: latency-bound, so one launch, not one per key);
+* the shard plan is cached per batch layout (`mol_idx` tensor identity + version, or the dense shape), so a step of an MD /
+  screening loop does no host round trip for the split.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable
 
 import numpy as np
@@ -15,78 +22,115 @@ import torch.distributed as dist
 
 
 def split_molecules(n_mol: int, world: int) -> list[tuple[int, int]]:
-    """Contiguous, balanced molecule ranges: rank r owns [n_mol*r/world, n_mol*(r+1)/world)."""
+    """Contiguous, count-balanced molecule ranges: rank r owns [n_mol*r/world, n_mol*(r+1)/world)."""
     return [(n_mol * r // world, n_mol * (r + 1) // world) for r in range(world)]
 
 
-def shard_batch(data: dict, rank: int, world: int) -> tuple[dict, dict]:
-    """Slice a batch for `rank`.  Accepts the calculator's two batched input forms:
-    dense coord (B,N,3) / numbers (B,N) / charge (B,), or flat coord (Ntot,3) + sorted mol_idx + charge (B,).
-    Returns (local data, bookkeeping for the gather)."""
-    coord = np.asarray(data["coord"]) if not isinstance(data["coord"], torch.Tensor) else data["coord"]
+def split_molecules_balanced(atom_counts, world: int) -> list[tuple[int, int]]:
+    """Contiguous molecule ranges with (nearly) equal ATOM totals: boundary r sits at the molecule edge closest to
+    total * r / world.  Equal-size molecules give the count-balanced split."""
+    counts = np.asarray(atom_counts, dtype=np.int64)
+    n_mol = len(counts)
+    edges = np.concatenate([[0], np.cumsum(counts)])
+    total = int(edges[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(edges, target, "left"))
+        if k > 0 and (k > n_mol or abs(edges[k - 1] - target) <= abs(edges[min(k, n_mol)] - target)):
+            k -= 1
+        bounds.append(min(max(k, bounds[-1]), n_mol))
+    bounds.append(n_mol)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def make_plan(data: dict, world: int) -> dict:
+    """Shard plan of a batch in one of the calculator's two batched input forms: dense coord (B,N,3) / numbers (B,N) /
+    charge (B,), or flat coord (Ntot,3) + sorted mol_idx + charge (B,)."""
+    coord = data["coord"]
+    ndim = coord.ndim if isinstance(coord, torch.Tensor) else np.ndim(coord)
     charge = data["charge"]
     n_mol = int(np.shape(charge)[0]) if np.ndim(charge) else 1
-    lo, hi = split_molecules(n_mol, world)[rank]
+    if ndim == 3:
+        n_per = int(coord.shape[1])
+        ranges = split_molecules(n_mol, world)
+        return {"form": "dense", "n_mol": n_mol, "atoms_per_mol": n_per, "mol_ranges": ranges,
+                "atom_ranges": [(a * n_per, b * n_per) for a, b in ranges]}
+    mol_idx = data["mol_idx"]
+    mi = mol_idx.detach().cpu().numpy() if isinstance(mol_idx, torch.Tensor) else np.asarray(mol_idx)
+    counts = np.bincount(mi, minlength=n_mol)
+    ranges = split_molecules_balanced(counts, world)
+    edges = np.concatenate([[0], np.cumsum(counts)])
+    return {"form": "flat", "n_mol": n_mol, "mol_ranges": ranges,
+            "atom_ranges": [(int(edges[a]), int(edges[b])) for a, b in ranges],
+            "atoms_per_rank": [int(edges[b] - edges[a]) for a, b in ranges]}
+
+
+def shard_batch(data: dict, rank: int, world: int, plan: dict | None = None) -> tuple[dict, dict]:
+    """Slice a batch for `rank` (views for tensors / arrays; only `mol_idx` is rebased).  Returns (local data, plan)."""
+    plan = plan or make_plan(data, world)
+    lo, hi = plan["mol_ranges"][rank]
+    a0, a1 = plan["atom_ranges"][rank]
     out = {}
-    if coord.ndim == 3:
-        for k, v in data.items():
-            if v is None:
-                continue
-            if k in ("coord", "numbers", "charge", "mult") or (k == "cell" and np.ndim(v) == 3):
-                out[k] = v[lo:hi]
-            else:
-                out[k] = v
-        info = {"form": "dense", "n_mol": n_mol, "atoms_per_mol": coord.shape[1]}
-    else:
-        mol_idx = data["mol_idx"]
-        mi = mol_idx.cpu().numpy() if isinstance(mol_idx, torch.Tensor) else np.asarray(mol_idx)
-        a0, a1 = int(np.searchsorted(mi, lo, "left")), int(np.searchsorted(mi, hi, "left"))
-        for k, v in data.items():
-            if v is None:
-                continue
-            if k in ("coord", "numbers"):
-                out[k] = v[a0:a1]
-            elif k == "mol_idx":
-                out[k] = v[a0:a1] - lo
-            elif k in ("charge", "mult") or (k == "cell" and np.ndim(v) == 3):
-                out[k] = v[lo:hi]
-            else:
-                out[k] = v
-        counts = np.bincount(mi, minlength=n_mol)
-        info = {"form": "flat", "n_mol": n_mol,
-                "atoms_per_rank": [int(counts[a:b].sum()) for a, b in split_molecules(n_mol, world)]}
-    info["mol_ranges"] = split_molecules(n_mol, world)
-    return out, info
-
-
-def _all_gather_var(x: torch.Tensor, sizes: list[int], group=None) -> torch.Tensor:
-    """all_gather of tensors whose first dimension differs per rank (padded to the max)."""
-    world = dist.get_world_size(group)
-    mx = max(sizes)
-    pad = torch.zeros((mx, *x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    if len(set(sizes)) == 1:
-        out = torch.empty((world * mx, *x.shape[1:]), dtype=x.dtype, device=x.device)
-        dist.all_gather_into_tensor(out, pad, group=group)
-        return out
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
-
-
-def gather_results(local: dict, info: dict, group=None) -> dict:
-    """Rank-ordered gather of energy (per molecule) and per-atom outputs; every rank gets the full batch."""
-    world = dist.get_world_size(group)
-    mol_sizes = [b - a for a, b in info["mol_ranges"]]
-    out = {}
-    for k, v in local.items():
-        if k in ("energy", "stress"):
-            out[k] = _all_gather_var(v, mol_sizes, group)
-        elif info["form"] == "dense":
-            out[k] = _all_gather_var(v, mol_sizes, group)
+    for k, v in data.items():
+        if v is None:
+            continue
+        per_mol = k in ("charge", "mult") or (k == "cell" and np.ndim(v) == 3) or (k == "pbc" and np.ndim(v) == 2)
+        if plan["form"] == "dense":
+            out[k] = v[lo:hi] if (per_mol or k in ("coord", "numbers")) else v
+        elif k in ("coord", "numbers"):
+            out[k] = v[a0:a1]
+        elif k == "mol_idx":
+            out[k] = v[a0:a1] - lo
+        elif per_mol:
+            out[k] = v[lo:hi]
         else:
-            out[k] = _all_gather_var(v, info["atoms_per_rank"], group)
-    assert world == len(mol_sizes)
+            out[k] = v
+    return out, plan
+
+
+_PER_MOL = ("energy", "stress")
+
+
+def gather_results(local: dict, plan: dict, group=None) -> dict:
+    """Rank-ordered gather of every output with ONE collective: each rank packs its tensors into a byte buffer (padded to
+    the largest rank), `all_gather_into_tensor` moves it, and the per-key tensors are rebuilt in rank order.  Every rank
+    gets the full batch."""
+    world = dist.get_world_size(group)
+    keys = sorted(local)
+    dense = plan["form"] == "dense"
+    rows = {}   # key -> rows per rank
+    for k in keys:
+        if k in _PER_MOL or dense:
+            rows[k] = [b - a for a, b in plan["mol_ranges"]]
+        else:
+            rows[k] = [b - a for a, b in plan["atom_ranges"]]
+    row_bytes = {k: (local[k][0].numel() if local[k].shape[0] else int(np.prod(local[k].shape[1:]))) * local[k].element_size()
+                 for k in keys}
+    # 16-byte aligned segments so that every dtype can be viewed in place
+    seg = {k: (max(rows[k]) * row_bytes[k] + 15) // 16 * 16 for k in keys}
+    offs, tot = {}, 0
+    for k in keys:
+        offs[k] = tot
+        tot += seg[k]
+    dev = local[keys[0]].device
+    send = torch.zeros(tot, dtype=torch.uint8, device=dev)
+    for k in keys:
+        v = local[k].contiguous()
+        n = v.numel() * v.element_size()
+        if n:
+            send[offs[k]: offs[k] + n] = v.view(-1).view(torch.uint8)
+    recv = torch.empty(world * tot, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    out = {}
+    for k in keys:
+        tail = tuple(local[k].shape[1:])
+        parts = []
+        for r in range(world):
+            n = rows[k][r] * row_bytes[k]
+            b0 = r * tot + offs[k]
+            parts.append(recv[b0: b0 + n].view(local[k].dtype).view(rows[k][r], *tail))
+        out[k] = torch.cat(parts, dim=0)
     return out
 
 
@@ -101,11 +145,33 @@ class ShardedCalculator:
     def __init__(self, calc: Callable, group=None):
         self.calc = calc
         self.group = group
+        self._plan_cache = None   # (key, weakref or None, plan)
+
+    def _plan(self, data: dict, world: int) -> dict:
+        coord, mi = data["coord"], data.get("mol_idx")
+        nd = coord.ndim if isinstance(coord, torch.Tensor) else np.ndim(coord)
+        if nd == 3:
+            key, ref = ("dense", tuple(coord.shape), world), None
+        elif isinstance(mi, torch.Tensor):
+            key, ref = ("flat", id(mi), mi.data_ptr(), mi._version, tuple(mi.shape), world), weakref.ref(mi)
+        else:
+            return make_plan(data, world)   # numpy / list mol_idx: cheap host arithmetic, mutation undetectable
+        c = self._plan_cache
+        if c is not None and c[0] == key and (c[1] is None or c[1]() is mi):
+            return c[2]
+        plan = make_plan(data, world)
+        self._plan_cache = (key, ref, plan)
+        return plan
 
     def __call__(self, data: dict, forces: bool = False, stress: bool = False, gather: bool = True) -> dict:
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return self.calc(data, forces=forces, stress=stress)
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        local_in, info = shard_batch(data, rank, world)
+        local_in, plan = shard_batch(data, rank, world, self._plan(data, world))
         local = self.calc(local_in, forces=forces, stress=stress)
-        return gather_results(local, info, self.group) if gather else local
+        if not gather:
+            return local
+        out = gather_results(local, plan, self.group)
+        if plan["form"] == "dense":
+            return out
+        return out

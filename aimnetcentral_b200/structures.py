@@ -146,3 +146,44 @@ def read_xyz_frame(path: str, frame: int = 0):
     z = np.array([SYMBOLS[ln.split()[0]] for ln in block], dtype=np.int32)
     xyz = np.array([[float(t) for t in ln.split()[1:4]] for ln in block], dtype=np.float32)
     return z, xyz
+
+
+def benchmark_workload(name: str, seed: int = 1234):
+    """The synthetic inputs of BASELINE.json configs 1-5 as flat arrays: what bench.py times and what the
+    full-size parity fixtures (oracle/make_golden_full.py, tests/test_gpu_fullsize.py) are generated from."""
+    import os
+
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if name == "cfg2":
+        coord, numbers = random_molecules(1024, 50, seed=seed)
+        B, n = coord.shape[:2]
+        return dict(coord=coord.reshape(-1, 3), numbers=numbers.reshape(-1).astype(np.int32),
+                    charge=np.zeros(B, np.float32), mol_idx=np.repeat(np.arange(B), n).astype(np.int32), cell=None,
+                    desc="cfg-2: 1024 x 50-atom random organic molecules, aimnet2, E+F, Coulomb simple + DFT-D3",
+                    stress=False)
+    if name == "cfg3":
+        z, x, cell = allose_supercell((7, 3, 5), jitter=0.02, seed=seed)
+        return dict(coord=x, numbers=z.astype(np.int32), charge=np.zeros(1, np.float32), mol_idx=None, cell=cell,
+                    desc="cfg-3: 10 080-atom allose supercell, PBC, DSF Coulomb + DFT-D3, E+F+stress", stress=True)
+    if name == "cfg5":
+        z, x, cell = allose_supercell((14, 6, 10), jitter=0.02, seed=seed)
+        return dict(coord=x, numbers=z.astype(np.int32), charge=np.zeros(1, np.float32), mol_idx=None, cell=cell,
+                    desc="cfg-5: 80 640-atom allose supercell, PBC, Ewald Coulomb (1e-6) + DFT-D3, E+F+stress (one "
+                         "replica per GPU)", stress=True, coulomb="ewald")
+    if name == "cfg1":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "taxol_q0.npz"))
+        return dict(coord=g["in_coord"].astype(np.float32), numbers=g["in_numbers"].astype(np.int32),
+                    charge=np.zeros(1, np.float32), mol_idx=None, cell=None,
+                    desc="cfg-1: taxol, 113 atoms, single molecule, E+F, Coulomb simple + DFT-D3", stress=False)
+    if name == "cfg4":
+        coord, numbers = random_molecules(512, 80, seed=4321 + seed, box=8.5)
+        B, n = coord.shape[:2]
+        rng = np.random.default_rng(seed)
+        charge = rng.integers(-1, 2, size=B).astype(np.float32)
+        nelec = numbers.sum(axis=1) - charge.astype(np.int64)
+        mult = np.where(nelec % 2 == 0, rng.choice([1, 3], size=B), 2).astype(np.float32)
+        return dict(coord=coord.reshape(-1, 3), numbers=numbers.reshape(-1).astype(np.int32), charge=charge, mult=mult,
+                    mol_idx=np.repeat(np.arange(B), n).astype(np.int32), cell=None, channels=2,
+                    desc="cfg-4: aimnet2-nse graph (2 charge channels), 512 x 80-atom molecules, E+F+charges+spin charges",
+                    stress=False)
+    raise ValueError(name)

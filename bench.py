@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the AIMNet2 E+F hot path (BASELINE.json metric: atom-steps/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg1..cfg5]
+                    [--scaling weak|strong] [--no-extra] [--no-cpu-baseline] [--gemm-backend B]
 
 One "step" = one energy+forces evaluation of one batch of synthetic input, neighbor construction included.
-Default workload (N=1): cfg-2 of BASELINE.json — 1024 random 50-atom organic molecules (51 200 atoms), aimnet2 graph
-with seeded random weights, Coulomb "simple" + DFT-D3, coordinates jittered every step.
+Default workload: cfg-2 of BASELINE.json — 1024 random 50-atom organic molecules (51 200 atoms), aimnet2 graph with
+seeded random weights, Coulomb "simple" + DFT-D3, coordinates jittered every step.
 
 Printed JSON line (rank 0):
-  value      whole-job atom-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same metric through the C-ABI host-buffer entry (aimnet2_engine_eval_host): H2D of coord/numbers/
-             charge/mol_idx from pinned memory + compute + D2H of energy/forces/charges, every step
-  roofline   the dominant kernel class (per-atom MLP GEMMs): algorithmic FLOPs / summed GEMM launch time measured
-             with CUDA events around every GEMM launch (engine timing level 2) in a separate instrumented pass
-  cpu_baseline  the CPU oracle (a PyTorch-CPU restatement with the reference's computational shape) on a bounded
-             sample of the same workload, all host threads
-`--impl reference` times that CPU path alone (the Python reference tree cannot travel to the GPU box).
+  value       whole-job atom-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks.  N = 1: the C-ABI call with
+              device pointers (aimnet2_engine_eval).  N > 1: the product's multi-GPU module (ShardedCalculator around
+              AIMNet2Calculator): contiguous atom-balanced molecule shards, one fused NCCL all_gather of all outputs per step
+              inside the timed region; weak scaling (1024 molecules per GPU) unless --scaling strong.
+  e2e         the same metric through the C-ABI host-buffer entry (aimnet2_engine_eval_host): H2D of coord / numbers /
+              charge / mol_idx from pinned memory + compute + D2H of energy / forces / charges, every step
+  api         the same through AIMNet2Calculator.__call__ with numpy inputs and .cpu() of the outputs (the front door)
+  roofline    the kernel class that takes the largest share of the step, `roofline_classes` both classes (per-atom MLP
+              GEMMs on the tensor pipe, AEV / conv_sv on the fp32 FMA pipe) from CUDA events around every launch of the
+              class in a separate instrumented pass, `step_roofline` the t_roof / t_measured of SURVEY.md section 8(d)
+  cpu_baseline  the UNMODIFIED reference modules (oracle/_ref, vendored by oracle/make_ref.py) on the host cores on a
+              bounded sample of the same workload (kind "reference"), else the oracle port (kind "port")
+  extra_workloads  (N = 1) short runs of cfg-1 / cfg-3 / cfg-4 / cfg-5 in the same process, each with its own clocks
+`--impl reference` times the reference's own CPU path alone on this arm's config / metric / steps / warmup.
 """
 from __future__ import annotations
 
@@ -26,54 +33,30 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from aimnetcentral_b200.structures import benchmark_workload as make_workload  # noqa: E402
+
 METRIC = "atom-steps/sec (E+F)"
 UNIT = "atom-steps/s"
-# algorithmic work per atom-step of the MLP stacks, forward + input-gradient backward
-MLP_MACS_PER_ATOM = {1: 2_181_760, 2: 2_212_976}
+# algorithmic work per atom-step
+MLP_MACS_PER_ATOM = {1: 2_181_760, 2: 2_212_976}          # fwd; x2 for the input-gradient backward, x2 FLOP per MAC
+CONV_FLOP_PER_PAIR = {1: 19_200, 2: 19_968}               # 3 passes x 2 x (3 A G 4 + 2 C G 4): fwd + grad_a + grad_g
+AGH_FLOP_PER_ATOM = 0.17e6
+REF_SAMPLE_MOLS = 64                                      # CPU sample of the molecule workloads (>= 64)
 
 
-def make_workload(name: str, seed: int):
-    from aimnetcentral_b200.structures import allose_supercell, random_molecules
-
-    if name == "cfg2":
-        coord, numbers = random_molecules(1024, 50, seed=seed)
-        B, n = coord.shape[:2]
-        return dict(coord=coord.reshape(-1, 3), numbers=numbers.reshape(-1).astype(np.int32),
-                    charge=np.zeros(B, np.float32), mol_idx=np.repeat(np.arange(B), n).astype(np.int32), cell=None,
-                    desc="cfg-2: 1024 x 50-atom random organic molecules, aimnet2, E+F, Coulomb simple + DFT-D3",
-                    stress=False)
-    if name == "cfg3":
-        z, x, cell = allose_supercell((7, 3, 5), jitter=0.02, seed=seed)
-        return dict(coord=x, numbers=z.astype(np.int32), charge=np.zeros(1, np.float32), mol_idx=None, cell=cell,
-                    desc="cfg-3: 10 080-atom allose supercell, PBC, DSF Coulomb + DFT-D3, E+F+stress", stress=True)
-    if name == "cfg5":
-        z, x, cell = allose_supercell((14, 6, 10), jitter=0.02, seed=seed)
-        return dict(coord=x, numbers=z.astype(np.int32), charge=np.zeros(1, np.float32), mol_idx=None, cell=cell,
-                    desc="cfg-5: 80 640-atom allose supercell, PBC, Ewald Coulomb (1e-6) + DFT-D3, E+F+stress (one "
-                         "replica per GPU)", stress=True, coulomb="ewald")
-    if name == "cfg1":
-        g = np.load(os.path.join(ROOT, "tests", "golden", "taxol_q0.npz"))
-        return dict(coord=g["in_coord"].astype(np.float32), numbers=g["in_numbers"].astype(np.int32),
-                    charge=np.zeros(1, np.float32), mol_idx=None, cell=None,
-                    desc="cfg-1: taxol, 113 atoms, single molecule, E+F, Coulomb simple + DFT-D3", stress=False)
-    if name == "cfg4":
-        coord, numbers = random_molecules(512, 80, seed=4321 + seed, box=8.5)
-        B, n = coord.shape[:2]
-        rng = np.random.default_rng(seed)
-        charge = rng.integers(-1, 2, size=B).astype(np.float32)
-        nelec = numbers.sum(axis=1) - charge.astype(np.int64)
-        mult = np.where(nelec % 2 == 0, rng.choice([1, 3], size=B), 2).astype(np.float32)
-        return dict(coord=coord.reshape(-1, 3), numbers=numbers.reshape(-1).astype(np.int32), charge=charge, mult=mult,
-                    mol_idx=np.repeat(np.arange(B), n).astype(np.int32), cell=None, channels=2,
-                    desc="cfg-4: aimnet2-nse graph (2 charge channels), 512 x 80-atom molecules, E+F+charges+spin charges",
-                    stress=False)
-    raise ValueError(name)
+def workload_config(w: dict, n_atoms: int, n_mol: int) -> dict:
+    """Identical in both arms (the driver compares the arms' `config`)."""
+    return {"workload": w["desc"], "atoms_per_gpu": int(n_atoms), "molecules_per_gpu": int(n_mol),
+            "weights": "seeded random, aimnet2 architecture (2.2M params)",
+            "l2": "per-step working set (activations + saved tensors, > 1 GB) exceeds the 126 MB L2; coordinates change "
+                  "every step"}
 
 
 class ClockSampler:
@@ -97,6 +80,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -121,52 +105,91 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(workload: str, seed: int, budget_s: float = 20.0, steps: int | None = None):
-    """Time the CPU oracle on a bounded sample of the workload. Returns (atom-steps/s, description, cores)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side: the reference itself (oracle/_ref) or, when it is not vendored, the oracle port
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_sample(workload: str, seed: int):
+    """Bounded sample of the workload for the host cores: (workload, inputs, kwargs, description)."""
+    w = make_workload(workload, seed)
+    if w["mol_idx"] is not None:   # molecule batches: the first REF_SAMPLE_MOLS molecules (molecules are independent)
+        B = len(w["charge"])
+        nmol = min(REF_SAMPLE_MOLS, B)
+        a1 = int(np.searchsorted(w["mol_idx"], nmol))
+        inp = dict(coord=w["coord"][:a1], numbers=w["numbers"][:a1], charge=w["charge"][:nmol],
+                   mol_idx=w["mol_idx"][:a1].astype(np.int64))
+        if w.get("mult") is not None:
+            inp["mult"] = w["mult"][:nmol]
+        sample = (f"{nmol} of the {B} molecules ({a1} atoms) per step; the reference's mode-1 path needs an N_total^2 "
+                  "scratch for the all-pairs list, so the batch is run as a chunk (atom-steps/s is chunk-invariant)")
+        return w, inp, dict(stress=False), sample
+    if workload == "cfg1":
+        return w, dict(coord=w["coord"], numbers=w["numbers"], charge=w["charge"]), dict(stress=False), "the whole system"
+    from aimnetcentral_b200.structures import allose_supercell
+
+    z, x, cell = allose_supercell((2, 1, 1), jitter=0.02, seed=seed)
+    inp = dict(coord=x, numbers=z, charge=np.zeros(1, np.float32), cell=cell)
+    sample = ("2x1x1 allose supercell (192 atoms), DSF + D3, E+F+stress (the torch D3 path materialises (N,M,5,5) "
+              "temporaries, so the full box does not fit the time budget)")
+    return w, inp, dict(stress=True), sample
+
+
+def cpu_runner(workload: str, seed: int):
+    """Returns (step(coord) callable, inputs, sample description, kind, cores)."""
     import torch
 
     from aimnetcentral_b200 import ModelSpec, random_state_dict
-    from oracle.calculator_oracle import oracle_calculate
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    spec = ModelSpec()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w, inp, kw, sample = cpu_sample(workload, seed)
+    spec = ModelSpec(num_charge_channels=w.get("channels", 1))
     sd = random_state_dict(0, spec)
-    w = make_workload(workload, seed)
-    if workload == "cfg2":
-        nmol = 32
-        sel = slice(0, nmol * 50)
-        inp = dict(coord=w["coord"][sel], numbers=w["numbers"][sel], charge=w["charge"][:nmol], mol_idx=w["mol_idx"][sel])
-        sample = f"{nmol} of the 1024 molecules ({nmol * 50} atoms) per step, Coulomb simple + D3, E+F (the reference's "\
-                 "mode-1 path needs an N_total^2 scratch for the all-pairs list, so it is run in chunks; atom-steps/s is "\
-                 "chunk-invariant)"
-        kw = dict(stress=False)
-    else:
-        from aimnetcentral_b200.structures import allose_supercell
+    kind = "port"
+    try:
+        from oracle import ref_harness as rh
 
-        z, x, cell = allose_supercell((2, 1, 1), jitter=0.02, seed=seed)
-        inp = dict(coord=x, numbers=z, charge=np.zeros(1, np.float32), cell=cell)
-        sample = "2x1x1 allose supercell (192 atoms), DSF + D3, E+F+stress (the torch D3 path materialises (N,M,5,5) "\
-                 "temporaries, so the 10 080-atom box does not fit the time budget)"
-        kw = dict(stress=True)
-    natoms = len(inp["numbers"])
+        if not rh.reference_available():
+            raise RuntimeError("no reference tree (oracle/_ref is made by `python -m oracle.make_ref`)")
+        calc = rh.build_reference_calculator(sd, spec)
+        if "cell" in inp:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                calc.set_lrcoulomb_method("dsf")
+        kind = "reference"
+
+        def step(coord):
+            return rh.run_reference(calc, dict(inp, coord=coord), forces=True, stress=kw["stress"])
+    except Exception as ex:  # noqa: BLE001
+        print(f"[bench] reference modules unavailable ({ex}); timing the oracle port", file=sys.stderr)
+        from oracle.calculator_oracle import oracle_calculate
+
+        def step(coord):
+            return oracle_calculate(sd, dict(inp, coord=coord), num_charge_channels=spec.C, **kw)
+    return step, inp, sample, kind, torch.get_num_threads()
+
+
+def time_cpu(workload: str, seed: int, warmup: int, steps: int | None, budget_s: float):
+    step, inp, sample, kind, cores = cpu_runner(workload, seed)
     rng = np.random.default_rng(seed)
-    t_all = []
-    oracle_calculate(sd, inp, **kw)  # warm-up
+    jit = lambda: (inp["coord"] + rng.normal(0, 0.01, inp["coord"].shape)).astype(np.float32)   # noqa: E731
+    for _ in range(max(1, warmup)):
+        step(jit())
+    ts = []
     t0 = time.perf_counter()
-    n = 0
     while True:
-        step_in = dict(inp, coord=(inp["coord"] + rng.normal(0, 0.01, inp["coord"].shape)).astype(np.float32))
+        c = jit()
         t1 = time.perf_counter()
-        oracle_calculate(sd, step_in, **kw)
-        t_all.append(time.perf_counter() - t1)
-        n += 1
+        step(c)
+        ts.append(time.perf_counter() - t1)
         if steps is not None:
-            if n >= steps:
+            if len(ts) >= steps:
                 break
-        elif time.perf_counter() - t0 > budget_s or n >= 50:
+        elif time.perf_counter() - t0 > budget_s or len(ts) >= 50:
             break
-    dt = float(np.median(t_all))
-    return natoms / dt, sample, torch.get_num_threads(), dt, n
+    dt = float(np.mean(ts))
+    n = len(inp["numbers"])
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "s_per_step": dt, "steps": len(ts),
+            "sample_atoms": n}
 
 
 def run_reference_arm(args):
@@ -174,18 +197,213 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w = make_workload(args.workload, args.seed)
-    for _ in range(max(0, args.warmup - 1)):
-        pass
-    value, sample, cores, dt, n = cpu_baseline(args.workload, args.seed, steps=max(1, args.steps))
+    W, K = max(3, args.warmup), max(1, args.steps)
+    # bounded: every step is the CPU sample of the workload
+    cb = time_cpu(args.workload, args.seed, warmup=W, steps=K, budget_s=240.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, len(w["numbers"]), len(w["charge"])),
+        "device": "cpu", "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "sample_atoms")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def mean_neighbors(w, dev, cutoff):
+    """Mean row length of the full neighbor list at `cutoff` (for the algorithmic-work figures)."""
+    import torch
+
+    from aimnetcentral_b200 import ops
+
+    x = torch.as_tensor(w["coord"], device=dev)
+    kw = {}
+    if w["cell"] is not None:
+        cell = torch.as_tensor(w["cell"], device=dev).reshape(1, 3, 3)
+        x = ops.wrap_positions(x, cell[0])
+        kw = dict(cell=cell, pbc=torch.ones(1, 3, dtype=torch.bool, device=dev))
+    if w["mol_idx"] is not None:
+        kw["batch_idx"] = torch.as_tensor(w["mol_idx"], device=dev)
+    cap = 256 if cutoff <= 6 else 2400
+    _, cnt, *_ = ops.neighbor_list(x, cutoff, max_neighbors=cap, **kw)
+    return float(cnt.float().mean().item())
+
+
+class Runner:
+    """One workload on one device: engine, calculator, host / device copies of every step's coordinates."""
+
+    def __init__(self, name, seed, dev, n_sets, gemm_backend=None, jitter_seed=0):
+        import torch
+
+        from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+
+        self.torch = torch
+        self.dev = dev
+        self.w = w = make_workload(name, seed)
+        self.spec = ModelSpec(num_charge_channels=w.get("channels", 1))
+        self.sd = random_state_dict(0, self.spec)
+        self.calc = AIMNet2Calculator((self.sd, self.spec), device=str(dev))
+        self.eng = self.calc.engine
+        if gemm_backend is not None:
+            self.eng.set_gemm_backend(gemm_backend)
+        self.pbc = w["cell"] is not None
+        self.calc.set_lrcoulomb_method(w.get("coulomb", "dsf" if self.pbc else "simple"))
+        self.N, self.B = len(w["numbers"]), len(w["charge"])
+        rng = np.random.default_rng(seed + 17 * jitter_seed)
+        self.coords_np = [(w["coord"] + rng.normal(0, 0.01, w["coord"].shape)).astype(np.float32) for _ in range(n_sets)]
+        self.coords_h = [torch.from_numpy(c).pin_memory() for c in self.coords_np]
+        self.coords_d = [c.to(dev) for c in self.coords_h]
+        pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+        self.numbers_h, self.charge_h = pin(w["numbers"]), pin(w["charge"])
+        self.mol_h, self.mult_h = pin(w["mol_idx"]), pin(w.get("mult"))
+        to = lambda t: None if t is None else t.to(dev)   # noqa: E731
+        self.numbers_d, self.charge_d, self.mol_d, self.mult_d = to(self.numbers_h), to(self.charge_h), to(self.mol_h), to(self.mult_h)
+        self.cell_d = torch.from_numpy(w["cell"]).to(dev) if self.pbc else None
+        self.out_h = {"energy": torch.empty(self.B, dtype=torch.float64).pin_memory().numpy(),
+                      "charges": torch.empty(self.N, dtype=torch.float32).pin_memory().numpy(),
+                      "forces": torch.empty(self.N, 3, dtype=torch.float32).pin_memory().numpy()}
+        if w["stress"]:
+            self.out_h["stress"] = torch.empty(3, 3, dtype=torch.float32).pin_memory().numpy()
+        if self.spec.C == 2:
+            self.out_h["spin_charges"] = torch.empty(self.N, dtype=torch.float32).pin_memory().numpy()
+
+    def step_device(self, i):
+        return self.eng.eval(self.coords_d[i], self.numbers_d, self.charge_d, mol_idx=self.mol_d, mult=self.mult_d,
+                             cell=self.cell_d, host_cell=self.w["cell"], forces=True, stress=self.w["stress"])
+
+    def step_host(self, i):
+        self.eng.eval_host(self.coords_h[i], self.numbers_h, self.charge_h, mol_idx=self.mol_h, mult=self.mult_h,
+                           cell=self.w["cell"], forces=True, stress=self.w["stress"], out=self.out_h)
+
+    def api_inputs(self, i):
+        d = {"coord": self.coords_np[i], "numbers": self.w["numbers"], "charge": self.w["charge"]}
+        if self.w["mol_idx"] is not None:
+            d["mol_idx"] = self.w["mol_idx"]
+        if self.w.get("mult") is not None:
+            d["mult"] = self.w["mult"]
+        if self.pbc:
+            d["cell"] = self.w["cell"]
+        return d
+
+    def step_api(self, i):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = self.calc(self.api_inputs(i), forces=True, stress=self.w["stress"])
+        return {k: v.cpu() for k, v in out.items()}
+
+    def h2d_bytes(self):
+        n = self.coords_h[0].numel() * 4 + self.numbers_h.numel() * 4 + self.charge_h.numel() * 4
+        n += self.mol_h.numel() * 4 if self.mol_h is not None else 0
+        n += self.mult_h.numel() * 4 if self.mult_h is not None else 0
+        return int(n + (36 if self.pbc else 0))
+
+    def d2h_bytes(self):
+        return int(sum(int(v.nbytes) for v in self.out_h.values()))
+
+    def time_events(self, fn, W, K):
+        torch = self.torch
+        for i in range(W):
+            fn(i)
+        torch.cuda.synchronize(self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(W + i)
+        e1.record()
+        torch.cuda.synchronize(self.dev)
+        return e0.elapsed_time(e1)
+
+    def time_wall(self, fn, W, K):
+        for i in range(W):
+            fn(i)
+        self.torch.cuda.synchronize(self.dev)
+        t0 = time.perf_counter()
+        for i in range(K):
+            fn(W + i)
+        self.torch.cuda.synchronize(self.dev)
+        return (time.perf_counter() - t0) * 1e3
+
+
+def rooflines(r: Runner, step_ms: float, timed_region_s: float, traffic: dict):
+    """Instrumented pass (CUDA events around every launch of the two dominant kernel classes; not the timed region)."""
+    torch, eng = r.torch, r.eng
+    eng.enable_timing(2)
+    rows = []
+    r.step_device(0)
+    torch.cuda.synchronize(r.dev)
+    for i in range(5):
+        r.step_device(i)
+        torch.cuda.synchronize(r.dev)
+        rows.append(eng.last_timing())
+    eng.enable_timing(0)
+    med = {k: float(np.median([x[k] for x in rows])) for k in rows[0]}
+    peaks = load_peaks()
+    burst = timed_region_s < 1.0   # burst peak for a short timed region, the sustained one inside a long step loop
+    bf16 = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1662.9 if burst else 1398.5)
+    hbm = peaks.get("hbm_gbs", 6550.7)
+    tc16 = eng.gemm_backend in (2, 3)
+    peak_tensor = bf16 / 3.0 if tc16 else bf16 / 2.0 / 3.0   # three error-compensating MMAs per product (tf32: half rate)
+    peak_src = (("MEASURED_PEAKS.json" if peaks else "fallback") +
+                (" bf16_tflops (burst: timed region %.2f s)" % timed_region_s if burst else " bf16_tflops_sustained") +
+                (" / 3 (3xFP16 split on the kind::f16 pipe)" if tc16 else " / 2 (tf32) / 3 (3xTF32 split)"))
+    C, N = r.spec.C, r.N
+    m_sr = mean_neighbors(r.w, r.dev, 5.0)
+    m_lr = mean_neighbors(r.w, r.dev, 15.0) if r.pbc else 0.0   # non-periodic: pair walkers iterate molecule segments, no list
+    f_mlp = 2.0 * 2.0 * MLP_MACS_PER_ATOM[C] * N
+    f_conv = CONV_FLOP_PER_PAIR[C] * m_sr * N
+    gemm_ms, conv_ms = med["gemm_ms"], med["conv_ms"]
+    sms, sm_ghz = 148, peaks.get("sm_max_mhz", 1965.0) / 1e3
+    peak_fma = sms * 128 * 2 * sm_ghz / 1e3   # TFLOP/s fp32: SMs x 128 lanes x 2 FLOP x clock (computed, not measured)
+    g = {"kernel": "gemm_nt: per-atom MLP stacks, fwd + input-gradient bwd (%d launches/step incl. presplit)" % int(med["gemm_launches"]),
+         "bound": "tensor", "achieved": f_mlp / (gemm_ms * 1e-3) / 1e12, "peak": peak_tensor, "unit": "TFLOP/s",
+         "peak_source": peak_src, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / step_ms,
+         "algorithmic": "%.3f MFLOP/atom-step x %d atoms" % (f_mlp / N / 1e6, N), "traffic": traffic.get("gemm")}
+    c = {"kernel": "conv_sv: AEV recomputed in flight + gather / contraction, fwd + analytic bwd (%d calls/step)" % int(med["conv_calls"]),
+         "bound": "simt-fp32-fma", "achieved": f_conv / (conv_ms * 1e-3) / 1e12, "peak": peak_fma, "unit": "TFLOP/s",
+         "peak_source": "computed: %d SMs x 128 lanes x 2 x %.3f GHz (MEASURED_PEAKS.json has no fp32 figure)" % (sms, sm_ghz),
+         "ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms,
+         "algorithmic": "%d FLOP/pair x mean %.1f short-range neighbors x %d atoms" % (CONV_FLOP_PER_PAIR[C], m_sr, N),
+         "traffic": traffic.get("conv")}
+    for d in (g, c):
+        d["frac"] = d["achieved"] / d["peak"]
+    # SURVEY.md §8(d): t_roof = max(N F_total / P_tensor_eff, N Bytes / HBM)
+    f_total = f_mlp + f_conv + AGH_FLOP_PER_ATOM * N
+    bytes_total = N * (32 + 48 * m_sr + 32 * m_lr + 69_000)
+    t_tensor, t_hbm = f_total / (peak_tensor * 1e12) * 1e3, bytes_total / (hbm * 1e9) * 1e3
+    step = {"t_roof_ms": max(t_tensor, t_hbm), "t_tensor_ms": t_tensor, "t_hbm_ms": t_hbm, "t_measured_ms": step_ms,
+            "frac": max(t_tensor, t_hbm) / step_ms, "flop_per_atom_step": f_total / N, "bytes_per_atom_step": bytes_total / N,
+            "mean_sr_neighbors": m_sr, "mean_lr_neighbors": m_lr,
+            "definition": "SURVEY.md 8(d): max(N F_total / P_tensor_eff, N Bytes / measured HBM GB/s) / measured step"}
+    phases = {k: med[k] for k in ("neighbors_ms", "forward_ms", "pair_terms_ms", "backward_ms", "total_ms")}
+    dominant = dict(g if gemm_ms >= conv_ms else c)
+    dominant["dominant_class"] = "gemm" if gemm_ms >= conv_ms else "conv"
+    dominant["gemm_ms_per_step"], dominant["conv_ms_per_step"], dominant["phase_ms"] = gemm_ms, conv_ms, phases
+    return dominant, [g, c], step
+
+
+def load_traffic(eng_backend: int, workload: str):
+    """DRAM bytes per launch of the largest launch of each class from the committed `ncu --set full` capture of THIS build
+    (profiles/ncu_traffic.json, keyed by the sha256 of the kernel sources); null when the library has changed since."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        from aimnetcentral_b200 import build as b
+
+        if t.get("build_sha256") != b._digest() or t.get("workload") != workload or t.get("gemm_backend") != eng_backend:
+            return {}
+        return {"gemm": t.get("gemm"), "conv": t.get("conv")}
+    except Exception:
+        return {}
 
 
 def main():
@@ -195,9 +413,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--gemm-backend", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -205,8 +425,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from aimnetcentral_b200 import ModelSpec, random_state_dict
-    from aimnetcentral_b200.engine import Engine
+    from aimnetcentral_b200.sharded import ShardedCalculator
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,160 +434,123 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W = max(3, args.warmup)
-    K = max(1, args.steps)
-
-    w = make_workload(args.workload, args.seed + rank)  # weak scaling: every rank owns its own batch
-    spec = ModelSpec(num_charge_channels=w.get("channels", 1))
-    sd = random_state_dict(0, spec)
-    eng = Engine(sd, spec.C, dev)
-    if args.gemm_backend is not None:
-        eng.set_gemm_backend(args.gemm_backend)
-    pbc = w["cell"] is not None
-    eng.set_options(coulomb_method=w.get("coulomb", "dsf" if pbc else "simple"), dispersion=True)
-    N = len(w["numbers"])
-    B = len(w["charge"])
-    rng = np.random.default_rng(args.seed + 17 * rank)
+    W, K = max(3, args.warmup), max(1, args.steps)
     n_sets = W + K
-    # host (pinned) and device copies of every step's jittered coordinates
-    coords_h = [torch.from_numpy((w["coord"] + rng.normal(0, 0.01, w["coord"].shape)).astype(np.float32)).pin_memory()
-                for _ in range(n_sets)]
-    coords_d = [c.to(dev) for c in coords_h]
-    numbers_h = torch.from_numpy(w["numbers"]).pin_memory()
-    charge_h = torch.from_numpy(w["charge"]).pin_memory()
-    mol_h = torch.from_numpy(w["mol_idx"]).pin_memory() if w["mol_idx"] is not None else None
-    numbers_d, charge_d = numbers_h.to(dev), charge_h.to(dev)
-    mult_h = torch.from_numpy(w["mult"]).pin_memory() if w.get("mult") is not None else None
-    mult_d = mult_h.to(dev) if mult_h is not None else None
-    mol_d = mol_h.to(dev) if mol_h is not None else None
-    cell_d = torch.from_numpy(w["cell"]).to(dev) if pbc else None
-    gather_e = gather_f = None
-    if world > 1:
-        gather_e = torch.empty(world * B, dtype=torch.float64, device=dev)
-        gather_f = torch.empty(world * N, 3, dtype=torch.float32, device=dev)
+    r = Runner(args.workload, args.seed + rank, dev, n_sets, args.gemm_backend, jitter_seed=rank)
+    N, B, w = r.N, r.B, r.w
+    sampler = ClockSampler(local).start() if rank == 0 else None
 
-    def step(i):
-        out = eng.eval(coords_d[i], numbers_d, charge_d, mol_idx=mol_d, mult=mult_d, cell=cell_d, forces=True,
-                       stress=w["stress"])
-        if world > 1:  # result gather of the batch split (NCCL over NVLink)
-            dist.all_gather_into_tensor(gather_e, out["energy"])
-            dist.all_gather_into_tensor(gather_f, out["forces"])
-        return out
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def sync_all():
+    def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for i in range(W):
-        step(i)
-    sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(K):
-        step(W + i)
-    ev1.record()
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.last_launches() * K
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * N * K / (ms_max * 1e-3)
+    multi = None
+    if world == 1:
+        barrier()
+        ms = r.time_events(r.step_device, W, K)
+        atoms_total = N
+    else:
+        # The product's multi-GPU module.  The GLOBAL batch is resident on every rank (weak: world x 1024 molecules, built
+        # from the same seeds on every rank; strong: the N = 1 batch); ShardedCalculator evaluates this rank's contiguous
+        # atom-balanced shard and gathers every output with one fused NCCL all_gather per step, inside the timed region.
+        if w["mol_idx"] is None:
+            reps, mode = world, "replicas"   # independent periodic replicas, one box per GPU
+            base = Runner(args.workload, args.seed, dev, n_sets)
+            glob = [dict(coord=base.coords_d[i].unsqueeze(0).repeat(reps, 1, 1), numbers=base.numbers_d.unsqueeze(0).repeat(reps, 1),
+                         charge=base.charge_d.repeat(reps), cell=base.cell_d.unsqueeze(0).repeat(reps, 1, 1)) for i in range(n_sets)]
+            del base
+        else:
+            reps, mode = (world if args.scaling == "weak" else 1), args.scaling
+            parts = [Runner(args.workload, args.seed + k, dev, n_sets, jitter_seed=k) for k in range(reps)]
+            mol = torch.cat([x.mol_d + k * B for k, x in enumerate(parts)])
+            numbers, charge = torch.cat([x.numbers_d for x in parts]), torch.cat([x.charge_d for x in parts])
+            mult = torch.cat([x.mult_d for x in parts]) if r.mult_d is not None else None
+            glob = []
+            for i in range(n_sets):
+                d = dict(coord=torch.cat([x.coords_d[i] for x in parts]), numbers=numbers, charge=charge, mol_idx=mol)
+                if mult is not None:
+                    d["mult"] = mult
+                glob.append(d)
+            del parts
+        atoms_total = reps * N
+        sharded = ShardedCalculator(r.calc)
 
-    # ---- e2e: host buffers through the C ABI (H2D + compute + D2H inside every step) ----
-    out_h = {"energy": torch.empty(B, dtype=torch.float64).pin_memory().numpy(),
-             "charges": torch.empty(N, dtype=torch.float32).pin_memory().numpy(),
-             "forces": torch.empty(N, 3, dtype=torch.float32).pin_memory().numpy()}
-    if w["stress"]:
-        out_h["stress"] = torch.empty(3, 3, dtype=torch.float32).pin_memory().numpy()
-    if spec.C == 2:
-        out_h["spin_charges"] = torch.empty(N, dtype=torch.float32).pin_memory().numpy()
+        def step_sharded(i):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return sharded(glob[i], forces=True, stress=w["stress"])
 
-    def step_host(i):
-        eng.eval_host(coords_h[i], numbers_h, charge_h, mol_idx=mol_h, mult=mult_h, cell=w["cell"], forces=True,
-                      stress=w["stress"], out=out_h)
+        for i in range(W):
+            step_sharded(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            out = step_sharded(W + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        multi = {"module": "aimnetcentral_b200.sharded.ShardedCalculator(AIMNet2Calculator)", "mode": mode,
+                 "global_atoms": atoms_total, "global_forces_shape": list(out["forces"].shape),
+                 "gather": "one fused all_gather_into_tensor of every output per step (NCCL), inside the timed region"}
+    launches = r.eng.last_launches() * K
+    ms_max = maxr(ms)
+    value = atoms_total * K / (ms_max * 1e-3)
 
-    for i in range(2):
-        step_host(i)
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(K):
-        step_host(W + i)
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * K / float(t.item())
-    h2d = coords_h[0].numel() * 4 + numbers_h.numel() * 4 + charge_h.numel() * 4 + (mol_h.numel() * 4 if mol_h is not None else 0) + (36 if pbc else 0)
-    d2h = sum(int(v.nbytes) for v in out_h.values())
+    # ---- e2e: host buffers through the C ABI (H2D + compute + D2H inside every step); every rank its own batch ----
+    barrier()
+    e2e_ms = maxr(r.time_wall(r.step_host, 2, K))
+    e2e_value = world * N * K / (e2e_ms * 1e-3)
+    # ---- api: the front door (AIMNet2Calculator.__call__, numpy in, .cpu() out) ----
+    api_ms = maxr(r.time_wall(r.step_api, 2, K))
+    api_value = world * N * K / (api_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel class (instrumented pass, not part of the timed region) ----
-    eng.enable_timing(2)
-    gemm_ms, tot_ms, phases = [], [], []
-    step(0)
-    torch.cuda.synchronize(dev)
-    for i in range(5):
-        step(i)
-        torch.cuda.synchronize(dev)
-        tm = eng.last_timing()
-        gemm_ms.append(tm["gemm_ms"])
-        tot_ms.append(tm["total_ms"])
-        phases.append(tm)
-    eng.enable_timing(0)
-    gms = float(np.median(gemm_ms))
-    n_gemm = int(phases[-1]["gemm_launches"])
-    flops = 2.0 * 2.0 * MLP_MACS_PER_ATOM[spec.C] * N  # fwd + dgrad
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-    # three error-compensating MMAs per product; kind::f16 runs at the bf16 rate, kind::tf32 at half of it
-    peak_tf = bf16 / 3.0 if eng.gemm_backend in (2, 3) else bf16 / 2.0 / 3.0
-    achieved = flops / (gms * 1e-3) / 1e12
-    roofline = {"kernel": "gemm_nt (per-atom MLP stacks, %d launches/step)" % n_gemm, "bound": "tensor",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                # DRAM bytes of the largest GEMM launch (51 200 x 512 x 704, GELU + pre-split output) from the committed
-                # `ncu --set full` capture profiles/r1_prof_gemm_tc16_summary.csv: 159 MB read + 163 MB written, against
-                # 144 MB (A hi+lo) + 210 MB (y hi+lo, gelu') algorithmic -- no re-reads; null for the other workloads
-                "traffic": 321.8e6 if (args.workload == "cfg2" and eng.gemm_backend == 2) else None,
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained") +
-                               (" / 3 (3xFP16 split on the kind::f16 pipe)" if eng.gemm_backend in (2, 3) else
-                                " / 2 (tf32) / 3 (3xTF32 split)"),
-                "gemm_ms_per_step": gms, "gemm_share_of_step": gms / (ms_max / K),
-                "phase_ms": {k: float(np.median([p[k] for p in phases])) for k in
-                             ("neighbors_ms", "forward_ms", "pair_terms_ms", "backward_ms", "total_ms")}}
+    step_ms = ms_max / K if world == 1 else r.time_events(r.step_device, 1, 3) / 3
+    dominant, classes, step_roof = rooflines(r, step_ms, ms_max * 1e-3, load_traffic(r.eng.gemm_backend, args.workload))
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "atoms_per_gpu": N, "molecules_per_gpu": B,
-                       "weights": "seeded random, aimnet2 architecture (2.2M params)",
-                       "l2": "per-step working set (activations + saved tensors, >1 GB) exceeds the 126 MB L2; "
-                             "coordinates change every step",
-                       "gemm_backend": {2: "tcgen05-3xfp16-rowchunk-scaled", 3: "tcgen05-3xfp16-rowchunk-scaled-pipelined-epilogue (experimental)",
-                                        1: "tcgen05-3xtf32"}.get(eng.gemm_backend, "simt-fp32"),
-                       "multi_gpu": "independent batches per rank + all_gather of energy/forces (NCCL)" if world > 1 else "single"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, N, B),
+            "impl_detail": {"gemm_backend": {2: "tcgen05-3xfp16-rowchunk-scaled", 3: "tcgen05-3xfp16-rowchunk-scaled-pipelined-epilogue",
+                                             1: "tcgen05-3xtf32"}.get(r.eng.gemm_backend, "simt-fp32"),
+                            "value_path": "aimnet2_engine_eval (C ABI, device pointers)" if world == 1 else "ShardedCalculator",
+                            "multi_gpu": multi or "single"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(),
+                    "path": "aimnet2_engine_eval_host (C ABI, pinned host buffers)"},
+            "api": {"value": api_value, "unit": UNIT, "ratio_to_e2e": api_value / e2e_value,
+                    "path": "AIMNet2Calculator.__call__(numpy inputs) + .cpu() of every output"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roofline,
+            "roofline": dominant, "roofline_classes": classes, "step_roofline": step_roof,
         }
-        if world == 1 and not args.no_cpu_baseline and args.workload in ("cfg2", "cfg3"):
-            v, sample, cores, dtc, n = cpu_baseline(args.workload, args.seed, budget_s=15.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                    "s_per_step": dtc, "steps": n}
+        if world == 1 and not args.no_extra and args.workload == "cfg2":
+            extra = {}
+            del r
+            for name, k in (("cfg1", 50), ("cfg3", 10), ("cfg4", 10), ("cfg5", 5)):
+                torch.cuda.empty_cache()
+                s = ClockSampler(local).start()
+                rx = Runner(name, args.seed, dev, 3 + k)
+                ms_x = rx.time_events(rx.step_device, 3, k)
+                ms_h = rx.time_wall(rx.step_host, 2, k)
+                extra[name] = {"workload": rx.w["desc"], "atoms": rx.N, "steps": k, "warmup": 3, "ms_per_step": ms_x / k,
+                               "value": rx.N * k / (ms_x * 1e-3), "e2e": rx.N * k / (ms_h * 1e-3), "unit": UNIT,
+                               "gpu_launches_per_step": rx.eng.last_launches(), "clocks": s.stop()}
+                del rx
+            line["extra_workloads"] = extra
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = time_cpu(args.workload, args.seed, warmup=1, steps=None, budget_s=15.0)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -196,7 +196,8 @@ int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int* lr_width,
 int aimnet2_engine_skin_stats(const aimnet2_engine_t* e, int* builds, int* reuses);
 /* per-phase device times (ms) of the last eval when timing was enabled (level 1: phase events, level 2: also one
  * event pair around every GEMM launch); slots: 0 neighbors, 1 forward,
- * 2 long-range, 3 backward, 4 total; returns number of phases written */
+ * 2 long-range, 3 backward, 4 total, then (level 2) 5 summed GEMM ms, 6 GEMM launches, 7 summed AEV / conv_sv ms,
+ * 8 conv calls; returns the number of slots written */
 int aimnet2_engine_enable_timing(aimnet2_engine_t* e, int on);
 int aimnet2_engine_last_timing(const aimnet2_engine_t* e, float* ms, int n);
 

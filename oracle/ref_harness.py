@@ -1,5 +1,6 @@
 """Run the UNMODIFIED reference (/root/reference) on CPU.  TEST INFRASTRUCTURE ONLY; works only in the build container
-(the reference tree does not travel to the GPU box — nothing in `-m gpu` tests, smoke() or bench.py imports this).
+(nothing in `-m gpu` tests or smoke() imports this; `bench.py --impl reference` / `cpu_baseline` use it on the GPU box
+through the copy that oracle/make_ref.py vendors into the git-ignored oracle/_ref/).
 
 Recipe: put import stubs for the two absent third-party packages (`warp`,
 `nvalchemiops`) ahead of the reference on sys.path, build the production graph from the reference's own YAML
@@ -16,9 +17,22 @@ import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get("AIMNET_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
+
+
+def _find_reference_root() -> str:
+    """The reference tree itself (build container), else the byte-for-byte copy vendored by oracle/make_ref.py into
+    the git-ignored oracle/_ref/ (what travels to the GPU box)."""
+    env = os.environ.get("AIMNET_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/aimnet"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REF_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
