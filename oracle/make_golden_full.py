@@ -5,6 +5,7 @@ Inputs are regenerated from seeds by aimnetcentral_b200.structures.benchmark_wor
 reference outputs, the input checksum and the weight recipe:
   full_cfg2.npz  1024 x 50 atoms, aimnet2, Coulomb simple + DFT-D3, charges {0,+1,-1}; reference run in 16 chunks of 64
                  molecules (molecules are independent; the mode-1 all-pairs list needs an N_total^2 scratch otherwise)
+                 (+ the float64 twin of the same modules, `*64` arrays: the arbiter where |F| is large)
   full_cfg4.npz  512 x 80 atoms, aimnet2-nse (2 charge channels), charge / mult per molecule; 16 chunks of 32
   full_cfg3.npz  10 080-atom allose supercell, PBC, NN + DSF Coulomb (no D3: the reference's torch D3 path materialises
                  (N, M, 5, 5) temporaries, ~2 GB each at this size), E + F + stress in ONE reference call
@@ -30,7 +31,7 @@ def checksum(*arrays) -> float:
     return float(sum(np.abs(np.asarray(a, np.float64)).sum() for a in arrays))
 
 
-def chunked(calc, w, n_chunks, extra=()):
+def chunked(calc, w, n_chunks, extra=(), calc64=None):
     B = len(w["charge"])
     per = B // n_chunks
     outs = []
@@ -41,7 +42,12 @@ def chunked(calc, w, n_chunks, extra=()):
         inp = dict(coord=w["coord"][a0:a1], numbers=w["numbers"][a0:a1], charge=w["charge"][lo:hi], mol_idx=(mi[a0:a1] - lo).astype(np.int64))
         for k in extra:
             inp[k] = w[k][lo:hi]
-        outs.append(rh.run_reference(calc, inp, forces=True))
+        o = rh.run_reference(calc, inp, forces=True)
+        if calc64 is not None:   # the float64 twin of the same reference modules: the arbiter of SURVEY.md Appendix C.2
+            # per-atom arrays of the twin are stored rounded once to fp32 (6e-8 relative: far below what they arbitrate)
+            o.update({k + "64": (v if k == "energy" else v.astype(np.float32))
+                      for k, v in rh.run_reference(calc64, inp, forces=True).items()})
+        outs.append(o)
         print(f"  chunk {c + 1}/{n_chunks}", flush=True)
     return {k: np.concatenate([o[k] for o in outs]) for k in outs[0]}
 
@@ -65,7 +71,7 @@ def main(which):
         w["charge"][3::11] = -1.0
         calc = rh.build_reference_calculator(sd, spec)
         t = time.time()
-        out = chunked(calc, w, 16)
+        out = chunked(calc, w, 16, calc64=rh.build_reference_calculator(sd, spec, double=True))
         save("full_cfg2", 0, spec, sd, w, out, charge=w["charge"])
         print("cfg2", time.time() - t, "s")
     if "cfg4" in which:
@@ -74,7 +80,7 @@ def main(which):
         w = benchmark_workload("cfg4", 1234)
         calc = rh.build_reference_calculator(sd2, spec2)
         t = time.time()
-        out = chunked(calc, w, 16, extra=("mult",))
+        out = chunked(calc, w, 16, extra=("mult",), calc64=rh.build_reference_calculator(sd2, spec2, double=True))
         save("full_cfg4", 1, spec2, sd2, w, out)
         print("cfg4", time.time() - t, "s")
     if "d3" in which:
