@@ -631,11 +631,8 @@ int launch_conv_fwd(int C, int n_atoms, const NbView& nb, const float* coord, co
 }
 
 template <int C>
-static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
-                           const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
-                           const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
-                           const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
-                           double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
+static int conv_bwd_prep_launch(int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
+                                const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st) {
     const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
     static int prep_ctas_dev[kMaxDevices] = {};
     int& prep_ctas = prep_ctas_dev[current_device_slot()];
@@ -649,6 +646,25 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
     conv_bwd_prep_kernel<C><<<n_groups < prep_ctas ? n_groups : prep_ctas, 256, 0, st>>>(n_atoms, n_groups, dx, ldx, T_a, T_q,
                                                                                           agh_a, agh_q, dS_a, dS_q, with_q);
     AIM_LAUNCH_CHECK();
+    return AIMNET_OK;
+}
+
+// backward step 1 alone (the gather step is launch_conv_bwd's second half or conv2.cu's launch_conv2_bwd_gather)
+int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
+                         const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st) {
+    if (n_atoms == 0) return AIMNET_OK;
+    if (C == 1) return conv_bwd_prep_launch<1>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, st);
+    return conv_bwd_prep_launch<2>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, st);
+}
+
+template <int C>
+static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, const CellView& cv,
+                           const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
+                           const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
+                           const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
+                           double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
+    const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    AIM_TRY(conv_bwd_prep_launch<C>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, st));
     int grid = n_groups;
 #define AIM_CONV_BWD(GA, VIR)                                                                                       \
     conv_bwd_kernel<C, GA, VIR><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a, \

@@ -60,6 +60,9 @@ struct aimnet2_engine {
     aimnet2_options_t opt{};
     int gemm_backend = 0;
     int poison = -1;              // test seam: byte written over the workspace before every evaluation (-1 = off)
+    int conv_impl = 2;            // 0 = first-generation kernels (conv.cu), 1 = conv2.cu list walk, 2 = conv2.cu, dense walk for batches of small molecules
+    bool dense_now = false;       // the evaluation in flight walks molecule segments instead of matrix rows
+    int last_max_seg = 0;         // largest molecule (atoms) of the last batch whose lists the engine built
     int small_m_rows = kSmallM;   // at or below this many atoms the MLPs run on the small-M fp32 SIMT kernel (0 = never)
     int backend_now = 0;    // backend of the evaluation in flight (gemm_backend or 0 for small systems)
     // workspace (grow-only)
@@ -89,7 +92,7 @@ struct aimnet2_engine {
     struct {
         bool valid = false;
         int N = 0, B = 0, n_cells = 0, sr_cap = 0, lr_cap = 0;
-        bool need_lr = false;
+        bool need_lr = false, dense = false;
         float sr_cut = 0.f, lr_cut = 0.f, skin = 0.f;
         const char* ws = nullptr;
         bool has_mol = false;
@@ -471,6 +474,9 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             AIM_CUDA_CHECK(cudaMemsetAsync(e->ws, e->poison, e->ws_bytes, st));
             e->skin.valid = false;
         }
+        // molecule segment pointers; the largest segment lands in nb_scratch[1] and comes back with the list builder's
+        // overflow read-back (no extra synchronisation)
+        AIM_TRY(launch_mol_ptr(sys->mol_idx, N, B, b.mol_ptr, b.nb_scratch + 1, st));
         if (skin > 0.f && attempt == 0 && skin_matches()) {
             // lists built at cutoff + skin are still complete if no atom has moved by more than skin / 2 since the build
             AIM_TRY(launch_skin_check(N, sys->coord, b.coord_ref, 0.25f * skin * skin, sys->mol_idx, b.mol_ref, b.skin_flag, st));
@@ -480,6 +486,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 // same lattice offsets as at build time: the stored shifts refer to those images
                 if (pbc) AIM_TRY(launch_skin_apply(N, sys->coord, b.wrap_off, b.coord_w, st));
                 e->skin.reuses++;
+                e->dense_now = e->skin.dense;
                 break;
             }
         }
@@ -500,6 +507,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             } else if (rc != AIMNET_OK)
                 return rc;
             e->last_sr_width = std::max(1, maxc);
+            e->last_max_seg = e->pinned_int[1];
         }
         if (!retry && need_lr_list) {
             int maxc = 0;
@@ -513,11 +521,17 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             e->last_lr_width = std::max(1, maxc);
         }
         if (!retry) {
+            // Dense conv walk (conv2.cu): both centres of a warp iterate over the atoms of their molecule in lock step.  Worth it
+            // when most atoms of a molecule are inside the cutoff anyway: small molecules, or at least half of the molecule in
+            // the widest row.  Needs the engine's own (complete) list semantics: not with a caller-supplied matrix or a cell.
+            e->dense_now = e->conv_impl == 2 && own_sr && !pbc && e->last_max_seg >= 2 && e->last_max_seg <= 128 &&
+                           (e->last_max_seg <= 64 || 2 * e->last_sr_width >= e->last_max_seg);
             if (skin > 0.f) {
                 AIM_TRY(launch_skin_save(N, sys->coord, pbc ? b.coord_w : nullptr, b.coord_ref, b.wrap_off, sys->mol_idx, b.mol_ref, st));
                 auto& k = e->skin;
                 k.N = N, k.B = B, k.n_cells = sys->n_cells, k.sr_cap = e->sr_cap, k.lr_cap = e->lr_cap;
                 k.need_lr = need_lr_list, k.sr_cut = o.sr_cutoff, k.lr_cut = lr_cut, k.skin = skin;
+                k.dense = e->dense_now;
                 k.ws = e->ws, k.has_mol = sys->mol_idx != nullptr;
                 k.cell.assign(sys->host_cell ? sys->host_cell : nullptr, sys->host_cell ? sys->host_cell + 9 * sys->n_cells : nullptr);
                 k.pbc.assign((size_t)3 * sys->n_cells, (uint8_t)1);
@@ -534,7 +548,8 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     // calculator.py:1071, 1521-1529), so the short-range kernels then read sys->coord.
     const float* coord_lr = pbc ? b.coord_w : sys->coord;
     const float* coord = (pbc && own_sr) ? b.coord_w : sys->coord;
-    AIM_TRY(launch_mol_ptr(sys->mol_idx, N, B, b.mol_ptr, st));
+    if (!own_sr || N == 0) e->dense_now = false;
+    const int dense = e->dense_now ? 1 : 0;
 
     NbView sr;
     if (own_sr) {
@@ -554,8 +569,12 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         const int nl = (int)L.size();
         const float* qin = (p == 0) ? nullptr : b.q[p - 1];
         class_mark(e, 1, st);
-        AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
-                                b.T_a[p], b.T_q[p], p > 0, st));
+        if (e->conv_impl == 0)
+            AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
+                                    b.T_a[p], b.T_q[p], p > 0, st));
+        else
+            AIM_TRY(launch_conv2_fwd(C, dense, N, sr, b.mol_ptr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a,
+                                     e->agh_q, b.x, ldx, b.T_a[p], b.T_q[p], p > 0, st));
         class_mark(e, 1, st);
         if (tc16) {
             AIM_TRY(presplit(e, b.x, ldx, N, L[0].in_pad, b.x16, st));
@@ -692,8 +711,14 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             }
             const float* qin = (p == 0) ? nullptr : b.q[p - 1];
             class_mark(e, 1, st);
-            AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
-                                    e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
+            if (e->conv_impl == 0) {
+                AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
+                                        e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
+            } else {
+                AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[p], b.T_q[p], e->agh_a, e->agh_q, b.dS_a, b.dS_q, p > 0, st));
+                AIM_TRY(launch_conv2_bwd_gather(C, dense, N, sr, b.mol_ptr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dS_a,
+                                                b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
+            }
             class_mark(e, 1, st);
             if (p == 0) break;
             // dE/da_p and dE/dq_{p-1}
@@ -850,6 +875,14 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
     return AIMNET_OK;
 }
 
+extern "C" int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl) {
+    AIM_REQUIRE(e, "set_conv_impl: null engine");
+    AIM_REQUIRE(impl >= 0 && impl <= 2, "set_conv_impl: 0 = first-generation kernels, 1 = conv2 list walk, 2 = conv2 with the dense molecule walk (default)");
+    e->conv_impl = impl;
+    e->skin.valid = false;
+    return AIMNET_OK;
+}
+
 extern "C" int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows) {
     AIM_REQUIRE(e, "set_small_m_rows: null engine");
     AIM_REQUIRE(rows >= 0 && rows <= kSmallM, "set_small_m_rows: rows must be in [0, 512]");
@@ -973,6 +1006,14 @@ extern "C" int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int
     if (sr_width) *sr_width = e->last_sr_width;
     if (lr_width) *lr_width = e->last_lr_width;
     if (workspace_bytes) *workspace_bytes = (int64_t)e->ws_bytes;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_conv_mode(const aimnet2_engine_t* e, int* impl, int* dense_last, int* max_molecule_last) {
+    AIM_REQUIRE(e, "conv_mode: null engine");
+    if (impl) *impl = e->conv_impl;
+    if (dense_last) *dense_last = e->dense_now ? 1 : 0;
+    if (max_molecule_last) *max_molecule_last = e->last_max_seg;
     return AIMNET_OK;
 }
 

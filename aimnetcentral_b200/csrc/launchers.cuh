@@ -24,6 +24,20 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
                     float* dS_q, float* grad_a, float* grad_q, float* forces, double* virial_atom, int with_q,
                     int want_grad_a, cudaStream_t st);
 
+int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
+                         const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st);
+
+// ---- conv2.cu: second-generation conv kernels (two centres per warp, all 16 channels per lane; dense = both centres walk
+// their molecule's atom segment in lock step instead of their matrix rows)
+int launch_conv2_fwd(int C, int dense, int n_atoms, const NbView& nb, const int32_t* mol_ptr, const float* coord,
+                     const CellView& cv, const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
+                     const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q,
+                     cudaStream_t st);
+int launch_conv2_bwd_gather(int C, int dense, int n_atoms, const NbView& nb, const int32_t* mol_ptr, const float* coord,
+                            const CellView& cv, const int32_t* mol_idx, const AevParams& aev, const float* aT,
+                            const float* q, const float* dS_a, const float* dS_q, float* grad_a, float* grad_q,
+                            float* forces, double* virial_atom, int with_q, int want_grad_a, cudaStream_t st);
+
 // ---- gemm.cu: per-atom MLP GEMMs: backend dispatch
 int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, float* Y, int ldy, float* aux, int ldaux,
             int M, int N, int K, int mode, int backend, cudaStream_t st);
@@ -54,7 +68,7 @@ int gemm_nt_tc16p(const SplitMat& A, const void* Whi, const void* Wlo, const flo
 
 // ---- pointwise.cu: embedding, NSE charge equilibration, reductions, Verlet-skin bookkeeping
 int launch_embed(int n, const int32_t* numbers, const float* afv, float* a0, cudaStream_t st);
-int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, cudaStream_t st);
+int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, int32_t* max_segment, cudaStream_t st);
 int launch_nse_fwd(int C, int n, int n_mol, const int32_t* mol_idx, const int32_t* mol_ptr, const float* charge,
                    const float* mult, const float* y, int ldy, const float* q_prev, float* sumq, float* sumf,
                    const float* a_old, float* a_new, float* q_new, cudaStream_t st);

@@ -533,7 +533,8 @@ int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, cons
     if (max_count_host != nullptr) {
         int32_t h = 0;
         int32_t* dst = pinned_host ? pinned_host : &h;
-        AIM_CUDA_CHECK(cudaMemcpyAsync(dst, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        // with the caller's scratch and pinned buffer, slot 1 (the engine's largest-molecule count) rides along
+        AIM_CUDA_CHECK(cudaMemcpyAsync(dst, d_max, sizeof(int32_t) * ((scratch && pinned_host) ? 2 : 1), cudaMemcpyDeviceToHost, st));
         AIM_CUDA_CHECK(cudaStreamSynchronize(st));
         h = *dst;
         *max_count_host = h;

@@ -37,6 +37,15 @@ __global__ void mol_ptr_kernel(const int32_t* __restrict__ mol_idx, int n, int n
     for (int s = prev + 1; s <= cur && s <= n_mol; ++s) ptr[s] = i;
 }
 
+// largest molecule (atoms) of the batch, for the engine's choice of the dense conv walk
+__global__ void max_segment_kernel(const int32_t* __restrict__ ptr, int n_mol, int32_t* __restrict__ out) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = (m < n_mol) ? ptr[m + 1] - ptr[m] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* smem) {
     v = warp_sum(v);
@@ -328,8 +337,12 @@ int launch_embed(int n, const int32_t* numbers, const float* afv, float* a0, cud
     if (n) AIM_K(embed_kernel<<<(n + 3) / 4, 256, 0, st>>>(n, numbers, afv, a0));
     return AIMNET_OK;
 }
-int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, cudaStream_t st) {
+int launch_mol_ptr(const int32_t* mol_idx, int n, int n_mol, int32_t* ptr, int32_t* max_segment, cudaStream_t st) {
     AIM_K(mol_ptr_kernel<<<(n + 256) / 256, 256, 0, st>>>(mol_idx, n, n_mol, ptr));
+    if (max_segment != nullptr) {
+        AIM_CUDA_CHECK(cudaMemsetAsync(max_segment, 0, sizeof(int32_t), st));
+        AIM_K(max_segment_kernel<<<(n_mol + 255) / 256, 256, 0, st>>>(ptr, n_mol, max_segment));
+    }
     return AIMNET_OK;
 }
 int launch_nse_fwd(int C, int n, int n_mol, const int32_t* mol_idx, const int32_t* mol_ptr, const float* charge,

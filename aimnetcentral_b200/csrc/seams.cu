@@ -109,7 +109,7 @@ extern "C" int aimnet2_dsf_coulomb(const float* positions, const float* charges,
     SeamScratch s;
     const bool own_forces = virial != nullptr && forces == nullptr;   // the pair kernel writes virials next to forces
     AIM_TRY(seam_alloc(s, n_atoms, n_systems, false, virial != nullptr, own_forces, st));
-    AIM_TRY(launch_mol_ptr(batch_idx, n_atoms, n_systems, s.mol_ptr, st));
+    AIM_TRY(launch_mol_ptr(batch_idx, n_atoms, n_systems, s.mol_ptr, nullptr, st));
     float* F = forces ? forces : s.forces;
     float* gq = charge_grad ? charge_grad : s.f0;
     if (n_atoms > 0) {
@@ -148,7 +148,7 @@ extern "C" int aimnet2_dftd3(const float* positions, const int32_t* numbers, int
     SeamScratch s;
     const bool own_forces = virial != nullptr && forces == nullptr;
     AIM_TRY(seam_alloc(s, n_atoms, n_systems, true, virial != nullptr, own_forces, st));
-    AIM_TRY(launch_mol_ptr(batch_idx, n_atoms, n_systems, s.mol_ptr, st));
+    AIM_TRY(launch_mol_ptr(batch_idx, n_atoms, n_systems, s.mol_ptr, nullptr, st));
     float* F = forces ? forces : s.forces;
     float* cn = coord_num ? coord_num : s.f0;
     if (n_atoms > 0) {

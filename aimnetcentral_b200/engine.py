@@ -126,6 +126,15 @@ class Engine:
         """Evaluations with at most `rows` atoms use the small-M fp32 SIMT GEMM (default 512, 0 = never)."""
         _capi.check(self._lib.aimnet2_engine_set_small_m_rows(self._h, int(rows)), "set_small_m_rows")
 
+    def set_conv_impl(self, impl: int):
+        """0 = first-generation conv kernels, 1 = conv2 list walk, 2 = conv2 with the dense molecule walk (default)."""
+        _capi.check(self._lib.aimnet2_engine_set_conv_impl(self._h, int(impl)), "set_conv_impl")
+
+    def conv_mode(self) -> dict:
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._lib.aimnet2_engine_conv_mode(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"impl": a.value, "dense_last": bool(b.value), "max_molecule_last": c.value}
+
     def debug_poison(self, byte: int):
         """Test seam: fill the device workspace with `byte` before every evaluation (-1 = off)."""
         _capi.check(self._lib.aimnet2_engine_debug_poison(self._h, int(byte)), "debug_poison")
