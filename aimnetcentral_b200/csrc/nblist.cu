@@ -348,17 +348,27 @@ __global__ void wrap_kernel(const float* __restrict__ pos, float* __restrict__ o
     inv[7] = (a[1] * a[6] - a[0] * a[7]) * id;
     inv[8] = (a[0] * a[4] - a[1] * a[3]) * id;
     float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
-    float f[3];
+    // The reference computes ((x @ inv(cell)) mod 1) @ cell (aimnet/calculators/neighbors.py:331-381).  The same image is
+    // x - floor(x @ inv(cell)) @ cell; written this way an atom that already lies inside the cell keeps its coordinates bit for
+    // bit, where the fractional round trip moves it by up to an ulp of the cell length (4e-6 A at 60 A, which stiff
+    // potentials turn into 1e-4 eV/A of force noise), and a moved atom is rounded once instead of twice.
+    float nsh[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float v = x * inv[k] + y * inv[3 + k] + z * inv[6 + k];
         bool per = pbc == nullptr ? true : (pbc[3 * s + k] != 0);
-        if (per) v = v - floorf(v);   // python-style modulo 1
-        if (per && v >= 1.0f) v = 0.0f;
-        f[k] = v;
+        // fractional coordinates within a few ulps of the faces count as inside (a wrapped atom re-evaluates to -1e-8 or
+        // 1 + 1e-7 as often as not): wrapping is idempotent bit for bit
+        nsh[k] = (per && (v < -1.0e-6f || v >= 1.0f + 1.0e-6f)) ? floorf(v) : 0.0f;
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[3 * i + k] = f[0] * a[k] + f[1] * a[3 + k] + f[2] * a[6 + k];
+    for (int k = 0; k < 3; ++k) {
+        float p = pos[3 * i + k];
+        p = fmaf(-nsh[0], a[k], p);
+        p = fmaf(-nsh[1], a[3 + k], p);
+        p = fmaf(-nsh[2], a[6 + k], p);
+        out[3 * i + k] = p;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -416,6 +416,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--gemm-backend", type=int, default=None)
+    ap.add_argument("--conv-impl", type=int, default=None, help="0 conv.cu, 1 conv2 list walk, 2 conv2 + dense molecule walk (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -437,6 +438,8 @@ def main():
     W, K = max(3, args.warmup), max(1, args.steps)
     n_sets = W + K
     r = Runner(args.workload, args.seed + rank, dev, n_sets, args.gemm_backend, jitter_seed=rank)
+    if args.conv_impl is not None:
+        r.eng.set_conv_impl(args.conv_impl)
     N, B, w = r.N, r.B, r.w
     sampler = ClockSampler(local).start() if rank == 0 else None
 
@@ -525,6 +528,7 @@ def main():
             "config": workload_config(w, N, B),
             "impl_detail": {"gemm_backend": {2: "tcgen05-3xfp16-rowchunk-scaled", 3: "tcgen05-3xfp16-rowchunk-scaled-pipelined-epilogue",
                                              1: "tcgen05-3xtf32"}.get(r.eng.gemm_backend, "simt-fp32"),
+                            "conv": r.eng.conv_mode(),
                             "value_path": "aimnet2_engine_eval (C ABI, device pointers)" if world == 1 else "ShardedCalculator",
                             "multi_gpu": multi or "single"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(),

@@ -107,6 +107,9 @@ def test_wrap_positions_matches_reference_formula():
     frac = (w - ref) @ np.linalg.inv(cell)
     assert np.abs(frac - np.round(frac)).max() < 1e-4  # equal up to a lattice vector at the wrap boundary
     assert (np.abs(np.round(frac)) > 0).mean() < 0.02
+    # atoms already inside the cell are not touched: wrapping is idempotent bit for bit
+    w2 = wrap_positions(torch.as_tensor(w, device="cuda:0"), torch.as_tensor(cell, device="cuda:0")).cpu().numpy()
+    assert np.array_equal(w2, w)
 
 
 def test_conv_sv_op_against_reference_einsum():
