@@ -60,7 +60,7 @@ struct aimnet2_engine {
     aimnet2_options_t opt{};
     int gemm_backend = 0;
     int poison = -1;              // test seam: byte written over the workspace before every evaluation (-1 = off)
-    int conv_impl = 2;            // 0 = first-generation kernels (conv.cu), 1 = conv2.cu list walk, 2 = conv2.cu, dense walk for batches of small molecules
+    int conv_impl = 1;            // 0 = list kernels (conv.cu) always, 1 = shared-memory dense walk (conv_dense.cu) for batches of small molecules
     bool dense_now = false;       // the evaluation in flight walks molecule segments instead of matrix rows
     int last_max_seg = 0;         // largest molecule (atoms) of the last batch whose lists the engine built
     int small_m_rows = kSmallM;   // at or below this many atoms the MLPs run on the small-M fp32 SIMT kernel (0 = never)
@@ -224,6 +224,7 @@ struct Buffers {
     // h1 / dzA,dzB (fp16 hi + fp16 lo = the bytes of the fp32 matrix they replace); only x16, dz32 and the scales are extra.
     SplitMat x16, h16[2], aim16, h1_16, d16[2];
     float* dz32;
+    float *dense_fpart, *dense_gqpart;   // dense conv walk: per-quarter partial forces (4, N, 3) / charge gradients (4, N, C)
     float *coord_ref, *wrap_off;   // Verlet skin: positions at list-build time, lattice offset applied by the wrap
     int32_t *skin_flag, *mol_ref;
 };
@@ -298,6 +299,8 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.dq_base = bp.take<float>(n * C, "dq_base");
     b.virial_atom = bp.take<double>(n * 9, "virial_atom");
     b.forces_tmp = bp.take<float>(n * 3, "forces_tmp");
+    b.dense_fpart = bp.take<float>(n * 12, "dense_fpart");
+    b.dense_gqpart = bp.take<float>(n * 4 * C, "dense_gqpart");
     b.x16 = SplitMat{bp.take<__half>(n * ldx, "x16_hi"), bp.take<__half>(n * ldx, "x16_lo"), bp.take<float>(n * (ldx / 32), "x16_inv"), ldx, ldx / 32};
     b.h16[0] = alias_split(b.hA, n, 512, bp.take<float>(n * 16, "hA_inv"));
     b.h16[1] = alias_split(b.hB, n, 512, bp.take<float>(n * 16, "hB_inv"));
@@ -521,10 +524,11 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             e->last_lr_width = std::max(1, maxc);
         }
         if (!retry) {
-            // Dense conv walk (conv2.cu): both centres of a warp iterate over the atoms of their molecule in lock step.  Worth it
-            // when most atoms of a molecule are inside the cutoff anyway: small molecules, or at least half of the molecule in
-            // the widest row.  Needs the engine's own (complete) list semantics: not with a caller-supplied matrix or a cell.
-            e->dense_now = e->conv_impl == 2 && own_sr && !pbc && e->last_max_seg >= 2 && e->last_max_seg <= 128 &&
+            // Dense conv walk (conv_dense.cu): the molecule's feature tables staged in shared memory, every centre walks all
+            // atoms of its molecule.  Worth it when most atoms of a molecule are inside the cutoff anyway: small molecules, or
+            // at least half of the molecule in the widest row.  Not with a caller-supplied matrix or a cell.
+            e->dense_now = e->conv_impl == 1 && own_sr && !pbc && e->last_max_seg >= 2 &&
+                           e->last_max_seg <= conv_dense_max_atoms(C) &&
                            (e->last_max_seg <= 64 || 2 * e->last_sr_width >= e->last_max_seg);
             if (skin > 0.f) {
                 AIM_TRY(launch_skin_save(N, sys->coord, pbc ? b.coord_w : nullptr, b.coord_ref, b.wrap_off, sys->mol_idx, b.mol_ref, st));
@@ -549,7 +553,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     const float* coord_lr = pbc ? b.coord_w : sys->coord;
     const float* coord = (pbc && own_sr) ? b.coord_w : sys->coord;
     if (!own_sr || N == 0) e->dense_now = false;
-    const int dense = e->dense_now ? 1 : 0;
+    const bool dense = e->dense_now;
 
     NbView sr;
     if (own_sr) {
@@ -569,12 +573,12 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         const int nl = (int)L.size();
         const float* qin = (p == 0) ? nullptr : b.q[p - 1];
         class_mark(e, 1, st);
-        if (e->conv_impl == 0)
+        if (dense)
+            AIM_TRY(launch_conv_dense_fwd(C, N, B, e->last_max_seg, b.mol_ptr, coord, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x,
+                                          ldx, b.T_a[p], b.T_q[p], p > 0, st));
+        else
             AIM_TRY(launch_conv_fwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a, e->agh_q, b.x, ldx,
                                     b.T_a[p], b.T_q[p], p > 0, st));
-        else
-            AIM_TRY(launch_conv2_fwd(C, dense, N, sr, b.mol_ptr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, e->agh_a,
-                                     e->agh_q, b.x, ldx, b.T_a[p], b.T_q[p], p > 0, st));
         class_mark(e, 1, st);
         if (tc16) {
             AIM_TRY(presplit(e, b.x, ldx, N, L[0].in_pad, b.x16, st));
@@ -711,13 +715,13 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             }
             const float* qin = (p == 0) ? nullptr : b.q[p - 1];
             class_mark(e, 1, st);
-            if (e->conv_impl == 0) {
+            if (dense) {
+                AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[p], b.T_q[p], e->agh_a, e->agh_q, b.dS_a, b.dS_q, p > 0, st));
+                AIM_TRY(launch_conv_dense_bwd_gather(C, N, B, e->last_max_seg, b.mol_ptr, coord, e->aev, b.a[p], qin, b.dS_a, b.dS_q,
+                                                     b.grad_a, b.grad_q, F, b.dense_fpart, b.dense_gqpart, p > 0, p > 0, st));
+            } else {
                 AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
                                         e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
-            } else {
-                AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[p], b.T_q[p], e->agh_a, e->agh_q, b.dS_a, b.dS_q, p > 0, st));
-                AIM_TRY(launch_conv2_bwd_gather(C, dense, N, sr, b.mol_ptr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dS_a,
-                                                b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
             }
             class_mark(e, 1, st);
             if (p == 0) break;
@@ -877,7 +881,7 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
 
 extern "C" int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl) {
     AIM_REQUIRE(e, "set_conv_impl: null engine");
-    AIM_REQUIRE(impl >= 0 && impl <= 2, "set_conv_impl: 0 = first-generation kernels, 1 = conv2 list walk, 2 = conv2 with the dense molecule walk (default)");
+    AIM_REQUIRE(impl >= 0 && impl <= 1, "set_conv_impl: 0 = list kernels always, 1 = shared-memory dense walk for batches of small molecules (default)");
     e->conv_impl = impl;
     e->skin.valid = false;
     return AIMNET_OK;

@@ -27,16 +27,16 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
 int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                          const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st);
 
-// ---- conv2.cu: second-generation conv kernels (two centres per warp, all 16 channels per lane; dense = both centres walk
-// their molecule's atom segment in lock step instead of their matrix rows)
-int launch_conv2_fwd(int C, int dense, int n_atoms, const NbView& nb, const int32_t* mol_ptr, const float* coord,
-                     const CellView& cv, const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
-                     const float* agh_a, const float* agh_q, float* x, int ldx, float* T_a, float* T_q, int with_q,
-                     cudaStream_t st);
-int launch_conv2_bwd_gather(int C, int dense, int n_atoms, const NbView& nb, const int32_t* mol_ptr, const float* coord,
-                            const CellView& cv, const int32_t* mol_idx, const AevParams& aev, const float* aT,
-                            const float* q, const float* dS_a, const float* dS_q, float* grad_a, float* grad_q,
-                            float* forces, double* virial_atom, int with_q, int want_grad_a, cudaStream_t st);
+// ---- conv_dense.cu: the same convolutions for batches of small molecules: feature tables of one molecule staged into
+// shared memory with TMA, every pair of the molecule walked from there
+int conv_dense_max_atoms(int C);
+int launch_conv_dense_fwd(int C, int n_atoms, int n_mol, int max_seg, const int32_t* mol_ptr, const float* coord,
+                          const AevParams& aev, const float* aT, const float* q, const float* agh_a, const float* agh_q,
+                          float* x, int ldx, float* T_a, float* T_q, int with_q, cudaStream_t st);
+int launch_conv_dense_bwd_gather(int C, int n_atoms, int n_mol, int max_seg, const int32_t* mol_ptr, const float* coord,
+                                 const AevParams& aev, const float* aT, const float* q, const float* dS_a, const float* dS_q,
+                                 float* grad_a, float* grad_q, float* forces, float* f_part, float* gq_part, int with_q,
+                                 int want_grad_a, cudaStream_t st);
 
 // ---- gemm.cu: per-atom MLP GEMMs: backend dispatch
 int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, float* Y, int ldy, float* aux, int ldaux,

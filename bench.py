@@ -343,7 +343,7 @@ def rooflines(r: Runner, step_ms: float, timed_region_s: float, traffic: dict):
     r.step_device(0)
     torch.cuda.synchronize(r.dev)
     for i in range(5):
-        r.step_device(i)
+        r.step_device(i % len(r.coords_d))
         torch.cuda.synchronize(r.dev)
         rows.append(eng.last_timing())
     eng.enable_timing(0)
@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--gemm-backend", type=int, default=None)
-    ap.add_argument("--conv-impl", type=int, default=None, help="0 conv.cu, 1 conv2 list walk, 2 conv2 + dense molecule walk (default)")
+    ap.add_argument("--conv-impl", type=int, default=None, help="0 list kernels always, 1 dense shared-memory walk for small molecules (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -517,7 +517,7 @@ def main():
     api_value = world * N * K / (api_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
-    step_ms = ms_max / K if world == 1 else r.time_events(r.step_device, 1, 3) / 3
+    step_ms = ms_max / K if world == 1 else r.time_events(lambda i: r.step_device(i % n_sets), 1, 3) / 3
     dominant, classes, step_roof = rooflines(r, step_ms, ms_max * 1e-3, load_traffic(r.eng.gemm_backend, args.workload))
 
     if rank == 0:

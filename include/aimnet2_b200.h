@@ -168,11 +168,13 @@ int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt
  * (default when available), 3 = backend 2's arithmetic with the experimental pipelined tile epilogue (gemm_tc16p.cu; not
  * validated on a GPU yet) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
-/* AEV / conv_sv kernels: 0 = first-generation kernels (csrc/conv.cu: one centre per warp, matrix rows), 1 = csrc/conv2.cu
- * walking matrix rows (two centres per warp, all 16 channels per lane), 2 (default) = conv2.cu, and for batches of small
- * non-periodic molecules both centres of a warp walk their molecule's atom segment in lock step (pairs beyond the cutoff
- * contribute exactly zero, so results do not depend on the choice beyond fp32 summation order in the backward pass).
- * aimnet2_engine_conv_mode reports the setting, whether the last evaluation took the dense walk, and the largest molecule. */
+/* AEV / conv_sv kernels: 0 = the list kernels (csrc/conv.cu: one centre per warp walks its matrix row, neighbour rows gathered
+ * through L1 / L2) for every input; 1 (default) = for batches of small non-periodic molecules (at most ~100 atoms each) the
+ * dense walk of csrc/conv_dense.cu: the molecule's feature tables staged into shared memory with TMA, every centre walks all
+ * atoms of its molecule (pairs beyond the cutoff contribute exactly zero, so the results do not depend on the choice beyond
+ * fp32 summation order in the backward pass); periodic systems, large molecules and caller-supplied matrices keep the list
+ * kernels.  aimnet2_engine_conv_mode reports the setting, whether the last evaluation took the dense walk, and the largest
+ * molecule of that batch. */
 int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl);
 int aimnet2_engine_conv_mode(const aimnet2_engine_t* e, int* impl, int* dense_last, int* max_molecule_last);
 /* Evaluations with at most `rows` atoms run the MLPs on the small-M fp32 SIMT kernel whatever the backend (the

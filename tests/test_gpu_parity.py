@@ -84,16 +84,17 @@ def test_calculator_matches_reference_golden(name, kw, mlp):
 
 @pytest.mark.parametrize("name,kw", [("mols_8x50", {}), ("mols_ragged", {}), ("taxol_q1", {}), ("pbc_box60_dsf", {"stress": True}),
                                      ("nse_4x20", {})], ids=lambda v: v if isinstance(v, str) else "")
-def test_conv_generations_agree(name, kw):
-    """conv.cu (one centre per warp) vs conv2.cu walking matrix rows vs conv2.cu walking molecule segments (dense): the
-    forward sums run over the same neighbours in the same order (pairs beyond the cutoff add exactly zero), so energies and
-    charges must agree BITWISE; the backward pass reduces per-lane partial forces in a different tree, so forces agree to
-    fp32 round-off.  The dense walk must be what batches of small molecules take and must not be taken with a cell."""
+def test_conv_list_and_dense_walks_agree(name, kw):
+    """conv.cu (matrix rows, neighbour rows gathered through L1 / L2) vs conv_dense.cu (the molecule's tables staged into
+    shared memory with TMA, every centre walks all atoms of its molecule): the forward sums run over the same neighbours in
+    the same order (pairs beyond the cutoff add exactly zero), so energies and charges must agree BITWISE; the backward
+    pass reduces per-lane partial forces in a different tree, so forces agree to fp32 round-off.  The dense walk must be what
+    batches of small molecules take, and must not be taken with a cell."""
     inputs, ref, meta = load_golden(name)
     calc = get_calc(meta)
     res = {}
     try:
-        for impl in (0, 1, 2):
+        for impl in (0, 1):
             calc.engine.set_conv_impl(impl)
             for rows in (0, 512):   # both MLP paths
                 calc.engine.set_small_m_rows(rows)
@@ -103,23 +104,20 @@ def test_conv_generations_agree(name, kw):
                 res[impl, rows] = {k: v.cpu().numpy() for k, v in out.items()}
             mode = calc.engine.conv_mode()
             assert mode["impl"] == impl
-            assert mode["dense_last"] == (impl == 2 and "cell" not in inputs), mode
+            assert mode["dense_last"] == (impl == 1 and "cell" not in inputs), mode
     finally:
-        calc.engine.set_conv_impl(2)
+        calc.engine.set_conv_impl(1)
         calc.engine.set_small_m_rows(512)
     for rows in (0, 512):
-        base = res[0, rows]
-        for impl in (1, 2):
-            r = res[impl, rows]
-            assert np.array_equal(r["energy"], base["energy"]) is True or np.abs(r["energy"] - base["energy"]).max() < 2e-6, (impl, rows)
-            assert np.abs(r["charges"] - base["charges"]).max() < 1e-6
-            df = np.abs(r["forces"] - base["forces"]).max()
-            print(f"[conv2] {name} impl {impl} small_m_rows {rows}: bitwise E {np.array_equal(r['energy'], base['energy'])} "
-                  f"bitwise q {np.array_equal(r['charges'], base['charges'])} max|dF| vs conv.cu {df:.2e}")
-            assert df < 3e-5
-            assert np.abs(r["forces"] - ref["forces"]).max() < FORCE_ATOL
-            if kw.get("stress"):
-                assert np.abs(r["stress"] - ref["stress"]).max() < 1e-5
+        base, r = res[0, rows], res[1, rows]
+        df = np.abs(r["forces"] - base["forces"]).max()
+        print(f"[conv_dense] {name} small_m_rows {rows}: bitwise E {np.array_equal(r['energy'], base['energy'])} "
+              f"bitwise q {np.array_equal(r['charges'], base['charges'])} max|dF| vs list kernels {df:.2e}")
+        assert np.array_equal(r["energy"], base["energy"]) and np.array_equal(r["charges"], base["charges"])
+        assert df < 3e-5
+        assert np.abs(r["forces"] - ref["forces"]).max() < FORCE_ATOL
+        if kw.get("stress"):
+            assert np.abs(r["stress"] - ref["stress"]).max() < 1e-5
 
 
 def test_components_against_reference():
