@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, int n_g
                                                             const float* __restrict__ T_q,
                                                             const float* __restrict__ agh_a,
                                                             const float* __restrict__ agh_q, float* __restrict__ dS_a,
-                                                            float* __restrict__ dS_q, int with_q) {
+                                                            float* __restrict__ dS_q, int with_q, int permute) {
     // one warp per atom, 8 atoms per block.  agh is staged once per block in its natural (a,g,h) layout: a lane reads
     // the 12 weights of its (a,g) as three 16-byte loads (row stride 12 words: 8 consecutive rows cover all banks);
     // dT[a] (36 floats, row stride 36) comes in as nine 16-byte broadcast loads.
@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(int n_atoms, int n_g
             s1 = fmaf(w[h], tv[3 * h + 1], s1);
             s2 = fmaf(w[h], tv[3 * h + 2], s2);
         }
-        reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + e] = make_float4(dxr[kAG + e], s0, s1, s2);
+        // permute: channel rows in the order the dense walk reads them (conv_dense.cu: the two channel halves of a warp read
+        // neighbouring rows, i.e. different shared-memory banks): row = 2 t + h with h = bit 2 of a, t = a & 3 | (a >> 3) << 2
+        const int row = permute ? 2 * ((aa & 3) + ((aa >> 3) << 2)) + ((aa >> 2) & 1) : aa;
+        reinterpret_cast<float4*>(dS_a)[(size_t)i * kAG + row * kG + (e & 15)] = make_float4(dxr[kAG + e], s0, s1, s2);
     }
     if (with_q && lane < C * kG) {
         int cc = lane >> 4, gq = lane & 15;
@@ -632,7 +635,7 @@ int launch_conv_fwd(int C, int n_atoms, const NbView& nb, const float* coord, co
 
 template <int C>
 static int conv_bwd_prep_launch(int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
-                                const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st) {
+                                const float* agh_q, float* dS_a, float* dS_q, int with_q, int permute, cudaStream_t st) {
     const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
     static int prep_ctas_dev[kMaxDevices] = {};
     int& prep_ctas = prep_ctas_dev[current_device_slot()];
@@ -644,17 +647,17 @@ static int conv_bwd_prep_launch(int n_atoms, const float* dx, int ldx, const flo
         prep_ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
     conv_bwd_prep_kernel<C><<<n_groups < prep_ctas ? n_groups : prep_ctas, 256, 0, st>>>(n_atoms, n_groups, dx, ldx, T_a, T_q,
-                                                                                          agh_a, agh_q, dS_a, dS_q, with_q);
+                                                                                          agh_a, agh_q, dS_a, dS_q, with_q, permute);
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }
 
 // backward step 1 alone (the gather step is launch_conv_bwd's second half or conv2.cu's launch_conv2_bwd_gather)
 int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
-                         const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st) {
+                         const float* agh_q, float* dS_a, float* dS_q, int with_q, int permute, cudaStream_t st) {
     if (n_atoms == 0) return AIMNET_OK;
-    if (C == 1) return conv_bwd_prep_launch<1>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, st);
-    return conv_bwd_prep_launch<2>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, st);
+    if (C == 1) return conv_bwd_prep_launch<1>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, permute, st);
+    return conv_bwd_prep_launch<2>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, permute, st);
 }
 
 template <int C>
@@ -664,7 +667,7 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
                            double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
     const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    AIM_TRY(conv_bwd_prep_launch<C>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, st));
+    AIM_TRY(conv_bwd_prep_launch<C>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, 0, st));
     int grid = n_groups;
 #define AIM_CONV_BWD(GA, VIR)                                                                                       \
     conv_bwd_kernel<C, GA, VIR><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a, \

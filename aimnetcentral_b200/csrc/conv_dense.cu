@@ -1,25 +1,31 @@
 // AEV + conv_sv message passing for batches of small molecules: the molecule's feature tables are staged into shared memory
-// with TMA and every pair of the molecule is walked from there ("dense walk").  Forward and analytic backward.
+// with TMA and every pair of the molecule is walked from there ("dense walk").  Forward (the engine's default for such
+// batches) and analytic backward (a measured alternative, slower than the list backward: see below).
 //
 // Same arithmetic and reference semantics as conv.cu (calc_distances aimnet/ops.py:37-66, AEVSV._calc_aev
 // aimnet/modules/aev.py:94-110, ConvSV.forward aimnet/modules/aev.py:156-189, Warp kernels
 // aimnet/kernels/conv_sv_2d_sp_wp.py:90-164).  Why a second implementation: the list kernels of conv.cu gather every
-// neighbour row (1 KB of a[j], 4 KB of dS[j]) through L1 / L2, and ncu shows them waiting on those gathers (long-scoreboard
-// stalls 5.5 / 3.5 per issued instruction, FMA pipe 35 / 45 %; an intermediate version that only re-mapped the threads,
-// two centres per warp and all 16 channels per lane, executed 25 % fewer instructions and was SLOWER, 8.3 stalls per issue:
-// profiles/r2e_conv2_*).  For a molecule of n <= 128 atoms everything a CTA gathers is one contiguous block of the feature
-// table (atoms of a molecule are contiguous), so:
+// neighbour row (1 KB of a[j], 4 KB of dS[j]) through L1 / L2 and wait for those gathers (ncu: long-scoreboard stalls 5.5 /
+// 3.5 per issued instruction, FMA pipe 35 / 45 %).  For a molecule of n <= ~100 atoms everything a CTA gathers is one
+// contiguous block of the feature table (atoms of a molecule are contiguous), so:
 //
 //   * one CTA works on one molecule (forward) or one (molecule, quarter of the radial shifts) item (backward) at a time;
 //     a single elected thread fetches the block with cp.async.bulk.tensor (2-D tensor maps over the (N, 4 q, 16 g, 4 a) feature
 //     table and the (N, 16 a, 16 g, 4 d) gradient table; the box selects the item's radial-shift columns), double-buffered
 //     where it fits: the next item's block lands while this one is computed, completion through an mbarrier;
 //   * every centre atom walks ALL atoms of its molecule in index order (pairs beyond the cutoff contribute exactly zero:
-//     fc(d >= rc) == 0; the order equals that of the canonical sorted list rows, so the forward sums are bitwise those of the
-//     list walk); the centres of a warp move in lock step, so one shared-memory read of a neighbour row serves 2 (forward) or
-//     8 (backward) pairs and there is no global gather left in the pair loop;
-//   * lane = (centre, radial shift g) owns all 16 feature channels of its (i, g): accumulators are register pairs over two
-//     neighbouring channels fed straight by the float4 reads, the pair weight is the packed broadcast operand.
+//     fc(d >= rc) == 0; the order equals that of the canonical sorted list rows): no global gather is left in the pair loop;
+//   * what the shared-memory pipe charges is one wavefront per 128 bytes per quarter-warp WHATEVER the addresses are
+//     (a 16-byte warp load is four wavefronts even when all lanes read the same row: measured, profiles/r2g_convd_*: a first
+//     version whose lanes shared neighbour rows ran at 89 % of the shared-memory pipe with 44 % of its wavefronts bank
+//     conflicts).  Reuse therefore has to happen in registers: every THREAD handles TWO centre atoms, so each 16-byte read
+//     of a neighbour row feeds twice the FMAs, and every lane of a warp reads a distinct address (pair geometry is staged in a
+//     small per-warp table read back as 8-byte broadcasts);
+//   * measured on 1024 x 50 atoms (profiles/r2k_convd_*): forward 242 us vs 279 us for the list kernel.  Backward 1 012 us vs
+//     646 us: both execute at ~40 % issue utilisation, and the dense backward executes 451 M warp instructions against 300 M
+//     (walking all 50 atoms instead of the 42 inside the cutoff, per-pair force algebra that does not amortise over more
+//     channels at 168 registers per thread, 7 warps per SM).  The engine therefore pairs the dense forward with the list
+//     backward; the dense backward stays selectable (conv_impl 2) and tested.
 //   * backward: per atom from its OWN pairs only (gather form, no atomics, deterministic; see conv.cu); the four
 //     radial-shift quarters of an atom write partial forces / charge gradients that a last kernel adds in fixed order.
 #include <cuda.h>
@@ -34,17 +40,9 @@ namespace convd {
 
 constexpr int kSlots = 16;           // forward: neighbour slots staged per centre and round
 // shared-memory layouts of the forward epilogue, as in conv.cu
-constexpr int kAghRow = 20;
 constexpr int kSvRow = 52;
 constexpr int kSvAtom = kA * kSvRow + 16;
 __device__ __forceinline__ int sv_off(int a) { return a * kSvRow + ((a >> 3) << 4); }
-
-struct PairEntry {
-    float ux, uy, uz, d;
-    float fc, dfc;
-    int j;       // index of the neighbour inside the molecule
-    float inv;   // 1/d
-};
 
 __device__ __forceinline__ float aev_exp(float x) { return __expf(x); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,30 +73,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-__device__ __forceinline__ void mix16(const float* __restrict__ w, const float* __restrict__ s, float* t) {
-    const float4* w4 = reinterpret_cast<const float4*>(w);
-    const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float4* s4 = reinterpret_cast<const float4*>(s + k * kG);
-        const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
-        float2 acc = make_float2(0.f, 0.f);
-        acc = ffma2(make_float2(w0.x, w0.y), make_float2(s0.x, s0.y), acc);
-        acc = ffma2(make_float2(w0.z, w0.w), make_float2(s0.z, s0.w), acc);
-        acc = ffma2(make_float2(w1.x, w1.y), make_float2(s1.x, s1.y), acc);
-        acc = ffma2(make_float2(w1.z, w1.w), make_float2(s1.z, s1.w), acc);
-        acc = ffma2(make_float2(w2.x, w2.y), make_float2(s2.x, s2.y), acc);
-        acc = ffma2(make_float2(w2.z, w2.w), make_float2(s2.z, s2.w), acc);
-        acc = ffma2(make_float2(w3.x, w3.y), make_float2(s3.x, s3.y), acc);
-        acc = ffma2(make_float2(w3.z, w3.w), make_float2(s3.z, s3.w), acc);
-        t[k] = acc.x + acc.y;
-    }
-}
-
 // geometry + cutoff of the pair (centre il, neighbour k) of one molecule, coordinates from shared memory
+struct PairGeom {
+    float ux, uy, uz, d, fc, dfc, inv;
+};
 template <bool kWithDeriv>
-__device__ __forceinline__ PairEntry pair_entry(int il, bool atom_ok, int k, int n, const float4* __restrict__ xyz,
-                                                const AevParams& aev) {
+__device__ __forceinline__ PairGeom pair_geom(int il, bool atom_ok, int k, int n, const float4* __restrict__ xyz,
+                                              const AevParams& aev) {
     const bool ok = atom_ok && k < n && k != il;
     float rx = 1.f, ry = 1.f, rz = 1.f;
     if (ok) {
@@ -113,24 +94,19 @@ __device__ __forceinline__ PairEntry pair_entry(int il, bool atom_ok, int k, int
     const float dc = fminf(fmaxf(d, 1e-6f), aev.rc);
     float sn, cs;
     sincosf(dc * (kPi / aev.rc), &sn, &cs);
-    PairEntry e;
+    PairGeom e;
     e.ux = rx * inv;
     e.uy = ry * inv;
     e.uz = rz * inv;
     e.d = d;
     e.fc = ok ? 0.5f * (cs + 1.0f) : 0.f;
     e.dfc = (kWithDeriv && ok && d > 1e-6f && d < aev.rc) ? -0.5f * (kPi / aev.rc) * sn : 0.f;
-    e.j = ok ? k : (atom_ok ? il : 0);
     e.inv = inv;
     return e;
 }
 
-// channel pair ap (0..7) of a lane <-> channels a_lo = 4 (ap >> 1) + 2 (ap & 1), a_lo + 1: the (x,y) / (z,w) halves of the
-// float4 of quad ap >> 1 in the gather layout
-__device__ __forceinline__ int pair_lo(int ap) { return 4 * (ap >> 1) + 2 * (ap & 1); }
-
 struct Layout {     // byte offsets into dynamic shared memory (host-computed)
-    int tiles, agh, sv, xyz, q, dsq, bars, buf;   // buf is 1024-aligned
+    int ent, agh, aghq, sv, xyz, q, dsq, bars, buf;   // buf is 1024-aligned
     int buf_bytes;    // one buffer (all boxes of one item)
     int nbuf;         // 1 or 2
     int total;
@@ -146,8 +122,14 @@ struct Params {
     Layout L;
 };
 
+constexpr int kAghPad = 196;         // agh[a] row (16 g x 12 h = 192 floats) padded: 8 consecutive rows hit disjoint banks
+constexpr int kEntFwd = 5 * 16 * 2;  // forward pair table of a warp: [field d, fc, ux, uy, uz][16 slots][2 centres]
+constexpr int kEntBwd = 7 * 4 * 8;   // backward: [field d, fc, ux, uy, uz, dfc, inv][4 slots][8 centres]
+
 // ------------------------------------------------------------------------------------------------------------
-// forward
+// forward: one CTA = one molecule at a time; one warp = one PAIR of centre atoms, lane = (channel half h, radial shift g);
+// every THREAD accumulates both centres of the pair, so each neighbour row read from shared memory (2 x 16 bytes per lane,
+// every lane a distinct address: full shared-memory bandwidth) feeds 64 FMAs.
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUtensorMap tmA, Params p,
@@ -157,26 +139,22 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
                                                      float* __restrict__ x, int ldx, float* __restrict__ T_a,
                                                      float* __restrict__ T_q, int with_q) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    PairEntry* tiles = reinterpret_cast<PairEntry*>(smem + p.L.tiles);
-    float* aghT_a = reinterpret_cast<float*>(smem + p.L.agh);   // [a][h][g], row stride kAghRow
-    float* aghT_q = aghT_a + kA * kH * kAghRow;                 // [c][h][g]
+    // 1 KB alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access a generic
+    // LD / ST instead of LDS / STS)
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    float* ent_all = reinterpret_cast<float*>(smem + p.L.ent);
+    float* aghS = reinterpret_cast<float*>(smem + p.L.agh);     // [a][g][h], row stride kAghPad
+    float* aghqS = reinterpret_cast<float*>(smem + p.L.aghq);   // [c][g][h]
     float* sv_all = reinterpret_cast<float*>(smem + p.L.sv);    // per warp: one atom's [a][k][g] (sv_off) + [c][k][g]
     float4* xyz = reinterpret_cast<float4*>(smem + p.L.xyz);
     float* q_s = reinterpret_cast<float*>(smem + p.L.q);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, c = lane >> 4, g = lane & 15;
+    const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, g = lane & 15;
     const float shift_g = aev.shifts[g];
-    for (int e = tid; e < kA * kG * kH; e += nthr) {
-        int a = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
-        aghT_a[(a * kH + hh) * kAghRow + gg] = agh_a[e];
-    }
+    for (int e = tid; e < kA * kG * kH; e += nthr) aghS[(e / (kG * kH)) * kAghPad + e % (kG * kH)] = agh_a[e];
     if (with_q)
-        for (int e = tid; e < C * kG * kH; e += nthr) {
-            int cc = e / (kG * kH), gg = (e / kH) % kG, hh = e % kH;
-            aghT_q[(cc * kH + hh) * kAghRow + gg] = agh_q[e];
-        }
+        for (int e = tid; e < C * kG * kH; e += nthr) aghqS[e] = agh_q[e];
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -196,7 +174,8 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
             const int m = blockIdx.x + b * gridDim.x;
             if (m < p.n_mol) issue(m, b);
         }
-    PairEntry* tile = tiles + warp * 32;
+    float* ent = ent_all + warp * kEntFwd;
+    const float2* ent2 = reinterpret_cast<const float2*>(ent);
     float* svl = sv_all + warp * (kSvAtom + 2 * kSvRow);
     float* svql = svl + kSvAtom;
     int it = 0;
@@ -214,127 +193,166 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
         const float4* abuf = reinterpret_cast<const float4*>(smem + p.L.buf + b * p.L.buf_bytes);   // [atom][quad][g] float4
         const int n_pairs = (n + 1) >> 1;
         for (int cp = warp; cp < n_pairs; cp += p.warps) {
-            const int il = 2 * cp + c;
-            const bool atom_ok = il < n;
-            const int ilc = atom_ok ? il : 0;
-            float2 S[8][4];   // [channel pair][d]
+            const int il0 = 2 * cp;
+            const bool ok1 = il0 + 1 < n;
+            // S[c][channel pair][d]: channel pairs of this half are the (x,y) / (z,w) halves of quads 2h, 2h + 1
+            float2 S[2][4][4];
 #pragma unroll
-            for (int ap = 0; ap < 8; ++ap)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int d = 0; d < 4; ++d) S[ap][d] = make_float2(0.f, 0.f);
-            float Sq[C][4];
+                for (int ap = 0; ap < 4; ++ap)
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc)
+                    for (int d = 0; d < 4; ++d) S[c][ap][d] = make_float2(0.f, 0.f);
+            float Sq[2][C][4];
 #pragma unroll
-                for (int d = 0; d < 4; ++d) Sq[cc][d] = 0.f;
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) Sq[c][cc][d] = 0.f;
             for (int k0 = 0; k0 < n; k0 += kSlots) {
                 __syncwarp();
-                tile[lane] = pair_entry<false>(ilc, atom_ok, k0 + (lane & 15), n, xyz, aev);
+                {   // lane = (centre, slot) stages one pair of the warp's table
+                    const int c = lane >> 4, sl = lane & 15;
+                    const PairGeom e = pair_geom<false>(min(il0 + c, n - 1), il0 + c < n, k0 + sl, n, xyz, aev);
+                    ent[(0 * kSlots + sl) * 2 + c] = e.d;
+                    ent[(1 * kSlots + sl) * 2 + c] = e.fc;
+                    ent[(2 * kSlots + sl) * 2 + c] = e.ux;
+                    ent[(3 * kSlots + sl) * 2 + c] = e.uy;
+                    ent[(4 * kSlots + sl) * 2 + c] = e.uz;
+                }
                 __syncwarp();
                 const int lim = min(kSlots, n - k0);
 #pragma unroll 2
                 for (int s = 0; s < lim; ++s) {
-                    const PairEntry e = tile[c * kSlots + s];
-                    const float4* row = abuf + e.j * 64 + g;
-                    const float4 v0 = row[0], v1 = row[16], v2 = row[32], v3 = row[48];
-                    const float xg = e.d - shift_g;
-                    const float w0 = aev_exp(-aev.eta * xg * xg) * e.fc;
-                    const float wv[4] = {w0, w0 * e.ux, w0 * e.uy, w0 * e.uz};
-                    float2 wd[4];
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) wd[d] = make_float2(wv[d], wv[d]);
-                    const float2 av[8] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y),
-                                          make_float2(v1.z, v1.w), make_float2(v2.x, v2.y), make_float2(v2.z, v2.w),
-                                          make_float2(v3.x, v3.y), make_float2(v3.z, v3.w)};
-#pragma unroll
-                    for (int ap = 0; ap < 8; ++ap)
-#pragma unroll
-                        for (int d = 0; d < 4; ++d) S[ap][d] = ffma2(av[ap], wd[d], S[ap][d]);
+                    const float4* row = abuf + (k0 + s) * 64 + 32 * h + g;
+                    const float4 v0 = row[0], v1 = row[16];
+                    const float2 e_d = ent2[0 * kSlots + s], e_fc = ent2[1 * kSlots + s], e_ux = ent2[2 * kSlots + s],
+                                 e_uy = ent2[3 * kSlots + s], e_uz = ent2[4 * kSlots + s];
+                    const float2 av[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y),
+                                          make_float2(v1.z, v1.w)};
+                    const float dd[2] = {e_d.x, e_d.y}, fcv[2] = {e_fc.x, e_fc.y}, uxv[2] = {e_ux.x, e_ux.y},
+                                uyv[2] = {e_uy.x, e_uy.y}, uzv[2] = {e_uz.x, e_uz.y};
+                    float qj[C];
                     if (with_q) {
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) {
-                            const float qj = q_s[e.j * C + cc];
+                        for (int cc = 0; cc < C; ++cc) qj[cc] = q_s[(k0 + s) * C + cc];
+                    }
 #pragma unroll
-                            for (int d = 0; d < 4; ++d) Sq[cc][d] = fmaf(qj, wv[d], Sq[cc][d]);
+                    for (int c = 0; c < 2; ++c) {
+                        const float xg = dd[c] - shift_g;
+                        const float w0 = aev_exp(-aev.eta * xg * xg) * fcv[c];
+                        const float wv[4] = {w0, w0 * uxv[c], w0 * uyv[c], w0 * uzv[c]};
+                        float2 wd[4];
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) wd[d] = make_float2(wv[d], wv[d]);
+#pragma unroll
+                        for (int ap = 0; ap < 4; ++ap)
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) S[c][ap][d] = ffma2(av[ap], wd[d], S[c][ap][d]);
+                        if (with_q) {
+#pragma unroll
+                            for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                                for (int d = 0; d < 4; ++d) Sq[c][cc][d] = fmaf(qj[cc], wv[d], Sq[c][cc][d]);
                         }
                     }
                 }
             }
-            // ---- epilogue: scalar part and the atom's own features straight to x ----
-            if (atom_ok) {
-                const int i = lo + il;
+            // ---- epilogue, one centre after the other: scalar part and the atom's own features straight to x, vector
+            //      part through the warp's scratch for T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c == 1 && !ok1) break;
+                const int il = il0 + c, i = lo + il;
                 float* xr = x + (size_t)i * ldx;
-                const float4* own = abuf + il * 64 + g;
-                const float4 o0 = own[0], o1 = own[16], o2 = own[32], o3 = own[48];
-                const float ov[kA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+                __syncwarp();   // the previous centre's mixing is done with the scratch
+                {
+                    const float4* own = abuf + il * 64 + 32 * h + g;
+                    const float4 o0 = own[0], o1 = own[16];
+                    const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
-                for (int a = 0; a < kA; ++a) xr[a * kG + g] = ov[a];
+                    for (int k = 0; k < 8; ++k) xr[(8 * h + k) * kG + g] = ov[k];
 #pragma unroll
-                for (int ap = 0; ap < 8; ++ap) {
-                    xr[kAG + pair_lo(ap) * kG + g] = S[ap][0].x;
-                    xr[kAG + (pair_lo(ap) + 1) * kG + g] = S[ap][0].y;
-                }
-                int base = 2 * kAG + kAH;
-                if (with_q) {
-                    if (g < C) xr[base + g] = q_s[il * C + g];
-#pragma unroll
-                    for (int cc = 0; cc < C; ++cc) xr[base + C + cc * kG + g] = Sq[cc][0];
-                    base += C * (1 + kG + kH);
-                }
-                for (int cidx = base + g; cidx < ldx; cidx += kG) xr[cidx] = 0.f;
-            }
-            // ---- vector part through the warp's scratch, one centre after the other:
-            //      T[a,h,k] = sum_g agh[a,g,h] * Sv[a,g,k]   (aimnet/modules/aev.py:188), mixed by the whole warp ----
-#pragma unroll 1
-            for (int cc2 = 0; cc2 < 2; ++cc2) {
-                __syncwarp();
-                if (c == cc2) {
-#pragma unroll
-                    for (int ap = 0; ap < 8; ++ap) {
-                        const int o = sv_off(pair_lo(ap)) + g;   // channels a_lo, a_lo + 1 never straddle the pad between 7 and 8
-                        svl[o] = S[ap][1].x;
-                        svl[o + kG] = S[ap][2].x;
-                        svl[o + 2 * kG] = S[ap][3].x;
-                        svl[o + kSvRow] = S[ap][1].y;
-                        svl[o + kSvRow + kG] = S[ap][2].y;
-                        svl[o + kSvRow + 2 * kG] = S[ap][3].y;
+                    for (int ap = 0; ap < 4; ++ap) {
+                        const int a = 8 * h + 2 * ap;
+                        xr[kAG + a * kG + g] = S[c][ap][0].x;
+                        xr[kAG + (a + 1) * kG + g] = S[c][ap][0].y;
+                        const int o = sv_off(a) + g;   // channels a, a + 1 never straddle the pad between 7 and 8
+                        svl[o] = S[c][ap][1].x;
+                        svl[o + kG] = S[c][ap][2].x;
+                        svl[o + 2 * kG] = S[c][ap][3].x;
+                        svl[o + kSvRow] = S[c][ap][1].y;
+                        svl[o + kSvRow + kG] = S[c][ap][2].y;
+                        svl[o + kSvRow + 2 * kG] = S[c][ap][3].y;
                     }
+                    int base = 2 * kAG + kAH;
                     if (with_q) {
+                        if (h == 0) {
+                            if (g < C) xr[base + g] = q_s[il * C + g];
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) {
-                            svql[cc * kSvRow + g] = Sq[cc][1];
-                            svql[cc * kSvRow + kG + g] = Sq[cc][2];
-                            svql[cc * kSvRow + 2 * kG + g] = Sq[cc][3];
+                            for (int cc = 0; cc < C; ++cc) {
+                                xr[base + C + cc * kG + g] = Sq[c][cc][0];
+                                svql[cc * kSvRow + g] = Sq[c][cc][1];
+                                svql[cc * kSvRow + kG + g] = Sq[c][cc][2];
+                                svql[cc * kSvRow + 2 * kG + g] = Sq[c][cc][3];
+                            }
+                        }
+                        base += C * (1 + kG + kH);
+                    }
+                    for (int cidx = base + lane; cidx < ldx; cidx += 32) xr[cidx] = 0.f;
+                }
+                __syncwarp();
+                {   // lane = (channel a, half hh of the 12 mixed components): 6 x 3 outputs from 16 g
+                    const int a = lane >> 1, hh = lane & 1;
+                    float t[6][3];
+#pragma unroll
+                    for (int jj = 0; jj < 6; ++jj) t[jj][0] = t[jj][1] = t[jj][2] = 0.f;
+                    const float* wrow = aghS + a * kAghPad + 6 * hh;
+                    const float* srow = svl + sv_off(a);
+#pragma unroll
+                    for (int g0 = 0; g0 < kG; g0 += 4) {
+                        const float4 s0 = *reinterpret_cast<const float4*>(srow + g0);
+                        const float4 s1 = *reinterpret_cast<const float4*>(srow + kG + g0);
+                        const float4 s2 = *reinterpret_cast<const float4*>(srow + 2 * kG + g0);
+                        const float sk[4][3] = {{s0.x, s1.x, s2.x}, {s0.y, s1.y, s2.y}, {s0.z, s1.z, s2.z}, {s0.w, s1.w, s2.w}};
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg) {
+                            const float2* w2 = reinterpret_cast<const float2*>(wrow + (g0 + gg) * kH);
+                            const float2 wa = w2[0], wb = w2[1], wc = w2[2];
+                            const float wv[6] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y};
+#pragma unroll
+                            for (int jj = 0; jj < 6; ++jj)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) t[jj][k] = fmaf(wv[jj], sk[gg][k], t[jj][k]);
                         }
                     }
-                }
-                __syncwarp();
-                if (2 * cp + cc2 >= n) break;
-                const int ia = lo + 2 * cp + cc2;
-                float* xr = x + (size_t)ia * ldx;
-#pragma unroll 2
-                for (int e = lane; e < kAH; e += 32) {
-                    const int a = e / kH;
-                    float t[3];
-                    mix16(aghT_a + e * kAghRow, svl + sv_off(a), t);
-                    float* To = T_a + (size_t)ia * kTA + e * 3;
-                    To[0] = t[0];
-                    To[1] = t[1];
-                    To[2] = t[2];
-                    xr[2 * kAG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
-                }
-                if (with_q) {
-                    const int base = 2 * kAG + kAH;
-                    for (int e = lane; e < C * kH; e += 32) {
-                        const int cq = e / kH;
-                        float t[3];
-                        mix16(aghT_q + e * kAghRow, svql + cq * kSvRow, t);
-                        float* To = T_q + (size_t)ia * (C * kH * 3) + e * 3;
-                        To[0] = t[0];
-                        To[1] = t[1];
-                        To[2] = t[2];
-                        xr[base + C + C * kG + e] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+                    float2* To = reinterpret_cast<float2*>(T_a + (size_t)i * kTA + a * (kH * 3) + 18 * hh);
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) To[u] = make_float2(t[(2 * u) / 3][(2 * u) % 3], t[(2 * u + 1) / 3][(2 * u + 1) % 3]);
+                    float2* xo = reinterpret_cast<float2*>(xr + 2 * kAG + a * kH + 6 * hh);
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const float n0 = t[2 * u][0] * t[2 * u][0] + t[2 * u][1] * t[2 * u][1] + t[2 * u][2] * t[2 * u][2];
+                        const float n1 = t[2 * u + 1][0] * t[2 * u + 1][0] + t[2 * u + 1][1] * t[2 * u + 1][1] + t[2 * u + 1][2] * t[2 * u + 1][2];
+                        xo[u] = make_float2(n0, n1);
                     }
+                }
+                if (with_q && lane < C * kH) {   // charge channels: lane = (c, mixed component)
+                    const int cq = lane / kH, hq = lane % kH;
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                    for (int gg = 0; gg < kG; ++gg) {
+                        const float wq = aghqS[(cq * kG + gg) * kH + hq];
+                        t0 = fmaf(wq, svql[cq * kSvRow + gg], t0);
+                        t1 = fmaf(wq, svql[cq * kSvRow + kG + gg], t1);
+                        t2 = fmaf(wq, svql[cq * kSvRow + 2 * kG + gg], t2);
+                    }
+                    float* To = T_q + (size_t)i * (C * kH * 3) + lane * 3;
+                    To[0] = t0;
+                    To[1] = t1;
+                    To[2] = t2;
+                    xr[2 * kAG + kAH + C + C * kG + lane] = t0 * t0 + t1 * t1 + t2 * t2;
                 }
             }
         }
@@ -347,26 +365,32 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward: item = (molecule, quarter gq of the radial shifts); lane = (centre c8 of the warp's eight, g4), g = 4 gq + g4
+// backward: item = (molecule, quarter gq of the radial shifts); lane = (centre pair cp of the warp's four, channel half h,
+// g4), g = 4 gq + g4; every THREAD handles both centres of its pair for 8 channels: a neighbour's rows (a[j]: 2 x 16 bytes,
+// dS[j]: 8 x 16 bytes per lane) feed 192 FMAs.  Channel half h owns channels 4h..4h+3 and 8+4h..8+4h+3 (feature quads h and
+// h + 2); the gradient table arrives with its channel rows permuted (conv_bwd_prep, permute = 1) so that row 2 t + h is
+// the t-th channel of half h: the two halves read neighbouring rows, all eight lanes of a quarter-warp distinct banks.
 //   grad_a[i,a,g]  = sum_j <dS[j,a,g,:], g_sv(j->i)[g,:]>            g_sv(j->i) = (gs, -gs u_{i->j})
 //   F_i            = sum_j ( w(i->j) - w(j->i) )                       w = dE/dr of a pair
 // ------------------------------------------------------------------------------------------------------------
 template <int C, bool kGradA>
-__global__ void __launch_bounds__(384, 1) bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
+__global__ void __launch_bounds__(320, 1) bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
                                                      Params p, const int32_t* __restrict__ mol_ptr,
                                                      const float* __restrict__ coord, AevParams aev,
                                                      const float* __restrict__ q, const float* __restrict__ dS_q,
                                                      float* __restrict__ grad_a, float* __restrict__ gq_part,
                                                      float* __restrict__ f_part, int with_q) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    PairEntry* tiles = reinterpret_cast<PairEntry*>(smem + p.L.tiles);
+    // 1 KB alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access a generic
+    // LD / ST instead of LDS / STS)
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    float* ent_all = reinterpret_cast<float*>(smem + p.L.ent);
     float4* xyz = reinterpret_cast<float4*>(smem + p.L.xyz);
     float* q_s = reinterpret_cast<float*>(smem + p.L.q);
     float4* dsq_s = reinterpret_cast<float4*>(smem + p.L.dsq);   // [atom][c][g4]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, c8 = lane >> 2, g4 = lane & 3;
+    const int warp = tid >> 5, lane = tid & 31, cp = lane >> 3, h = (lane >> 2) & 1, g4 = lane & 3;
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -391,7 +415,8 @@ __global__ void __launch_bounds__(384, 1) bwd_kernel(const __grid_constant__ CUt
             const int item = blockIdx.x + b * gridDim.x;
             if (item < n_items) issue(item, b);
         }
-    PairEntry* tile = tiles + warp * 32;
+    float* ent = ent_all + warp * kEntBwd;
+    const float2* ent2 = reinterpret_cast<const float2*>(ent);
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int b = it % p.L.nbuf;
@@ -412,137 +437,178 @@ __global__ void __launch_bounds__(384, 1) bwd_kernel(const __grid_constant__ CUt
             }
         mbar_wait(&full[b], phase);
         __syncthreads();
-        const float4* abuf = reinterpret_cast<const float4*>(smem + p.L.buf + b * p.L.buf_bytes);   // [atom][quad][g4] float4
-        const float4* dbuf = reinterpret_cast<const float4*>(smem + p.L.buf + b * p.L.buf_bytes + a_bytes);   // [atom][a][g4] float4
+        const float4* abuf = reinterpret_cast<const float4*>(smem + p.L.buf + b * p.L.buf_bytes);            // [atom][quad][g4]
+        const float4* dbuf = reinterpret_cast<const float4*>(smem + p.L.buf + b * p.L.buf_bytes + a_bytes);  // [atom][row][g4]
         for (int base = 0; base < n; base += 8 * p.warps) {
-            const int il = base + warp * 8 + c8;
-            const bool atom_ok = il < n;
-            const int ilc = atom_ok ? il : 0;
-            // own atom: dS_i[a][g][:] as (scalar,x) / (y,z) register pairs and a_i[a][g] for all 16 channels
-            float2 dSi01[kA], dSi23[kA];
-            float ai[kA];
+            const int il0 = base + warp * 8 + 2 * cp;   // this thread's centres: il0, il0 + 1
+            // own atoms: dS_i[t][g][:] as (scalar,x) / (y,z) register pairs and a_i[t][g], t = this half's 8 channels
+            float2 dSi01[2][8], dSi23[2][8];
+            float ai[2][8];
 #pragma unroll
-            for (int a = 0; a < kA; ++a) {
-                const float4 v = dbuf[(ilc * 16 + a) * 4 + g4];
-                dSi01[a] = make_float2(v.x, v.y);
-                dSi23[a] = make_float2(v.z, v.w);
+            for (int c = 0; c < 2; ++c) {
+                const int ilc = min(il0 + c, n - 1);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float4 v = dbuf[(ilc * 16 + 2 * t + h) * 4 + g4];
+                    dSi01[c][t] = make_float2(v.x, v.y);
+                    dSi23[c][t] = make_float2(v.z, v.w);
+                }
+                const float4 o0 = abuf[(ilc * 4 + h) * 4 + g4], o1 = abuf[(ilc * 4 + h + 2) * 4 + g4];
+                ai[c][0] = o0.x, ai[c][1] = o0.y, ai[c][2] = o0.z, ai[c][3] = o0.w;
+                ai[c][4] = o1.x, ai[c][5] = o1.y, ai[c][6] = o1.z, ai[c][7] = o1.w;
             }
+            // charge channels ride on the h == 0 half only (their contribution is added once)
+            float2 dSqi01[2][C], dSqi23[2][C];
+            float qi[2][C];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                const float4 o = abuf[(ilc * 4 + qd) * 4 + g4];
-                ai[4 * qd + 0] = o.x;
-                ai[4 * qd + 1] = o.y;
-                ai[4 * qd + 2] = o.z;
-                ai[4 * qd + 3] = o.w;
+            for (int c = 0; c < 2; ++c) {
+                const int ilc = min(il0 + c, n - 1);
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) {
+                    const float4 v = (with_q && h == 0) ? dsq_s[(ilc * C + cc) * 4 + g4] : make_float4(0, 0, 0, 0);
+                    dSqi01[c][cc] = make_float2(v.x, v.y);
+                    dSqi23[c][cc] = make_float2(v.z, v.w);
+                    qi[c][cc] = (with_q && h == 0) ? q_s[ilc * C + cc] : 0.f;
+                }
             }
-            float2 dSqi01[C], dSqi23[C];
-            float qi[C];
+            float2 ga2[2][8];
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) {
-                const float4 v = with_q ? dsq_s[(ilc * C + cc) * 4 + g4] : make_float4(0, 0, 0, 0);
-                dSqi01[cc] = make_float2(v.x, v.y);
-                dSqi23[cc] = make_float2(v.z, v.w);
-                qi[cc] = with_q ? q_s[ilc * C + cc] : 0.f;
-            }
-            float2 ga2[kA];
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int a = 0; a < kA; ++a) ga2[a] = make_float2(0.f, 0.f);
-            float2 gq2[C];
+                for (int t = 0; t < 8; ++t) ga2[c][t] = make_float2(0.f, 0.f);
+            float2 gq2[2][C];
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) gq2[cc] = make_float2(0.f, 0.f);
-            float fx = 0.f, fy = 0.f, fz = 0.f;
-            for (int k0 = 0; k0 < n; k0 += 4) {   // four neighbours per round: lane = (centre, slot) stages one pair
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) gq2[c][cc] = make_float2(0.f, 0.f);
+            float fx[2] = {0.f, 0.f}, fy[2] = {0.f, 0.f}, fz[2] = {0.f, 0.f};
+            for (int k0 = 0; k0 < n; k0 += 4) {   // four neighbours per round
                 __syncwarp();
-                tile[lane] = pair_entry<true>(ilc, atom_ok, k0 + g4, n, xyz, aev);
+                {   // lane = (centre of the warp's eight, slot) stages one pair of the warp's table
+                    const int ce = lane >> 2, sl = lane & 3;
+                    const int ilx = base + warp * 8 + ce;
+                    const PairGeom e = pair_geom<true>(min(ilx, n - 1), ilx < n, k0 + sl, n, xyz, aev);
+                    ent[(0 * 4 + sl) * 8 + ce] = e.d;
+                    ent[(1 * 4 + sl) * 8 + ce] = e.fc;
+                    ent[(2 * 4 + sl) * 8 + ce] = e.ux;
+                    ent[(3 * 4 + sl) * 8 + ce] = e.uy;
+                    ent[(4 * 4 + sl) * 8 + ce] = e.uz;
+                    ent[(5 * 4 + sl) * 8 + ce] = e.dfc;
+                    ent[(6 * 4 + sl) * 8 + ce] = e.inv;
+                }
                 __syncwarp();
                 const int lim = min(4, n - k0);
                 for (int s = 0; s < lim; ++s) {
-                    const PairEntry e = tile[c8 * 4 + s];
-                    const float4* arow = abuf + e.j * 16 + g4;
-                    const float4* drow = dbuf + e.j * 64 + g4;
-                    const float xg = e.d - shift_g;
-                    const float ex = aev_exp(-aev.eta * xg * xg);
-                    const float gs = ex * e.fc;
-                    const float dgs = ex * (e.dfc - 2.0f * aev.eta * xg * e.fc);
-                    // g_sv(j->i)[g,:] = (gs, -gs u): grad_a[i] += <dS[j], g_sv(j->i)> as two packed FMAs per channel
-                    const float2 G01 = make_float2(gs, -gs * e.ux), G23 = make_float2(-gs * e.uy, -gs * e.uz);
-                    // p = contraction for the pair (i -> j), r = for the reverse pair (j -> i), over all 16 channels of (i, g)
-                    float2 p01 = make_float2(0.f, 0.f), p23 = p01, r01 = p01, r23 = p01;
+                    const int j = k0 + s;
+                    const float4 a0 = abuf[(j * 4 + h) * 4 + g4], a1 = abuf[(j * 4 + h + 2) * 4 + g4];
+                    const float aj[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float4* drow = dbuf + (j * 16 + h) * 4 + g4;   // row 2 t + h at drow[8 t]
+                    const float2 e_d = ent2[(0 * 4 + s) * 4 + cp], e_fc = ent2[(1 * 4 + s) * 4 + cp], e_ux = ent2[(2 * 4 + s) * 4 + cp],
+                                 e_uy = ent2[(3 * 4 + s) * 4 + cp], e_uz = ent2[(4 * 4 + s) * 4 + cp], e_dfc = ent2[(5 * 4 + s) * 4 + cp],
+                                 e_inv = ent2[(6 * 4 + s) * 4 + cp];
+                    const float dd[2] = {e_d.x, e_d.y}, fcv[2] = {e_fc.x, e_fc.y}, uxv[2] = {e_ux.x, e_ux.y}, uyv[2] = {e_uy.x, e_uy.y},
+                                uzv[2] = {e_uz.x, e_uz.y}, dfcv[2] = {e_dfc.x, e_dfc.y}, invv[2] = {e_inv.x, e_inv.y};
+                    float gs[2], dgs[2];
+                    float2 G01[2], G23[2];
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float4 av = arow[4 * qd];
-                        const float aj[4] = {av.x, av.y, av.z, av.w};
+                    for (int c = 0; c < 2; ++c) {
+                        const float xg = dd[c] - shift_g;
+                        const float ex = aev_exp(-aev.eta * xg * xg);
+                        gs[c] = ex * fcv[c];
+                        dgs[c] = ex * (dfcv[c] - 2.0f * aev.eta * xg * fcv[c]);
+                        // g_sv(j->i)[g,:] = (gs, -gs u): grad_a[i] += <dS[j], g_sv(j->i)> as two packed FMAs per channel
+                        G01[c] = make_float2(gs[c], -gs[c] * uxv[c]);
+                        G23[c] = make_float2(-gs[c] * uyv[c], -gs[c] * uzv[c]);
+                    }
+                    // p = contraction for the pair (i -> j), r = for the reverse pair (j -> i), over this half's 8 channels
+                    float2 p01[2], p23[2], r01[2], r23[2];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int a = 4 * qd + k;
-                            const float4 dj = drow[4 * a];
-                            const float2 dj01 = make_float2(dj.x, dj.y), dj23 = make_float2(dj.z, dj.w);
+                    for (int c = 0; c < 2; ++c) p01[c] = p23[c] = r01[c] = r23[c] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float4 dj = drow[8 * t];
+                        const float2 dj01 = make_float2(dj.x, dj.y), dj23 = make_float2(dj.z, dj.w);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
                             if (kGradA) {
-                                ga2[a] = ffma2(dj01, G01, ga2[a]);
-                                ga2[a] = ffma2(dj23, G23, ga2[a]);
+                                ga2[c][t] = ffma2(dj01, G01[c], ga2[c][t]);
+                                ga2[c][t] = ffma2(dj23, G23[c], ga2[c][t]);
                             }
-                            p01 = ffma2s(aj[k], dSi01[a], p01);
-                            p23 = ffma2s(aj[k], dSi23[a], p23);
-                            r01 = ffma2s(ai[a], dj01, r01);
-                            r23 = ffma2s(ai[a], dj23, r23);
+                            p01[c] = ffma2s(aj[t], dSi01[c][t], p01[c]);
+                            p23[c] = ffma2s(aj[t], dSi23[c][t], p23[c]);
+                            r01[c] = ffma2s(ai[c][t], dj01, r01[c]);
+                            r23[c] = ffma2s(ai[c][t], dj23, r23[c]);
                         }
                     }
                     if (with_q) {
 #pragma unroll
                         for (int cc = 0; cc < C; ++cc) {
-                            const float qj = q_s[e.j * C + cc];
-                            const float4 dqj = dsq_s[(e.j * C + cc) * 4 + g4];
+                            const float qj = q_s[j * C + cc];
+                            const float4 dqj = dsq_s[(j * C + cc) * 4 + g4];
                             const float2 dq01 = make_float2(dqj.x, dqj.y), dq23 = make_float2(dqj.z, dqj.w);
-                            if (kGradA) {
-                                gq2[cc] = ffma2(dq01, G01, gq2[cc]);
-                                gq2[cc] = ffma2(dq23, G23, gq2[cc]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                if (kGradA) {
+                                    gq2[c][cc] = ffma2(dq01, G01[c], gq2[c][cc]);
+                                    gq2[c][cc] = ffma2(dq23, G23[c], gq2[c][cc]);
+                                }
+                                p01[c] = ffma2s(qj, dSqi01[c][cc], p01[c]);
+                                p23[c] = ffma2s(qj, dSqi23[c][cc], p23[c]);
+                                r01[c] = ffma2s(qi[c][cc], dq01, r01[c]);
+                                r23[c] = ffma2s(qi[c][cc], dq23, r23[c]);
                             }
-                            p01 = ffma2s(qj, dSqi01[cc], p01);
-                            p23 = ffma2s(qj, dSqi23[cc], p23);
-                            r01 = ffma2s(qi[cc], dq01, r01);
-                            r23 = ffma2s(qi[cc], dq23, r23);
                         }
                     }
-                    const float gsi = gs * e.inv;
-                    // this thread's share of w(i->j) = u (A + C.u) + (B - u (B.u))/d
-                    const float pu = p01.y * e.ux + p23.x * e.uy + p23.y * e.uz;
-                    const float sc = (p01.x + pu) * dgs - pu * gsi;
-                    // reverse pair (j->i): u' = -u;  w' = -u (A' - (r.u) dgs) + (B' - u (B'.u))/d
-                    const float ru = r01.y * e.ux + r23.x * e.uy + r23.y * e.uz;
-                    const float scr = (ru - r01.x) * dgs - ru * gsi;
-                    // F_i += w - w' = u (sc - scr) + (B - B') gs/d
-                    const float ds = sc - scr;
-                    fx += fmaf(e.ux, ds, (p01.y - r01.y) * gsi);
-                    fy += fmaf(e.uy, ds, (p23.x - r23.x) * gsi);
-                    fz += fmaf(e.uz, ds, (p23.y - r23.y) * gsi);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float gsi = gs[c] * invv[c];
+                        // this thread's share of w(i->j) = u (A + C.u) + (B - u (B.u))/d
+                        const float pu = p01[c].y * uxv[c] + p23[c].x * uyv[c] + p23[c].y * uzv[c];
+                        const float sc = (p01[c].x + pu) * dgs[c] - pu * gsi;
+                        // reverse pair (j->i): u' = -u;  w' = -u (A' - (r.u) dgs) + (B' - u (B'.u))/d
+                        const float ru = r01[c].y * uxv[c] + r23[c].x * uyv[c] + r23[c].y * uzv[c];
+                        const float scr = (ru - r01[c].x) * dgs[c] - ru * gsi;
+                        // F_i += w - w' = u (sc - scr) + (B - B') gs/d
+                        const float ds = sc - scr;
+                        fx[c] += fmaf(uxv[c], ds, (p01[c].y - r01[c].y) * gsi);
+                        fy[c] += fmaf(uyv[c], ds, (p23[c].x - r23[c].x) * gsi);
+                        fz[c] += fmaf(uzv[c], ds, (p23[c].y - r23[c].y) * gsi);
+                    }
                 }
             }
-            // reduce the force / grad_q shares over the four radial shifts of this quarter
-            auto quad_sum = [](float v) {
+            // reduce the force / grad_q shares over the eight lanes (two channel halves x four radial shifts) of the pair
+            auto oct_sum = [](float v) {
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
                 return v;
             };
-            fx = quad_sum(fx);
-            fy = quad_sum(fy);
-            fz = quad_sum(fz);
-            float gqs[C];
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) gqs[cc] = (kGradA && with_q) ? quad_sum(gq2[cc].x + gq2[cc].y) : 0.f;
-            if (atom_ok) {
-                const int i = lo + il;
-                if (kGradA) {
+            for (int c = 0; c < 2; ++c) {
+                const float sx = oct_sum(fx[c]), sy = oct_sum(fy[c]), sz = oct_sum(fz[c]);
+                float gqs[C];
 #pragma unroll
-                    for (int a = 0; a < kA; ++a) grad_a[(size_t)i * kAG + a * kG + g] = ga2[a].x + ga2[a].y;
-                }
-                if (g4 == 0) {
-                    float* fp = f_part + ((size_t)gq * p.n_atoms + i) * 3;
-                    fp[0] = fx;
-                    fp[1] = fy;
-                    fp[2] = fz;
-                    if (kGradA && with_q) {
+                for (int cc = 0; cc < C; ++cc)
+                    gqs[cc] = (kGradA && with_q) ? oct_sum(h == 0 ? gq2[c][cc].x + gq2[c][cc].y : 0.f) : 0.f;
+                const int il = il0 + c;
+                if (il < n) {
+                    const int i = lo + il;
+                    if (kGradA) {
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) gq_part[((size_t)gq * p.n_atoms + i) * C + cc] = gqs[cc];
+                        for (int t = 0; t < 8; ++t) {
+                            const int a = 4 * h + (t & 3) + ((t >> 2) << 3);
+                            grad_a[(size_t)i * kAG + a * kG + g] = ga2[c][t].x + ga2[c][t].y;
+                        }
+                    }
+                    if ((lane & 7) == 0) {
+                        float* fp = f_part + ((size_t)gq * p.n_atoms + i) * 3;
+                        fp[0] = sx;
+                        fp[1] = sy;
+                        fp[2] = sz;
+                        if (kGradA && with_q) {
+#pragma unroll
+                            for (int cc = 0; cc < C; ++cc) gq_part[((size_t)gq * p.n_atoms + i) * C + cc] = gqs[cc];
+                        }
                     }
                 }
             }
@@ -629,8 +695,9 @@ static bool plan_fwd(int C, int max_seg, Params& p) {
     p.warps = (n_pairs + sweeps - 1) / sweeps;   // <= 16
     Layout& L = p.L;
     int o = 0;
-    L.tiles = o, o += p.warps * 32 * (int)sizeof(PairEntry);
-    L.agh = o, o += (kA + 2) * kH * kAghRow * 4;
+    L.ent = o, o += p.warps * kEntFwd * 4;
+    L.agh = o = up(o, 16), o += kA * kAghPad * 4;
+    L.aghq = o, o += 2 * kG * kH * 4;
     L.sv = o, o += p.warps * (kSvAtom + 2 * kSvRow) * 4;
     L.xyz = o = up(o, 16), o += max_seg * 16;
     L.q = o, o += up(max_seg * C * 4, 16);
@@ -646,11 +713,11 @@ static bool plan_fwd(int C, int max_seg, Params& p) {
 static bool plan_bwd(int C, int max_seg, Params& p) {
     feature_boxes(max_seg, p.rows_box_a, p.n_box_a);
     p.n_box_d = (16 * max_seg + 255) / 256;
-    p.warps = std::min(12, (max_seg + 7) / 8);
+    p.warps = std::min(10, (max_seg + 7) / 8);
     Layout& L = p.L;
     int o = 0;
-    L.tiles = o, o += p.warps * 32 * (int)sizeof(PairEntry);
-    L.agh = L.sv = o;
+    L.ent = o, o += p.warps * kEntBwd * 4;
+    L.agh = L.aghq = L.sv = o;
     L.xyz = o = up(o, 16), o += max_seg * 16;
     L.q = o, o += up(max_seg * C * 4, 16);
     L.dsq = o, o += max_seg * C * 4 * 16;

@@ -60,7 +60,7 @@ struct aimnet2_engine {
     aimnet2_options_t opt{};
     int gemm_backend = 0;
     int poison = -1;              // test seam: byte written over the workspace before every evaluation (-1 = off)
-    int conv_impl = 1;            // 0 = list kernels (conv.cu) always, 1 = shared-memory dense walk (conv_dense.cu) for batches of small molecules
+    int conv_impl = 1;            // 0 = list kernels (conv.cu) always; for batches of small molecules: 1 = dense shared-memory forward (conv_dense.cu) + list backward, 2 = dense forward and backward
     bool dense_now = false;       // the evaluation in flight walks molecule segments instead of matrix rows
     int last_max_seg = 0;         // largest molecule (atoms) of the last batch whose lists the engine built
     int small_m_rows = kSmallM;   // at or below this many atoms the MLPs run on the small-M fp32 SIMT kernel (0 = never)
@@ -527,7 +527,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             // Dense conv walk (conv_dense.cu): the molecule's feature tables staged in shared memory, every centre walks all
             // atoms of its molecule.  Worth it when most atoms of a molecule are inside the cutoff anyway: small molecules, or
             // at least half of the molecule in the widest row.  Not with a caller-supplied matrix or a cell.
-            e->dense_now = e->conv_impl == 1 && own_sr && !pbc && e->last_max_seg >= 2 &&
+            e->dense_now = e->conv_impl >= 1 && own_sr && !pbc && e->last_max_seg >= 2 &&
                            e->last_max_seg <= conv_dense_max_atoms(C) &&
                            (e->last_max_seg <= 64 || 2 * e->last_sr_width >= e->last_max_seg);
             if (skin > 0.f) {
@@ -715,8 +715,8 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             }
             const float* qin = (p == 0) ? nullptr : b.q[p - 1];
             class_mark(e, 1, st);
-            if (dense) {
-                AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[p], b.T_q[p], e->agh_a, e->agh_q, b.dS_a, b.dS_q, p > 0, st));
+            if (dense && e->conv_impl == 2) {
+                AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[p], b.T_q[p], e->agh_a, e->agh_q, b.dS_a, b.dS_q, p > 0, 1, st));
                 AIM_TRY(launch_conv_dense_bwd_gather(C, N, B, e->last_max_seg, b.mol_ptr, coord, e->aev, b.a[p], qin, b.dS_a, b.dS_q,
                                                      b.grad_a, b.grad_q, F, b.dense_fpart, b.dense_gqpart, p > 0, p > 0, st));
             } else {
@@ -881,7 +881,7 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
 
 extern "C" int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl) {
     AIM_REQUIRE(e, "set_conv_impl: null engine");
-    AIM_REQUIRE(impl >= 0 && impl <= 1, "set_conv_impl: 0 = list kernels always, 1 = shared-memory dense walk for batches of small molecules (default)");
+    AIM_REQUIRE(impl >= 0 && impl <= 2, "set_conv_impl: 0 = list kernels always, 1 = dense shared-memory forward for batches of small molecules (default), 2 = dense forward and backward");
     e->conv_impl = impl;
     e->skin.valid = false;
     return AIMNET_OK;

@@ -25,7 +25,7 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
                     int want_grad_a, cudaStream_t st);
 
 int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
-                         const float* agh_q, float* dS_a, float* dS_q, int with_q, cudaStream_t st);
+                         const float* agh_q, float* dS_a, float* dS_q, int with_q, int permute, cudaStream_t st);
 
 // ---- conv_dense.cu: the same convolutions for batches of small molecules: feature tables of one molecule staged into
 // shared memory with TMA, every pair of the molecule walked from there

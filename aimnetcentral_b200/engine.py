@@ -127,7 +127,8 @@ class Engine:
         _capi.check(self._lib.aimnet2_engine_set_small_m_rows(self._h, int(rows)), "set_small_m_rows")
 
     def set_conv_impl(self, impl: int):
-        """0 = list kernels always, 1 = shared-memory dense walk for batches of small molecules (default)."""
+        """0 = list kernels always; batches of small molecules: 1 = dense shared-memory forward + list backward (default),
+        2 = dense forward and backward."""
         _capi.check(self._lib.aimnet2_engine_set_conv_impl(self._h, int(impl)), "set_conv_impl")
 
     def conv_mode(self) -> dict:

@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--gemm-backend", type=int, default=None)
-    ap.add_argument("--conv-impl", type=int, default=None, help="0 list kernels always, 1 dense shared-memory walk for small molecules (default)")
+    ap.add_argument("--conv-impl", type=int, default=None, help="0 list kernels always, 1 dense shared-memory forward for small molecules (default), 2 dense forward + backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

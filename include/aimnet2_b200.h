@@ -169,12 +169,14 @@ int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt
  * validated on a GPU yet) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
 /* AEV / conv_sv kernels: 0 = the list kernels (csrc/conv.cu: one centre per warp walks its matrix row, neighbour rows gathered
- * through L1 / L2) for every input; 1 (default) = for batches of small non-periodic molecules (at most ~100 atoms each) the
- * dense walk of csrc/conv_dense.cu: the molecule's feature tables staged into shared memory with TMA, every centre walks all
- * atoms of its molecule (pairs beyond the cutoff contribute exactly zero, so the results do not depend on the choice beyond
- * fp32 summation order in the backward pass); periodic systems, large molecules and caller-supplied matrices keep the list
- * kernels.  aimnet2_engine_conv_mode reports the setting, whether the last evaluation took the dense walk, and the largest
- * molecule of that batch. */
+ * through L1 / L2) for every input.  For batches of small non-periodic molecules (at most ~100 atoms each): 1 (default) = the
+ * FORWARD convolutions take the dense walk of csrc/conv_dense.cu (the molecule's feature table staged into shared memory with
+ * TMA, every centre walks all atoms of its molecule; measured 13 % faster than the list forward on 1024 x 50 atoms), the
+ * backward pass keeps the list kernel; 2 = dense forward and dense backward (the dense backward executes 50 % more
+ * instructions than the list backward and is slower: kept as a measured alternative, profiles/r2k_convd_*).  Pairs beyond the
+ * cutoff contribute exactly zero, so the results do not depend on the choice beyond fp32 round-off.  Periodic systems, large
+ * molecules and caller-supplied matrices always take the list kernels.  aimnet2_engine_conv_mode reports the setting, whether
+ * the last evaluation took the dense walk, and the largest molecule of that batch. */
 int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl);
 int aimnet2_engine_conv_mode(const aimnet2_engine_t* e, int* impl, int* dense_last, int* max_molecule_last);
 /* Evaluations with at most `rows` atoms run the MLPs on the small-M fp32 SIMT kernel whatever the backend (the
