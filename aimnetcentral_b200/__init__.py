@@ -1,7 +1,7 @@
 """B200-native AIMNet2 inference engine behind the AIMNet2Calculator API."""
 from .model_spec import ModelSpec, random_state_dict  # noqa: F401
 
-__all__ = ["AIMNet2Calculator", "Engine", "ModelSpec", "random_state_dict"]
+__all__ = ["AIMNet2Calculator", "AIMNet2ASE", "AIMNet2TorchSim", "AIMNet2Pysis", "Engine", "ModelSpec", "random_state_dict"]
 
 
 def __getattr__(name):
@@ -11,6 +11,18 @@ def __getattr__(name):
         from .calculator import AIMNet2Calculator
 
         return AIMNet2Calculator
+    if name == "AIMNet2ASE":
+        from .aimnet2ase import AIMNet2ASE
+
+        return AIMNet2ASE
+    if name == "AIMNet2TorchSim":
+        from .aimnet2torchsim import AIMNet2TorchSim
+
+        return AIMNet2TorchSim
+    if name == "AIMNet2Pysis":
+        from .aimnet2pysis import AIMNet2Pysis
+
+        return AIMNet2Pysis
     if name == "Engine":
         from .engine import Engine
 

@@ -677,3 +677,40 @@ def test_cache_static_reuses_lists_for_unchanged_geometry():
     out = cached(moved, forces=True)
     assert float((out["forces"] - plain(moved, forces=True)["forces"]).abs().max()) < 1e-6
     assert cached.engine.skin_stats()[0] == 2
+
+
+def test_torchsim_and_pysis_adapters_on_the_engine(monkeypatch):
+    """The TorchSim / PySisyphus adapters (aimnet2torchsim.py:110-151, aimnet2pysis.py:44-108 of the reference) drive the real
+    engine: a flat multi-system state reproduces the golden batch, and the PySisyphus unit round trip reproduces taxol."""
+    from types import SimpleNamespace
+
+    from aimnetcentral_b200 import aimnet2pysis, aimnet2torchsim
+
+    inputs, ref, meta = load_golden("mols_8x50")
+    calc = get_calc(meta)
+    monkeypatch.setattr(aimnet2torchsim, "_TORCHSIM_IMPORT_ERROR", None)
+    dev = torch.device("cuda:0")
+    state = SimpleNamespace(positions=torch.as_tensor(inputs["coord"], device=dev), atomic_numbers=torch.as_tensor(inputs["numbers"], device=dev),
+                            system_idx=torch.as_tensor(inputs["mol_idx"], device=dev), n_systems=8, pbc=torch.zeros(3, dtype=torch.bool),
+                            row_vector_cell=torch.zeros(8, 3, 3, device=dev), device=dev, dtype=torch.float32,
+                            charge=torch.as_tensor(inputs["charge"], device=dev))
+    out = aimnet2torchsim.AIMNet2TorchSim(calc)(state)
+    assert np.abs(out["forces"].cpu().numpy() - ref["forces"]).max() < FORCE_ATOL
+    assert np.abs(out["energy"].cpu().numpy() - ref["energy"]).max() < ENERGY_ATOL
+    assert out["partial_charges"].data_ptr() == out["charges"].data_ptr()
+
+    inputs, ref, meta = load_golden("taxol_q0")
+    monkeypatch.setattr(aimnet2pysis, "_PYSIS_IMPORT_ERROR", None)
+    sym = {1: "H", 6: "C", 7: "N", 8: "O"}
+    monkeypatch.setattr(aimnet2pysis, "ATOMIC_NUMBERS", {v.lower(): k for k, v in sym.items()})
+    bohr, ha = 0.5291772105638411, 27.211386024367243
+    monkeypatch.setattr(aimnet2pysis, "BOHR2ANG", bohr)
+    monkeypatch.setattr(aimnet2pysis, "ANG2BOHR", 1.0 / bohr)
+    monkeypatch.setattr(aimnet2pysis, "AU2EV", ha)
+    p = aimnet2pysis.AIMNet2Pysis(get_calc(meta), charge=0, mult=1)
+    atoms = [sym[int(z)] for z in inputs["numbers"]]
+    r = p.get_forces(atoms, (inputs["coord"].astype(np.float64) / bohr).reshape(-1))
+    assert abs(r["energy"] * ha - ref["energy"][0]) < ENERGY_ATOL
+    assert np.abs(r["forces"].reshape(-1, 3) * ha / bohr - ref["forces"]).max() < FORCE_ATOL
+    with pytest.raises(NotImplementedError):
+        p.get_hessian(atoms, (inputs["coord"].astype(np.float64) / bohr).reshape(-1))

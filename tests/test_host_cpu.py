@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from conftest import ROOT
 
@@ -285,3 +286,105 @@ def test_pair_term_seams_reject_bad_arguments_before_touching_the_gpu():
     assert rc == -1 and b"null argument" in lib.aimnet2_last_error()
     with pytest.raises(ValueError):
         _capi.check(rc, "dftd3")
+
+
+# ---- TorchSim / PySisyphus adapters: host logic with stand-ins (neither package is in the image) ----------------------
+class _FakeCalc:
+    """Duck-typed calculator, the contract of tests/test_torchsim.py:20-50 of the reference."""
+
+    def __init__(self, is_nse=False):
+        self.device, self.is_nse = "cpu", is_nse
+        self.calls = []
+
+    @property
+    def metadata(self):
+        return {"family": "fake"}
+
+    def __call__(self, data, forces=False, stress=False, hessian=False, validate_species=True):
+        self.calls.append(dict(data=data, forces=forces, stress=stress, validate_species=validate_species))
+        n_sys = int(torch.as_tensor(data["mol_idx"]).max().item()) + 1 if "mol_idx" in data else 1
+        out = {"energy": torch.arange(n_sys, dtype=torch.float64) + 1.0, "charges": torch.zeros(data["coord"].shape[0])}
+        if forces:
+            out["forces"] = torch.ones_like(data["coord"])
+        if stress:
+            out["stress"] = torch.zeros(n_sys, 3, 3)
+        if self.is_nse:
+            out["spin_charges"] = torch.zeros(data["coord"].shape[0])
+        return out
+
+
+class _State:
+    def __init__(self, n_sys=2, n_per=3, periodic=False, **extras):
+        self.positions = torch.arange(n_sys * n_per * 3, dtype=torch.float32).reshape(-1, 3)
+        self.atomic_numbers = torch.full((n_sys * n_per,), 6)
+        self.system_idx = torch.arange(n_sys).repeat_interleave(n_per)
+        self.n_systems = n_sys
+        self.pbc = torch.tensor([periodic] * 3)
+        self.row_vector_cell = (torch.eye(3) * 10.0).repeat(n_sys, 1, 1) if periodic else torch.zeros(n_sys, 3, 3)
+        self.device, self.dtype = torch.device("cpu"), torch.float32
+        for k, v in extras.items():
+            setattr(self, k, v)
+
+    def to(self, device, dtype):
+        return self
+
+
+def test_torchsim_adapter_host_logic(monkeypatch):
+    from aimnetcentral_b200 import aimnet2torchsim as m
+
+    with pytest.raises(ImportError):
+        m.AIMNet2TorchSim(_FakeCalc())          # TorchSim is not installed here: same failure as the reference
+    monkeypatch.setattr(m, "_TORCHSIM_IMPORT_ERROR", None)
+    calc = _FakeCalc()
+    w = m.AIMNet2TorchSim(calc)
+    assert w.implemented_properties == ["energy", "forces", "charges", "partial_charges"]
+    st = _State()
+    pos0 = st.positions.clone()
+    res = w(st)
+    d = calc.calls[-1]["data"]
+    assert d["coord"].data_ptr() != st.positions.data_ptr() and torch.equal(st.positions, pos0)
+    assert torch.equal(d["charge"], torch.zeros(2)) and "cell" not in d and "mult" not in d
+    assert calc.calls[-1]["forces"] is True and calc.calls[-1]["stress"] is False
+    assert res["partial_charges"].data_ptr() == res["charges"].data_ptr()
+    w.compute_stress = True
+    assert "stress" in w.implemented_properties
+    with pytest.raises(ValueError, match="periodic TorchSim state"):
+        w(st)
+    res = w(_State(periodic=True))
+    d = calc.calls[-1]["data"]
+    assert d["cell"].shape == (2, 3, 3) and "pbc" in d and res["stress"].shape == (2, 3, 3)
+    # per-system extras: scalar broadcast, one value per system, wrong count
+    nse = m.AIMNet2TorchSim(_FakeCalc(is_nse=True), compute_forces=False)
+    assert nse.implemented_properties == ["energy", "charges", "partial_charges", "spin_charges"]
+    nse(_State(charge=torch.tensor([1.0, -1.0]), spin=2.0))
+    d = nse.base_calc.calls[-1]["data"]
+    assert d["charge"].tolist() == [1.0, -1.0] and d["mult"].tolist() == [2.0, 2.0]
+    with pytest.raises(ValueError, match="one value per system"):
+        nse(_State(charge=torch.tensor([1.0, 0.0, 0.0])))
+
+
+def test_pysis_adapter_host_logic(monkeypatch):
+    from aimnetcentral_b200 import aimnet2pysis as m
+
+    with pytest.raises(ImportError):
+        m.AIMNet2Pysis(_FakeCalc())
+    monkeypatch.setattr(m, "_PYSIS_IMPORT_ERROR", None)
+    monkeypatch.setattr(m, "ATOMIC_NUMBERS", {"c": 6, "h": 1})
+    monkeypatch.setattr(m, "BOHR2ANG", 0.5)
+    monkeypatch.setattr(m, "ANG2BOHR", 2.0)
+    monkeypatch.setattr(m, "AU2EV", 4.0)
+    calc = _FakeCalc()
+    p = m.AIMNet2Pysis(calc, charge=1, mult=2)
+    atoms, coords = ("C", "H"), np.arange(6, dtype=np.float64)
+    f = p.get_forces(atoms, coords)
+    d = calc.calls[-1]["data"]
+    assert d["numbers"].tolist() == [6, 1] and d["coord"].dtype == torch.float32
+    assert np.allclose(d["coord"].numpy().reshape(-1), coords * 0.5)          # Bohr -> Angstrom
+    assert d["charge"].tolist() == [1.0] and d["mult"].tolist() == [2.0]
+    assert f["energy"] == pytest.approx(1.0 / 4.0) and np.allclose(f["forces"], 1.0 / 4.0 / 2.0) and f["forces"].dtype == np.float64
+    n = len(calc.calls)
+    assert p.get_energy(atoms, coords)["energy"] == pytest.approx(0.25) and len(calc.calls) == n   # served from the cache
+    p.get_energy(atoms, coords + 1.0)
+    assert len(calc.calls) == n + 1 and calc.calls[-1]["forces"] is False
+    p.get_forces(atoms, coords + 1.0)                                         # an energy-only entry is not a forces hit
+    assert len(calc.calls) == n + 2
