@@ -68,7 +68,7 @@ EXPORTS = [
     "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_small_m_rows", "aimnet2_engine_set_conv_impl", "aimnet2_engine_conv_mode", "aimnet2_engine_debug_poison", "aimnet2_engine_debug_layout", "aimnet2_engine_debug_read_workspace", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
     "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_skin_stats", "aimnet2_engine_enable_timing",
     "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace",
-    "aimnet2_dsf_coulomb", "aimnet2_dftd3", "aimnet2_estimate_ewald_parameters",
+    "aimnet2_dsf_coulomb", "aimnet2_dftd3", "aimnet2_ewald_summation", "aimnet2_estimate_ewald_parameters",
 ]
 
 
@@ -118,6 +118,7 @@ def load():
     lib.aimnet2_dsf_coulomb.argtypes = [vp, vp, ci, cf, cf, vp, ci, vp, ci, vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.aimnet2_dftd3.argtypes = [vp, vp, ci, cf, cf, cf, cf, cf, cf, vp, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, ci, vp, vp, vp,
                                   vp, vp]
+    lib.aimnet2_ewald_summation.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, ci, ci, cd, vp, vp, vp, vp, vp]
     lib.aimnet2_estimate_ewald_parameters.argtypes = [c_float_p, ci, cd, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     for name in EXPORTS:
         if name != "aimnet2_last_error":

@@ -359,8 +359,8 @@ class AIMNet2Calculator:
             raise ValueError(f"Coulomb method '{method}' requires a periodic 'cell' in the input data. Provide a (3,3) "
                              "or (B,3,3) cell tensor, or switch to a non-periodic method via "
                              "set_lrcoulomb_method('simple' | 'dsf').")
-        if method == "ewald" and (cell.ndim != 2 or (coord.ndim == 3 and coord.shape[0] != 1)):
-            raise NotImplementedError("Ewald Coulomb is implemented for one periodic system per call")
+        if method == "ewald" and cell.ndim == 2 and charge.shape[0] != 1:
+            raise ValueError("Ewald Coulomb with several systems needs one cell per system: pass cell with shape (B, 3, 3)")
         if stress and cell is None:
             raise AssertionError("Stress calculation requires cell")
         # ---- flatten (mol_flatten, calculator.py:1475-1511): the engine always runs the sparse layout ----

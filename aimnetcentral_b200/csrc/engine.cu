@@ -87,7 +87,8 @@ struct aimnet2_engine {
     int gemm_ev_used = 0;
     float last_gemm_ms = 0.f, last_conv_ms = 0.f;
     int last_gemm_launches = 0, last_conv_launches = 0;
-    EwaldPlan ewald;
+    std::vector<EwaldPlan> ewald;   // one reciprocal-space plan per periodic system of the batch
+    std::vector<int32_t> sys_lo;    // host copy of the molecule segment pointers (batched Ewald)
     // Verlet-skin reuse of the neighbor lists (options.neighbor_skin > 0): what the lists in the workspace were built for
     struct {
         bool valid = false;
@@ -412,8 +413,10 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     const aimnet2_options_t& o = e->opt;
     const bool ewald = o.coulomb_method == AIMNET_COULOMB_EWALD;
     if (ewald) {
-        AIM_REQUIRE(sys->cell != nullptr && sys->n_cells == 1 && B == 1, "engine_eval: Ewald needs one periodic system with a cell");
-        if (sys->pbc_host) AIM_REQUIRE(sys->pbc_host[0] && sys->pbc_host[1] && sys->pbc_host[2], "engine_eval: Ewald needs pbc on all three axes");
+        AIM_REQUIRE(sys->cell != nullptr && sys->n_cells == B, "engine_eval: Ewald needs a cell for every system of the batch");
+        if (sys->pbc_host)
+            for (int c = 0; c < 3 * sys->n_cells; ++c)
+                AIM_REQUIRE(sys->pbc_host[c], "engine_eval: Ewald needs pbc on all three axes");
     }
     AIM_REQUIRE(!o.dispersion || e->d3_c6ref, "engine_eval: dispersion requested but no D3 tables were loaded");
     g_launch_count = 0;
@@ -434,8 +437,25 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     if (o.coulomb_method == AIMNET_COULOMB_DSF) lr_cut = std::max(lr_cut, o.dsf_rc);
     if (o.dispersion) lr_cut = std::max(lr_cut, o.d3_cutoff);
     if (ewald) {
-        AIM_TRY(ewald_prepare(e->ewald, sys->host_cell, N, o.ewald_accuracy, 15.0, st));
-        lr_cut = std::max(lr_cut, (float)e->ewald.rc);
+        // per-system splitting parameters need the atom counts of the systems: one segment-pointer read-back for a batch
+        e->sys_lo.assign(B + 1, 0);
+        e->sys_lo[B] = N;
+        if (B > 1) {
+            std::vector<int32_t> mi(N);
+            AIM_CUDA_CHECK(cudaMemcpyAsync(mi.data(), sys->mol_idx, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+            AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+            int s0 = 0;
+            for (int i = 0; i < N; ++i)
+                while (s0 < mi[i] && s0 < B) e->sys_lo[++s0] = i;
+            while (s0 < B) e->sys_lo[++s0] = N;
+        }
+        if ((int)e->ewald.size() < B) e->ewald.resize(B);
+        for (int s0 = 0; s0 < B; ++s0) {
+            const int ns = e->sys_lo[s0 + 1] - e->sys_lo[s0];
+            AIM_REQUIRE(ns >= 1, "engine_eval: Ewald system without atoms");
+            AIM_TRY(ewald_prepare(e->ewald[s0], sys->host_cell + 9 * s0, ns, o.ewald_accuracy, 15.0, st));
+            lr_cut = std::max(lr_cut, (float)e->ewald[s0].rc);
+        }
     }
     const bool own_sr = sys->nbmat == nullptr;
     if (e->timing) cudaEventRecord(e->ev[0], st);
@@ -527,7 +547,8 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             // Dense conv walk (conv_dense.cu): the molecule's feature tables staged in shared memory, every centre walks all
             // atoms of its molecule.  Worth it when most atoms of a molecule are inside the cutoff anyway: small molecules, or
             // at least half of the molecule in the widest row.  Not with a caller-supplied matrix or a cell.
-            e->dense_now = e->conv_impl >= 1 && own_sr && !pbc && e->last_max_seg >= 2 &&
+            // ... and when there are enough molecules to give every SM one (a CTA works on one molecule at a time)
+            e->dense_now = e->conv_impl >= 1 && own_sr && !pbc && B >= 64 && e->last_max_seg >= 2 &&
                            e->last_max_seg <= conv_dense_max_atoms(C) &&
                            (e->last_max_seg <= 64 || 2 * e->last_sr_width >= e->last_max_seg);
             if (skin > 0.f) {
@@ -663,9 +684,16 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         have_lr = true;
     }
     else if (ewald) {
-        CoulombParams cp{(float)e->ewald.rc, (float)e->ewald.alpha, 0.f, 0.f, 0.f, k};
-        AIM_TRY(launch_coulomb(PAIR_EWALD, N, lrs, coord_lr, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st));
-        AIM_TRY(launch_ewald_recip(e->ewald, N, coord_lr, qfin, b.e_lr, b.gq, backward ? F : nullptr, vir, st));
+        // every periodic system with its own alpha / r_c / k vectors (lr.py:687-696 carries batch_idx); the real-space part
+        // walks the shared long-range list, the reciprocal part only sees the system's own atoms
+        for (int s0 = 0; s0 < B; ++s0) {
+            const EwaldPlan& pl = e->ewald[s0];
+            const int lo = e->sys_lo[s0], ns = e->sys_lo[s0 + 1] - lo;
+            CoulombParams cp{(float)pl.rc, (float)pl.alpha, 0.f, 0.f, 0.f, k};
+            AIM_TRY(launch_coulomb(PAIR_EWALD, ns, lrs, coord_lr, cv, qfin, cp, b.e_lr, b.gq, backward ? F : nullptr, vir, 0, st, lo));
+            AIM_TRY(launch_ewald_recip(pl, ns, coord_lr + 3 * (size_t)lo, qfin + lo, b.e_lr + lo, b.gq + lo,
+                                       backward ? F + 3 * (size_t)lo : nullptr, vir ? vir + 9 * (size_t)lo : nullptr, st));
+        }
         have_lr = true;
     }
     if (o.dispersion) {
@@ -852,7 +880,7 @@ extern "C" int aimnet2_engine_destroy(aimnet2_engine_t* e) {
     for (void* p : e->owned) cudaFree(p);
     if (e->ws) cudaFree(e->ws);
     if (e->stage) cudaFree(e->stage);
-    ewald_release(e->ewald);
+    for (EwaldPlan& pl : e->ewald) ewald_release(pl);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->pinned_int) cudaFreeHost(e->pinned_int);
     for (int k = 0; k < 6; ++k)

@@ -311,9 +311,8 @@ void ewald_release(EwaldPlan& pl) {
 
 // adds the reciprocal, self and background terms to e_atom / gq / forces / virial_atom
 int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const float* q, double* e_atom, float* gq,
-                       float* forces, double* virial_atom, cudaStream_t st) {
+                       float* forces, double* virial_atom, cudaStream_t st, double ke) {
     if (n == 0) return AIMNET_OK;
-    const double ke = kHartree * kBohr;
     const double pref = ke * 4.0 * M_PI / pl.volume;
     const double self_coeff = -ke * pl.alpha / std::sqrt(M_PI);
     const double bg_unit = -ke * M_PI / (2.0 * pl.volume * pl.alpha * pl.alpha);

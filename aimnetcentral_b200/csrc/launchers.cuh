@@ -95,13 +95,14 @@ int launch_charges_out(int C, int n, const float* q, float* charges, float* spin
 // ---- lr.cu: pair terms: Coulomb (simple / DSF / Ewald real space), DFT-D3
 int launch_coulomb(int mode, int n, const PairSource& ps, const float* coord, const CellView& cv, const float* q,
                    const CoulombParams& p, double* e_atom, float* gq, float* forces, double* virial_atom,
-                   int accumulate_e, cudaStream_t st);
+                   int accumulate_e, cudaStream_t st, int atom_lo = 0);
 int launch_d3(int n, const PairSource& ps, const float* coord, const CellView& cv, const int32_t* numbers,
               const D3Params& p, float* cn, float* wtab, float* dEdCN, double* e_atom, float* forces,
               double* virial_atom, cudaStream_t st);
 
 // ---- ewald.cu: Ewald reciprocal space
+// ke: Coulomb constant of the output units (eV A by default; 1 for the operator seam, whose caller applies Hartree*Bohr)
 int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const float* q, double* e_atom, float* gq,
-                       float* forces, double* virial_atom, cudaStream_t st);
+                       float* forces, double* virial_atom, cudaStream_t st, double ke = kHartree * kBohr);
 
 }  // namespace aimnet

@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(256) coulomb_pair_kernel(int n, PairSource ps,
                                                            CellView cv, const float* __restrict__ q,
                                                            CoulombParams p, double* __restrict__ e_atom,
                                                            float* __restrict__ gq, float* __restrict__ forces,
-                                                           double* __restrict__ virial_atom, int accumulate_e) {
+                                                           double* __restrict__ virial_atom, int accumulate_e,
+                                                           int atom_lo) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
-    int i = warp;
+    int i = atom_lo + warp;   // atoms [atom_lo, atom_lo + n): one periodic system of a batch (per-system Ewald parameters)
     const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (ps.mol_idx ? ps.mol_idx[i] : 0)) : nullptr;
     int b, e;
     row_range(ps, i, b, e);
@@ -452,24 +453,24 @@ __global__ void __launch_bounds__(256) d3_cn_force_kernel(int n, PairSource ps, 
 // ------------------------------------------------------------------------------------------------------------
 int launch_coulomb(int mode, int n, const PairSource& ps, const float* coord, const CellView& cv, const float* q,
                    const CoulombParams& p, double* e_atom, float* gq, float* forces, double* virial_atom,
-                   int accumulate_e, cudaStream_t st) {
+                   int accumulate_e, cudaStream_t st, int atom_lo) {
     if (n == 0) return AIMNET_OK;
     dim3 grid((n + 7) / 8);
     switch (mode) {
         case PAIR_SR_EXP:
-            coulomb_pair_kernel<PAIR_SR_EXP><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
+            coulomb_pair_kernel<PAIR_SR_EXP><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e, atom_lo);
             break;
         case PAIR_SR_COS:
-            coulomb_pair_kernel<PAIR_SR_COS><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
+            coulomb_pair_kernel<PAIR_SR_COS><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e, atom_lo);
             break;
         case PAIR_SIMPLE:
-            coulomb_pair_kernel<PAIR_SIMPLE><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
+            coulomb_pair_kernel<PAIR_SIMPLE><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e, atom_lo);
             break;
         case PAIR_EWALD:
-            coulomb_pair_kernel<PAIR_EWALD><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
+            coulomb_pair_kernel<PAIR_EWALD><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e, atom_lo);
             break;
         default:
-            coulomb_pair_kernel<PAIR_DSF><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e);
+            coulomb_pair_kernel<PAIR_DSF><<<grid, 256, 0, st>>>(n, ps, coord, cv, q, p, e_atom, gq, forces, virial_atom, accumulate_e, atom_lo);
             break;
     }
     AIM_LAUNCH_CHECK();

@@ -2,6 +2,8 @@
 // points shaped like the third-party calls the reference makes (aimnet/modules/lr.py:526-540 dsf_coulomb,
 // :1204-1228 dftd3; aimnet/calculators/calculator.py:1566-1587 estimate_ewald_parameters).  Thin host code: scratch from
 // the stream-ordered allocator, the engine's own launchers, per-system reductions.
+#include <vector>
+
 #include "common.cuh"
 #include "launchers.cuh"
 
@@ -160,6 +162,65 @@ extern "C" int aimnet2_dftd3(const float* positions, const int32_t* numbers, int
     CellView cv{cell, n_cells};
     AIM_TRY(launch_d3(n_atoms, ps, positions, cv, numbers, dp, cn, s.wtab, s.f1, s.e_atom, F, s.virial_atom, st));
     return seam_finish(s, n_systems, energy, virial, st);
+}
+
+// Ewald summation; replaces nvalchemiops...ewald_summation as called at aimnet/modules/lr.py:687-696 (energy-only call
+// there: forces / stress / charge response come from autograd through the returned energies; here they are explicit
+// optional outputs like in the DSF seam).  Per-system splitting parameters from `accuracy` (calculator.py:663-666), real
+// space over the caller's neighbor matrix (which must reach every system's real-space cutoff), reciprocal space, self and
+// neutralising-background terms per system.  Units e^2/A: the caller multiplies by Hartree*Bohr (lr.py:697).
+//   host_cell            the cells in host memory (n_systems x 9 floats): k vectors are enumerated on the host
+//   host_system_offsets  n_systems + 1 ints in HOST memory: atoms [off[s], off[s+1]) form system s (NULL when n_systems == 1)
+//   energies_per_atom    (n_atoms) f64 device out.  The real-space and self terms are per atom; the reciprocal-space
+//                        energy of a system is booked on its first atom (only per-system sums are defined:
+//                        lr.py:698-703 scatter-adds them)
+// Reciprocal-space plans (k vectors, structure factors) are cached per system slot in process-wide storage: one caller
+// thread at a time, the reference's own threading contract.
+static std::vector<EwaldPlan> g_seam_plans;
+
+extern "C" int aimnet2_ewald_summation(const float* positions, const float* charges, int n_atoms, const float* cell,
+                                       const float* host_cell, const int32_t* batch_idx, const int32_t* host_system_offsets,
+                                       int n_systems, const int32_t* nbmat, const int32_t* shifts, int nb_width, int fill_value,
+                                       double accuracy, double* energies_per_atom, float* forces, float* charge_grad,
+                                       double* virial, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AIM_TRY(check_lists("ewald_summation", n_atoms, cell, n_systems, n_systems, nbmat, shifts, nb_width));
+    AIM_REQUIRE(positions && charges && energies_per_atom && cell && host_cell, "ewald_summation: null argument (a cell per system is required)");
+    AIM_REQUIRE(n_systems == 1 || (host_system_offsets != nullptr && batch_idx != nullptr), "ewald_summation: batches need batch_idx and host_system_offsets");
+    AIM_REQUIRE(accuracy > 0.0 && accuracy < 1.0, "ewald_summation: accuracy must be in (0, 1)");
+    SeamScratch s;
+    const bool own_forces = virial != nullptr && forces == nullptr;
+    AIM_TRY(seam_alloc(s, n_atoms, n_systems, false, virial != nullptr, own_forces, st));
+    AIM_TRY(launch_mol_ptr(batch_idx, n_atoms, n_systems, s.mol_ptr, nullptr, st));
+    float* F = forces ? forces : s.forces;
+    float* gq = charge_grad ? charge_grad : s.f0;
+    if (n_atoms > 0) {
+        AIM_CUDA_CHECK(cudaMemsetAsync(gq, 0, sizeof(float) * n_atoms, st));
+        if (F) AIM_CUDA_CHECK(cudaMemsetAsync(F, 0, sizeof(float) * 3 * n_atoms, st));
+        if (virial) AIM_CUDA_CHECK(cudaMemsetAsync(s.virial_atom, 0, sizeof(double) * 9 * n_atoms, st));
+    }
+    if ((int)g_seam_plans.size() < n_systems) g_seam_plans.resize(n_systems);
+    PairSource ps{NbView{nbmat, shifts, nullptr, nb_width, fill_value}, batch_idx, s.mol_ptr, 0.f};
+    CellView cv{cell, n_systems};
+    for (int k = 0; k < n_systems; ++k) {
+        const int lo = host_system_offsets ? host_system_offsets[k] : 0;
+        const int ns = (host_system_offsets ? host_system_offsets[k + 1] : n_atoms) - lo;
+        AIM_REQUIRE(lo >= 0 && ns >= 0 && lo + ns <= n_atoms, "ewald_summation: bad system offsets");
+        if (ns == 0) continue;
+        EwaldPlan& pl = g_seam_plans[k];
+        AIM_TRY(ewald_prepare(pl, host_cell + 9 * k, ns, accuracy, 0.0, st));
+        CoulombParams cp{(float)pl.rc, (float)pl.alpha, 0.f, 0.f, 0.f, 0.5};
+        AIM_TRY(launch_coulomb(PAIR_EWALD, ns, ps, positions, cv, charges, cp, s.e_atom, gq, F, s.virial_atom, 0, st, lo));
+        AIM_TRY(launch_ewald_recip(pl, ns, positions + 3 * (size_t)lo, charges + lo, s.e_atom + lo, gq + lo,
+                                   F ? F + 3 * (size_t)lo : nullptr, s.virial_atom ? s.virial_atom + 9 * (size_t)lo : nullptr, st, 1.0));
+    }
+    if (n_atoms > 0)
+        AIM_CUDA_CHECK(cudaMemcpyAsync(energies_per_atom, s.e_atom, sizeof(double) * n_atoms, cudaMemcpyDeviceToDevice, st));
+    if (virial) {
+        virial_reduce_kernel<<<n_systems, 256, 0, st>>>(s.mol_ptr, s.virial_atom, -1.0, virial);
+        AIM_LAUNCH_CHECK();
+    }
+    return AIMNET_OK;
 }
 
 extern "C" int aimnet2_estimate_ewald_parameters(const float* host_cell, int n_atoms, double accuracy, double* alpha,

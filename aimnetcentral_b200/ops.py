@@ -354,6 +354,70 @@ def dftd3(positions: Tensor, numbers: Tensor, a1: float, a2: float, s8: float, s
     return tuple(out)
 
 
+class _EwaldEnergy(torch.autograd.Function):
+    """Per-atom energies with the charge response attached (d E / d q_i at fixed geometry from the kernel)."""
+
+    @staticmethod
+    def forward(ctx, charges, energies, charge_grad):
+        ctx.save_for_backward(charge_grad)
+        return energies.clone()
+
+    @staticmethod
+    def backward(ctx, grad_e):
+        (charge_grad,) = ctx.saved_tensors
+        # E_total = sum_i e_i and dE_total/dq_i = charge_grad_i; a caller that weights atoms of one system equally (the
+        # reference scatter-adds per system, lr.py:698-703) gets the exact chain rule
+        return (grad_e.to(charge_grad.dtype) * charge_grad), None, None
+
+
+def ewald_summation(positions: Tensor, charges: Tensor, cell: Tensor, batch_idx: Tensor | None = None,
+                    neighbor_matrix: Tensor | None = None, neighbor_matrix_shifts: Tensor | None = None,
+                    mask_value: int | None = None, accuracy: float = 1e-6, compute_forces: bool = False,
+                    compute_virial: bool = False):
+    """Ewald summation with the call signature of `nvalchemiops…ewald_summation` at aimnet/modules/lr.py:687-696.
+    Returns `energies_per_atom (N,) f64 [e^2/A]` (differentiable with respect to `charges`); with `compute_forces` /
+    `compute_virial` additionally `forces (N,3) f32 [e^2/A^2]` / `virial (S,3,3) f32` — the reference takes those from
+    autograd through the energies, this library returns them explicitly.  The neighbor matrix must reach every system's
+    real-space cutoff (`estimate_ewald_parameters`)."""
+    if neighbor_matrix is None or cell is None:
+        raise ValueError("ewald_summation needs a cell and a neighbor_matrix")
+    lib = _capi.load()
+    cells = cell.detach().reshape(-1, 3, 3)
+    S = int(cells.shape[0])
+    dev, n, nb, bidx, cell_t, n_cells, sh = _pair_inputs(positions, cells, batch_idx, neighbor_matrix, neighbor_matrix_shifts, S)
+    if S > 1 and bidx is None:
+        raise ValueError("batch_idx is required with more than one cell")
+    host_cell = np.ascontiguousarray(cell_t.cpu().numpy(), dtype=np.float32)
+    offs = None
+    if S > 1:
+        counts = torch.bincount(bidx.to(torch.int64), minlength=S).cpu().numpy()
+        offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+    pos = positions.detach().to(torch.float32).contiguous()
+    q = charges.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:n].contiguous()
+    e_atom = torch.empty(n, dtype=torch.float64, device=dev)
+    want_f = bool(compute_forces or compute_virial)
+    forces = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_f else None
+    gq = torch.empty(n, dtype=torch.float32, device=dev)
+    virial = torch.empty(S, 3, 3, dtype=torch.float64, device=dev) if compute_virial else None
+    p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+    with torch.cuda.device(dev):
+        rc = lib.aimnet2_ewald_summation(pos.data_ptr(), q.data_ptr(), n, cell_t.data_ptr(), host_cell.ctypes.data, p(bidx),
+                                         None if offs is None else offs.ctypes.data, S, nb.data_ptr(), p(sh), nb.shape[1],
+                                         int(n if mask_value is None else mask_value), float(accuracy), e_atom.data_ptr(),
+                                         p(forces), gq.data_ptr(), p(virial), _stream(dev))
+    _capi.check(rc, "ewald_summation")
+    if charges.requires_grad:
+        full_gq = gq if charges.reshape(-1).shape[0] == n else torch.cat([gq, gq.new_zeros(charges.numel() - n)])
+        full_e = e_atom if charges.reshape(-1).shape[0] == n else torch.cat([e_atom, e_atom.new_zeros(charges.numel() - n)])
+        e_atom = _EwaldEnergy.apply(charges.reshape(-1), full_e, full_gq.to(charges.dtype))[:n]
+    out = [e_atom]
+    if want_f:
+        out.append(forces)
+    if compute_virial:
+        out.append(virial.to(torch.float32))
+    return out[0] if len(out) == 1 else tuple(out)
+
+
 class EwaldParameters:
     """What the reference reads from `estimate_ewald_parameters` (aimnet/calculators/calculator.py:1566-1587)."""
 

@@ -245,6 +245,24 @@ int aimnet2_dftd3(const float* positions, const int32_t* numbers, int n_atoms, f
                   const int32_t* nbmat, const int32_t* shifts, int nb_width, int fill_value, double* energy,
                   float* forces, float* coord_num, double* virial, void* stream);
 
+/* Ewald summation; replaces nvalchemiops...ewald_summation as called at aimnet/modules/lr.py:687-696 (an energy-only call
+ * there: forces, stress and the charge response come from autograd through the returned energies; here they are explicit
+ * optional outputs, like in the DSF seam).  Splitting parameters per system from `accuracy`
+ * (aimnet/calculators/calculator.py:663-666); real space over the caller's neighbor matrix, which must reach every system's
+ * real-space cutoff (aimnet2_estimate_ewald_parameters); reciprocal space, self and neutralising-background terms per system.
+ * Units e^2/Angstrom (the caller multiplies by Hartree*Bohr, lr.py:697).
+ *   cell                (n_systems,3,3) f32 device, one cell per system; host_cell: the same values in host memory
+ *   host_system_offsets n_systems + 1 ints in HOST memory, atoms [off[s], off[s+1]) = system s; NULL when n_systems == 1
+ *   energies_per_atom   (n_atoms) f64 device out; real-space and self terms per atom, the reciprocal-space energy of a
+ *                       system booked on its first atom (only per-system sums are defined: lr.py:698-703)
+ *   forces (n_atoms,3) f32 / charge_grad (n_atoms) f32 / virial (n_systems,3,3) f64 device out, each may be NULL
+ * Reciprocal-space plans are cached per system slot in process-wide storage: one caller thread at a time. */
+int aimnet2_ewald_summation(const float* positions, const float* charges, int n_atoms, const float* cell,
+                            const float* host_cell, const int32_t* batch_idx, const int32_t* host_system_offsets,
+                            int n_systems, const int32_t* nbmat, const int32_t* shifts, int nb_width, int fill_value,
+                            double accuracy, double* energies_per_atom, float* forces, float* charge_grad, double* virial,
+                            void* stream);
+
 /* Ewald splitting parameters for a target accuracy (host arithmetic only); replaces
  * nvalchemiops...estimate_ewald_parameters as used at aimnet/calculators/calculator.py:1566-1587, formulas
  * calculator.py:663-666: eta = (V^2/N)^(1/6)/sqrt(2 pi), r_c = sqrt(-2 ln eps) eta, k_c = sqrt(-2 ln eps)/eta,

@@ -241,3 +241,57 @@ def test_engine_with_pipelined_gemm_equals_backend2():
         calc.engine.set_gemm_backend(2)
     for k in ref:
         assert torch.equal(ref[k], out[k]), (k, float((ref[k].double() - out[k].double()).abs().max()))
+
+
+def test_ewald_summation_seam_against_oracle():
+    """`ops.ewald_summation` (call-site signature of aimnet/modules/lr.py:687-696) against the float64 textbook Ewald of the
+    oracle (oracle/aimnet2_oracle.py: coulomb_ewald, checked against the rock-salt Madelung constant): per-system energy,
+    forces and charge response via autograd on the oracle, for one system and for a batch of two different cells."""
+    from aimnetcentral_b200 import ops
+    from aimnetcentral_b200.structures import allose_supercell, random_periodic_box
+    from oracle.aimnet2_oracle import coulomb_ewald
+
+    ke = HARTREE * BOHR
+    systems = []
+    z1, x1, c1 = random_periodic_box(60, seed=7)
+    z2, x2, c2 = allose_supercell((1, 1, 1), jitter=0.02, seed=3)
+    rng = np.random.default_rng(4)
+    for x, c in ((x1, c1), (x2, c2)):
+        q = rng.normal(0, 0.4, len(x)).astype(np.float32)
+        q[0] += 0.3   # net charge: the neutralising background term is exercised
+        systems.append((x, c, q))
+
+    def oracle(x, c, q):
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        qt = torch.tensor(q, dtype=torch.float64, requires_grad=True)
+        e = coulomb_ewald(xt, qt, torch.tensor(c, dtype=torch.float64), accuracy=1e-6)
+        gx, gq = torch.autograd.grad(e, [xt, qt])
+        return float(e) / ke, (-gx / ke).numpy(), (gq / ke).numpy()
+
+    def seam(xs, cs, qs):
+        dev = "cuda"
+        x = torch.as_tensor(np.concatenate(xs), dtype=torch.float32, device=dev)
+        q = torch.as_tensor(np.concatenate(qs), dtype=torch.float32, device=dev).requires_grad_(True)
+        cells = torch.as_tensor(np.stack(cs), dtype=torch.float32, device=dev)
+        bidx = torch.as_tensor(np.concatenate([np.full(len(a), k) for k, a in enumerate(xs)]), dtype=torch.int32, device=dev)
+        par = ops.estimate_ewald_parameters(x, cells, bidx, accuracy=1e-6)
+        rc = float(par.real_space_cutoff.max())
+        xw = torch.cat([ops.wrap_positions(x[bidx == k], cells[k]) for k in range(len(xs))])
+        nb, cnt, sh = ops.neighbor_list(xw, rc, cell=cells, pbc=torch.ones(len(xs), 3, dtype=torch.bool, device=dev), batch_idx=bidx,
+                                        max_neighbors=int(1.5 * 4.19 * rc**3 * 0.12) + 64)
+        e_atom, f = ops.ewald_summation(positions=xw, charges=q, cell=cells, batch_idx=bidx, neighbor_matrix=nb,
+                                        neighbor_matrix_shifts=sh, mask_value=xw.shape[0], accuracy=1e-6, compute_forces=True)
+        e_sys = torch.zeros(len(xs), dtype=torch.float64, device=dev).scatter_add(0, bidx.long(), e_atom)
+        (gq,) = torch.autograd.grad(e_sys.sum(), q)
+        return e_sys.detach().cpu().numpy(), f.cpu().numpy(), gq.cpu().numpy(), bidx.cpu().numpy()
+
+    for label, sel in (("one system", [0]), ("batch of two cells", [0, 1])):
+        xs, cs, qs = zip(*[systems[k] for k in sel])
+        e, f, gq, b = seam(xs, cs, qs)
+        for k, s in enumerate(sel):
+            eo, fo, gqo = oracle(*systems[s])
+            m = b == k
+            print(f"[seam] ewald {label} system {s}: dE={abs(e[k] - eo):.2e} (E {eo:.3f} e^2/A) dF={np.abs(f[m] - fo).max():.2e} dgq={np.abs(gq[m] - gqo).max():.2e}")
+            assert abs(e[k] - eo) < 2e-5 * max(1.0, abs(eo))
+            assert np.abs(f[m] - fo).max() < 2e-5
+            assert np.abs(gq[m] - gqo).max() < 2e-5
