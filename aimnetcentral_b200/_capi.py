@@ -65,7 +65,7 @@ ABI_VERSION = 2   # include/aimnet2_b200.h AIMNET2_ABI_VERSION
 EXPORTS = [
     "aimnet2_last_error", "aimnet2_abi_version", "aimnet2_abi_struct_sizes", "aimnet2_neighbor_matrix", "aimnet2_wrap_positions",
     "aimnet2_conv_sv_2d_sp_fwd", "aimnet2_conv_sv_2d_sp_bwd", "aimnet2_engine_create", "aimnet2_engine_destroy",
-    "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_small_m_rows", "aimnet2_engine_set_conv_impl", "aimnet2_engine_conv_mode", "aimnet2_engine_debug_poison", "aimnet2_engine_debug_layout", "aimnet2_engine_debug_read_workspace", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
+    "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_small_m_rows", "aimnet2_engine_set_conv_impl", "aimnet2_engine_conv_mode", "aimnet2_engine_set_dense_min_molecules", "aimnet2_engine_debug_poison", "aimnet2_engine_debug_layout", "aimnet2_engine_debug_read_workspace", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
     "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_skin_stats", "aimnet2_engine_enable_timing",
     "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace",
     "aimnet2_dsf_coulomb", "aimnet2_dftd3", "aimnet2_ewald_summation", "aimnet2_estimate_ewald_parameters",
@@ -102,6 +102,7 @@ def load():
     lib.aimnet2_engine_set_small_m_rows.argtypes = [vp, ci]
     lib.aimnet2_engine_set_conv_impl.argtypes = [vp, ci]
     lib.aimnet2_engine_conv_mode.argtypes = [vp, c_int_p, c_int_p, c_int_p]
+    lib.aimnet2_engine_set_dense_min_molecules.argtypes = [vp, ci]
     lib.aimnet2_engine_debug_poison.argtypes = [vp, ci]
     lib.aimnet2_engine_debug_layout.argtypes = [vp, C.c_char_p, ci]
     lib.aimnet2_engine_debug_read_workspace.argtypes = [vp, vp, C.c_int64, C.c_int64]

@@ -61,6 +61,7 @@ struct aimnet2_engine {
     int gemm_backend = 0;
     int poison = -1;              // test seam: byte written over the workspace before every evaluation (-1 = off)
     int conv_impl = 1;            // 0 = list kernels (conv.cu) always; for batches of small molecules: 1 = dense shared-memory forward (conv_dense.cu) + list backward, 2 = dense forward and backward
+    int dense_min_mol = 64;       // the dense walk needs enough molecules to give every SM one (a CTA works on one molecule at a time)
     bool dense_now = false;       // the evaluation in flight walks molecule segments instead of matrix rows
     int last_max_seg = 0;         // largest molecule (atoms) of the last batch whose lists the engine built
     int small_m_rows = kSmallM;   // at or below this many atoms the MLPs run on the small-M fp32 SIMT kernel (0 = never)
@@ -548,7 +549,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             // atoms of its molecule.  Worth it when most atoms of a molecule are inside the cutoff anyway: small molecules, or
             // at least half of the molecule in the widest row.  Not with a caller-supplied matrix or a cell.
             // ... and when there are enough molecules to give every SM one (a CTA works on one molecule at a time)
-            e->dense_now = e->conv_impl >= 1 && own_sr && !pbc && B >= 64 && e->last_max_seg >= 2 &&
+            e->dense_now = e->conv_impl >= 1 && own_sr && !pbc && B >= e->dense_min_mol && e->last_max_seg >= 2 &&
                            e->last_max_seg <= conv_dense_max_atoms(C) &&
                            (e->last_max_seg <= 64 || 2 * e->last_sr_width >= e->last_max_seg);
             if (skin > 0.f) {
@@ -911,6 +912,14 @@ extern "C" int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl) {
     AIM_REQUIRE(e, "set_conv_impl: null engine");
     AIM_REQUIRE(impl >= 0 && impl <= 2, "set_conv_impl: 0 = list kernels always, 1 = dense shared-memory forward for batches of small molecules (default), 2 = dense forward and backward");
     e->conv_impl = impl;
+    e->skin.valid = false;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_set_dense_min_molecules(aimnet2_engine_t* e, int n_mol) {
+    AIM_REQUIRE(e, "set_dense_min_molecules: null engine");
+    AIM_REQUIRE(n_mol >= 1, "set_dense_min_molecules: need at least one molecule");
+    e->dense_min_mol = n_mol;
     e->skin.valid = false;
     return AIMNET_OK;
 }

@@ -131,6 +131,10 @@ class Engine:
         2 = dense forward and backward."""
         _capi.check(self._lib.aimnet2_engine_set_conv_impl(self._h, int(impl)), "set_conv_impl")
 
+    def set_dense_min_molecules(self, n_mol: int):
+        """Batches with at least `n_mol` molecules take the dense conv walk (default 64)."""
+        _capi.check(self._lib.aimnet2_engine_set_dense_min_molecules(self._h, int(n_mol)), "set_dense_min_molecules")
+
     def conv_mode(self) -> dict:
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         self._lib.aimnet2_engine_conv_mode(self._h, C.byref(a), C.byref(b), C.byref(c))

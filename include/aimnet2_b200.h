@@ -179,6 +179,9 @@ int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
  * the last evaluation took the dense walk, and the largest molecule of that batch. */
 int aimnet2_engine_set_conv_impl(aimnet2_engine_t* e, int impl);
 int aimnet2_engine_conv_mode(const aimnet2_engine_t* e, int* impl, int* dense_last, int* max_molecule_last);
+/* The dense walk is taken for batches of at least this many molecules (default 64: one CTA works on one molecule at a time,
+ * fewer molecules leave SMs idle and the list kernels win); tests lower it to run small fixtures through the dense kernels. */
+int aimnet2_engine_set_dense_min_molecules(aimnet2_engine_t* e, int n_mol);
 /* Evaluations with at most `rows` atoms run the MLPs on the small-M fp32 SIMT kernel whatever the backend (the
  * tensor-core pipelines are latency-bound for a single molecule); default 512, 0 = never. */
 int aimnet2_engine_set_small_m_rows(aimnet2_engine_t* e, int rows);

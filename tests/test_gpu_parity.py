@@ -93,6 +93,7 @@ def test_conv_list_and_dense_walks_agree(name, kw):
     calc = get_calc(meta)
     res = {}
     try:
+        calc.engine.set_dense_min_molecules(1)   # the fixtures are small: take the dense kernels whatever the batch size
         for impl in (0, 1, 2):
             calc.engine.set_conv_impl(impl)
             for rows in (0, 512):   # both MLP paths
@@ -106,6 +107,7 @@ def test_conv_list_and_dense_walks_agree(name, kw):
             assert mode["dense_last"] == (impl >= 1 and "cell" not in inputs), mode
     finally:
         calc.engine.set_conv_impl(1)
+        calc.engine.set_dense_min_molecules(64)
         calc.engine.set_small_m_rows(512)
     for rows, impl in ((0, 1), (512, 1), (0, 2), (512, 2)):
         base, r = res[0, rows], res[impl, rows]
