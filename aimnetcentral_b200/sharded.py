@@ -66,26 +66,38 @@ def make_plan(data: dict, world: int) -> dict:
             "atoms_per_rank": [int(edges[b] - edges[a]) for a, b in ranges]}
 
 
-def shard_batch(data: dict, rank: int, world: int, plan: dict | None = None) -> tuple[dict, dict]:
-    """Slice a batch for `rank` (views for tensors / arrays; only `mol_idx` is rebased).  Returns (local data, plan)."""
+def shard_batch(data: dict, rank: int, world: int, plan: dict | None = None, cache: dict | None = None) -> tuple[dict, dict]:
+    """Slice a batch for `rank` (views for tensors / arrays; only `mol_idx` is rebased).  Returns (local data, plan).
+    `cache` (optional, owned by the caller): slices of tensors that do not change from call to call (species, molecule
+    index, charges ...) are handed out as the SAME tensor objects while the source tensor is unchanged (identity +
+    `_version`), so that the calculator's per-tensor caches (species validation) keep hitting."""
     plan = plan or make_plan(data, world)
     lo, hi = plan["mol_ranges"][rank]
     a0, a1 = plan["atom_ranges"][rank]
+
+    def cut(k, v):
+        per_mol = k in ("charge", "mult") or (k == "cell" and np.ndim(v) == 3) or (k == "pbc" and np.ndim(v) == 2)
+        if plan["form"] == "dense":
+            return v[lo:hi] if (per_mol or k in ("coord", "numbers")) else v
+        if k in ("coord", "numbers"):
+            return v[a0:a1]
+        if k == "mol_idx":
+            return v[a0:a1] - lo
+        return v[lo:hi] if per_mol else v
+
     out = {}
     for k, v in data.items():
         if v is None:
             continue
-        per_mol = k in ("charge", "mult") or (k == "cell" and np.ndim(v) == 3) or (k == "pbc" and np.ndim(v) == 2)
-        if plan["form"] == "dense":
-            out[k] = v[lo:hi] if (per_mol or k in ("coord", "numbers")) else v
-        elif k in ("coord", "numbers"):
-            out[k] = v[a0:a1]
-        elif k == "mol_idx":
-            out[k] = v[a0:a1] - lo
-        elif per_mol:
-            out[k] = v[lo:hi]
+        if cache is not None and k != "coord" and isinstance(v, torch.Tensor):
+            key = (id(v), v.data_ptr(), v._version, tuple(v.shape), lo, hi, a0, a1)
+            hit = cache.get(k)
+            if hit is None or hit[0] != key or hit[1]() is not v:
+                hit = (key, weakref.ref(v), cut(k, v))
+                cache[k] = hit
+            out[k] = hit[2]
         else:
-            out[k] = v
+            out[k] = cut(k, v)
     return out, plan
 
 
@@ -146,6 +158,7 @@ class ShardedCalculator:
         self.calc = calc
         self.group = group
         self._plan_cache = None   # (key, weakref or None, plan)
+        self._slice_cache: dict = {}
 
     def _plan(self, data: dict, world: int) -> dict:
         coord, mi = data["coord"], data.get("mol_idx")
@@ -167,11 +180,8 @@ class ShardedCalculator:
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return self.calc(data, forces=forces, stress=stress)
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        local_in, plan = shard_batch(data, rank, world, self._plan(data, world))
+        local_in, plan = shard_batch(data, rank, world, self._plan(data, world), self._slice_cache)
         local = self.calc(local_in, forces=forces, stress=stress)
         if not gather:
             return local
-        out = gather_results(local, plan, self.group)
-        if plan["form"] == "dense":
-            return out
-        return out
+        return gather_results(local, plan, self.group)
