@@ -82,7 +82,7 @@ class AIMNet2Calculator:
                  compile_kwargs: dict | None = None, cache_static: bool = False, train: bool = False,
                  deterministic: bool = False, ensemble_member: int = 0, revision: str | None = None,
                  token: str | None = None, *, model_import_paths=None, model_import_mode: str = "extend",
-                 neighbor_skin: float = 0.0):
+                 neighbor_skin: float = 0.0, cuda_graph: bool = False):
         if device is None:
             device = "cuda"
         dev = torch.device(device)
@@ -145,6 +145,11 @@ class AIMNet2Calculator:
         # (aimnet/calculators/aimnet2ase.py:69, aimnet2torchsim.py:78-125)
         self.model = SimpleNamespace(_metadata=metadata, metadata=metadata, num_charge_channels=C)
         self.engine.set_deterministic(self._deterministic)
+        # extension over the reference API: replay repeated fixed-shape evaluations as one CUDA graph (MD / optimizer loops
+        # on small systems are launch-bound); see aimnet2_engine_enable_cuda_graph
+        self.cuda_graph = bool(cuda_graph)
+        if self.cuda_graph:
+            self.engine.enable_cuda_graph(True)
         self._push_options()
 
     # ---- properties (calculator.py:380-515) ------------------------------------------------------------------

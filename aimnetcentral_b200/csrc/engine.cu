@@ -102,6 +102,14 @@ struct aimnet2_engine {
         std::vector<uint8_t> pbc;
         int builds = 0, reuses = 0;
     } skin;
+    // CUDA-graph replay of the fixed-shape step: the kernels of one evaluation captured once per
+    // (sizes, flags, options, staging buffers) signature and relaunched as one graph
+    struct GraphState {
+        bool enabled = false, capturing = false, valid = false, pending = false;
+        cudaGraphExec_t exec = nullptr;
+        std::vector<unsigned char> sig, pending_sig;
+        int launches = 0, captures = 0, fallbacks = 0;
+    } graph;
     std::vector<void*> owned;
     std::vector<aimnet::Region> layout;   // names / offsets of the workspace buffers of the last evaluation (debug)
     bool deterministic = false;           // recorded only: every kernel of the engine is run-to-run reproducible
@@ -229,6 +237,7 @@ struct Buffers {
     float *dense_fpart, *dense_gqpart;   // dense conv walk: per-quarter partial forces (4, N, 3) / charge gradients (4, N, C)
     float *coord_ref, *wrap_off;   // Verlet skin: positions at list-build time, lattice offset applied by the wrap
     int32_t *skin_flag, *mol_ref;
+    int32_t* graph_counts;   // graph replay: widest short-range / long-range row of the replayed build (overflow check afterwards)
 };
 
 static SplitMat alias_split(float* base, size_t n, int width, float* inv) {
@@ -315,6 +324,7 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.wrap_off = bp.take<float>(n * 3, "wrap_off");
     b.skin_flag = bp.take<int32_t>(4, "skin_flag");
     b.mol_ref = bp.take<int32_t>(n, "mol_ref");
+    b.graph_counts = bp.take<int32_t>(4, "graph_counts");
 }
 
 static void class_mark(aimnet2_engine* e, int cls, cudaStream_t st) {
@@ -480,6 +490,8 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         Bump probe{nullptr};
         carve(e, probe, b, N, B, e->sr_cap, e->lr_cap, pbc, need_lr_list, ldx);
         size_t need = probe.off + 1024;
+        const bool capturing = e->graph.capturing;
+        AIM_REQUIRE(!capturing || need <= e->ws_bytes, "engine_eval: workspace changed during graph capture");
         if (need > e->ws_bytes) {
             AIM_CUDA_CHECK(cudaStreamSynchronize(st));
             if (e->ws) AIM_CUDA_CHECK(cudaFree(e->ws));
@@ -521,6 +533,20 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             coord = b.coord_w;
         }
         bool retry = false;
+        if (capturing) {
+            // replayed build: no read-back inside the graph; the widest rows are kept on the device and checked after the replay
+            AIM_REQUIRE(own_sr, "engine_eval: graph capture needs the engine's own lists");
+            AIM_TRY(build_list(e, coord, N, o.sr_cutoff, sys, sys->mol_idx, 1, e->sr_cap, b.nb_sr, b.sh_sr, b.cnt_sr, nullptr,
+                               b.nb_scratch, st));
+            AIM_CUDA_CHECK(cudaMemcpyAsync(b.graph_counts, b.nb_scratch, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            AIM_CUDA_CHECK(cudaMemsetAsync(b.graph_counts + 1, 0, sizeof(int32_t), st));
+            if (need_lr_list) {
+                AIM_TRY(build_list(e, coord, N, lr_cut, sys, sys->mol_idx, 0, e->lr_cap, b.nb_lr, b.sh_lr, b.cnt_lr, nullptr,
+                                   b.nb_scratch, st));
+                AIM_CUDA_CHECK(cudaMemcpyAsync(b.graph_counts + 1, b.nb_scratch, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            }
+            break;   // caps, widths and the dense / list choice are those of the eager evaluation that preceded the capture
+        }
         if (own_sr) {
             int maxc = 0;
             int rc = build_list(e, coord, N, o.sr_cutoff + skin, sys, sys->mol_idx, 1, e->sr_cap, b.nb_sr, b.sh_sr, b.cnt_sr,
@@ -881,6 +907,7 @@ extern "C" int aimnet2_engine_destroy(aimnet2_engine_t* e) {
     for (void* p : e->owned) cudaFree(p);
     if (e->ws) cudaFree(e->ws);
     if (e->stage) cudaFree(e->stage);
+    if (e->graph.exec) cudaGraphExecDestroy(e->graph.exec);
     for (EwaldPlan& pl : e->ewald) ewald_release(pl);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->pinned_int) cudaFreeHost(e->pinned_int);
@@ -962,13 +989,184 @@ extern "C" int aimnet2_engine_set_deterministic(aimnet2_engine_t* e, int on) {
     return AIMNET_OK;
 }
 
+namespace aimnet {
+
+// ---- CUDA-graph replay ------------------------------------------------------------------------------------------
+// What a captured graph depends on besides the kernels' code: sizes, request flags, options, kernel selection, the
+// neighbor capacities and every device pointer baked into the kernel nodes (the staging buffers and the workspace).
+static std::vector<unsigned char> graph_signature(const aimnet2_engine* e, const aimnet2_system_t* ds, const aimnet2_result_t* dr,
+                                                  int flags, cudaStream_t st) {
+    std::vector<unsigned char> sig;
+    auto put = [&sig](const void* p, size_t n) { sig.insert(sig.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+    const int ints[] = {ds->n_atoms, ds->n_mol, ds->n_cells, flags, e->sr_cap, e->lr_cap, e->gemm_backend, e->conv_impl,
+                        e->dense_min_mol, e->small_m_rows, e->dense_now ? 1 : 0, e->last_max_seg};
+    put(ints, sizeof(ints));
+    const void* ptrs[] = {ds->coord, ds->numbers, ds->mol_idx, ds->charge, ds->mult, ds->cell, dr->energy, dr->charges,
+                          dr->spin_charges, dr->forces, dr->stress, e->ws, (const void*)st};
+    put(ptrs, sizeof(ptrs));
+    put(&e->opt, sizeof(e->opt));
+    return sig;
+}
+
+static bool graph_eligible(const aimnet2_engine* e, const aimnet2_system_t* ds, const aimnet2_result_t* dr) {
+    const aimnet2_options_t& o = e->opt;
+    return e->graph.enabled && e->timing == 0 && e->poison < 0 && ds->n_atoms > 0 && ds->nbmat == nullptr &&
+           dr->nbmat_out == nullptr && o.coulomb_method != AIMNET_COULOMB_EWALD && !(o.neighbor_skin > 0.f) &&
+           ds->pbc_host == nullptr && !(ds->cell != nullptr && ds->n_atoms >= 512);   // the cell-list builder allocates and sorts: not captured
+}
+
+// ds / dr point into the engine's staging buffers (stable addresses from call to call)
+static int eval_staged(aimnet2_engine* e, const aimnet2_system_t* ds, const aimnet2_result_t* dr, int flags, cudaStream_t st) {
+    if (!graph_eligible(e, ds, dr)) return eval_impl(e, ds, dr, flags, st);
+    auto& g = e->graph;
+    if (g.valid && g.sig == graph_signature(e, ds, dr, flags, st)) {
+        AIM_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+        // the replayed neighbor build cannot grow its buffers: check the widest rows afterwards
+        Buffers b;
+        Bump bp{e->ws};
+        const int ldx = pad32(2 * kAG + kAH + e->C * (1 + kG + kH));
+        const bool need_lr = ds->cell != nullptr && (e->opt.coulomb_method != AIMNET_COULOMB_NONE || e->opt.dispersion);
+        carve(e, bp, b, ds->n_atoms, ds->n_mol, e->sr_cap, e->lr_cap, ds->cell != nullptr, need_lr, ldx);
+        AIM_CUDA_CHECK(cudaMemcpyAsync(e->pinned_int + 4, b.graph_counts, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        AIM_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (e->pinned_int[4] <= e->sr_cap && e->pinned_int[5] <= e->lr_cap) {
+            g.launches++;
+            e->last_launches = 1;
+            return AIMNET_OK;
+        }
+        g.valid = false;   // a row outgrew its buffer: redo this step eagerly (grows the buffers), capture again later
+        g.fallbacks++;
+    }
+    int rc = eval_impl(e, ds, dr, flags, st);
+    if (rc != AIMNET_OK) return rc;
+    std::vector<unsigned char> sig = graph_signature(e, ds, dr, flags, st);
+    if (!(g.pending && g.pending_sig == sig)) {   // first sighting of this shape: remember it, capture when it comes back
+        g.pending = true;
+        g.pending_sig = sig;
+        return AIMNET_OK;
+    }
+    // second evaluation with the same signature: record the step (nothing executes during capture; this call's results are
+    // those of the eager evaluation above)
+    cudaGraph_t graph = nullptr;
+    AIM_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    g.capturing = true;
+    const int saved_launches = e->last_launches;
+    rc = eval_impl(e, ds, dr, flags, st);
+    g.capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    e->last_launches = saved_launches;
+    if (rc != AIMNET_OK || ce != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        g.pending = false;
+        return AIMNET_OK;   // the eager results stand; stay on the eager path
+    }
+    if (g.exec) {
+        cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+    }
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        g.exec = nullptr;
+        g.valid = g.pending = false;
+        return AIMNET_OK;
+    }
+    g.sig = sig;
+    g.valid = true;
+    g.pending = false;
+    g.captures++;
+    return AIMNET_OK;
+}
+
+struct Staged {
+    aimnet2_system_t ds;
+    aimnet2_result_t dr;
+};
+
+// engine-owned device copies of every input / output array (grow-only), carved in a fixed order
+static int stage_buffers(aimnet2_engine* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, Staged& s) {
+    const int N = sys->n_atoms, B = sys->n_mol, nc = sys->n_cells;
+    const size_t n = (size_t)std::max(N, 1);
+    auto carve_stage = [&](Bump& bp) {
+        s.ds = *sys;
+        s.dr = *res;
+        s.ds.coord = bp.take<float>(n * 3);
+        s.ds.numbers = bp.take<int32_t>(n);
+        s.ds.mol_idx = sys->mol_idx ? bp.take<int32_t>(n) : nullptr;
+        s.ds.charge = bp.take<float>(B);
+        s.ds.mult = sys->mult ? bp.take<float>(B) : nullptr;
+        s.ds.cell = sys->cell ? bp.take<float>((size_t)9 * nc) : nullptr;
+        s.dr.energy = bp.take<double>(B);
+        s.dr.charges = bp.take<float>(n);
+        s.dr.spin_charges = res->spin_charges ? bp.take<float>(n) : nullptr;
+        s.dr.forces = res->forces ? bp.take<float>(n * 3) : nullptr;
+        s.dr.stress = res->stress ? bp.take<float>((size_t)9 * std::max(nc, 1)) : nullptr;
+        s.dr.nbmat_out = nullptr;
+        s.dr.shifts_out = nullptr;
+    };
+    Bump probe{nullptr};
+    carve_stage(probe);
+    if (probe.off + 1024 > e->stage_bytes) {
+        AIM_CUDA_CHECK(cudaDeviceSynchronize());
+        if (e->stage) AIM_CUDA_CHECK(cudaFree(e->stage));
+        e->stage = nullptr;
+        AIM_CUDA_CHECK(cudaMalloc((void**)&e->stage, probe.off + 1024));
+        e->stage_bytes = probe.off + 1024;
+        e->graph.valid = e->graph.pending = false;
+    }
+    Bump bp{e->stage};
+    carve_stage(bp);
+    return AIMNET_OK;
+}
+
+static int stage_copies(const aimnet2_system_t* sys, const aimnet2_result_t* res, const Staged& s, int flags, bool in,
+                        cudaMemcpyKind kind, cudaStream_t st) {
+    const int N = sys->n_atoms, B = sys->n_mol, nc = sys->n_cells;
+#define CP(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), (bytes), kind, st))
+    if (in) {
+        if (N > 0) {
+            CP(s.ds.coord, sys->coord, sizeof(float) * 3 * N);
+            CP(s.ds.numbers, sys->numbers, sizeof(int32_t) * N);
+            if (sys->mol_idx) CP(s.ds.mol_idx, sys->mol_idx, sizeof(int32_t) * N);
+        }
+        CP(s.ds.charge, sys->charge, sizeof(float) * B);
+        if (sys->mult) CP(s.ds.mult, sys->mult, sizeof(float) * B);
+        if (sys->cell) CP(s.ds.cell, sys->cell, sizeof(float) * 9 * nc);
+    } else {
+        CP(res->energy, s.dr.energy, sizeof(double) * B);
+        if (N > 0) {
+            CP(res->charges, s.dr.charges, sizeof(float) * N);
+            if (res->spin_charges) CP(res->spin_charges, s.dr.spin_charges, sizeof(float) * N);
+            if (res->forces && (flags & AIMNET_WANT_FORCES)) CP(res->forces, s.dr.forces, sizeof(float) * 3 * N);
+        }
+        if (res->stress && (flags & AIMNET_WANT_STRESS)) CP(res->stress, s.dr.stress, sizeof(float) * 9 * nc);
+    }
+#undef CP
+    return AIMNET_OK;
+}
+
+}  // namespace aimnet
+
 extern "C" int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags,
                                    void* stream) {
-    AIM_REQUIRE(e, "engine_eval: null engine");
+    AIM_REQUIRE(e && sys && res, "engine_eval: null argument");
     AIM_CUDA_CHECK(cudaSetDevice(e->device));
-    int rc = eval_impl(e, sys, res, flags, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (e->graph.enabled && graph_eligible(e, sys, res) && sys->n_mol >= 1) {
+        // graph replay needs stable addresses: inputs / outputs go through the engine's staging buffers (device-to-device)
+        Staged s;
+        AIM_TRY(stage_buffers(e, sys, res, s));
+        s.ds.host_cell = sys->host_cell;
+        AIM_TRY(stage_copies(sys, res, s, flags, true, cudaMemcpyDeviceToDevice, st));
+        rc = eval_staged(e, &s.ds, &s.dr, flags, st);
+        if (rc == AIMNET_OK) rc = stage_copies(sys, res, s, flags, false, cudaMemcpyDeviceToDevice, st);
+    } else {
+        rc = eval_impl(e, sys, res, flags, st);
+    }
     if (rc == AIMNET_OK && e->timing) {
-        cudaStream_t st = (cudaStream_t)stream;
         AIM_CUDA_CHECK(cudaStreamSynchronize(st));
         collect_timing(e);
     }
@@ -980,63 +1178,32 @@ extern "C" int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_syste
     AIM_REQUIRE(e && sys && res, "engine_eval_host: null argument");
     AIM_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->own_stream;
-    const int N = sys->n_atoms, B = sys->n_mol, nc = sys->n_cells;
-    AIM_REQUIRE(N >= 0 && B >= 1, "engine_eval_host: bad sizes");
+    AIM_REQUIRE(sys->n_atoms >= 0 && sys->n_mol >= 1, "engine_eval_host: bad sizes");
     AIM_REQUIRE(sys->nbmat == nullptr, "engine_eval_host: caller-supplied nbmat is only supported by engine_eval");
-    size_t n = (size_t)std::max(N, 1);
-    Bump probe{nullptr};
-    auto carve_stage = [&](Bump& bp, aimnet2_system_t& ds, aimnet2_result_t& dr) {
-        ds = *sys;
-        dr = *res;
-        ds.coord = bp.take<float>(n * 3);
-        ds.numbers = bp.take<int32_t>(n);
-        ds.mol_idx = sys->mol_idx ? bp.take<int32_t>(n) : nullptr;
-        ds.charge = bp.take<float>(B);
-        ds.mult = sys->mult ? bp.take<float>(B) : nullptr;
-        ds.cell = sys->cell ? bp.take<float>((size_t)9 * nc) : nullptr;
-        ds.host_cell = sys->cell;   // the caller's cell IS host memory here
-        dr.energy = bp.take<double>(B);
-        dr.charges = bp.take<float>(n);
-        dr.spin_charges = res->spin_charges ? bp.take<float>(n) : nullptr;
-        dr.forces = res->forces ? bp.take<float>(n * 3) : nullptr;
-        dr.stress = res->stress ? bp.take<float>((size_t)9 * std::max(nc, 1)) : nullptr;
-        dr.nbmat_out = nullptr;
-        dr.shifts_out = nullptr;
-    };
-    aimnet2_system_t ds;
-    aimnet2_result_t dr;
-    carve_stage(probe, ds, dr);
-    if (probe.off + 1024 > e->stage_bytes) {
-        if (e->stage) AIM_CUDA_CHECK(cudaFree(e->stage));
-        e->stage = nullptr;
-        AIM_CUDA_CHECK(cudaMalloc((void**)&e->stage, probe.off + 1024));
-        e->stage_bytes = probe.off + 1024;
-    }
-    Bump bp{e->stage};
-    carve_stage(bp, ds, dr);
-#define H2D(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st))
-#define D2H(dst, src, bytes) AIM_CUDA_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st))
-    if (N > 0) {
-        H2D(ds.coord, sys->coord, sizeof(float) * 3 * N);
-        H2D(ds.numbers, sys->numbers, sizeof(int32_t) * N);
-        if (sys->mol_idx) H2D(ds.mol_idx, sys->mol_idx, sizeof(int32_t) * N);
-    }
-    H2D(ds.charge, sys->charge, sizeof(float) * B);
-    if (sys->mult) H2D(ds.mult, sys->mult, sizeof(float) * B);
-    if (sys->cell) H2D(ds.cell, sys->cell, sizeof(float) * 9 * nc);
-    int rc = eval_impl(e, &ds, &dr, flags, st);
+    Staged s;
+    AIM_TRY(stage_buffers(e, sys, res, s));
+    s.ds.host_cell = sys->cell;   // the caller's cell IS host memory here
+    AIM_TRY(stage_copies(sys, res, s, flags, true, cudaMemcpyHostToDevice, st));
+    int rc = eval_staged(e, &s.ds, &s.dr, flags, st);
     if (rc != AIMNET_OK) return rc;
-    D2H(res->energy, dr.energy, sizeof(double) * B);
-    if (N > 0) {
-        D2H(res->charges, dr.charges, sizeof(float) * N);
-        if (res->spin_charges) D2H(res->spin_charges, dr.spin_charges, sizeof(float) * N);
-        if (res->forces && (flags & AIMNET_WANT_FORCES)) D2H(res->forces, dr.forces, sizeof(float) * 3 * N);
-    }
-    if (res->stress && (flags & AIMNET_WANT_STRESS)) D2H(res->stress, dr.stress, sizeof(float) * 9 * nc);
-#undef H2D
-#undef D2H
+    AIM_TRY(stage_copies(sys, res, s, flags, false, cudaMemcpyDeviceToHost, st));
     AIM_CUDA_CHECK(cudaStreamSynchronize(st));
     if (e->timing) collect_timing(e);
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_enable_cuda_graph(aimnet2_engine_t* e, int on) {
+    AIM_REQUIRE(e, "enable_cuda_graph: null engine");
+    e->graph.enabled = on != 0;
+    e->graph.valid = e->graph.pending = false;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_graph_stats(const aimnet2_engine_t* e, int* captures, int* launches, int* fallbacks) {
+    AIM_REQUIRE(e, "graph_stats: null engine");
+    if (captures) *captures = e->graph.captures;
+    if (launches) *launches = e->graph.launches;
+    if (fallbacks) *fallbacks = e->graph.fallbacks;
     return AIMNET_OK;
 }
 

@@ -550,7 +550,14 @@ def main():
                 ms_h = rx.time_wall(rx.step_host, 2, k)
                 extra[name] = {"workload": rx.w["desc"], "atoms": rx.N, "steps": k, "warmup": 3, "ms_per_step": ms_x / k,
                                "value": rx.N * k / (ms_x * 1e-3), "e2e": rx.N * k / (ms_h * 1e-3), "unit": UNIT,
-                               "gpu_launches_per_step": rx.eng.last_launches(), "clocks": s.stop()}
+                               "gpu_launches_per_step": rx.eng.last_launches()}
+                if name == "cfg1":   # launch-bound: the same step replayed as one CUDA graph (AIMNet2Calculator(cuda_graph=True))
+                    rx.eng.enable_cuda_graph(True)
+                    ms_g = rx.time_events(rx.step_device, 3, k)
+                    ms_gh = rx.time_wall(rx.step_host, 3, k)
+                    extra[name]["cuda_graph"] = {"ms_per_step": ms_g / k, "value": rx.N * k / (ms_g * 1e-3), "e2e": rx.N * k / (ms_gh * 1e-3),
+                                                 "stats": rx.eng.graph_stats()}
+                extra[name]["clocks"] = s.stop()
                 del rx
             line["extra_workloads"] = extra
         if world == 1 and not args.no_cpu_baseline:

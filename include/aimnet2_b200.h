@@ -203,6 +203,18 @@ int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* sys, const 
 /* same with every pointer of sys/res in HOST memory: H2D copies, evaluation, D2H copies, stream sync inside */
 int aimnet2_engine_eval_host(aimnet2_engine_t* e, const aimnet2_system_t* sys, const aimnet2_result_t* res, int flags);
 
+/* CUDA-graph replay of the fixed-shape step (the MD / optimizer loop of SURVEY.md section 8f f1; the reference's
+ * counterpart is the static-shape contract of compile_model / cache_static, aimnet/calculators/calculator.py:1091-1238).
+ * With on = 1, an evaluation whose sizes, flags and options repeat is captured once (on its second occurrence) and from
+ * then on replayed as one graph launch; inputs / outputs pass through engine-owned staging buffers so that the recorded
+ * addresses stay valid (engine_eval: device-to-device copies, engine_eval_host: the H2D / D2H copies it makes anyway).  The
+ * replayed neighbor build cannot grow its buffers: the widest rows are read back after the replay and, on overflow, the step
+ * is redone eagerly.  Not captured (such calls silently take the eager path): Ewald, Verlet skin, caller-supplied
+ * matrices, partial pbc, periodic systems of >= 512 atoms (cell-list builder), timing / poison modes.
+ * graph_stats: graphs captured, replays, replays redone eagerly after an overflow. */
+int aimnet2_engine_enable_cuda_graph(aimnet2_engine_t* e, int on);
+int aimnet2_engine_graph_stats(const aimnet2_engine_t* e, int* captures, int* launches, int* fallbacks);
+
 /* introspection: kernels launched by the last eval, last short-range / long-range list widths, workspace bytes */
 int aimnet2_engine_last_launches(const aimnet2_engine_t* e);
 int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int* lr_width, int64_t* workspace_bytes);

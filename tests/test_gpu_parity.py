@@ -748,3 +748,53 @@ def test_torchsim_and_pysis_adapters_on_the_engine(monkeypatch):
     assert np.abs(r["forces"].reshape(-1, 3) * ha / bohr - ref["forces"]).max() < FORCE_ATOL
     with pytest.raises(NotImplementedError):
         p.get_hessian(atoms, (inputs["coord"].astype(np.float64) / bohr).reshape(-1))
+
+
+def test_cuda_graph_replay_equals_eager():
+    """cuda_graph=True: the second evaluation of a repeating shape captures the step, later ones replay it as one graph
+    launch; results are BITWISE those of the eager path (same kernels, same order), for an isolated molecule, a small
+    periodic cell with stress, and through the host-buffer entry.  A geometry whose rows outgrow the recorded neighbor
+    buffers is detected after the replay and redone eagerly."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import allose_supercell
+
+    spec = ModelSpec()
+    sd = random_state_dict(0, spec)
+    eager = AIMNet2Calculator((sd, spec), device="cuda:0")
+    graphed = AIMNet2Calculator((sd, spec), device="cuda:0", cuda_graph=True)
+    inputs, _, _ = load_golden("taxol_q0")
+    rng = np.random.default_rng(3)
+    for step in range(6):
+        x = (inputs["coord"] + rng.normal(0, 0.02, inputs["coord"].shape)).astype(np.float32)
+        d = {"coord": x, "numbers": inputs["numbers"], "charge": np.zeros(1, np.float32)}
+        a, b = eager(dict(d), forces=True), graphed(dict(d), forces=True)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (step, k)
+    st = graphed.engine.graph_stats()
+    assert st["captures"] == 1 and st["launches"] == 4 and st["fallbacks"] == 0, st
+    # squeezed geometry: more neighbors than the recorded buffers hold -> replay detects it, the step is redone eagerly
+    xs = (inputs["coord"] * 0.55).astype(np.float32)
+    d = {"coord": xs, "numbers": inputs["numbers"], "charge": np.zeros(1, np.float32)}
+    a, b = eager(dict(d), forces=True), graphed(dict(d), forces=True)
+    assert torch.equal(a["forces"], b["forces"]) and torch.equal(a["energy"], b["energy"])
+    assert graphed.engine.graph_stats()["fallbacks"] == 1
+    # periodic cell + stress
+    z, x0, cell = allose_supercell((1, 1, 1), jitter=0.02, seed=3)
+    for calc in (eager, graphed):
+        calc.set_lrcoulomb_method("dsf")
+    for step in range(4):
+        x = (x0 + rng.normal(0, 0.01, x0.shape)).astype(np.float32)
+        d = {"coord": x, "numbers": z, "charge": np.zeros(1, np.float32), "cell": cell}
+        a, b = eager(dict(d), forces=True, stress=True), graphed(dict(d), forces=True, stress=True)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (step, k)
+    assert graphed.engine.graph_stats()["captures"] >= 2
+    # host-buffer entry
+    n0 = graphed.engine.graph_stats()["launches"]
+    for step in range(4):
+        x = (x0 + rng.normal(0, 0.01, x0.shape)).astype(np.float32)
+        oa = eager.engine.eval_host(x, z.astype(np.int32), np.zeros(1, np.float32), cell=cell, forces=True, stress=True)
+        ob = graphed.engine.eval_host(x, z.astype(np.int32), np.zeros(1, np.float32), cell=cell, forces=True, stress=True)
+        for k in oa:
+            assert np.array_equal(oa[k], ob[k]), (step, k)
+    assert graphed.engine.graph_stats()["launches"] >= n0 + 2
