@@ -132,6 +132,7 @@ class AIMNet2Calculator:
         self._impl_lut = None
         self._host_cell_cache = None            # (key, weakref(cell tensor), host copy)
         self._upload_cache: dict = {}           # key -> (host copy, device tensor) of static per-system inputs
+        self._validated_numbers = None          # the cached host copy of `numbers` that passed species validation
         self._batch: int | None = None
         # extension over the reference API: Verlet skin (A) for neighbor-list reuse across MD steps; 0 = rebuild every call
         self._neighbor_skin = float(neighbor_skin)
@@ -240,6 +241,13 @@ class AIMNet2Calculator:
             cached = self._species_validation_cache
             hit = (key is not None and cached is not None and cached[0] == key and cached[1]() is numbers
                    and cached[2] is impl)
+            if not hit and key is None:
+                # host input (numpy / list): unchanged VALUES since the last validated call count as validated (the same
+                # comparison decides whether the device copy is reused, see _upload)
+                c = self._upload_cache.get("numbers")
+                host = np.asarray(numbers)
+                hit = (c is not None and self._validated_numbers is c[0] and c[0].shape == host.shape
+                       and c[0].dtype == host.dtype and np.array_equal(c[0], host))
             if not hit:
                 self._validate_numbers(numbers, impl)
                 if key is not None:
@@ -353,6 +361,9 @@ class AIMNet2Calculator:
         if hessian:
             raise NotImplementedError("Hessians are outside this engine's hot path (SURVEY.md §8f f4)")
         d = self.to_input_tensors(data)
+        if validate_species and not isinstance(data.get("numbers"), Tensor):
+            c = self._upload_cache.get("numbers")
+            self._validated_numbers = c[0] if c is not None else None
         coord, numbers, charge = d["coord"], d["numbers"], d["charge"]
         cell = d.get("cell")
         method = self._coulomb_method

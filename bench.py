@@ -15,7 +15,8 @@ Printed JSON line (rank 0):
               inside the timed region; weak scaling (1024 molecules per GPU) unless --scaling strong.
   e2e         the same metric through the C-ABI host-buffer entry (aimnet2_engine_eval_host): H2D of coord / numbers /
               charge / mol_idx from pinned memory + compute + D2H of energy / forces / charges, every step
-  api         the same through AIMNet2Calculator.__call__ with numpy inputs and .cpu() of the outputs (the front door)
+  api         the same through AIMNet2Calculator.__call__ with numpy inputs and a copy of every output tensor into pinned
+              host buffers (the front door, as an MD / screening driver uses it)
   roofline    the kernel class that takes the largest share of the step, `roofline_classes` both classes (per-atom MLP
               GEMMs on the tensor pipe, AEV / conv_sv on the fp32 FMA pipe) from CUDA events around every launch of the
               class in a separate instrumented pass, `step_roofline` the t_roof / t_measured of SURVEY.md section 8(d)
@@ -300,7 +301,14 @@ class Runner:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             out = self.calc(self.api_inputs(i), forces=True, stress=self.w["stress"])
-        return {k: v.cpu() for k, v in out.items()}
+        # what an MD / screening driver does with the returned device tensors: one asynchronous copy per output into
+        # page-locked host buffers, one synchronisation
+        if not hasattr(self, "_api_pinned"):
+            self._api_pinned = {k: self.torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+        for k, v in out.items():
+            self._api_pinned[k].copy_(v, non_blocking=True)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        return self._api_pinned
 
     def h2d_bytes(self):
         n = self.coords_h[0].numel() * 4 + self.numbers_h.numel() * 4 + self.charge_h.numel() * 4
@@ -534,7 +542,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(),
                     "path": "aimnet2_engine_eval_host (C ABI, pinned host buffers)"},
             "api": {"value": api_value, "unit": UNIT, "ratio_to_e2e": api_value / e2e_value,
-                    "path": "AIMNet2Calculator.__call__(numpy inputs) + .cpu() of every output"},
+                    "path": "AIMNet2Calculator.__call__(numpy inputs) + copy of every output into pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dominant, "roofline_classes": classes, "step_roofline": step_roof,
