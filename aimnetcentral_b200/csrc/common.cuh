@@ -27,6 +27,7 @@ extern thread_local int g_launch_count;
         cudaError_t _e = (expr);                                                                    \
         if (_e != cudaSuccess) {                                                                    \
             ::aimnet::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+            cudaGetLastError(); /* reported here: do not leave it for the next launch check */      \
             return AIMNET_ECUDA;                                                                    \
         }                                                                                           \
     } while (0)

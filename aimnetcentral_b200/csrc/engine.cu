@@ -1156,13 +1156,20 @@ extern "C" int aimnet2_engine_eval(aimnet2_engine_t* e, const aimnet2_system_t* 
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (e->graph.enabled && graph_eligible(e, sys, res) && sys->n_mol >= 1) {
-        // graph replay needs stable addresses: inputs / outputs go through the engine's staging buffers (device-to-device)
+        // Graph replay needs stable addresses and a capturable stream: inputs / outputs go through the engine's staging
+        // buffers (device-to-device) and the step runs on the engine's own stream (the caller's may be the legacy default
+        // stream, which cannot be captured), ordered after / before the caller's stream with two events.
+        cudaStream_t own = e->own_stream;
+        AIM_CUDA_CHECK(cudaEventRecord(e->ev[5], st));
+        AIM_CUDA_CHECK(cudaStreamWaitEvent(own, e->ev[5], 0));
         Staged s;
         AIM_TRY(stage_buffers(e, sys, res, s));
         s.ds.host_cell = sys->host_cell;
-        AIM_TRY(stage_copies(sys, res, s, flags, true, cudaMemcpyDeviceToDevice, st));
-        rc = eval_staged(e, &s.ds, &s.dr, flags, st);
-        if (rc == AIMNET_OK) rc = stage_copies(sys, res, s, flags, false, cudaMemcpyDeviceToDevice, st);
+        AIM_TRY(stage_copies(sys, res, s, flags, true, cudaMemcpyDeviceToDevice, own));
+        rc = eval_staged(e, &s.ds, &s.dr, flags, own);
+        if (rc == AIMNET_OK) rc = stage_copies(sys, res, s, flags, false, cudaMemcpyDeviceToDevice, own);
+        AIM_CUDA_CHECK(cudaEventRecord(e->ev[5], own));
+        AIM_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev[5], 0));
     } else {
         rc = eval_impl(e, sys, res, flags, st);
     }
