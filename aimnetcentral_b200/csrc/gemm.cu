@@ -106,22 +106,24 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
     }
 }
 
-// Small-M variant of the fp32 SIMT kernel: 16 x 16 output tiles, 64 threads (one row x four columns each), K in chunks
-// of 32 with register prefetch.  For a single molecule (M = number of atoms, ~100) the tensor-core kernels are
-// latency-bound (TMEM allocation, 22 dependent TMA stages, one or two CTAs busy): ~17 us per layer.  This kernel spreads
-// the same layer over (M/16) x (N/16) small CTAs (256 for 113 x 512) so that every SM works on it; it is what the
-// engine uses at or below kSmallM rows.
-constexpr int SBM = 16, SBN = 16, SBK = 32;
+// Small-M variant of the fp32 SIMT kernel: 16 x 16 output tiles; 256 threads = four groups of 64 (one row x four columns
+// each), every group accumulates a quarter of the K chunks (chunks of 32 with register prefetch, own double buffer), the
+// partial sums are added in fixed order at the end.  For a single molecule (M = number of atoms, ~100) the tensor-core
+// kernels are latency-bound (TMEM allocation, 22 dependent TMA stages, one or two CTAs busy): ~17 us per layer.  This
+// kernel spreads the same layer over (M/16) x (N/16) small CTAs (256 for 113 x 512) so that every SM works on it, and the
+// four-way split of K cuts the dependent chain of a layer (22 chunks for K = 704) to a quarter: the single-molecule step
+// is a chain of ~60 such kernels (profiles/r2_cfg1_*).  It is what the engine uses at or below kSmallM rows.
+constexpr int SBM = 16, SBN = 16, SBK = 32, SKG = 4;
 
 template <int MODE>
-__global__ void __launch_bounds__(64) gemm_nt_small_kernel(const float* __restrict__ A, int lda,
-                                                           const float* __restrict__ W, int ldw,
-                                                           const float* __restrict__ bias, float* __restrict__ Y,
-                                                           int ldy, float* __restrict__ aux, int ldaux, int M, int N,
-                                                           int K) {
-    __shared__ float As[2][SBK][SBM + 1];
-    __shared__ __align__(16) float Ws[2][SBK][SBN + 4];
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(64 * SKG) gemm_nt_small_kernel(const float* __restrict__ A, int lda,
+                                                                 const float* __restrict__ W, int ldw,
+                                                                 const float* __restrict__ bias, float* __restrict__ Y,
+                                                                 int ldy, float* __restrict__ aux, int ldaux, int M, int N,
+                                                                 int K) {
+    __shared__ float As[SKG][2][SBK][SBM + 1];
+    __shared__ __align__(16) float Ws[SKG][2][SBK][SBN + 4];
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
     const int tx = tid & 3, ty = tid >> 2;          // output: row ty, columns 4 tx .. 4 tx + 3
     const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
     // loads: tile rows lr and lr + 8, k offset lk (two float4 of A and of W per thread)
@@ -140,36 +142,56 @@ __global__ void __launch_bounds__(64) gemm_nt_small_kernel(const float* __restri
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int r = lr + 8 * u;
-            As[buf][lk + 0][r] = ra[u].x;
-            As[buf][lk + 1][r] = ra[u].y;
-            As[buf][lk + 2][r] = ra[u].z;
-            As[buf][lk + 3][r] = ra[u].w;
-            Ws[buf][lk + 0][r] = rw[u].x;
-            Ws[buf][lk + 1][r] = rw[u].y;
-            Ws[buf][lk + 2][r] = rw[u].z;
-            Ws[buf][lk + 3][r] = rw[u].w;
+            As[grp][buf][lk + 0][r] = ra[u].x;
+            As[grp][buf][lk + 1][r] = ra[u].y;
+            As[grp][buf][lk + 2][r] = ra[u].z;
+            As[grp][buf][lk + 3][r] = ra[u].w;
+            Ws[grp][buf][lk + 0][r] = rw[u].x;
+            Ws[grp][buf][lk + 1][r] = rw[u].y;
+            Ws[grp][buf][lk + 2][r] = rw[u].z;
+            Ws[grp][buf][lk + 3][r] = rw[u].w;
         }
     };
-    gload(0);
-    sstore(0);
-    __syncthreads();
+    // group g takes chunks g, g + 4, ...; every group runs the same number of rounds (empty chunks load nothing), so the
+    // block-wide barriers stay uniform
     const int nk = K / SBK;
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) gload((kt + 1) * SBK);
+    const int rounds = (nk + SKG - 1) / SKG;
+    if (grp < nk) gload(grp * SBK);
+    if (grp < nk) sstore(0);
+    __syncthreads();
+    for (int it = 0; it < rounds; ++it) {
+        const int buf = it & 1;
+        const int kt = it * SKG + grp, ktn = kt + SKG;
+        if (ktn < nk) gload(ktn * SBK);
+        if (kt < nk) {
 #pragma unroll
-        for (int k = 0; k < SBK; ++k) {
-            const float a = As[buf][k][ty];
-            const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
-            acc[0] = fmaf(a, b.x, acc[0]);
-            acc[1] = fmaf(a, b.y, acc[1]);
-            acc[2] = fmaf(a, b.z, acc[2]);
-            acc[3] = fmaf(a, b.w, acc[3]);
+            for (int k = 0; k < SBK; ++k) {
+                const float a = As[grp][buf][k][ty];
+                const float4 b = *reinterpret_cast<const float4*>(&Ws[grp][buf][k][tx * 4]);
+                acc[0] = fmaf(a, b.x, acc[0]);
+                acc[1] = fmaf(a, b.y, acc[1]);
+                acc[2] = fmaf(a, b.z, acc[2]);
+                acc[3] = fmaf(a, b.w, acc[3]);
+            }
         }
-        if (kt + 1 < nk) {
-            sstore(buf ^ 1);
+        if (it + 1 < rounds) {
+            if (ktn < nk) sstore(buf ^ 1);
             __syncthreads();
         }
+    }
+    // add the four partial sums in fixed order (group 0 + 1 + 2 + 3): deterministic
+    __syncthreads();
+    float4* part = reinterpret_cast<float4*>(&Ws[0][0][0][0]);   // 3 x 64 float4 = 3 KB of the (now idle) operand buffers
+    if (grp > 0) part[(grp - 1) * 64 + tid] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    if (grp > 0) return;
+#pragma unroll
+    for (int g2 = 0; g2 < SKG - 1; ++g2) {
+        const float4 pv = part[g2 * 64 + tid];
+        acc[0] += pv.x;
+        acc[1] += pv.y;
+        acc[2] += pv.z;
+        acc[3] += pv.w;
     }
     const int row = m0 + ty, col = n0 + tx * 4;
     if (row >= M || col >= N) return;
@@ -211,10 +233,10 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
     if (M <= kSmallM && K % SBK == 0) {
         dim3 sgrid((N + SBN - 1) / SBN, (M + SBM - 1) / SBM);
         switch (mode) {
-            case 0: gemm_nt_small_kernel<0><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
-            case 1: gemm_nt_small_kernel<1><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
-            case 2: gemm_nt_small_kernel<2><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
-            default: gemm_nt_small_kernel<3><<<sgrid, 64, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            case 0: gemm_nt_small_kernel<0><<<sgrid, 64 * SKG, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            case 1: gemm_nt_small_kernel<1><<<sgrid, 64 * SKG, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            case 2: gemm_nt_small_kernel<2><<<sgrid, 64 * SKG, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
+            default: gemm_nt_small_kernel<3><<<sgrid, 64 * SKG, 0, st>>>(A, lda, W, ldw, bias, Y, ldy, aux, ldaux, M, N, K); break;
         }
         AIM_LAUNCH_CHECK();
         return AIMNET_OK;
