@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libaimnet2_b200.so")
-SOURCES = ["engine.cu", "nblist.cu", "conv.cu", "conv_dense.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc16.cu", "gemm_tc16p.cu", "pointwise.cu", "lr.cu", "ewald.cu", "seams.cu"]
+SOURCES = ["engine.cu", "nblist.cu", "conv.cu", "conv_dense.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc16.cu", "gemm_tc16p.cu", "gemm_tc16d.cu", "gemm_tc16c.cu", "pointwise.cu", "lr.cu", "ewald.cu", "seams.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -362,7 +362,7 @@ static int linear_fwd16(aimnet2_engine* e, const Linear& L, const SplitMat& X, f
                         bool act, int M, cudaStream_t st) {
     gemm_mark(e, st);
     int rc = gemm_nt_split(X, L.fwd(), L.b, Y32, L.out_pad, Y16, gp, L.out_pad, M, L.out_pad, L.in_pad, act ? 2 : 1,
-                           e->backend_now == 3, st);
+                           e->backend_now - 2, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -370,7 +370,7 @@ static int linear_bwd16(aimnet2_engine* e, const Linear& L, const SplitMat& dZ, 
                         const float* gp_prev, int ldgp, int M, cudaStream_t st) {
     gemm_mark(e, st);
     int rc = gemm_nt_split(dZ, L.bwd(), nullptr, dX32, lddx, dX16, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
-                           gp_prev ? 3 : 0, e->backend_now == 3, st);
+                           gp_prev ? 3 : 0, e->backend_now - 2, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -436,7 +436,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
     const bool backward = want_f || want_s;
     // small systems: the tensor-core pipelines are latency-bound below a few hundred rows, the fp32 SIMT small-M kernel wins
     const int backend_eff = (e->gemm_backend != 0 && N <= e->small_m_rows) ? 0 : e->gemm_backend;
-    const bool tc16 = backend_eff >= 2;   // 2 = 3xFP16 (default), 3 = the same with the experimental pipelined epilogue
+    const bool tc16 = backend_eff >= 2;   // 3xFP16 kernels: 2 one tile stream, 3 experimental pipelined epilogue, 4 two tile streams
     e->backend_now = backend_eff;
     const int ldx = pad32(2 * kAG + kAH + C * (1 + kG + kH));
     const bool need_lr_terms = (o.coulomb_method == AIMNET_COULOMB_SIMPLE || o.coulomb_method == AIMNET_COULOMB_DSF ||
@@ -928,8 +928,9 @@ extern "C" int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_opt
 
 extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend) {
     AIM_REQUIRE(e, "set_gemm_backend: null engine");
-    AIM_REQUIRE(backend >= 0 && backend <= 3,
-                "set_gemm_backend: backend must be 0 (SIMT), 1 (3xTF32), 2 (3xFP16) or 3 (3xFP16 with the experimental pipelined epilogue)");
+    AIM_REQUIRE(backend >= 0 && backend <= 5,
+                "set_gemm_backend: backend must be 0 (SIMT), 1 (3xTF32), 2 (3xFP16), 3 (3xFP16 with the experimental pipelined "
+                "epilogue), 4 (3xFP16, two tile streams per SM) or 5 (two tile streams on CTA pairs)");
     AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backends not available in this build");
     e->gemm_backend = backend;
     return AIMNET_OK;

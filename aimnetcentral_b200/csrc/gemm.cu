@@ -254,14 +254,18 @@ int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, flo
 
 // 3xFP16 backend: A pre-split; output fp32 (Ysplit == nullptr) or pre-split for a consuming GEMM
 int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, float* Y, int ldy, const SplitMat* Ysplit,
-                  float* aux, int ldaux, int M, int N, int K, int mode, bool pipelined, cudaStream_t st) {
+                  float* aux, int ldaux, int M, int N, int K, int mode, int variant, cudaStream_t st) {
     AIM_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes");
     AIM_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad epilogue mode");
     AIM_REQUIRE(mode != 3 || aux != nullptr, "gemm: mode 3 needs aux");
     AIM_REQUIRE((mode != 1 && mode != 2) || bias != nullptr, "gemm: bias required");
     AIM_REQUIRE(w.Wh16 != nullptr && w.Wl16 != nullptr, "gemm: 3xFP16 backend needs the fp16 split weights");
     if (M == 0) return AIMNET_OK;
-    if (pipelined)   // experimental backend 3 (gemm_tc16p.cu)
+    if (variant == 3)   // backend 5: two tile streams per SM on CTA pairs (gemm_tc16c.cu)
+        return gemm_nt_tc16c(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
+    if (variant == 2)   // backend 4: two tile streams per SM (gemm_tc16d.cu)
+        return gemm_nt_tc16d(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
+    if (variant == 1)   // experimental backend 3 (gemm_tc16p.cu)
         return gemm_nt_tc16p(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
     return gemm_nt_tc16(A, w.Wh16, w.Wl16, w.inv_scale16, w.ldw, bias, Y, ldy, Ysplit, aux, ldaux, M, N, K, mode, st);
 }
@@ -276,15 +280,16 @@ extern "C" int aimnet2_gemm_set_trace(void* device_buf) {
 }
 
 // Operator seam for tests / tools: fp32 operands in; weights (and, for backend 2, activations) are split on the device.
-// Backends 2 and 3 (3 = the experimental pipelined-epilogue kernel of gemm_tc16p.cu, not used by the engine): mode | 16
+// Backends 2, 3 and 4 (3 = the experimental pipelined-epilogue kernel of gemm_tc16p.cu; 4 = gemm_tc16d.cu): mode | 16
 // makes the kernel write its output pre-split (the GEMM -> GEMM path of the engine), which is
 // then expanded back to fp32 into Y so that the caller can check it.
 extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                                float* aux, int ldaux, int M, int N, int K, int mode, int backend, void* stream) {
     using namespace aimnet;
     cudaStream_t st = (cudaStream_t)stream;
-    AIM_REQUIRE(backend >= 0 && backend <= 3,
-                "gemm: backend must be 0 (SIMT), 1 (3xTF32), 2 (3xFP16) or 3 (3xFP16, pipelined epilogue: experimental)");
+    AIM_REQUIRE(backend >= 0 && backend <= 5,
+                "gemm: backend must be 0 (SIMT), 1 (3xTF32), 2 (3xFP16), 3 (3xFP16, pipelined epilogue: experimental), 4 "
+                "(3xFP16, two tile streams per SM) or 5 (two tile streams on CTA pairs, cta_group::2)");
     const bool split_out = (mode & 16) != 0;
     mode &= 15;
     AIM_REQUIRE(!split_out || backend >= 2, "gemm: pre-split output exists only for the 3xFP16 backends");
@@ -321,7 +326,7 @@ extern "C" int aimnet2_gemm_nt(const float* A, int lda, const float* W, int ldw,
     int rc = split_fp16_device(W, buf + o_wh, buf + o_wl, inv, reinterpret_cast<unsigned int*>(inv + 16), n, st);
     if (rc == AIMNET_OK) rc = presplit_f32(A, lda, M, K, As, st);
     if (rc == AIMNET_OK)
-        rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, backend == 3, st);
+        rc = gemm_nt_split(As, wv, bias, Y, ldy, split_out ? &Ys : nullptr, aux, ldaux, M, N, K, mode, backend - 2, st);
     if (rc == AIMNET_OK && split_out) rc = unsplit_f32(Ys, M, N, Y, ldy, st);
     cudaFreeAsync(buf, st);
     return rc;

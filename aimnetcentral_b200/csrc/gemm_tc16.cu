@@ -615,6 +615,7 @@ static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int
 
 static unsigned long long* g_trace = nullptr;
 void gemm_tc16_set_trace(unsigned long long* buf) { g_trace = buf; }
+unsigned long long* gemm_tc16_get_trace() { return g_trace; }
 
 // hi / lo: (N, ldw) fp16 split of s_w * W, inv_scale: device scalar 1 / s_w
 int split_fp16_device(const float* w, void* hi, void* lo, float* inv_scale, unsigned int* scratch, size_t n,

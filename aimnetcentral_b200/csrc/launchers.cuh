@@ -42,7 +42,7 @@ int launch_conv_dense_bwd_gather(int C, int n_atoms, int n_mol, int max_seg, con
 int gemm_nt(const float* A, int lda, const WeightView& w, const float* bias, float* Y, int ldy, float* aux, int ldaux,
             int M, int N, int K, int mode, int backend, cudaStream_t st);
 int gemm_nt_split(const SplitMat& A, const WeightView& w, const float* bias, float* Y, int ldy,
-                  const SplitMat* Ysplit, float* aux, int ldaux, int M, int N, int K, int mode, bool pipelined,
+                  const SplitMat* Ysplit, float* aux, int ldaux, int M, int N, int K, int mode, int variant,
                   cudaStream_t st);
 
 // ---- gemm_tc.cu: tcgen05 3xTF32 backend
@@ -53,6 +53,7 @@ int gemm_nt_tc(const float* A, int lda, const float* Whi, const float* Wlo, int 
 
 // ---- gemm_tc16.cu: tcgen05 3xFP16 backend, pre-split activations
 void gemm_tc16_set_trace(unsigned long long* buf);
+unsigned long long* gemm_tc16_get_trace();
 int split_fp16_device(const float* w, void* hi, void* lo, float* inv_scale, unsigned int* scratch, size_t n,
                       cudaStream_t st);
 int presplit_f32(const float* X, int ldx, int M, int K, const SplitMat& out, cudaStream_t st);
@@ -63,6 +64,16 @@ int gemm_nt_tc16(const SplitMat& A, const void* Whi, const void* Wlo, const floa
 
 // ---- gemm_tc16p.cu: experimental backend 3 (software-pipelined tile epilogue); same contract as gemm_nt_tc16
 int gemm_nt_tc16p(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw,
+                  const float* bias, float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N,
+                  int K, int mode, cudaStream_t st);
+
+// ---- gemm_tc16d.cu: backend 4 (two tile streams per SM: epilogue of one under the MMAs of the other); same contract
+int gemm_nt_tc16d(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw,
+                  const float* bias, float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N,
+                  int K, int mode, cudaStream_t st);
+
+// ---- gemm_tc16c.cu: backend 5 (the two-stream kernel on CTA pairs, tcgen05 cta_group::2); same contract
+int gemm_nt_tc16c(const SplitMat& A, const void* Whi, const void* Wlo, const float* w_inv_scale, int ldw,
                   const float* bias, float* Y, int ldy, const SplitMat* Ysplit, float* aux, int ldaux, int M, int N,
                   int K, int mode, cudaStream_t st);
 

@@ -132,7 +132,7 @@ def test_conv_sv_op_against_reference_einsum():
         conv_sv_2d_sp(a.cpu(), idx.cpu(), g.cpu())
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2, 18])   # 18 = backend 2 writing its output pre-split (mode | 16)
+@pytest.mark.parametrize("backend", [0, 1, 2, 18, 4, 20, 5, 21])   # +16 = the backend writing its output pre-split (mode | 16)
 @pytest.mark.parametrize("M,N,K,mode", [(300, 512, 704, 2), (1000, 288, 384, 1), (77, 736, 512, 0), (513, 384, 512, 3),
                                         (1, 128, 256, 2)])
 def test_gemm_epilogues(M, N, K, mode, backend):
@@ -148,8 +148,8 @@ def test_gemm_epilogues(M, N, K, mode, backend):
     Y = torch.empty(M, N, device=dev)
     aux = aux_in.clone() if mode == 3 else torch.empty(M, N, device=dev)
     flag = 0
-    if backend == 18:
-        backend, flag = 2, 16
+    if backend >= 16:
+        backend, flag = backend - 16, 16
     rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K,
                              mode | flag, backend, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     if backend >= 1 and rc != 0 and "not available" in lib.aimnet2_last_error().decode():

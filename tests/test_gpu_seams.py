@@ -154,6 +154,26 @@ def test_gemm_pipelined_epilogue_equals_backend2_bitwise(M, N, K, mode, split_ou
         assert torch.equal(aux2, aux3)
 
 
+@pytest.mark.parametrize("split_out", [0, 16])
+@pytest.mark.parametrize("M,N,K,mode", [(300, 512, 704, 2), (1000, 288, 384, 1), (77, 736, 512, 0), (513, 384, 512, 3),
+                                        (1, 128, 256, 2), (640, 128, 128, 2), (51200, 512, 704, 2), (51200, 704, 512, 3),
+                                        (40000, 288, 384, 1), (39999, 256, 512, 0), (30000, 96, 96, 2), (51200, 512, 32, 3)])
+@pytest.mark.parametrize("backend", [4, 5])
+def test_gemm_two_streams_equals_backend2_bitwise(M, N, K, mode, split_out, backend):
+    """Backend 4 (gemm_tc16d.cu: two 128x128 tile streams per SM, each with its own operand ring, TMEM half, MMA issuer and
+    four epilogue warps) does per output element exactly what backend 2 does, in the same order: bit-identical results,
+    including CTAs whose second stream has no tile, short K loops (one chunk), ragged last tiles in M and N, and
+    many tiles per stream (51 200 x 704: 2 400 tiles, eight per stream).  Backend 5 (gemm_tc16c.cu) is the same kernel on
+    CTA pairs (cta_group::2: 256 x 128 pair tiles, the W tile split between the two CTAs, accumulator rows split between
+    their TMEMs); M = 1 / 77 / 300 leave the second CTA of the pair with no or few rows."""
+    A, W, b, aux_in = _gemm_operands(M, N, K)
+    Y2, aux2 = _gemm_seam(A, W, b, aux_in, mode, 2 + split_out)
+    Y4, aux4 = _gemm_seam(A, W, b, aux_in, mode, backend + split_out)
+    assert torch.equal(Y2, Y4), float((Y2 - Y4).abs().max())
+    if mode == 2:
+        assert torch.equal(aux2, aux4)
+
+
 _MANY_TILES = [(20000, 512, 704, 2), (20000, 288, 384, 1), (20000, 704, 512, 3), (19999, 512, 512, 0)]
 
 
@@ -164,7 +184,7 @@ def test_gemm_more_tiles_than_sms_pipelined(M, N, K, mode, backend):
     test_gemm_more_tiles_than_sms(M, N, K, mode, backend)
 
 
-@pytest.mark.parametrize("backend", [2, 18])   # +16 = the backend writing its output pre-split (mode | 16)
+@pytest.mark.parametrize("backend", [2, 18, 4, 20, 5, 21])   # +16 = the backend writing its output pre-split (mode | 16)
 @pytest.mark.parametrize("M,N,K,mode", _MANY_TILES)
 def test_gemm_more_tiles_than_sms(M, N, K, mode, backend):
     """157 row tiles x 2-3 column tiles = 314-471 tiles on 148 persistent CTAs: each CTA runs 2-4 tiles back to back

@@ -9,7 +9,7 @@ from aimnetcentral_b200 import _capi
 lib = _capi.load()
 dev = "cuda:0"
 M = 51200
-shapes = [(512, 704, 2), (384, 512, 2), (288, 384, 1), (512, 384, 3), (736, 512, 0), (256, 384, 2), (128, 256, 2)]
+shapes = [(512, 704, 2), (384, 512, 2), (288, 384, 1), (512, 384, 3), (736, 512, 0), (256, 384, 2), (128, 256, 2), (704, 512, 3)]
 backends = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1").split(",")]
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for N, K, mode in shapes:
