@@ -161,7 +161,23 @@ class AIMNet2ASE(Calculator):
         return self.results["spin_charges"]
 
     def get_hessian(self, atoms=None):
-        raise PropertyNotImplementedError("Hessians are outside the B200 engine's hot path (SURVEY.md §8f f4)")
+        """Cartesian Hessian as a (3N, 3N) ndarray in eV/A^2, usable as Sella's `hessian_function` (aimnet2ase.py:163-226)."""
+        if atoms is None:
+            atoms = getattr(self, "atoms", None)
+            if atoms is None:
+                raise PropertyNotImplementedError("get_hessian() requires an attached Atoms object or an explicit argument.")
+        if np.asarray(atoms.pbc).any():
+            raise PropertyNotImplementedError(
+                "Hessian for periodic systems is not supported by AIMNet2ASE.get_hessian(). "
+                "For periodic transition states, use pysisyphus dimer or climbing-image NEB.")
+        self._adopt_info(atoms)
+        self.update_tensors(atoms)
+        device = self.base_calc.device
+        system = {"coord": torch.tensor(np.asarray(atoms.positions), dtype=torch.float32, device=device),
+                  "numbers": self._dev.numbers, "charge": self._dev.charge, "mult": self._dev.mult}
+        H = self.base_calc(system, forces=True, hessian=True, validate_species=self.validate_species)["hessian"].detach()
+        n = H.shape[0]
+        return H.reshape(3 * n, 3 * n).cpu().numpy()
 
     # ---- the step ---------------------------------------------------------------------------------------------
     def _inputs_for(self, atoms) -> tuple[dict, bool]:

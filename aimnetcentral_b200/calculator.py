@@ -337,6 +337,188 @@ class AIMNet2Calculator:
             return t
         return torch.as_tensor(v, device=self.device, dtype=dt).detach()
 
+    # ---- second derivatives (calculator.py:904-910, 1247-1450, 1755-1985; derivatives.py:149-192) ----------
+    # The reference differentiates its autograd force graph a second time (3N reverse passes; its periodic long-range block is
+    # itself a float64 central difference, lr.py `_coul_nvalchemi_fd_hessian`).  The engine has analytic first derivatives and
+    # is at its best on batches of molecules, so the Hessian is the central difference of the analytic forces over the 6N
+    # displaced copies of the structure, evaluated as molecule batches (taxol: 678 x 113 atoms, two engine calls).
+    # fp32 forces carry ~1e-6 eV/A of rounding noise, which a difference over 2h amplifies by 1/h, while the truncation error
+    # of the two-point formula grows as h^2 (tools/hessian_step_scan.py: no step gets both below 5e-3 eV/A^2 on the fixtures).
+    # The six-point stencil (error h^6) allows a step of 8e-3 A: max error 1-3e-3 eV/A^2 (2-5e-5 of |H|max), rms 2-4e-4.  The
+    # stencil weights are solved per displaced coordinate from the displacements actually realised in fp32 (x + h is
+    # rounded to the grid of x), and the result is symmetrised (the noise of H[ia,jb] and H[jb,ia] is independent).
+    hessian_step = 8.0e-3          # Angstrom
+    hessian_stencil = 6            # points per displaced coordinate: 2, 4 or 6
+    hessian_batch_atoms = 65_536   # displaced copies are evaluated in chunks of at most this many atoms
+
+    def _fd_weights(self, nodes: Tensor) -> Tensor:
+        """First-derivative weights for the (K, m) stencil nodes (in units of the step): solve sum_t w_t u_t^p = [p == 1]."""
+        m = nodes.shape[1]
+        u = nodes.double()
+        V = torch.stack([u ** p for p in range(m)], dim=1)                 # (K, m, m): row p, column t
+        rhs = torch.zeros((u.shape[0], m, 1), dtype=torch.float64, device=u.device)
+        rhs[:, 1, 0] = 1.0
+        return torch.linalg.solve(V, rhs).squeeze(2)                       # (K, m)
+
+    def _single_structures(self, data: dict) -> list[dict] | None:
+        """Per-structure inputs of a batched Hessian request (calculator.py:1247-1330), None for a single structure."""
+        coord = torch.as_tensor(data["coord"])
+        pick = lambda v, b, n: (lambda t: t[b] if t.ndim >= 1 and t.shape[0] == n else t)(torch.as_tensor(v))
+        subs = None
+        if coord.ndim == 3 and coord.shape[0] > 1:
+            B = int(coord.shape[0])
+            subs = []
+            for b in range(B):
+                sub = {}
+                for k, v in data.items():
+                    if v is None or k.startswith(("nbmat", "shifts")) or k == "mol_idx":
+                        continue
+                    if k in ("coord", "numbers"):
+                        sub[k] = torch.as_tensor(v)[b]
+                    elif k in ("charge", "mult"):
+                        sub[k] = pick(v, b, B)
+                    elif k == "cell":
+                        t = torch.as_tensor(v)
+                        sub[k] = t[b] if t.ndim == 3 else t
+                    else:
+                        sub[k] = v
+                subs.append(sub)
+        elif coord.ndim == 2 and data.get("mol_idx") is not None:
+            mi = torch.as_tensor(data["mol_idx"]).to("cpu")
+            if mi.numel() and int(mi.max()) > 0:
+                n_mol = int(mi.max()) + 1
+                subs = []
+                for m in range(n_mol):
+                    sel = (mi == m).nonzero().squeeze(1)
+                    sub = {}
+                    for k, v in data.items():
+                        if v is None or k.startswith(("nbmat", "shifts")) or k == "mol_idx":
+                            continue
+                        if k in ("coord", "numbers"):
+                            t = torch.as_tensor(v)
+                            sub[k] = t[sel.to(t.device)]
+                        elif k in ("charge", "mult"):
+                            sub[k] = pick(v, m, n_mol)
+                        elif k == "cell":
+                            t = torch.as_tensor(v)
+                            sub[k] = t[m] if t.ndim == 3 else t
+                        else:
+                            sub[k] = v
+                    subs.append(sub)
+        return subs
+
+    def _eval_hessian(self, data: dict, *, forces: bool, stress: bool, validate_species: bool) -> dict:
+        subs = self._single_structures(data)
+        if subs is not None:
+            stack = torch.as_tensor(data["coord"]).ndim == 3
+            results = [self._eval_hessian(sub, forces=forces, stress=stress, validate_species=validate_species) for sub in subs]
+            out = {}
+            for k in results[0]:
+                vals = [r[k] for r in results]
+                if stack and all(v.shape == vals[0].shape for v in vals):
+                    out[k] = torch.stack(vals, dim=0)
+                else:
+                    out[k] = vals
+            return out
+        d = self.to_input_tensors(data)
+        coord = d["coord"]
+        single = {k: v for k, v in data.items() if v is not None and not k.startswith(("nbmat", "shifts")) and k != "mol_idx"}
+        if coord.ndim == 3:   # a batch of one
+            coord = coord[0]
+            single["coord"], single["numbers"] = coord, d["numbers"].reshape(coord.shape[0])
+        numbers = d["numbers"].reshape(-1)
+        real = (numbers > 0).nonzero().squeeze(1)
+        base = self.eval({**single, "coord": coord, "numbers": numbers}, forces=True, stress=stress, validate_species=validate_species)
+        x = coord.index_select(0, real).contiguous()          # real atoms only: padding rows get zero blocks
+        z = numbers.index_select(0, real)
+        n = int(x.shape[0])
+        per_struct = {k: d[k].reshape(-1)[:1] for k in ("charge", "mult") if k in d}
+        cell, pbc = d.get("cell"), d.get("pbc")
+        if cell is not None and cell.ndim == 3:
+            cell = cell[0]
+        H = torch.zeros((3 * n, 3 * n), dtype=torch.float32, device=self.device)
+        m = int(self.hessian_stencil)
+        if m not in (2, 4, 6):
+            raise ValueError("hessian_stencil must be 2, 4 or 6")
+        offsets = torch.tensor([o for q in range(1, m // 2 + 1) for o in (q, -q)], dtype=torch.float32, device=self.device)
+        h = float(self.hessian_step)
+        comps_per_call = max(1, self.hessian_batch_atoms // (m * max(n, 1)))
+        for c0 in range(0, 3 * n, comps_per_call):
+            comps = torch.arange(c0, min(3 * n, c0 + comps_per_call), device=self.device)
+            k = int(comps.numel())
+            ia, ax = comps // 3, comps % 3
+            xb = x.unsqueeze(0).repeat(m * k, 1, 1).view(m, k, n, 3)
+            rows = torch.arange(k, device=self.device)
+            xb[:, rows, ia, ax] += offsets.unsqueeze(1) * h
+            nodes = ((xb[:, rows, ia, ax] - x[ia, ax].unsqueeze(0)) / h).t()          # (k, m): realised, exact in fp32
+            batch = {"coord": xb.view(m * k, n, 3), "numbers": z.unsqueeze(0).expand(m * k, n)}
+            for key, v in per_struct.items():
+                batch[key] = v.expand(m * k)
+            if cell is not None:
+                batch["cell"] = cell.unsqueeze(0).expand(m * k, 3, 3).contiguous()
+                if pbc is not None:
+                    batch["pbc"] = pbc
+            f = self.eval(batch, forces=True, validate_species=False)["forces"].view(m, k, 3 * n)
+            w = self._fd_weights(nodes)                                                # (k, m)
+            H[comps] = (-(w.t().unsqueeze(2) * f.double()).sum(dim=0) / h).float()
+        n_all = int(numbers.shape[0])
+        H = 0.5 * (H + H.t())
+        Hn = H.view(n, 3, n, 3)
+        if n != n_all:
+            full = torch.zeros((n_all, 3, n_all, 3), dtype=H.dtype, device=H.device)
+            full[real.unsqueeze(1), :, real.unsqueeze(0), :] = Hn.permute(0, 2, 1, 3)
+            Hn = full
+        out = dict(base)
+        out["hessian"] = Hn
+        return {k: v for k, v in out.items() if k in self.keys_out}
+
+    def hessian_vector_product(self, data: dict, vectors, *, eps: float = 5e-4, validate_species: bool = True,
+                               create_graph: bool = False) -> Tensor:
+        """`H @ v` for one structure without forming H (calculator.py:1755-1985): directional central difference of the
+        analytic forces (the `hessian_stencil`-point formula), all K directions in one molecule batch.  The step along a
+        direction is `max(eps, hessian_step) / max|v|`.  The result is a detached value (`create_graph` is not available: there is no
+        autograd graph behind the engine)."""
+        if create_graph:
+            raise NotImplementedError("hessian_vector_product(create_graph=True): the engine has no autograd graph")
+        if validate_species:
+            self._validate_species_and_charge(data)
+        self._maybe_warn_mult_ignored(data)
+        coord_in = torch.as_tensor(data["coord"])
+        if coord_in.ndim == 3 and coord_in.shape[0] > 1:
+            raise NotImplementedError("hessian_vector_product supports a single structure only (got 3D batch).")
+        if coord_in.ndim == 2 and data.get("mol_idx") is not None:
+            mi = torch.as_tensor(data["mol_idx"])
+            if mi.numel() and int(mi.max()) > 0:
+                raise NotImplementedError("hessian_vector_product supports a single structure only (got mol_idx batch).")
+        d = self.to_input_tensors(data)
+        coord = d["coord"][0] if d["coord"].ndim == 3 else d["coord"]
+        numbers = d["numbers"].reshape(-1)
+        n = int(coord.shape[0])
+        vecs = torch.as_tensor(vectors, device=self.device, dtype=torch.float32)
+        one = vecs.ndim == 2
+        if one:
+            vecs = vecs.unsqueeze(0)
+        if tuple(vecs.shape[-2:]) != (n, 3):
+            raise ValueError(f"vectors must have trailing shape ({n}, 3); got {tuple(vecs.shape)}")
+        K = int(vecs.shape[0])
+        m = int(self.hessian_stencil)
+        offsets = torch.tensor([o for q in range(1, m // 2 + 1) for o in (q, -q)], dtype=torch.float32, device=self.device)
+        step = max(float(eps), self.hessian_step) / vecs.abs().amax(dim=(1, 2)).clamp(min=1e-12)      # (K,): max |dx| = step
+        xb = coord.view(1, 1, n, 3) + offsets.view(m, 1, 1, 1) * (step.view(1, K, 1, 1) * vecs.unsqueeze(0))
+        batch = {"coord": xb.reshape(m * K, n, 3), "numbers": numbers.unsqueeze(0).expand(m * K, n)}
+        for key in ("charge", "mult"):
+            if key in d:
+                batch[key] = d[key].reshape(-1)[:1].expand(m * K)
+        if d.get("cell") is not None:
+            cell = d["cell"][0] if d["cell"].ndim == 3 else d["cell"]
+            batch["cell"] = cell.unsqueeze(0).expand(m * K, 3, 3).contiguous()
+            if d.get("pbc") is not None:
+                batch["pbc"] = d["pbc"]
+        f = self.eval(batch, forces=True, validate_species=False)["forces"].view(m, K, n, 3)
+        w = self._fd_weights(offsets.unsqueeze(0))[0]                                                  # nominal nodes
+        hv = (-(w.view(m, 1, 1, 1) * f.double()).sum(dim=0) / step.view(K, 1, 1).double()).float()
+        return hv[0] if one else hv
+
     def to_input_tensors(self, data: dict) -> dict[str, Tensor]:
         """calculator.py:1452-1473."""
         ret = {}
@@ -359,7 +541,7 @@ class AIMNet2Calculator:
             self._validate_species_and_charge(data)
         self._maybe_warn_mult_ignored(data)
         if hessian:
-            raise NotImplementedError("Hessians are outside this engine's hot path (SURVEY.md §8f f4)")
+            return self._eval_hessian(data, forces=forces, stress=stress, validate_species=False)
         d = self.to_input_tensors(data)
         if validate_species and not isinstance(data.get("numbers"), Tensor):
             c = self._upload_cache.get("numbers")

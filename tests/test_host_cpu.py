@@ -185,8 +185,12 @@ def test_ase_adapter_host_logic(monkeypatch):
         def __init__(self, nse=False):
             self.is_nse, self.calls = nse, []
 
-        def __call__(self, data, forces=False, stress=False, validate_species=True):
+        def __call__(self, data, forces=False, stress=False, hessian=False, validate_species=True):
             self.calls.append((data, forces, stress, validate_species))
+            if hessian:
+                n = data["coord"].shape[-2]
+                return {"energy": torch.tensor([-7.25], dtype=torch.float64), "forces": torch.ones(n, 3),
+                        "hessian": torch.arange(9 * n * n, dtype=torch.float32).reshape(n, 3, n, 3)}
             batched = data["coord"].ndim == 3
             n = data["coord"].shape[-2]
             lead = (1,) if batched else ()
@@ -247,8 +251,15 @@ def test_ase_adapter_host_logic(monkeypatch):
         ase_calc.set_atoms(Atoms([6, 26], pos[:2]))
     with pytest.raises(RuntimeError):
         ase_calc.get_spin_charges()
+    # Hessian: Sella's callback contract (atoms) -> (3N, 3N) ndarray; flat single-structure input; periodic / no atoms raise
+    H = ase_calc.get_hessian(Atoms([6, 1, 1, 8], pos))
+    assert H.shape == (12, 12) and H[1, 0] == 12.0 and fake.calls[-1][0]["coord"].shape == (4, 3)
+    with pytest.raises(RuntimeError):
+        ase_calc.get_hessian(Atoms([6, 1, 1, 8], pos, cell=cell, pbc=True))
+    ase_calc.atoms = None
     with pytest.raises(RuntimeError):
         ase_calc.get_hessian()
+    ase_calc.atoms = a0
     # open-shell model: multiplicity from atoms.info ("mult" or "spin"), spin populations in the results
     nse = AIMNet2ASE(FakeCalc(nse=True), charge=0, mult=1)
     assert "spin_charges" in nse.implemented_properties
