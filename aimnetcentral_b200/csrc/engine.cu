@@ -69,7 +69,9 @@ struct aimnet2_engine {
     // workspace (grow-only)
     char* ws = nullptr;
     size_t ws_bytes = 0;
-    int sr_cap = 64, lr_cap = 256;
+    int sr_cap = 64, lr_cap = 256;   // row capacities of the neighbor matrices: grow on overflow, shrink with hysteresis
+    int sr_cap_next = 0, lr_cap_next = 0;   // shrunk capacities, adopted at the start of the next evaluation
+    int ws_slack_evals = 0;          // consecutive evaluations that needed less than half of the workspace
     int last_sr_width = 0, last_lr_width = 0;
     int last_launches = 0;
     // host staging for eval_host
@@ -246,6 +248,16 @@ static SplitMat alias_split(float* base, size_t n, int width, float* inv) {
 static SplitMat with_ld(SplitMat m, int ld) {
     m.ld = ld;
     return m;
+}
+
+// Row capacity of a neighbor matrix after a successful build whose widest row holds `widest` entries: the reference's
+// AdaptiveNeighborList rule (aimnet/calculators/neighbors.py:135-140) -- shrink to widest / 0.75 once the widest row falls
+// below 2/3 of the 75 % target, i.e. below half of the capacity, so that small fluctuations do not thrash.  The new
+// capacity (0 = keep) applies from the next evaluation: this one's lists are already built in the old layout.
+static int shrink_cap(int cap, int widest, int floor_cap) {
+    if (2 * widest >= cap) return 0;
+    const int want = std::max(floor_cap, round16((widest * 4 + 2) / 3));
+    return want < cap ? want : 0;
 }
 
 static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_cap, int lr_cap, bool pbc,
@@ -485,6 +497,9 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             if (k.pbc[c] != (sys->pbc_host ? sys->pbc_host[c] : (uint8_t)1)) return false;
         return true;
     };
+    if (e->sr_cap_next > 0) e->sr_cap = e->sr_cap_next;
+    if (e->lr_cap_next > 0) e->lr_cap = e->lr_cap_next;
+    e->sr_cap_next = e->lr_cap_next = 0;
     for (int attempt = 0;; ++attempt) {
         AIM_REQUIRE(attempt < 8, "engine_eval: neighbor buffers failed to converge");
         Bump probe{nullptr};
@@ -492,10 +507,15 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
         size_t need = probe.off + 1024;
         const bool capturing = e->graph.capturing;
         AIM_REQUIRE(!capturing || need <= e->ws_bytes, "engine_eval: workspace changed during graph capture");
-        if (need > e->ws_bytes) {
+        // the workspace follows the demand down as well: after 32 evaluations in a row that needed less than half of it
+        e->ws_slack_evals = (!capturing && attempt == 0 && 2 * need < e->ws_bytes) ? e->ws_slack_evals + 1 : (attempt == 0 ? 0 : e->ws_slack_evals);
+        const bool trim = e->ws_slack_evals >= 32 && !e->graph.enabled;
+        if (need > e->ws_bytes || trim) {
             AIM_CUDA_CHECK(cudaStreamSynchronize(st));
             if (e->ws) AIM_CUDA_CHECK(cudaFree(e->ws));
             e->ws = nullptr;
+            e->ws_bytes = 0;
+            e->ws_slack_evals = 0;
             e->skin.valid = false;
             size_t want = need + need / 8;
             AIM_CUDA_CHECK(cudaMalloc((void**)&e->ws, want));
@@ -558,6 +578,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 return rc;
             e->last_sr_width = std::max(1, maxc);
             e->last_max_seg = e->pinned_int[1];
+            if (rc == AIMNET_OK && !e->graph.enabled) e->sr_cap_next = shrink_cap(e->sr_cap, maxc, 16);
         }
         if (!retry && need_lr_list) {
             int maxc = 0;
@@ -569,6 +590,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             } else if (rc != AIMNET_OK)
                 return rc;
             e->last_lr_width = std::max(1, maxc);
+            if (rc == AIMNET_OK && !e->graph.enabled) e->lr_cap_next = shrink_cap(e->lr_cap, maxc, 32);
         }
         if (!retry) {
             // Dense conv walk (conv_dense.cu): the molecule's feature tables staged in shared memory, every centre walks all
@@ -1222,6 +1244,13 @@ extern "C" int aimnet2_engine_info(const aimnet2_engine_t* e, int* sr_width, int
     if (sr_width) *sr_width = e->last_sr_width;
     if (lr_width) *lr_width = e->last_lr_width;
     if (workspace_bytes) *workspace_bytes = (int64_t)e->ws_bytes;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_neighbor_caps(const aimnet2_engine_t* e, int* sr_cap, int* lr_cap) {
+    AIM_REQUIRE(e, "neighbor_caps: null engine");
+    if (sr_cap) *sr_cap = e->sr_cap;
+    if (lr_cap) *lr_cap = e->lr_cap;
     return AIMNET_OK;
 }
 

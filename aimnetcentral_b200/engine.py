@@ -203,7 +203,9 @@ class Engine:
     def info(self) -> dict:
         a, b, c = C.c_int(), C.c_int(), C.c_int64()
         self._lib.aimnet2_engine_info(self._h, C.byref(a), C.byref(b), C.byref(c))
-        return {"sr_width": a.value, "lr_width": b.value, "workspace_bytes": c.value}
+        sr, lr = C.c_int(), C.c_int()
+        self._lib.aimnet2_engine_neighbor_caps(self._h, C.byref(sr), C.byref(lr))
+        return {"sr_width": a.value, "lr_width": b.value, "workspace_bytes": c.value, "sr_cap": sr.value, "lr_cap": lr.value}
 
     # ------------------------------------------------------------------------------------------------------
     def eval(self, coord: torch.Tensor, numbers: torch.Tensor, charge: torch.Tensor, mol_idx: torch.Tensor | None = None,

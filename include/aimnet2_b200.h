@@ -168,6 +168,12 @@ int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt
  * (default when available), 3 = backend 2's arithmetic with the experimental pipelined tile epilogue (gemm_tc16p.cu; not
  * validated on a GPU yet) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
+/* Row capacities of the engine's neighbor matrices.  They grow when a build overflows (the build is retried) and shrink
+ * with the reference's hysteresis (aimnet/calculators/neighbors.py:127-140: to widest / 0.75 once the widest row is below
+ * half of the capacity); the device workspace is re-allocated smaller after 32 evaluations in a row that needed less than
+ * half of it. */
+int aimnet2_engine_neighbor_caps(const aimnet2_engine_t* e, int* sr_cap, int* lr_cap);
+
 /* AEV / conv_sv kernels: 0 = the list kernels (csrc/conv.cu: one centre per warp walks its matrix row, neighbour rows gathered
  * through L1 / L2) for every input.  For batches of small non-periodic molecules (at most ~100 atoms each): 1 (default) = the
  * FORWARD convolutions take the dense walk of csrc/conv_dense.cu (the molecule's feature table staged into shared memory with

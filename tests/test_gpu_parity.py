@@ -869,3 +869,38 @@ def test_hessian_batched_inputs():
            "numbers": np.concatenate([inputs["numbers"][0], [0]])[None].astype(inputs["numbers"].dtype), "charge": inputs["charge"][:1]}
     Hp = calc(pad, hessian=True)["hessian"].cpu().numpy()
     assert Hp.shape == (13, 3, 13, 3) and np.abs(Hp[:12, :, :12] - H[0]).max() < 1e-4 and not Hp[12].any() and not Hp[:, :, 12].any()
+
+
+@pytest.mark.gpu
+def test_neighbor_capacity_grows_and_shrinks():
+    """Row capacities follow the geometry both ways (aimnet/calculators/neighbors.py:118-140): a compressed geometry overflows
+    the short-range rows and grows them, the relaxed geometry brings them back down one evaluation later (shrink below half
+    of the capacity, to widest / 0.75), results stay those of a fresh engine, and the device workspace follows after 32
+    evaluations that needed less than half of it."""
+    inputs, ref, meta = load_golden("taxol_q0")
+    calc = get_calc(meta)
+    eng = calc.engine
+    dev = "cuda:0"
+    z = torch.tensor(inputs["numbers"], dtype=torch.int32, device=dev)
+    q = torch.tensor(inputs["charge"], dtype=torch.float32, device=dev)
+    x = torch.tensor(inputs["coord"], dtype=torch.float32, device=dev)
+    base = eng.eval(x, z, q, forces=True)
+    cap0 = eng.info()["sr_cap"]
+    big_n = 40
+    xs = (x * 0.45).contiguous()                       # everything within the 5 A cutoff of everything: rows of ~112 entries
+    xb = xs.repeat(big_n, 1) + torch.arange(big_n, device=dev).repeat_interleave(x.shape[0]).unsqueeze(1) * 100.0
+    mol = torch.arange(big_n, dtype=torch.int32, device=dev).repeat_interleave(x.shape[0])
+    eng.eval(xb.contiguous(), z.repeat(big_n), q.repeat(big_n), mol_idx=mol, forces=True)
+    grown = eng.info()
+    assert grown["sr_cap"] > cap0 and grown["sr_width"] >= 100
+    out = eng.eval(x, z, q, forces=True)              # built in the wide layout; the shrink is adopted by the next evaluation
+    out2 = eng.eval(x, z, q, forces=True)
+    shrunk = eng.info()
+    assert shrunk["sr_cap"] < grown["sr_cap"] and shrunk["sr_cap"] >= shrunk["sr_width"]
+    for o in (out, out2):
+        assert torch.equal(o["energy"], base["energy"]) and torch.equal(o["forces"], base["forces"])
+    assert shrunk["workspace_bytes"] == grown["workspace_bytes"]
+    for _ in range(34):
+        out3 = eng.eval(x, z, q, forces=True)
+    assert eng.info()["workspace_bytes"] < grown["workspace_bytes"] // 2
+    assert torch.equal(out3["forces"], base["forces"])
