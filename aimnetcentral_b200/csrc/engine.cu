@@ -253,7 +253,9 @@ static SplitMat with_ld(SplitMat m, int ld) {
 // Row capacity of a neighbor matrix after a successful build whose widest row holds `widest` entries: the reference's
 // AdaptiveNeighborList rule (aimnet/calculators/neighbors.py:135-140) -- shrink to widest / 0.75 once the widest row falls
 // below 2/3 of the 75 % target, i.e. below half of the capacity, so that small fluctuations do not thrash.  The new
-// capacity (0 = keep) applies from the next evaluation: this one's lists are already built in the old layout.
+// capacity (0 = keep) applies from the next evaluation: this one's lists are already built in the old layout.  The floor is
+// the capacity a fresh engine starts with (rows that narrow cost nothing, and a fresh engine must not rebuild a skin list
+// just because its first system was small).
 static int shrink_cap(int cap, int widest, int floor_cap) {
     if (2 * widest >= cap) return 0;
     const int want = std::max(floor_cap, round16((widest * 4 + 2) / 3));
@@ -578,7 +580,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 return rc;
             e->last_sr_width = std::max(1, maxc);
             e->last_max_seg = e->pinned_int[1];
-            if (rc == AIMNET_OK && !e->graph.enabled) e->sr_cap_next = shrink_cap(e->sr_cap, maxc, 16);
+            if (rc == AIMNET_OK && !e->graph.enabled) e->sr_cap_next = shrink_cap(e->sr_cap, maxc, 64);
         }
         if (!retry && need_lr_list) {
             int maxc = 0;
@@ -590,7 +592,7 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
             } else if (rc != AIMNET_OK)
                 return rc;
             e->last_lr_width = std::max(1, maxc);
-            if (rc == AIMNET_OK && !e->graph.enabled) e->lr_cap_next = shrink_cap(e->lr_cap, maxc, 32);
+            if (rc == AIMNET_OK && !e->graph.enabled) e->lr_cap_next = shrink_cap(e->lr_cap, maxc, 256);
         }
         if (!retry) {
             // Dense conv walk (conv_dense.cu): the molecule's feature tables staged in shared memory, every centre walks all

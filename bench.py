@@ -360,7 +360,7 @@ def rooflines(r: Runner, step_ms: float, timed_region_s: float, traffic: dict):
     burst = timed_region_s < 1.0   # burst peak for a short timed region, the sustained one inside a long step loop
     bf16 = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1662.9 if burst else 1398.5)
     hbm = peaks.get("hbm_gbs", 6550.7)
-    tc16 = eng.gemm_backend in (2, 3)
+    tc16 = eng.gemm_backend in (2, 3, 4, 5)
     peak_tensor = bf16 / 3.0 if tc16 else bf16 / 2.0 / 3.0   # three error-compensating MMAs per product (tf32: half rate)
     peak_src = (("MEASURED_PEAKS.json" if peaks else "fallback") +
                 (" bf16_tflops (burst: timed region %.2f s)" % timed_region_s if burst else " bf16_tflops_sustained") +

@@ -170,7 +170,7 @@ int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
 /* Row capacities of the engine's neighbor matrices.  They grow when a build overflows (the build is retried) and shrink
  * with the reference's hysteresis (aimnet/calculators/neighbors.py:127-140: to widest / 0.75 once the widest row is below
- * half of the capacity); the device workspace is re-allocated smaller after 32 evaluations in a row that needed less than
+ * half of the capacity, never below the capacities a fresh engine starts with: 64 / 256); the device workspace is re-allocated smaller after 32 evaluations in a row that needed less than
  * half of it. */
 int aimnet2_engine_neighbor_caps(const aimnet2_engine_t* e, int* sr_cap, int* lr_cap);
 

@@ -690,13 +690,15 @@ def test_verlet_skin_reuse_matches_rebuild():
     coord, numbers = random_molecules(8, 40, seed=2)
     ref_calc.set_lrcoulomb_method("simple")
     skin_calc.set_lrcoulomb_method("simple")
-    for step in range(3):
+    for step in range(4):
         inp = {"coord": coord, "numbers": numbers, "charge": np.zeros(8, np.float32)}
         a = ref_calc(dict(inp), forces=True)
         b = skin_calc(dict(inp), forces=True)
         assert float((a["forces"] - b["forces"]).abs().max()) < 2e-5
         coord = coord + rng.normal(0, 0.02, coord.shape).astype(np.float32)
-    assert skin_calc.engine.skin_stats()[1] >= reuses + 2   # the molecule batch reused its list too
+    # the molecule batch reused its list too; its first list was built in the crystal's wide rows, the row capacity shrank
+    # one evaluation later (neighbors.py:135-140 hysteresis), which costs one extra build
+    assert skin_calc.engine.skin_stats()[1] >= reuses + 2
 
 
 def test_cache_static_reuses_lists_for_unchanged_geometry():
