@@ -27,13 +27,8 @@
 
 namespace aimnet {
 
-__device__ __forceinline__ void phase_sincos(int h, int k, int l, const uint32_t* __restrict__ F, float& s, float& c) {
-    const uint32_t ph = (uint32_t)h * F[0] + (uint32_t)k * F[1] + (uint32_t)l * F[2];   // modulo 2^32 = one period
-    // the argument is already reduced to [-pi, pi): the SFU sine / cosine (abs error 4e-7 there) replace the ~30
-    // instruction sincospi polynomial
-    __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &s, &c);                     // pi * ph / 2^31
-}
-
+// (uint32_t)h * F1 + k * F2 + l * F3 is the phase modulo 2^32 = one period; as int32 times pi / 2^31 it is an argument in
+// [-pi, pi): the SFU sine / cosine (abs error 4e-7 there) replace the ~30-instruction sincospi polynomial.
 // per atom: fractional coordinates in 32-bit fixed point, F_j = frac(sum_c r_c inv[3c + j]) * 2^32, and the charge,
 // packed into one 16-byte word (the structure-factor kernel reads one word per (k, atom) pair)
 __global__ void __launch_bounds__(256) ewald_frac_kernel(int n, const float* __restrict__ coord, const float* __restrict__ q,
@@ -52,35 +47,54 @@ __global__ void __launch_bounds__(256) ewald_frac_kernel(int n, const float* __r
     F[i] = make_uint4(o[0], o[1], o[2], __float_as_uint(q[i]));
 }
 
-// one warp per k vector: S(k) = sum_i q_i exp(i k.r_i)
+// S(k) = sum_i q_i exp(i k.r_i): one warp per group of kSfBlock k vectors, lanes stride over the atoms.  With one k vector per
+// warp every warp streamed all atom words through L1 / L2 (1.3 MB per k vector, 42 GB per call at cfg-5: bandwidth-bound at
+// 6.8 ms); eight k vectors per loaded word leave the SFU sine / cosine as the limit.
+constexpr int kSfBlock = 8;
 __global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint4* __restrict__ F,
                                                        const int32_t* __restrict__ hkl, double* __restrict__ S) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= nk) return;
-    const int h = hkl[3 * w], k = hkl[3 * w + 1], l = hkl[3 * w + 2];
-    double re = 0.0, im = 0.0;
-    float pre = 0.f, pim = 0.f;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int k0 = w * kSfBlock;
+    if (k0 >= nk) return;
+    uint32_t H[kSfBlock], K[kSfBlock], L[kSfBlock];
+#pragma unroll
+    for (int t = 0; t < kSfBlock; ++t) {
+        const int kk = min(k0 + t, nk - 1);   // the tail group repeats its last vector (results of the copies are dropped)
+        H[t] = (uint32_t)hkl[3 * kk], K[t] = (uint32_t)hkl[3 * kk + 1], L[t] = (uint32_t)hkl[3 * kk + 2];
+    }
+    double re[kSfBlock], im[kSfBlock];
+    float pre[kSfBlock], pim[kSfBlock];
+#pragma unroll
+    for (int t = 0; t < kSfBlock; ++t) re[t] = im[t] = 0.0, pre[t] = pim[t] = 0.f;
     int cnt = 0;
     for (int i = lane; i < n; i += 32) {
         const uint4 a = __ldg(F + i);
-        const uint32_t Fi[3] = {a.x, a.y, a.z};
-        float s, c;
-        phase_sincos(h, k, l, Fi, s, c);
         const float qi = __uint_as_float(a.w);
-        pre = fmaf(qi, c, pre);
-        pim = fmaf(qi, s, pim);
+#pragma unroll
+        for (int t = 0; t < kSfBlock; ++t) {
+            const uint32_t ph = H[t] * a.x + K[t] * a.y + L[t] * a.z;   // modulo 2^32 = one period
+            float sn, cs;
+            __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &sn, &cs);
+            pre[t] = fmaf(qi, cs, pre[t]);
+            pim[t] = fmaf(qi, sn, pim[t]);
+        }
         if (++cnt == 16) {
-            re += (double)pre;
-            im += (double)pim;
-            pre = pim = 0.f;
+#pragma unroll
+            for (int t = 0; t < kSfBlock; ++t) {
+                re[t] += (double)pre[t];
+                im[t] += (double)pim[t];
+                pre[t] = pim[t] = 0.f;
+            }
             cnt = 0;
         }
     }
-    re = warp_sum(re + (double)pre);
-    im = warp_sum(im + (double)pim);
-    if (lane == 0) {
-        S[2 * w] = re;
-        S[2 * w + 1] = im;
+#pragma unroll
+    for (int t = 0; t < kSfBlock; ++t) {
+        const double r = warp_sum(re[t] + (double)pre[t]), m = warp_sum(im[t] + (double)pim[t]);
+        if (lane == 0 && k0 + t < nk) {
+            S[2 * (k0 + t)] = r;
+            S[2 * (k0 + t) + 1] = m;
+        }
     }
 }
 
@@ -112,52 +126,70 @@ __global__ void __launch_bounds__(256) ewald_pack_kernel(int nk, const int32_t* 
                                  __int_as_float(hkl[3 * k + 2]));
 }
 
-// one warp per atom: dE/dq_i and F_i
+// dE/dq_i and F_i: one warp per group of kAtomBlock atoms, lanes stride over the k records.  (One atom per warp streamed the
+// 1 MB of k records per atom: 84 GB per call at cfg-5.)
+constexpr int kAtomBlock = 8;
 __global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const uint4* __restrict__ F,
                                                          const float* __restrict__ q, const float4* __restrict__ rec,
                                                          double pref, double self_coeff, double bg_unit,
                                                          const double* __restrict__ qsum,
                                                          double* __restrict__ e_atom, float* __restrict__ gq,
                                                          float* __restrict__ forces) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n) return;
-    int i = w;
-    const uint4 fa = F[i];
-    const uint32_t Fi[3] = {fa.x, fa.y, fa.z};
-    double g = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-    float pg = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int i0 = w * kAtomBlock;
+    if (i0 >= n) return;
+    uint32_t F0[kAtomBlock], F1[kAtomBlock], F2[kAtomBlock];
+#pragma unroll
+    for (int t = 0; t < kAtomBlock; ++t) {
+        const uint4 fa = F[min(i0 + t, n - 1)];
+        F0[t] = fa.x, F1[t] = fa.y, F2[t] = fa.z;
+    }
+    double g[kAtomBlock], fx[kAtomBlock], fy[kAtomBlock], fz[kAtomBlock];
+    float pg[kAtomBlock], px[kAtomBlock], py[kAtomBlock], pz[kAtomBlock];
+#pragma unroll
+    for (int t = 0; t < kAtomBlock; ++t) g[t] = fx[t] = fy[t] = fz[t] = 0.0, pg[t] = px[t] = py[t] = pz[t] = 0.f;
     int cnt = 0;
     for (int k = lane; k < nk; k += 32) {
         const float4 r0 = __ldg(rec + 2 * k), r1 = __ldg(rec + 2 * k + 1);
-        float s, c;
-        phase_sincos(__float_as_int(r1.y), __float_as_int(r1.z), __float_as_int(r1.w), Fi, s, c);
-        pg += r0.x * c + r0.y * s;
-        const float t = r0.x * s - r0.y * c;
-        px = fmaf(t, r0.z, px);
-        py = fmaf(t, r0.w, py);
-        pz = fmaf(t, r1.x, pz);
+        const uint32_t h = (uint32_t)__float_as_int(r1.y), kk = (uint32_t)__float_as_int(r1.z), l = (uint32_t)__float_as_int(r1.w);
+#pragma unroll
+        for (int t = 0; t < kAtomBlock; ++t) {
+            const uint32_t ph = h * F0[t] + kk * F1[t] + l * F2[t];
+            float s, c;
+            __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &s, &c);
+            pg[t] += r0.x * c + r0.y * s;
+            const float tt = r0.x * s - r0.y * c;
+            px[t] = fmaf(tt, r0.z, px[t]);
+            py[t] = fmaf(tt, r0.w, py[t]);
+            pz[t] = fmaf(tt, r1.x, pz[t]);
+        }
         if (++cnt == 16) {
-            g += (double)pg;
-            fx += (double)px;
-            fy += (double)py;
-            fz += (double)pz;
-            pg = px = py = pz = 0.f;
+#pragma unroll
+            for (int t = 0; t < kAtomBlock; ++t) {
+                g[t] += (double)pg[t];
+                fx[t] += (double)px[t];
+                fy[t] += (double)py[t];
+                fz[t] += (double)pz[t];
+                pg[t] = px[t] = py[t] = pz[t] = 0.f;
+            }
             cnt = 0;
         }
     }
-    g = warp_sum(g + (double)pg);
-    fx = warp_sum(fx + (double)px);
-    fy = warp_sum(fy + (double)py);
-    fz = warp_sum(fz + (double)pz);
-    if (lane == 0) {
-        double qi = (double)q[i];
-        // 2*pref = k_e 8 pi / V ; self: E = self_coeff q^2 ; background: dE/dq = bg_coeff (already times Q)
-        gq[i] += (float)(2.0 * pref * g + 2.0 * self_coeff * qi + 2.0 * bg_unit * qsum[0]);
-        e_atom[i] += self_coeff * qi * qi;
-        if (forces) {
-            forces[3 * i + 0] += (float)(2.0 * pref * qi * fx);
-            forces[3 * i + 1] += (float)(2.0 * pref * qi * fy);
-            forces[3 * i + 2] += (float)(2.0 * pref * qi * fz);
+#pragma unroll
+    for (int t = 0; t < kAtomBlock; ++t) {
+        const double gs = warp_sum(g[t] + (double)pg[t]), xs = warp_sum(fx[t] + (double)px[t]);
+        const double ys = warp_sum(fy[t] + (double)py[t]), zs = warp_sum(fz[t] + (double)pz[t]);
+        const int i = i0 + t;
+        if (lane == 0 && i < n) {
+            const double qi = (double)q[i];
+            // 2*pref = k_e 8 pi / V ; self: E = self_coeff q^2 ; background: dE/dq = bg_coeff (already times Q)
+            gq[i] += (float)(2.0 * pref * gs + 2.0 * self_coeff * qi + 2.0 * bg_unit * qsum[0]);
+            e_atom[i] += self_coeff * qi * qi;
+            if (forces) {
+                forces[3 * i + 0] += (float)(2.0 * pref * qi * xs);
+                forces[3 * i + 1] += (float)(2.0 * pref * qi * ys);
+                forces[3 * i + 2] += (float)(2.0 * pref * qi * zs);
+            }
         }
     }
 }
@@ -326,7 +358,7 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
                                                        iv[8], fq);
     AIM_LAUNCH_CHECK();
     if (pl.nk > 0) {
-        ewald_sf_kernel<<<(pl.nk + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, pl.d_hkl, pl.d_S);
+        ewald_sf_kernel<<<((pl.nk + kSfBlock - 1) / kSfBlock + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, pl.d_hkl, pl.d_S);
         AIM_LAUNCH_CHECK();
     }
     float4* rec = reinterpret_cast<float4*>(pl.d_hkl + 4 * (size_t)pl.cap);   // 16-byte aligned: cap * 16 bytes in
@@ -334,7 +366,7 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
         ewald_pack_kernel<<<(pl.nk + 255) / 256, 256, 0, st>>>(pl.nk, pl.d_hkl, pl.d_kvec, pl.d_ck, pl.d_S, rec);
         AIM_LAUNCH_CHECK();
     }
-    ewald_atom_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, q, rec, pref, self_coeff, bg_unit, d_q, e_atom, gq,
+    ewald_atom_kernel<<<((n + kAtomBlock - 1) / kAtomBlock + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, q, rec, pref, self_coeff, bg_unit, d_q, e_atom, gq,
                                                   forces);
     AIM_LAUNCH_CHECK();
     ewald_energy_kernel<<<1, 256, 0, st>>>(pl.nk, pl.d_kvec, pl.d_ck, pl.d_S, pref, 1.0 / (4.0 * pl.alpha * pl.alpha), bg_unit,

@@ -202,7 +202,17 @@ __global__ void bin_start_kernel(const uint32_t* __restrict__ sorted_keys, int n
     for (int b = prev + 1; b <= cur; ++b) bin_start[b] = i;
 }
 
-__global__ void __launch_bounds__(256) nb_cells_kernel(const float* __restrict__ pos, int n_atoms, float rc2,
+// positions in bin order (x, y, z, original index): the scan below then reads a bin's atoms as consecutive 16-byte words
+// instead of gathering 12 bytes per lane through the index
+__global__ void bin_gather_kernel(const float* __restrict__ pos, int n, const int32_t* __restrict__ sorted_idx,
+                                  float4* __restrict__ pos_s) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int j = sorted_idx[p];
+    pos_s[p] = make_float4(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2], __int_as_float(j));
+}
+
+__global__ void __launch_bounds__(256) nb_cells_kernel(const float4* __restrict__ pos_s, int n_atoms, float rc2,
                                                        GridParams gp, const uint32_t* __restrict__ sorted_keys,
                                                        const int32_t* __restrict__ sorted_idx,
                                                        const int32_t* __restrict__ bin_start, int max_nb, int fill,
@@ -212,12 +222,13 @@ __global__ void __launch_bounds__(256) nb_cells_kernel(const float* __restrict__
     int lane = threadIdx.x & 31;
     if (warp >= n_atoms) return;
     // process atoms in bin order so that a warp's neighbours are hot in L1/L2
-    int i = sorted_idx[warp];
+    const float4 own = pos_s[warp];
+    int i = __float_as_int(own.w);
     uint32_t key = sorted_keys[warp];
     int bz = key % gp.nb[2];
     int by = (key / gp.nb[2]) % gp.nb[1];
     int bx = key / (gp.nb[2] * gp.nb[1]);
-    float xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+    float xi = own.x, yi = own.y, zi = own.z;
     int count = 0;
     int32_t* row = nbmat + (size_t)i * max_nb;
     int32_t* srow = shifts + (size_t)i * max_nb * 3;
@@ -247,10 +258,10 @@ __global__ void __launch_bounds__(256) nb_cells_kernel(const float* __restrict__
                     bool keep = false;
                     int j = 0;
                     if (p < p1) {
-                        j = sorted_idx[p];
+                        const float4 pj = pos_s[p];
+                        j = __float_as_int(pj.w);
                         if (!(zero && j == i)) {
-                            float d2 = canonical_d2(xi, yi, zi, pos[3 * j], pos[3 * j + 1], pos[3 * j + 2], (float)sx,
-                                                    (float)sy, (float)sz, gp.cell, true);
+                            float d2 = canonical_d2(xi, yi, zi, pj.x, pj.y, pj.z, (float)sx, (float)sy, (float)sz, gp.cell, true);
                             keep = d2 < rc2;
                         }
                     }
@@ -471,6 +482,8 @@ int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, cons
             AIM_CUDA_CHECK(cudaMallocAsync(&keys, sizeof(uint32_t) * n_atoms * 2, st));
             AIM_CUDA_CHECK(cudaMallocAsync(&vals, sizeof(int32_t) * n_atoms * 2, st));
             AIM_CUDA_CHECK(cudaMallocAsync(&bin_start, sizeof(int32_t) * (n_bins + 1), st));
+            float4* pos_s = nullptr;
+            AIM_CUDA_CHECK(cudaMallocAsync(&pos_s, sizeof(float4) * n_atoms, st));
             keys_s = keys + n_atoms;
             vals_s = vals + n_atoms;
             int bits = 1;
@@ -483,7 +496,9 @@ int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, cons
             g_launch_count += 2;
             bin_start_kernel<<<(n_atoms + 256) / 256, 256, 0, st>>>(keys_s, n_atoms, n_bins, bin_start);
             AIM_LAUNCH_CHECK();
-            nb_cells_kernel<<<(n_atoms + 7) / 8, 256, 0, st>>>(positions, n_atoms, rc2, gp, keys_s, vals_s, bin_start,
+            bin_gather_kernel<<<(n_atoms + 255) / 256, 256, 0, st>>>(positions, n_atoms, vals_s, pos_s);
+            AIM_LAUNCH_CHECK();
+            nb_cells_kernel<<<(n_atoms + 7) / 8, 256, 0, st>>>(pos_s, n_atoms, rc2, gp, keys_s, vals_s, bin_start,
                                                               max_nb, fill_value, nbmat, shifts, nnb, d_max);
             AIM_LAUNCH_CHECK();
             if (sorted) {
@@ -510,6 +525,7 @@ int neighbor_matrix_impl(const float* positions, int n_atoms, float cutoff, cons
             AIM_CUDA_CHECK(cudaFreeAsync(keys, st));
             AIM_CUDA_CHECK(cudaFreeAsync(vals, st));
             AIM_CUDA_CHECK(cudaFreeAsync(bin_start, st));
+            AIM_CUDA_CHECK(cudaFreeAsync(pos_s, st));
             AIM_CUDA_CHECK(cudaFreeAsync(tmp, st));
         } else {
             int32_t *seg = scratch ? scratch + 2 : nullptr, *nimg = nullptr;

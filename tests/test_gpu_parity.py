@@ -879,8 +879,10 @@ def test_neighbor_capacity_grows_and_shrinks():
     the short-range rows and grows them, the relaxed geometry brings them back down one evaluation later (shrink below half
     of the capacity, to widest / 0.75), results stay those of a fresh engine, and the device workspace follows after 32
     evaluations that needed less than half of it."""
+    from aimnetcentral_b200 import AIMNet2Calculator
+
     inputs, ref, meta = load_golden("taxol_q0")
-    calc = get_calc(meta)
+    calc = AIMNet2Calculator(golden_state_dict(meta), device="cuda:0")   # a fresh engine: capacities at their initial values
     eng = calc.engine
     dev = "cuda:0"
     z = torch.tensor(inputs["numbers"], dtype=torch.int32, device=dev)
