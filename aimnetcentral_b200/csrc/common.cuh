@@ -113,6 +113,8 @@ struct EwaldPlan {
     int32_t* d_hkl = nullptr;    // (cap, 3) integer reciprocal-lattice indices of the k vectors, then (cap, 8) fp32 records
     uint32_t* d_frac = nullptr;  // (frac_cap, 4) fixed-point fractional coordinates of the current positions + charge bits
     int frac_cap = 0;
+    double* d_part = nullptr;    // (slices, n_atoms, 4) partial sums of the per-atom reciprocal-space terms
+    size_t part_cap = 0;         // in (atom, slice) entries
     double inv[9] = {0};         // inverse cell
 };
 int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double accuracy, double rc_cap, cudaStream_t st);

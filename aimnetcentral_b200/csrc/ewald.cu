@@ -27,6 +27,9 @@
 
 namespace aimnet {
 
+constexpr int kEwaldRun = 8;                              // list entries per (h, k, l0 .. l0 + 7) group
+constexpr float kPhaseScale = 1.4629180792671596e-9f;     // pi / 2^31: fixed-point phase (int32) -> radians in [-pi, pi)
+
 // (uint32_t)h * F1 + k * F2 + l * F3 is the phase modulo 2^32 = one period; as int32 times pi / 2^31 it is an argument in
 // [-pi, pi): the SFU sine / cosine (abs error 4e-7 there) replace the ~30-instruction sincospi polynomial.
 // per atom: fractional coordinates in 32-bit fixed point, F_j = frac(sum_c r_c inv[3c + j]) * 2^32, and the charge,
@@ -50,35 +53,40 @@ __global__ void __launch_bounds__(256) ewald_frac_kernel(int n, const float* __r
 // S(k) = sum_i q_i exp(i k.r_i): one warp per group of kSfBlock k vectors, lanes stride over the atoms.  With one k vector per
 // warp every warp streamed all atom words through L1 / L2 (1.3 MB per k vector, 42 GB per call at cfg-5: bandwidth-bound at
 // 6.8 ms); eight k vectors per loaded word leave the SFU sine / cosine as the limit.
-constexpr int kSfBlock = 8;
+constexpr int kSfBlock = kEwaldRun;
 __global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint4* __restrict__ F,
                                                        const int32_t* __restrict__ hkl, double* __restrict__ S) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int k0 = w * kSfBlock;
-    if (k0 >= nk) return;
-    uint32_t H[kSfBlock], K[kSfBlock], L[kSfBlock];
-#pragma unroll
-    for (int t = 0; t < kSfBlock; ++t) {
-        const int kk = min(k0 + t, nk - 1);   // the tail group repeats its last vector (results of the copies are dropped)
-        H[t] = (uint32_t)hkl[3 * kk], K[t] = (uint32_t)hkl[3 * kk + 1], L[t] = (uint32_t)hkl[3 * kk + 2];
-    }
+    if (k0 >= nk) return;   // nk is a multiple of kSfBlock (ewald_prepare pads every (h, k) row)
+    const uint32_t H = (uint32_t)hkl[3 * k0], K = (uint32_t)hkl[3 * k0 + 1], L0 = (uint32_t)hkl[3 * k0 + 2];
     double re[kSfBlock], im[kSfBlock];
     float pre[kSfBlock], pim[kSfBlock];
 #pragma unroll
     for (int t = 0; t < kSfBlock; ++t) re[t] = im[t] = 0.0, pre[t] = pim[t] = 0.f;
     int cnt = 0;
-    for (int i = lane; i < n; i += 32) {
+    // two atoms per lane and iteration: the rotations of a run are a dependent chain, two chains keep the FMA pipe busier
+    for (int i = lane; i < n; i += 64) {
         const uint4 a = __ldg(F + i);
-        const float qi = __uint_as_float(a.w);
+        const bool two = i + 32 < n;
+        const uint4 b = two ? __ldg(F + i + 32) : make_uint4(0u, 0u, 0u, 0u);   // charge bits 0 = 0.0f: adds nothing
+        const float qa = __uint_as_float(a.w), qb = __uint_as_float(b.w);
+        float sa, ca, swa, cwa, sb, cb, swb, cwb;
+        __sincosf((float)(int32_t)(H * a.x + K * a.y + L0 * a.z) * kPhaseScale, &sa, &ca);   // phase of (h, k, l0)
+        __sincosf((float)(int32_t)a.z * kPhaseScale, &swa, &cwa);                            // one step in l
+        __sincosf((float)(int32_t)(H * b.x + K * b.y + L0 * b.z) * kPhaseScale, &sb, &cb);
+        __sincosf((float)(int32_t)b.z * kPhaseScale, &swb, &cwb);
 #pragma unroll
         for (int t = 0; t < kSfBlock; ++t) {
-            const uint32_t ph = H[t] * a.x + K[t] * a.y + L[t] * a.z;   // modulo 2^32 = one period
-            float sn, cs;
-            __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &sn, &cs);
-            pre[t] = fmaf(qi, cs, pre[t]);
-            pim[t] = fmaf(qi, sn, pim[t]);
+            pre[t] = fmaf(qa, ca, fmaf(qb, cb, pre[t]));
+            pim[t] = fmaf(qa, sa, fmaf(qb, sb, pim[t]));
+            const float ca2 = fmaf(ca, cwa, -sa * swa), cb2 = fmaf(cb, cwb, -sb * swb);
+            sa = fmaf(sa, cwa, ca * swa);
+            sb = fmaf(sb, cwb, cb * swb);
+            ca = ca2;
+            cb = cb2;
         }
-        if (++cnt == 16) {
+        if (++cnt == 8) {   // 16 terms per fp32 partial sum
 #pragma unroll
             for (int t = 0; t < kSfBlock; ++t) {
                 re[t] += (double)pre[t];
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(256) ewald_sf_kernel(int n, int nk, const uint
 #pragma unroll
     for (int t = 0; t < kSfBlock; ++t) {
         const double r = warp_sum(re[t] + (double)pre[t]), m = warp_sum(im[t] + (double)pim[t]);
-        if (lane == 0 && k0 + t < nk) {
+        if (lane == 0) {
             S[2 * (k0 + t)] = r;
             S[2 * (k0 + t) + 1] = m;
         }
@@ -126,72 +134,76 @@ __global__ void __launch_bounds__(256) ewald_pack_kernel(int nk, const int32_t* 
                                  __int_as_float(hkl[3 * k + 2]));
 }
 
-// dE/dq_i and F_i: one warp per group of kAtomBlock atoms, lanes stride over the k records.  (One atom per warp streamed the
-// 1 MB of k records per atom: 84 GB per call at cfg-5.)
-constexpr int kAtomBlock = 8;
-__global__ void __launch_bounds__(256) ewald_atom_kernel(int n, int nk, const uint4* __restrict__ F,
-                                                         const float* __restrict__ q, const float4* __restrict__ rec,
-                                                         double pref, double self_coeff, double bg_unit,
-                                                         const double* __restrict__ qsum,
-                                                         double* __restrict__ e_atom, float* __restrict__ gq,
-                                                         float* __restrict__ forces) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int i0 = w * kAtomBlock;
-    if (i0 >= n) return;
-    uint32_t F0[kAtomBlock], F1[kAtomBlock], F2[kAtomBlock];
+// dE/dq_i and F_i: thread = atom, every thread of a warp walks the SAME k records (uniform addresses: one broadcast
+// transaction per load), blockIdx.y selects a slice of the run list so that small systems still fill the machine; the slices'
+// partial sums are added in fixed order by ewald_atom_finish_kernel.  (Round-2 history: one atom per warp with the lanes over
+// the records streamed 1 MB of records per atom, 84 GB per call at cfg-5; eight atoms per warp with a run of records per lane
+// read them with a 256-byte lane stride and sat at 75 % of the L1 throughput.)
+__global__ void __launch_bounds__(128) ewald_atom_kernel(int n, int n_runs, int runs_per_slice, const uint4* __restrict__ F,
+                                                         const float4* __restrict__ rec, double4* __restrict__ part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 fa = F[min(i, n - 1)];
+    float cw, sw;
+    __sincosf((float)(int32_t)fa.z * kPhaseScale, &sw, &cw);   // the atom's phase step per unit of l
+    double g = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+    float pg = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    const int r0i = blockIdx.y * runs_per_slice, r1i = min(n_runs, r0i + runs_per_slice);
+    for (int r = r0i; r < r1i; ++r) {
+        const float4* rr = rec + 2 * (size_t)r * kEwaldRun;
+        const float4 h1 = __ldg(rr + 1);
+        const uint32_t h = (uint32_t)__float_as_int(h1.y), kk = (uint32_t)__float_as_int(h1.z), l = (uint32_t)__float_as_int(h1.w);
+        float c, s;
+        __sincosf((float)(int32_t)(h * fa.x + kk * fa.y + l * fa.z) * kPhaseScale, &s, &c);
 #pragma unroll
-    for (int t = 0; t < kAtomBlock; ++t) {
-        const uint4 fa = F[min(i0 + t, n - 1)];
-        F0[t] = fa.x, F1[t] = fa.y, F2[t] = fa.z;
-    }
-    double g[kAtomBlock], fx[kAtomBlock], fy[kAtomBlock], fz[kAtomBlock];
-    float pg[kAtomBlock], px[kAtomBlock], py[kAtomBlock], pz[kAtomBlock];
-#pragma unroll
-    for (int t = 0; t < kAtomBlock; ++t) g[t] = fx[t] = fy[t] = fz[t] = 0.0, pg[t] = px[t] = py[t] = pz[t] = 0.f;
-    int cnt = 0;
-    for (int k = lane; k < nk; k += 32) {
-        const float4 r0 = __ldg(rec + 2 * k), r1 = __ldg(rec + 2 * k + 1);
-        const uint32_t h = (uint32_t)__float_as_int(r1.y), kk = (uint32_t)__float_as_int(r1.z), l = (uint32_t)__float_as_int(r1.w);
-#pragma unroll
-        for (int t = 0; t < kAtomBlock; ++t) {
-            const uint32_t ph = h * F0[t] + kk * F1[t] + l * F2[t];
-            float s, c;
-            __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &s, &c);
-            pg[t] += r0.x * c + r0.y * s;
-            const float tt = r0.x * s - r0.y * c;
-            px[t] = fmaf(tt, r0.z, px[t]);
-            py[t] = fmaf(tt, r0.w, py[t]);
-            pz[t] = fmaf(tt, r1.x, pz[t]);
+        for (int t = 0; t < kEwaldRun; ++t) {
+            const float4 a = __ldg(rr + 2 * t), b = __ldg(rr + 2 * t + 1);
+            pg = fmaf(a.x, c, fmaf(a.y, s, pg));
+            const float tt = fmaf(a.x, s, -a.y * c);
+            px = fmaf(tt, a.z, px);
+            py = fmaf(tt, a.w, py);
+            pz = fmaf(tt, b.x, pz);
+            const float c2 = fmaf(c, cw, -s * sw);
+            s = fmaf(s, cw, c * sw);
+            c = c2;
         }
-        if (++cnt == 16) {
-#pragma unroll
-            for (int t = 0; t < kAtomBlock; ++t) {
-                g[t] += (double)pg[t];
-                fx[t] += (double)px[t];
-                fy[t] += (double)py[t];
-                fz[t] += (double)pz[t];
-                pg[t] = px[t] = py[t] = pz[t] = 0.f;
-            }
-            cnt = 0;
+        if ((r - r0i) & 1) {   // fp32 partial sums hold two runs (16 terms) between flushes into fp64
+            g += (double)pg;
+            fx += (double)px;
+            fy += (double)py;
+            fz += (double)pz;
+            pg = px = py = pz = 0.f;
         }
     }
-#pragma unroll
-    for (int t = 0; t < kAtomBlock; ++t) {
-        const double gs = warp_sum(g[t] + (double)pg[t]), xs = warp_sum(fx[t] + (double)px[t]);
-        const double ys = warp_sum(fy[t] + (double)py[t]), zs = warp_sum(fz[t] + (double)pz[t]);
-        const int i = i0 + t;
-        if (lane == 0 && i < n) {
-            const double qi = (double)q[i];
-            // 2*pref = k_e 8 pi / V ; self: E = self_coeff q^2 ; background: dE/dq = bg_coeff (already times Q)
-            gq[i] += (float)(2.0 * pref * gs + 2.0 * self_coeff * qi + 2.0 * bg_unit * qsum[0]);
-            e_atom[i] += self_coeff * qi * qi;
-            if (forces) {
-                forces[3 * i + 0] += (float)(2.0 * pref * qi * xs);
-                forces[3 * i + 1] += (float)(2.0 * pref * qi * ys);
-                forces[3 * i + 2] += (float)(2.0 * pref * qi * zs);
-            }
-        }
+    if (i < n) part[(size_t)blockIdx.y * n + i] = make_double4(g + (double)pg, fx + (double)px, fy + (double)py, fz + (double)pz);
+}
+
+__global__ void __launch_bounds__(256) ewald_atom_finish_kernel(int n, int n_slices, const double4* __restrict__ part,
+                                                                const float* __restrict__ q, double pref, double self_coeff,
+                                                                double bg_unit, const double* __restrict__ qsum,
+                                                                double* __restrict__ e_atom, float* __restrict__ gq,
+                                                                float* __restrict__ forces) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double gs = 0.0, xs = 0.0, ys = 0.0, zs = 0.0;
+    for (int sl = 0; sl < n_slices; ++sl) {
+        const double4 v = part[(size_t)sl * n + i];
+        gs += v.x, xs += v.y, ys += v.z, zs += v.w;
     }
+    const double qi = (double)q[i];
+    // 2*pref = k_e 8 pi / V ; self: E = self_coeff q^2 ; background: dE/dq = bg_coeff (already times Q)
+    gq[i] += (float)(2.0 * pref * gs + 2.0 * self_coeff * qi + 2.0 * bg_unit * qsum[0]);
+    e_atom[i] += self_coeff * qi * qi;
+    if (forces) {
+        forces[3 * i + 0] += (float)(2.0 * pref * qi * xs);
+        forces[3 * i + 1] += (float)(2.0 * pref * qi * ys);
+        forces[3 * i + 2] += (float)(2.0 * pref * qi * zs);
+    }
+}
+
+// slices of the run list per atom: enough threads (atoms x slices) to fill the machine
+static int ewald_atom_slices(int n_atoms, int n_runs) {
+    int s = (148 * 2048 + n_atoms - 1) / std::max(1, n_atoms);
+    return std::max(1, std::min(std::min(s, 64), std::max(1, n_runs)));
 }
 
 // single block: reciprocal energy and its strain derivative; added to atom 0's per-atom accumulators
@@ -291,14 +303,21 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
     std::vector<double> kv, ck;
     std::vector<int32_t> hk;
     double kc2 = pl.kc * pl.kc, inv4a2 = 1.0 / (4.0 * pl.alpha * pl.alpha);
+    // Rows of fixed (h, k) hold consecutive l (the part of the row inside the sphere is an interval); every row is padded to a
+    // multiple of kEwaldRun vectors with weight c_k = 0, so that each aligned group of kEwaldRun list entries shares (h, k)
+    // and steps l by one: the kernels evaluate one sine / cosine per group and rotate by the atom's own l-step phase.
     for (int h = 0; h <= nmax[0]; ++h)
-        for (int k = (h == 0 ? 0 : -nmax[1]); k <= nmax[1]; ++k)
+        for (int k = (h == 0 ? 0 : -nmax[1]); k <= nmax[1]; ++k) {
+            int in_row = 0, l_next = 0;
             for (int l = ((h == 0 && k == 0) ? 1 : -nmax[2]); l <= nmax[2]; ++l) {
                 double kx = h * b[0][0] + k * b[1][0] + l * b[2][0];
                 double ky = h * b[0][1] + k * b[1][1] + l * b[2][1];
                 double kz = h * b[0][2] + k * b[1][2] + l * b[2][2];
                 double k2 = kx * kx + ky * ky + kz * kz;
-                if (k2 > kc2) continue;
+                if (k2 > kc2) {
+                    if (in_row > 0) break;   // past the interval
+                    continue;
+                }
                 kv.push_back(kx);
                 kv.push_back(ky);
                 kv.push_back(kz);
@@ -306,7 +325,19 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
                 hk.push_back(h);
                 hk.push_back(k);
                 hk.push_back(l);
+                ++in_row;
+                l_next = l + 1;
             }
+            for (; in_row % kEwaldRun != 0; ++in_row, ++l_next) {   // padding: outside the sphere, weight zero
+                kv.push_back(h * b[0][0] + k * b[1][0] + l_next * b[2][0]);
+                kv.push_back(h * b[0][1] + k * b[1][1] + l_next * b[2][1]);
+                kv.push_back(h * b[0][2] + k * b[1][2] + l_next * b[2][2]);
+                ck.push_back(0.0);
+                hk.push_back(h);
+                hk.push_back(k);
+                hk.push_back(l_next);
+            }
+        }
     pl.nk = (int)ck.size();
     if (pl.nk > pl.cap) {
         if (pl.d_kvec) cudaFree(pl.d_kvec);
@@ -322,6 +353,14 @@ int ewald_prepare(EwaldPlan& pl, const float* host_cell, int n_atoms, double acc
         pl.frac_cap = n_atoms + n_atoms / 8 + 64;
         AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_frac, sizeof(uint32_t) * 4 * pl.frac_cap));
     }
+    {
+        const size_t need = (size_t)ewald_atom_slices(n_atoms, pl.nk / kEwaldRun) * n_atoms;
+        if (need > pl.part_cap) {
+            if (pl.d_part) cudaFree(pl.d_part);
+            pl.part_cap = need + need / 8 + 64;
+            AIM_CUDA_CHECK(cudaMalloc((void**)&pl.d_part, sizeof(double) * 4 * pl.part_cap));
+        }
+    }
     if (pl.nk > 0) {
         AIM_CUDA_CHECK(cudaMemcpyAsync(pl.d_kvec, kv.data(), sizeof(double) * 3 * pl.nk, cudaMemcpyHostToDevice, st));
         AIM_CUDA_CHECK(cudaMemcpyAsync(pl.d_ck, ck.data(), sizeof(double) * pl.nk, cudaMemcpyHostToDevice, st));
@@ -335,6 +374,9 @@ void ewald_release(EwaldPlan& pl) {
     if (pl.d_kvec) cudaFree(pl.d_kvec);
     if (pl.d_hkl) cudaFree(pl.d_hkl);
     if (pl.d_frac) cudaFree(pl.d_frac);
+    if (pl.d_part) cudaFree(pl.d_part);
+    pl.d_part = nullptr;
+    pl.part_cap = 0;
     pl.d_kvec = pl.d_ck = pl.d_S = nullptr;
     pl.d_hkl = nullptr;
     pl.d_frac = nullptr;
@@ -358,7 +400,7 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
                                                        iv[8], fq);
     AIM_LAUNCH_CHECK();
     if (pl.nk > 0) {
-        ewald_sf_kernel<<<((pl.nk + kSfBlock - 1) / kSfBlock + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, pl.d_hkl, pl.d_S);
+        ewald_sf_kernel<<<(pl.nk / kSfBlock + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, pl.d_hkl, pl.d_S);
         AIM_LAUNCH_CHECK();
     }
     float4* rec = reinterpret_cast<float4*>(pl.d_hkl + 4 * (size_t)pl.cap);   // 16-byte aligned: cap * 16 bytes in
@@ -366,8 +408,16 @@ int launch_ewald_recip(const EwaldPlan& pl, int n, const float* coord, const flo
         ewald_pack_kernel<<<(pl.nk + 255) / 256, 256, 0, st>>>(pl.nk, pl.d_hkl, pl.d_kvec, pl.d_ck, pl.d_S, rec);
         AIM_LAUNCH_CHECK();
     }
-    ewald_atom_kernel<<<((n + kAtomBlock - 1) / kAtomBlock + 7) / 8, 256, 0, st>>>(n, pl.nk, fq, q, rec, pref, self_coeff, bg_unit, d_q, e_atom, gq,
-                                                  forces);
+    const int n_runs = pl.nk / kEwaldRun, slices = ewald_atom_slices(n, n_runs);
+    AIM_REQUIRE((size_t)slices * n <= pl.part_cap, "ewald: plan prepared for fewer atoms");
+    double4* part = reinterpret_cast<double4*>(pl.d_part);
+    if (n_runs > 0) {
+        const int per = (n_runs + slices - 1) / slices;
+        ewald_atom_kernel<<<dim3((n + 127) / 128, slices), 128, 0, st>>>(n, n_runs, per, fq, rec, part);
+        AIM_LAUNCH_CHECK();
+    }
+    ewald_atom_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, n_runs > 0 ? slices : 0, part, q, pref, self_coeff, bg_unit, d_q,
+                                                             e_atom, gq, forces);
     AIM_LAUNCH_CHECK();
     ewald_energy_kernel<<<1, 256, 0, st>>>(pl.nk, pl.d_kvec, pl.d_ck, pl.d_S, pref, 1.0 / (4.0 * pl.alpha * pl.alpha), bg_unit,
                                            d_q, e_atom, virial_atom);
