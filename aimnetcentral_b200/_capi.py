@@ -67,7 +67,7 @@ EXPORTS = [
     "aimnet2_conv_sv_2d_sp_fwd", "aimnet2_conv_sv_2d_sp_bwd", "aimnet2_engine_create", "aimnet2_engine_destroy",
     "aimnet2_engine_set_options", "aimnet2_engine_set_gemm_backend", "aimnet2_engine_set_small_m_rows", "aimnet2_engine_set_conv_impl", "aimnet2_engine_conv_mode", "aimnet2_engine_set_dense_min_molecules", "aimnet2_engine_debug_poison", "aimnet2_engine_debug_layout", "aimnet2_engine_debug_read_workspace", "aimnet2_engine_set_deterministic", "aimnet2_engine_eval", "aimnet2_engine_eval_host",
     "aimnet2_engine_enable_cuda_graph", "aimnet2_engine_graph_stats", "aimnet2_engine_last_launches", "aimnet2_engine_info", "aimnet2_engine_skin_stats", "aimnet2_engine_enable_timing",
-    "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace", "aimnet2_engine_neighbor_caps",
+    "aimnet2_engine_last_timing", "aimnet2_gemm_nt", "aimnet2_gemm_set_trace", "aimnet2_engine_neighbor_caps", "aimnet2_engine_set_species_first_pass",
     "aimnet2_dsf_coulomb", "aimnet2_dftd3", "aimnet2_ewald_summation", "aimnet2_estimate_ewald_parameters",
 ]
 
@@ -113,6 +113,7 @@ def load():
     lib.aimnet2_engine_last_launches.argtypes = [vp]
     lib.aimnet2_engine_info.argtypes = [vp, c_int_p, c_int_p, C.POINTER(C.c_int64)]
     lib.aimnet2_engine_neighbor_caps.argtypes = [vp, c_int_p, c_int_p]
+    lib.aimnet2_engine_set_species_first_pass.argtypes = [vp, C.c_int]
     lib.aimnet2_engine_skin_stats.argtypes = [vp, c_int_p, c_int_p]
     lib.aimnet2_engine_enable_timing.argtypes = [vp, ci]
     lib.aimnet2_engine_last_timing.argtypes = [vp, c_float_p, ci]

@@ -355,8 +355,10 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
                                                           const float* __restrict__ q, const float* __restrict__ dS_a,
                                                           const float* __restrict__ dS_q, float* __restrict__ grad_a,
                                                           float* __restrict__ grad_q, float* __restrict__ forces,
-                                                          double* __restrict__ virial_atom, int with_q) {
+                                                          double* __restrict__ virial_atom, int with_q,
+                                                          const int* __restrict__ skip_if) {
     __shared__ PairEntry tile[256];
+    if (skip_if != nullptr && *skip_if != 0) return;   // the by-species kernels below have done this pass (uniform)
     const int tid = threadIdx.x;
     const int al = tid >> 5, lane = tid & 31, g = lane & 15, h = lane >> 4;
     const int i = blockIdx.x * kAtomsPerCta + al;
@@ -665,13 +667,13 @@ static int conv_bwd_launch(int n_atoms, const NbView& nb, const float* coord, co
                            const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q,
                            const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                            const float* agh_q, float* dS_a, float* dS_q, float* grad_a, float* grad_q, float* forces,
-                           double* virial_atom, int with_q, int want_grad_a, cudaStream_t st) {
+                           double* virial_atom, int with_q, int want_grad_a, const int* skip_if, bool prep, cudaStream_t st) {
     const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
-    AIM_TRY(conv_bwd_prep_launch<C>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, 0, st));
+    if (prep) AIM_TRY(conv_bwd_prep_launch<C>(n_atoms, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q, with_q, 0, st));
     int grid = n_groups;
 #define AIM_CONV_BWD(GA, VIR)                                                                                       \
     conv_bwd_kernel<C, GA, VIR><<<grid, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dS_a, dS_q, grad_a, \
-                                                      grad_q, forces, virial_atom, with_q)
+                                                      grad_q, forces, virial_atom, with_q, skip_if)
     if (want_grad_a) {
         if (virial_atom) AIM_CONV_BWD(true, true); else AIM_CONV_BWD(true, false);
     } else {
@@ -687,14 +689,212 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
                     const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q, const float* dx,
                     int ldx, const float* T_a, const float* T_q, const float* agh_a, const float* agh_q, float* dS_a,
                     float* dS_q, float* grad_a, float* grad_q, float* forces, double* virial_atom, int with_q,
-                    int want_grad_a, cudaStream_t st) {
+                    int want_grad_a, cudaStream_t st, const int* skip_if, bool prep) {
     if (n_atoms == 0) return AIMNET_OK;
     if (C == 1)
         return conv_bwd_launch<1>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q,
-                                  grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, st);
+                                  grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, skip_if, prep, st);
     return conv_bwd_launch<2>(n_atoms, nb, coord, cv, mol_idx, aev, aT, q, dx, ldx, T_a, T_q, agh_a, agh_q, dS_a, dS_q,
-                              grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, st);
+                              grad_a, grad_q, forces, virial_atom, with_q, want_grad_a, skip_if, prep, st);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward of the FIRST convolution by species.  In pass 0 the convolved features are the embedding, a[j] = afv[Z_j]
+// (aimnet/models/aimnet2.py:144-147): they depend on the neighbour only through its species, they need no gradient, and
+// there are no charge channels yet.  The two 1 024-FMA contractions the generic kernel does per pair,
+//     p[g,d] = sum_a a[j,a,g] dS[i,a,g,d]        r[g,d] = sum_a a[i,a,g] dS[j,a,g,d],
+// are therefore table look-ups  p = P[i][slot(Z_j)],  r = P[j][slot(Z_i)]  into
+//     P[i][s][g][d] = sum_a afv[z_s][a,g] dS[i,a,g,d]      (one contraction per atom and PRESENT species),
+// and the pair kernel reads 256 bytes of the neighbour's table instead of its 1 KB of features and 4 KB of dS: half a
+// warp per pair, lane = g.  Species slots are assigned on the device (no host round trip); with more than kMaxSlots
+// species in one evaluation the flag stays 0, these kernels return at once and the generic kernel runs instead.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxSlots = 16;
+// info: [0] 1 = by-species pass valid, [1] number of slots, [2 .. 2 + kMaxSlots) atomic number of a slot
+__global__ void __launch_bounds__(1024) species_scan_kernel(int n, const int32_t* __restrict__ numbers, int* __restrict__ info,
+                                                            uint8_t* __restrict__ atom_slot) {
+    __shared__ unsigned int mask[2];
+    __shared__ int slot_of_z[64];
+    if (threadIdx.x < 2) mask[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned int m0 = 0u, m1 = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int z = numbers[i];
+        z = (z < 0 || z > 63) ? 0 : z;
+        if (z < 32) m0 |= 1u << z; else m1 |= 1u << (z - 32);
+    }
+    if (m0) atomicOr(&mask[0], m0);
+    if (m1) atomicOr(&mask[1], m1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ns = 0;
+        for (int z = 0; z < 64; ++z) {
+            const bool present = (z < 32 ? (mask[0] >> z) : (mask[1] >> (z - 32))) & 1u;
+            slot_of_z[z] = 0;
+            if (present) {
+                if (ns < kMaxSlots) {
+                    slot_of_z[z] = ns;
+                    info[2 + ns] = z;
+                }
+                ++ns;
+            }
+        }
+        info[0] = (ns <= kMaxSlots) ? 1 : 0;
+        info[1] = ns <= kMaxSlots ? ns : kMaxSlots;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int z = numbers[i];
+        z = (z < 0 || z > 63) ? 0 : z;
+        atom_slot[i] = (uint8_t)slot_of_z[z];
+    }
+}
+
+// P[i][s][g][:] for the present species; warp = atom, lane = (channel half h, g) as in conv_bwd_kernel
+__global__ void __launch_bounds__(256) conv0_table_kernel(int n_atoms, const int* __restrict__ info,
+                                                          const float* __restrict__ afvT, const float* __restrict__ dS_a,
+                                                          float4* __restrict__ P) {
+    if (info[0] == 0) return;
+    const int al = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane & 15, h = lane >> 4;
+    const int i = blockIdx.x * kAtomsPerCta + al;
+    if (i >= n_atoms) return;
+    const int n_slots = info[1];
+    float2 d01[kHalfA], d23[kHalfA];
+    const float4* p = reinterpret_cast<const float4*>(dS_a) + (size_t)i * kAG + (kHalfA * h) * kG + g;
+#pragma unroll
+    for (int a = 0; a < kHalfA; ++a) {
+        const float4 v = p[a * kG];
+        d01[a] = make_float2(v.x, v.y);
+        d23[a] = make_float2(v.z, v.w);
+    }
+    for (int s = 0; s < n_slots; ++s) {
+        const float4* r = reinterpret_cast<const float4*>(afvT + (size_t)info[2 + s] * kAG) + g + 32 * h;
+        const float4 o0 = r[0], o1 = r[16];
+        const float av[kHalfA] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        float2 p01 = make_float2(0.f, 0.f), p23 = p01;
+#pragma unroll
+        for (int a = 0; a < kHalfA; ++a) {
+            p01 = ffma2s(av[a], d01[a], p01);
+            p23 = ffma2s(av[a], d23[a], p23);
+        }
+        // channels 0-7 (h = 0) + channels 8-15 (h = 1), in this fixed order
+        const float x0 = __shfl_xor_sync(0xffffffffu, p01.x, 16), x1 = __shfl_xor_sync(0xffffffffu, p01.y, 16);
+        const float x2 = __shfl_xor_sync(0xffffffffu, p23.x, 16), x3 = __shfl_xor_sync(0xffffffffu, p23.y, 16);
+        if (h == 0) P[((size_t)i * kMaxSlots + s) * kG + g] = make_float4(p01.x + x0, p01.y + x1, p23.x + x2, p23.y + x3);
+    }
+}
+
+template <bool kVirial>
+__global__ void __launch_bounds__(256) conv0_force_kernel(int n_atoms, NbView nb, const float* __restrict__ coord, CellView cv,
+                                                          const int32_t* __restrict__ mol_idx, AevParams aev,
+                                                          const int* __restrict__ info,
+                                                          const uint8_t* __restrict__ atom_slot,
+                                                          const float4* __restrict__ P, float* __restrict__ forces,
+                                                          double* __restrict__ virial_atom) {
+    __shared__ PairEntry tile[256];
+    __shared__ float4 own[kAtomsPerCta][kMaxSlots * kG];   // the centre's own table: 4 KB per warp
+    if (info[0] == 0) return;
+    const int tid = threadIdx.x;
+    const int al = tid >> 5, lane = tid & 31, g = lane & 15, hw = lane >> 4;
+    const int i = blockIdx.x * kAtomsPerCta + al;
+    const bool atom_ok = i < n_atoms;
+    const int ic = atom_ok ? i : 0;
+    const float* cell = cv.cell ? cv.cell + 9 * (cv.n_cells == 1 ? 0 : (mol_idx ? mol_idx[ic] : 0)) : nullptr;
+    const int len = atom_ok ? row_length(nb, i) : 0;
+    const float shift_g = aev.shifts[g];
+    const int n_slots = info[1];
+    for (int k = lane; k < n_slots * kG; k += 32) own[al][k] = P[(size_t)ic * kMaxSlots * kG + k];
+    const int zi = atom_slot[ic];
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    float vir[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) vir[k] = 0.f;
+    for (int m0 = 0; m0 < len; m0 += kSlotsPerTile) {
+        __syncwarp();
+        stage_pairs<true>(tile, ic, atom_ok, m0, len, nb, coord, cell, aev);
+        __syncwarp();
+        const int lim = min(kSlotsPerTile, len - m0);
+        for (int s = hw; s < lim; s += 2) {   // half a warp per pair
+            const PairEntry e = tile[al * 32 + s];
+            const float4 r = __ldg(P + ((size_t)e.j * kMaxSlots + zi) * kG + g);
+            const float4 p = own[al][(int)atom_slot[e.j] * kG + g];
+            const float xg = e.d - shift_g;
+            const float ex = aev_exp(-aev.eta * xg * xg);
+            const float gs = ex * e.fc;
+            const float dgs = ex * (e.dfc - 2.0f * aev.eta * xg * e.fc);
+            const float gsi = gs * e.inv;
+            // w(i->j) = u (A + C.u) + (B - u (B.u))/d  and the reverse slot with u' = -u: see conv_bwd_kernel
+            const float pu = p.y * e.ux + p.z * e.uy + p.w * e.uz;
+            const float sc = (p.x + pu) * dgs - pu * gsi;
+            const float ru = r.y * e.ux + r.z * e.uy + r.w * e.uz;
+            const float scr = (ru - r.x) * dgs - ru * gsi;
+            if (!kVirial) {
+                const float ds = sc - scr;
+                fx += fmaf(e.ux, ds, (p.y - r.y) * gsi);
+                fy += fmaf(e.uy, ds, (p.z - r.z) * gsi);
+                fz += fmaf(e.uz, ds, (p.w - r.w) * gsi);
+            } else {
+                const float wx = e.ux * sc + p.y * gsi, wy = e.uy * sc + p.z * gsi, wz = e.uz * sc + p.w * gsi;
+                const float vx = e.ux * scr + r.y * gsi, vy = e.uy * scr + r.z * gsi, vz = e.uz * scr + r.w * gsi;
+                fx += wx - vx;
+                fy += wy - vy;
+                fz += wz - vz;
+                const float rx = e.ux * e.d, ry = e.uy * e.d, rz = e.uz * e.d;
+                vir[0] = fmaf(rx, wx, vir[0]);
+                vir[1] = fmaf(rx, wy, vir[1]);
+                vir[2] = fmaf(rx, wz, vir[2]);
+                vir[3] = fmaf(ry, wx, vir[3]);
+                vir[4] = fmaf(ry, wy, vir[4]);
+                vir[5] = fmaf(ry, wz, vir[5]);
+                vir[6] = fmaf(rz, wx, vir[6]);
+                vir[7] = fmaf(rz, wy, vir[7]);
+                vir[8] = fmaf(rz, wz, vir[8]);
+            }
+        }
+    }
+    fx = warp_sum(fx);
+    fy = warp_sum(fy);
+    fz = warp_sum(fz);
+    if (kVirial) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vir[k] = warp_sum(vir[k]);
+    }
+    if (!atom_ok || lane != 0) return;
+    forces[3 * i + 0] += fx;
+    forces[3 * i + 1] += fy;
+    forces[3 * i + 2] += fz;
+    if (kVirial)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) virial_atom[(size_t)i * 9 + k] += (double)vir[k];
+}
+
+int launch_species_scan(int n_atoms, const int32_t* numbers, int* info, uint8_t* atom_slot, cudaStream_t st) {
+    if (n_atoms == 0) return AIMNET_OK;
+    species_scan_kernel<<<1, 1024, 0, st>>>(n_atoms, numbers, info, atom_slot);
+    AIM_LAUNCH_CHECK();
+    return AIMNET_OK;
+}
+
+// force (and virial) of the first convolution's backward from dS_a (already prepared), by species; returns at once on the
+// device when `info` says that the evaluation has too many species (the caller then also launches the generic kernel with
+// skip_if = info, which returns at once in the other case)
+int launch_conv0_bwd_species(int n_atoms, const NbView& nb, const float* coord, const CellView& cv, const int32_t* mol_idx,
+                             const AevParams& aev, const int* info, const uint8_t* atom_slot, const float* afvT,
+                             const float* dS_a, float* P, float* forces, double* virial_atom, cudaStream_t st) {
+    if (n_atoms == 0) return AIMNET_OK;
+    const int n_groups = (n_atoms + kAtomsPerCta - 1) / kAtomsPerCta;
+    conv0_table_kernel<<<n_groups, 256, 0, st>>>(n_atoms, info, afvT, dS_a, reinterpret_cast<float4*>(P));
+    AIM_LAUNCH_CHECK();
+    if (virial_atom)
+        conv0_force_kernel<true><<<n_groups, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, info, atom_slot,
+                                                          reinterpret_cast<const float4*>(P), forces, virial_atom);
+    else
+        conv0_force_kernel<false><<<n_groups, 256, 0, st>>>(n_atoms, nb, coord, cv, mol_idx, aev, info, atom_slot,
+                                                           reinterpret_cast<const float4*>(P), forces, virial_atom);
+    AIM_LAUNCH_CHECK();
+    return AIMNET_OK;
+}
+int conv0_species_bytes_per_atom() { return kMaxSlots * kG * 16; }
 
 }  // namespace aimnet
 

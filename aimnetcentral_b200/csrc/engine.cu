@@ -50,6 +50,8 @@ struct aimnet2_engine {
     int C = 1;
     AevParams aev{};
     float *afv = nullptr, *agh_a = nullptr, *agh_q = nullptr, *w3 = nullptr;
+    float* afvT = nullptr;            // the embedding table in the conv kernels' gather layout (first-pass backward by species)
+    int species_pass0 = 1;            // 1 = backward of the first convolution by species tables (conv.cu), 0 = generic kernel
     float b3 = 0.f;
     double* sae = nullptr;
     std::vector<Linear> mlp[3];
@@ -240,6 +242,9 @@ struct Buffers {
     float *coord_ref, *wrap_off;   // Verlet skin: positions at list-build time, lattice offset applied by the wrap
     int32_t *skin_flag, *mol_ref;
     int32_t* graph_counts;   // graph replay: widest short-range / long-range row of the replayed build (overflow check afterwards)
+    float* sp_table;         // first-pass backward by species: P[i][slot][g][4]
+    int32_t* sp_info;        // ... flag, number of slots, atomic number per slot
+    uint8_t* sp_slot;        // ... slot of every atom
 };
 
 static SplitMat alias_split(float* base, size_t n, int width, float* inv) {
@@ -324,6 +329,9 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.dq_base = bp.take<float>(n * C, "dq_base");
     b.virial_atom = bp.take<double>(n * 9, "virial_atom");
     b.forces_tmp = bp.take<float>(n * 3, "forces_tmp");
+    b.sp_table = bp.take<float>(n * (size_t)(conv0_species_bytes_per_atom() / 4), "sp_table");
+    b.sp_info = bp.take<int32_t>(32, "sp_info");
+    b.sp_slot = bp.take<uint8_t>(n, "sp_slot");
     b.dense_fpart = bp.take<float>(n * 12, "dense_fpart");
     b.dense_gqpart = bp.take<float>(n * 4 * C, "dense_gqpart");
     b.x16 = SplitMat{bp.take<__half>(n * ldx, "x16_hi"), bp.take<__half>(n * ldx, "x16_lo"), bp.take<float>(n * (ldx / 32), "x16_inv"), ldx, ldx / 32};
@@ -798,6 +806,15 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[p], b.T_q[p], e->agh_a, e->agh_q, b.dS_a, b.dS_q, p > 0, 1, st));
                 AIM_TRY(launch_conv_dense_bwd_gather(C, N, B, e->last_max_seg, b.mol_ptr, coord, e->aev, b.a[p], qin, b.dS_a, b.dS_q,
                                                      b.grad_a, b.grad_q, F, b.dense_fpart, b.dense_gqpart, p > 0, p > 0, st));
+            } else if (p == 0 && e->species_pass0) {
+                // the convolved features of pass 0 are the embedding: contraction tables per species instead of per pair
+                // (conv.cu); the generic kernel follows with skip_if and only runs if there were too many species
+                AIM_TRY(launch_conv_bwd_prep(C, N, b.dx, ldx, b.T_a[0], b.T_q[0], e->agh_a, e->agh_q, b.dS_a, b.dS_q, 0, 0, st));
+                AIM_TRY(launch_species_scan(N, sys->numbers, b.sp_info, b.sp_slot, st));
+                AIM_TRY(launch_conv0_bwd_species(N, sr, coord, cv, sys->mol_idx, e->aev, b.sp_info, b.sp_slot, e->afvT, b.dS_a,
+                                                 b.sp_table, F, vir, st));
+                AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[0], nullptr, b.dx, ldx, b.T_a[0], b.T_q[0],
+                                        e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, 0, 0, st, b.sp_info, false));
             } else {
                 AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
                                         e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
@@ -867,6 +884,13 @@ extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weigh
     e->aev.rc = w->rc_s;
     // embedding rows of unimplemented species are NaN in exported models (train/export_model.py:74-80): kept as is
     if ((rc = upload(e, &e->afv, w->afv, (size_t)64 * kAG))) return rc;
+    {   // gather layout of conv.cu: index(a, g) = ((a >> 2) * 16 + g) * 4 + (a & 3)
+        std::vector<float> t((size_t)64 * kAG);
+        for (int z = 0; z < 64; ++z)
+            for (int a = 0; a < kA; ++a)
+                for (int g = 0; g < kG; ++g) t[(size_t)z * kAG + ((a >> 2) * kG + g) * 4 + (a & 3)] = w->afv[(size_t)z * kAG + a * kG + g];
+        if ((rc = upload(e, &e->afvT, t.data(), t.size()))) return rc;
+    }
     if ((rc = upload(e, &e->agh_a, w->agh_a, (size_t)kA * kG * kH))) return rc;
     if ((rc = upload(e, &e->agh_q, w->agh_q, (size_t)C * kG * kH))) return rc;
     if ((rc = upload(e, &e->sae, w->sae, 64))) return rc;
@@ -957,6 +981,12 @@ extern "C" int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend)
                 "epilogue), 4 (3xFP16, two tile streams per SM) or 5 (two tile streams on CTA pairs)");
     AIM_REQUIRE(backend == 0 || gemm_tc_available(), "set_gemm_backend: tcgen05 backends not available in this build");
     e->gemm_backend = backend;
+    return AIMNET_OK;
+}
+
+extern "C" int aimnet2_engine_set_species_first_pass(aimnet2_engine_t* e, int on) {
+    AIM_REQUIRE(e, "set_species_first_pass: null engine");
+    e->species_pass0 = on ? 1 : 0;
     return AIMNET_OK;
 }
 

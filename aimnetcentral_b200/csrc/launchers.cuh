@@ -22,7 +22,13 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
                     const int32_t* mol_idx, const AevParams& aev, const float* aT, const float* q, const float* dx,
                     int ldx, const float* T_a, const float* T_q, const float* agh_a, const float* agh_q, float* dS_a,
                     float* dS_q, float* grad_a, float* grad_q, float* forces, double* virial_atom, int with_q,
-                    int want_grad_a, cudaStream_t st);
+                    int want_grad_a, cudaStream_t st, const int* skip_if = nullptr, bool prep = true);
+// first convolution's backward by species (conv.cu): slots of the present species, then table + pair kernels
+int launch_species_scan(int n_atoms, const int32_t* numbers, int* info, uint8_t* atom_slot, cudaStream_t st);
+int launch_conv0_bwd_species(int n_atoms, const NbView& nb, const float* coord, const CellView& cv, const int32_t* mol_idx,
+                             const AevParams& aev, const int* info, const uint8_t* atom_slot, const float* afvT,
+                             const float* dS_a, float* P, float* forces, double* virial_atom, cudaStream_t st);
+int conv0_species_bytes_per_atom();
 
 int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                          const float* agh_q, float* dS_a, float* dS_q, int with_q, int permute, cudaStream_t st);

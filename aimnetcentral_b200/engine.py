@@ -165,6 +165,10 @@ class Engine:
             snap[name] = arr
         return snap
 
+    def set_species_first_pass(self, on: bool):
+        """Backward of the first convolution through per-species tables (default) or through the generic pair kernel."""
+        _capi.check(self._lib.aimnet2_engine_set_species_first_pass(self._h, int(bool(on))), "set_species_first_pass")
+
     def set_gemm_backend(self, backend: int):
         _capi.check(self._lib.aimnet2_engine_set_gemm_backend(self._h, int(backend)), "set_gemm_backend")
         self.gemm_backend = int(backend)

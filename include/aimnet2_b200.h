@@ -168,6 +168,12 @@ int aimnet2_engine_set_options(aimnet2_engine_t* e, const aimnet2_options_t* opt
  * (default when available), 3 = backend 2's arithmetic with the experimental pipelined tile epilogue (gemm_tc16p.cu; not
  * validated on a GPU yet) */
 int aimnet2_engine_set_gemm_backend(aimnet2_engine_t* e, int backend);
+/* Backward of the first convolution (whose input features are the species embedding, aimnet/models/aimnet2.py:144-147) through
+ * per-species contraction tables instead of per-pair contractions (csrc/conv.cu: species_scan / conv0_table / conv0_force).
+ * 1 (default) = on; 0 = the generic pair kernel for every pass.  With more than 16 species in one evaluation the generic
+ * kernel runs regardless (decided on the device). */
+int aimnet2_engine_set_species_first_pass(aimnet2_engine_t* e, int on);
+
 /* Row capacities of the engine's neighbor matrices.  They grow when a build overflows (the build is retried) and shrink
  * with the reference's hysteresis (aimnet/calculators/neighbors.py:127-140: to widest / 0.75 once the widest row is below
  * half of the capacity, never below the capacities a fresh engine starts with: 64 / 256); the device workspace is re-allocated smaller after 32 evaluations in a row that needed less than

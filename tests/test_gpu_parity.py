@@ -938,3 +938,56 @@ def test_hessian_periodic_finite_symmetric_sumrule(method):
         fm = calc({**data, "coord": xm}, forces=True)["forces"].double().cpu().numpy()
         row = -(fp - fm).reshape(9) / float(xp[comp // 3, comp % 3] - xm[comp // 3, comp % 3])
         assert np.abs(row - Hf[comp]).max() < 2e-2, (method, comp, np.abs(row - Hf[comp]).max())
+
+
+@pytest.mark.gpu
+def test_first_pass_backward_by_species_equals_generic_kernel():
+    """The backward of the first convolution through per-species tables (conv.cu: species_scan / conv0_table / conv0_force)
+    against the generic pair kernel on the same engine: molecules, a periodic cell with stress, a batch with many species
+    present, and more species than slots (the generic kernel then runs, decided on the device: bitwise equal)."""
+    from aimnetcentral_b200 import AIMNet2Calculator, ModelSpec, random_state_dict
+    from aimnetcentral_b200.structures import random_molecules
+
+    spec = ModelSpec()
+    calc = AIMNet2Calculator((random_state_dict(0, spec), spec), device="cuda:0")
+    eng = calc.engine
+
+    def both(data, **kw):
+        eng.set_species_first_pass(True)
+        a = calc(dict(data), forces=True, **kw)
+        eng.set_species_first_pass(False)
+        b = calc(dict(data), forces=True, **kw)
+        eng.set_species_first_pass(True)
+        return a, b
+
+    coord, numbers = random_molecules(70, 40, seed=5)
+    a, b = both({"coord": coord, "numbers": numbers, "charge": np.zeros(70, np.float32)})
+    assert torch.equal(a["energy"], b["energy"]) and float((a["forces"] - b["forces"]).abs().max()) < 2e-5
+    inputs, ref, meta = load_golden("pbc_box60_dsf")
+    calc.set_lrcoulomb_method("dsf")
+    a, b = both(inputs, stress=True)
+    calc.set_lrcoulomb_method("simple")
+    assert float((a["forces"] - b["forces"]).abs().max()) < 2e-5 and float((a["stress"] - b["stress"]).abs().max()) < 1e-6
+    assert np.abs(a["forces"].cpu().numpy() - ref["forces"]).max() < FORCE_ATOL
+    # 14 species in one evaluation (all of aimnet2's elements), and 20 on a model that implements them: more than the 16
+    # slots, so the by-species kernels return at once and the generic kernel does the pass
+    spec20 = ModelSpec(implemented_species=tuple(range(1, 21)))
+    calc20 = AIMNet2Calculator((random_state_dict(0, spec20), spec20), device="cuda:0")
+    for zs, exact in (([1, 5, 6, 7, 8, 9, 14, 15, 16, 17, 33, 34, 35, 53], False), (list(range(1, 21)), True)):
+        eng = (calc20 if exact else calc).engine
+        nat = 60
+        x = random_molecules(1, nat, seed=17)[0][0].astype(np.float32)   # a sane geometry; only the species are replaced
+        z = np.array([zs[k % len(zs)] for k in range(nat)], np.int64)
+        eng.set_species_first_pass(True)
+        fa = eng.eval(torch.tensor(x, device="cuda:0"), torch.tensor(z, dtype=torch.int32, device="cuda:0"),
+                      torch.zeros(1, device="cuda:0"), forces=True)["forces"]
+        eng.set_species_first_pass(False)
+        fb = eng.eval(torch.tensor(x, device="cuda:0"), torch.tensor(z, dtype=torch.int32, device="cuda:0"),
+                      torch.zeros(1, device="cuda:0"), forces=True)["forces"]
+        eng.set_species_first_pass(True)
+        scale = float(fb.abs().max())
+        assert torch.isfinite(fb).all() and torch.isfinite(fa).all()
+        if exact:
+            assert torch.equal(fa, fb)
+        else:
+            assert float((fa - fb).abs().max()) < 1e-5 * max(1.0, scale), (float((fa - fb).abs().max()), scale)
