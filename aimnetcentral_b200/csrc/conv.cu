@@ -707,47 +707,67 @@ int launch_conv_bwd(int C, int n_atoms, const NbView& nb, const float* coord, co
 //     P[i][s][g][d] = sum_a afv[z_s][a,g] dS[i,a,g,d]      (one contraction per atom and PRESENT species),
 // and the pair kernel reads 256 bytes of the neighbour's table instead of its 1 KB of features and 4 KB of dS: half a
 // warp per pair, lane = g.  Species slots are assigned on the device (no host round trip); with more than kMaxSlots
-// species in one evaluation the flag stays 0, these kernels return at once and the generic kernel runs instead.
+// species in one evaluation the flag stays 0, these kernels return at once and the generic kernel runs instead (the engine
+// launches it behind them, with skip_if, only for models that implement more than kMaxSlots species).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 16;
-// info: [0] 1 = by-species pass valid, [1] number of slots, [2 .. 2 + kMaxSlots) atomic number of a slot
-__global__ void __launch_bounds__(1024) species_scan_kernel(int n, const int32_t* __restrict__ numbers, int* __restrict__ info,
-                                                            uint8_t* __restrict__ atom_slot) {
+// info: [0] 1 = by-species pass valid, [1] number of slots, [2 .. 2 + kMaxSlots) atomic number of a slot,
+//       [18 .. 82) slot of an atomic number, [82], [83] presence mask of the atomic numbers, [84] block counter
+constexpr int kInfoSlotOfZ = 2 + kMaxSlots, kInfoMask = kInfoSlotOfZ + 64, kInfoCount = kInfoMask + 2;
+constexpr int kSpeciesInfoInts = kInfoCount + 1;
+__global__ void __launch_bounds__(256) species_mask_kernel(int n, const int32_t* __restrict__ numbers, int* __restrict__ info) {
+    // presence mask over all atoms; the block that finishes last turns it into the slot tables
     __shared__ unsigned int mask[2];
-    __shared__ int slot_of_z[64];
+    __shared__ bool last;
     if (threadIdx.x < 2) mask[threadIdx.x] = 0u;
     __syncthreads();
     unsigned int m0 = 0u, m1 = 0u;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int z = numbers[i];
         z = (z < 0 || z > 63) ? 0 : z;
         if (z < 32) m0 |= 1u << z; else m1 |= 1u << (z - 32);
     }
-    if (m0) atomicOr(&mask[0], m0);
-    if (m1) atomicOr(&mask[1], m1);
+    m0 = __reduce_or_sync(0xffffffffu, m0);
+    m1 = __reduce_or_sync(0xffffffffu, m1);
+    if ((threadIdx.x & 31) == 0) {
+        if (m0) atomicOr(&mask[0], m0);
+        if (m1) atomicOr(&mask[1], m1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int ns = 0;
-        for (int z = 0; z < 64; ++z) {
-            const bool present = (z < 32 ? (mask[0] >> z) : (mask[1] >> (z - 32))) & 1u;
-            slot_of_z[z] = 0;
-            if (present) {
-                if (ns < kMaxSlots) {
-                    slot_of_z[z] = ns;
-                    info[2 + ns] = z;
-                }
-                ++ns;
-            }
-        }
-        info[0] = (ns <= kMaxSlots) ? 1 : 0;
-        info[1] = ns <= kMaxSlots ? ns : kMaxSlots;
+        if (mask[0]) atomicOr(reinterpret_cast<unsigned int*>(info) + kInfoMask, mask[0]);
+        if (mask[1]) atomicOr(reinterpret_cast<unsigned int*>(info) + kInfoMask + 1, mask[1]);
+        __threadfence();
+        last = atomicAdd(info + kInfoCount, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int z = numbers[i];
-        z = (z < 0 || z > 63) ? 0 : z;
-        atom_slot[i] = (uint8_t)slot_of_z[z];
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    const unsigned int g0 = atomicOr(reinterpret_cast<unsigned int*>(info) + kInfoMask, 0u);
+    const unsigned int g1 = atomicOr(reinterpret_cast<unsigned int*>(info) + kInfoMask + 1, 0u);
+    int ns = 0;
+    for (int z = 0; z < 64; ++z) {
+        const bool present = ((z < 32 ? (g0 >> z) : (g1 >> (z - 32))) & 1u) != 0u;
+        int slot = 0;
+        if (present) {
+            if (ns < kMaxSlots) {
+                slot = ns;
+                info[2 + ns] = z;
+            }
+            ++ns;
+        }
+        info[kInfoSlotOfZ + z] = slot;
     }
+    info[1] = ns <= kMaxSlots ? ns : kMaxSlots;
+    info[0] = (ns <= kMaxSlots) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) species_slot_kernel(int n, const int32_t* __restrict__ numbers, const int* __restrict__ info,
+                                                           uint8_t* __restrict__ atom_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int z = numbers[i];
+    z = (z < 0 || z > 63) ? 0 : z;
+    atom_slot[i] = (uint8_t)info[kInfoSlotOfZ + z];
 }
 
 // P[i][s][g][:] for the present species; warp = atom, lane = (channel half h, g) as in conv_bwd_kernel
@@ -870,7 +890,12 @@ __global__ void __launch_bounds__(256) conv0_force_kernel(int n_atoms, NbView nb
 
 int launch_species_scan(int n_atoms, const int32_t* numbers, int* info, uint8_t* atom_slot, cudaStream_t st) {
     if (n_atoms == 0) return AIMNET_OK;
-    species_scan_kernel<<<1, 1024, 0, st>>>(n_atoms, numbers, info, atom_slot);
+    AIM_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int) * kSpeciesInfoInts, st));
+    int blocks = (n_atoms + 1023) / 1024;   // four atoms per thread
+    if (blocks > 296) blocks = 296;
+    species_mask_kernel<<<blocks, 256, 0, st>>>(n_atoms, numbers, info);
+    AIM_LAUNCH_CHECK();
+    species_slot_kernel<<<(n_atoms + 255) / 256, 256, 0, st>>>(n_atoms, numbers, info, atom_slot);
     AIM_LAUNCH_CHECK();
     return AIMNET_OK;
 }
@@ -895,6 +920,8 @@ int launch_conv0_bwd_species(int n_atoms, const NbView& nb, const float* coord, 
     return AIMNET_OK;
 }
 int conv0_species_bytes_per_atom() { return kMaxSlots * kG * 16; }
+int conv0_species_info_ints() { return kSpeciesInfoInts; }
+int conv0_species_max_slots() { return kMaxSlots; }
 
 }  // namespace aimnet
 

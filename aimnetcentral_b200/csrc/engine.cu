@@ -52,6 +52,7 @@ struct aimnet2_engine {
     float *afv = nullptr, *agh_a = nullptr, *agh_q = nullptr, *w3 = nullptr;
     float* afvT = nullptr;            // the embedding table in the conv kernels' gather layout (first-pass backward by species)
     int species_pass0 = 1;            // 1 = backward of the first convolution by species tables (conv.cu), 0 = generic kernel
+    int n_impl_species = 0;           // embedding rows that are not NaN (exported models mark unimplemented species that way)
     float b3 = 0.f;
     double* sae = nullptr;
     std::vector<Linear> mlp[3];
@@ -330,7 +331,7 @@ static void carve(aimnet2_engine* e, Bump& bp, Buffers& b, int N, int B, int sr_
     b.virial_atom = bp.take<double>(n * 9, "virial_atom");
     b.forces_tmp = bp.take<float>(n * 3, "forces_tmp");
     b.sp_table = bp.take<float>(n * (size_t)(conv0_species_bytes_per_atom() / 4), "sp_table");
-    b.sp_info = bp.take<int32_t>(32, "sp_info");
+    b.sp_info = bp.take<int32_t>(conv0_species_info_ints(), "sp_info");
     b.sp_slot = bp.take<uint8_t>(n, "sp_slot");
     b.dense_fpart = bp.take<float>(n * 12, "dense_fpart");
     b.dense_gqpart = bp.take<float>(n * 4 * C, "dense_gqpart");
@@ -813,8 +814,9 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                 AIM_TRY(launch_species_scan(N, sys->numbers, b.sp_info, b.sp_slot, st));
                 AIM_TRY(launch_conv0_bwd_species(N, sr, coord, cv, sys->mol_idx, e->aev, b.sp_info, b.sp_slot, e->afvT, b.dS_a,
                                                  b.sp_table, F, vir, st));
-                AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[0], nullptr, b.dx, ldx, b.T_a[0], b.T_q[0],
-                                        e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, 0, 0, st, b.sp_info, false));
+                if (e->n_impl_species > conv0_species_max_slots())   // only then can an evaluation have too many species
+                    AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[0], nullptr, b.dx, ldx, b.T_a[0], b.T_q[0],
+                                            e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, 0, 0, st, b.sp_info, false));
             } else {
                 AIM_TRY(launch_conv_bwd(C, N, sr, coord, cv, sys->mol_idx, e->aev, b.a[p], qin, b.dx, ldx, b.T_a[p], b.T_q[p],
                                         e->agh_a, e->agh_q, b.dS_a, b.dS_q, b.grad_a, b.grad_q, F, vir, p > 0, p > 0, st));
@@ -885,6 +887,12 @@ extern "C" int aimnet2_engine_create(aimnet2_engine_t** out, const aimnet2_weigh
     // embedding rows of unimplemented species are NaN in exported models (train/export_model.py:74-80): kept as is
     if ((rc = upload(e, &e->afv, w->afv, (size_t)64 * kAG))) return rc;
     {   // gather layout of conv.cu: index(a, g) = ((a >> 2) * 16 + g) * 4 + (a & 3)
+        e->n_impl_species = 0;
+        for (int z = 0; z < 64; ++z) {
+            bool ok = true;
+            for (int k = 0; k < kAG && ok; ++k) ok = !std::isnan(w->afv[(size_t)z * kAG + k]);
+            e->n_impl_species += ok ? 1 : 0;
+        }
         std::vector<float> t((size_t)64 * kAG);
         for (int z = 0; z < 64; ++z)
             for (int a = 0; a < kA; ++a)

@@ -29,6 +29,8 @@ int launch_conv0_bwd_species(int n_atoms, const NbView& nb, const float* coord, 
                              const AevParams& aev, const int* info, const uint8_t* atom_slot, const float* afvT,
                              const float* dS_a, float* P, float* forces, double* virial_atom, cudaStream_t st);
 int conv0_species_bytes_per_atom();
+int conv0_species_info_ints();
+int conv0_species_max_slots();
 
 int launch_conv_bwd_prep(int C, int n_atoms, const float* dx, int ldx, const float* T_a, const float* T_q, const float* agh_a,
                          const float* agh_q, float* dS_a, float* dS_q, int with_q, int permute, cudaStream_t st);
