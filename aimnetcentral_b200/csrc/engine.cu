@@ -370,12 +370,20 @@ static int linear_fwd(aimnet2_engine* e, const Linear& L, const float* X, int ld
     gemm_mark(e, st);
     return rc;
 }
-// dX[M,in_pad] = dZ[M,out_pad] @ W  (* gp_prev)
+// the transposed weights from input feature `row0` on (rows of Wt are input features): an input-gradient GEMM that only
+// needs the columns row0 .. in_pad of dX
+static WeightView rows_from(const WeightView& w, int row0) {
+    const size_t o = (size_t)row0 * w.ldw;
+    return WeightView{w.W ? w.W + o : nullptr, w.Whi ? w.Whi + o : nullptr, w.Wlo ? w.Wlo + o : nullptr,
+                      w.Wh16 ? static_cast<const char*>(w.Wh16) + 2 * o : nullptr,
+                      w.Wl16 ? static_cast<const char*>(w.Wl16) + 2 * o : nullptr, w.inv_scale16, w.ldw};
+}
+// dX[M,in_pad] = dZ[M,out_pad] @ W  (* gp_prev); col0 > 0: only the columns col0 .. in_pad of dX are computed
 static int linear_bwd(aimnet2_engine* e, const Linear& L, const float* dZ, float* dX, int lddx, const float* gp_prev,
-                      int ldgp, int M, cudaStream_t st) {
+                      int ldgp, int M, cudaStream_t st, int col0 = 0) {
     gemm_mark(e, st);
-    int rc = gemm_nt(dZ, L.out_pad, L.bwd(), nullptr, dX, lddx, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
-                     gp_prev ? 3 : 0, e->backend_now, st);
+    int rc = gemm_nt(dZ, L.out_pad, rows_from(L.bwd(), col0), nullptr, dX + col0, lddx, const_cast<float*>(gp_prev), ldgp, M,
+                     L.in_pad - col0, L.out_pad, gp_prev ? 3 : 0, e->backend_now, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -390,10 +398,10 @@ static int linear_fwd16(aimnet2_engine* e, const Linear& L, const SplitMat& X, f
     return rc;
 }
 static int linear_bwd16(aimnet2_engine* e, const Linear& L, const SplitMat& dZ, float* dX32, int lddx, const SplitMat* dX16,
-                        const float* gp_prev, int ldgp, int M, cudaStream_t st) {
+                        const float* gp_prev, int ldgp, int M, cudaStream_t st, int col0 = 0) {
     gemm_mark(e, st);
-    int rc = gemm_nt_split(dZ, L.bwd(), nullptr, dX32, lddx, dX16, const_cast<float*>(gp_prev), ldgp, M, L.in_pad, L.out_pad,
-                           gp_prev ? 3 : 0, e->backend_now - 2, st);
+    int rc = gemm_nt_split(dZ, rows_from(L.bwd(), col0), nullptr, dX32 ? dX32 + col0 : nullptr, lddx, dX16,
+                           const_cast<float*>(gp_prev), ldgp, M, L.in_pad - col0, L.out_pad, gp_prev ? 3 : 0, e->backend_now - 2, st);
     gemm_mark(e, st);
     return rc;
 }
@@ -792,13 +800,14 @@ static int eval_impl(aimnet2_engine* e, const aimnet2_system_t* sys, const aimne
                         AIM_TRY(linear_bwd16(e, L[l], dz, nullptr, 0, &o, b.gp[p][l - 1], L[l - 1].out_pad, N, st));
                         c16 ^= 1;
                     } else {
-                        AIM_TRY(linear_bwd16(e, L[0], dz, b.dx, ldx, nullptr, nullptr, 0, N, st));
+                        // pass 0: the first 256 inputs are the atom's own embedding, nothing consumes their gradient
+                        AIM_TRY(linear_bwd16(e, L[0], dz, b.dx, ldx, nullptr, nullptr, 0, N, st, p == 0 ? kAG : 0));
                     }
                 } else if (l > 0) {
                     AIM_TRY(linear_bwd(e, L[l], cur, other, L[l].in_pad, b.gp[p][l - 1], L[l - 1].out_pad, N, st));
                     std::swap(cur, other);
                 } else {
-                    AIM_TRY(linear_bwd(e, L[0], cur, b.dx, ldx, nullptr, 0, N, st));
+                    AIM_TRY(linear_bwd(e, L[0], cur, b.dx, ldx, nullptr, 0, N, st, p == 0 ? kAG : 0));
                 }
             }
             const float* qin = (p == 0) ? nullptr : b.q[p - 1];
