@@ -186,7 +186,6 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    volatile int* chunk_last = reinterpret_cast<volatile int*>(bars + 2 * STAGES + 5);   // [2] last chunk of its tile?
     float* sbias = reinterpret_cast<float*>(smem + OFF_BARS + 256);                // [256]
     unsigned char* epi_buf = smem + OFF_EPI;                                       // 8 x 2 x 2 KB, 1 KB aligned
 
@@ -288,8 +287,6 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                             ph ^= 1;
                         }
                     }
-                    chunk_last[b] = (ks == nk) ? 1 : 0;
-                    __threadfence_block();
                     tc_commit(&tmem_full[b]);
                 }
             }
@@ -347,7 +344,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                 mbar_wait(&tmem_full[b], aph);
                 if (threadIdx.x == 0) stamp(p, 5, cit);
                 tc_fence_after();
-                last = chunk_last[b];
+                last = (kc + 1 == nchunk) ? 1 : 0;   // the tile's last chunk (the issuer runs the same count)
                 const uint32_t taddr = tmem_base + ((uint32_t)(ql * 32) << 16) + (uint32_t)(b * BN + ch * 128);
                 // two 32-column loads in flight at a time
 #pragma unroll

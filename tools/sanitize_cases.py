@@ -36,3 +36,26 @@ calc2.engine.set_small_m_rows(512 if which == "simt" else 0)
 out4 = calc2({**mol, "mult": np.ones(6, np.float32)}, forces=True)
 torch.cuda.synchronize()
 print("nse", float(out4["energy"].sum()))
+# round 2: the dense (shared-memory / TMA) conv forward needs a batch of >= 64 molecules; GEMM backends 4 and 5 through the
+# operator seam (two tile streams; CTA pairs), a Hessian (finite differences over a molecule batch), batched Ewald
+if which == "all":
+    import ctypes as C
+    from aimnetcentral_b200 import _capi
+    coord64, numbers64 = random_molecules(64, 12, seed=9)
+    calc.engine.set_small_m_rows(0)
+    calc.set_lrcoulomb_method("simple")
+    out5 = calc({"coord": coord64, "numbers": numbers64, "charge": np.zeros(64, np.float32)}, forces=True)
+    print("dense conv batch", float(out5["energy"].sum()), calc.engine.conv_mode())
+    H = calc({"coord": coord[0], "numbers": numbers[0], "charge": np.zeros(1, np.float32)}, hessian=True)["hessian"]
+    print("hessian", tuple(H.shape), float(H.abs().max()))
+    lib = _capi.load()
+    M, N, K = 700, 288, 96
+    A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") * 0.05; bias = torch.randn(N, device="cuda")
+    Y = torch.empty(M, N, device="cuda"); aux = torch.randn(M, N, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for be in (2, 4, 5):
+        for mode in (2, 3, 2 | 16):
+            rc = lib.aimnet2_gemm_nt(A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr(), Y.data_ptr(), N, aux.data_ptr(), N, M, N, K, mode, be, st)
+            assert rc == 0, lib.aimnet2_last_error()
+    torch.cuda.synchronize()
+    print("gemm backends 2/4/5", float(Y.abs().sum()))
