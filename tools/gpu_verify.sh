@@ -17,5 +17,5 @@ print(f"bench: {d['value'] / 1e6:.3f} M atom-steps/s  {d['ms_per_step']:.3f} ms/
 PY
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_cfg2.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra > gpurun_out/${tag}_ncu_bench.log 2>&1
-python tools/launch_shares.py gpurun_out/${tag}_launches_cfg2.csv | head -12
-python tools/merge_first_touch.py 2>/dev/null | tail -1
+python tools/launch_shares.py gpurun_out/${tag}_launches_cfg2.csv 2>/dev/null | head -12
+# back in the build container: python tools/merge_first_touch.py appends gpurun_out/first_touch_log.jsonl to profiles/

@@ -26,5 +26,8 @@ for k, v in step:
     agg[k][0] += 1
     agg[k][1] += v
 print(f"{len(step)} launches, {total:.0f} us summed (cold-cache, serialised: read the shares)")
-for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k[:64]:64s} {n:3d} x {v / n:8.1f} us  {100 * v / total:5.1f} %")
+try:
+    for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k[:64]:64s} {n:3d} x {v / n:8.1f} us  {100 * v / total:5.1f} %")
+except BrokenPipeError:   # piped into `head`
+    sys.stderr.close()
