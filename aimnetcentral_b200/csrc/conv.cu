@@ -384,24 +384,28 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
 #pragma unroll
         for (int a = 0; a < kHalfA; ++a) ai[a] = ov[a];
     }
-    // the charge channels are handled by the h == 0 half only (their partial sums are added once)
-    const bool qhalf = with_q && h == 0;
-    float2 dSqi01[C], dSqi23[C];
-    float qi[C];
+    // charge channels (their partial sums are added once).  One channel: the h == 0 half handles it.  Two channels (NSE):
+    // half h handles channel h -- the same instructions for both halves, only the addresses differ, so neither half idles
+    // while the other works (slot 0 of the arrays below then holds "this lane's channel").
+    const bool qhalf = with_q && (C == 2 || h == 0);
+    const int cm = (C == 2) ? h : 0;         // channel of slot 0
+    constexpr int CQ = (C == 2) ? 1 : C;     // channels per lane
+    float2 dSqi01[CQ], dSqi23[CQ];
+    float qi[CQ];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        float4 v = qhalf ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + c * kG + g] : make_float4(0, 0, 0, 0);
+    for (int c = 0; c < CQ; ++c) {
+        float4 v = qhalf ? reinterpret_cast<const float4*>(dS_q)[(size_t)ic * (C * kG) + (cm + c) * kG + g] : make_float4(0, 0, 0, 0);
         dSqi01[c] = make_float2(v.x, v.y);
         dSqi23[c] = make_float2(v.z, v.w);
-        qi[c] = qhalf ? q[(size_t)ic * C + c] : 0.f;
+        qi[c] = qhalf ? q[(size_t)ic * C + cm + c] : 0.f;
     }
     // grad_a / grad_q as two partial sums each (the halves of one packed accumulator), added at the end
     float2 ga2[kHalfA];
 #pragma unroll
     for (int a = 0; a < kHalfA; ++a) ga2[a] = make_float2(0.f, 0.f);
-    float2 gq2[C];
+    float2 gq2[CQ];
 #pragma unroll
-    for (int c = 0; c < C; ++c) gq2[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < CQ; ++c) gq2[c] = make_float2(0.f, 0.f);
     float fx = 0.f, fy = 0.f, fz = 0.f;
     float vir[9];
 #pragma unroll
@@ -441,9 +445,9 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
             }
             if (qhalf) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    float qj = q[(size_t)e.j * C + c];
-                    float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)e.j * (C * kG) + c * kG + g];
+                for (int c = 0; c < CQ; ++c) {
+                    float qj = q[(size_t)e.j * C + cm + c];
+                    float4 dqj = reinterpret_cast<const float4*>(dS_q)[(size_t)e.j * (C * kG) + (cm + c) * kG + g];
                     const float2 dq01 = make_float2(dqj.x, dqj.y), dq23 = make_float2(dqj.z, dqj.w);
                     if (kGradA) {
                         gq2[c] = ffma2(dq01, G01, gq2[c]);
@@ -504,7 +508,10 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(int n_atoms, NbView nb
     for (int c = 0; c < C; ++c) gq[c] = 0.f;
     if (kGradA && with_q) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) gq[c] = warp_sum(gq2[c].x + gq2[c].y);
+        for (int c = 0; c < C; ++c) {
+            const float mine = (C == 2) ? ((h == c) ? gq2[0].x + gq2[0].y : 0.f) : gq2[C == 2 ? 0 : c].x + gq2[C == 2 ? 0 : c].y;
+            gq[c] = warp_sum(mine);
+        }
     }
     if (!atom_ok) return;
     if (kGradA) {
