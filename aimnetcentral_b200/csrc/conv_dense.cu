@@ -203,11 +203,15 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
                 for (int ap = 0; ap < 4; ++ap)
 #pragma unroll
                     for (int d = 0; d < 4; ++d) S[c][ap][d] = make_float2(0.f, 0.f);
-            float Sq[2][C][4];
+            // charge channels: with one channel both halves accumulate it (the h == 0 half stores it); with two (NSE) the half h
+            // accumulates and stores channel h: half the FMAs per lane, identical instructions in both halves
+            constexpr int CQ = (C == 2) ? 1 : C;
+            const int cm = (C == 2) ? h : 0;
+            float Sq[2][CQ][4];
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc)
+                for (int cc = 0; cc < CQ; ++cc)
 #pragma unroll
                     for (int d = 0; d < 4; ++d) Sq[c][cc][d] = 0.f;
             for (int k0 = 0; k0 < n; k0 += kSlots) {
@@ -233,10 +237,10 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
                                           make_float2(v1.z, v1.w)};
                     const float dd[2] = {e_d.x, e_d.y}, fcv[2] = {e_fc.x, e_fc.y}, uxv[2] = {e_ux.x, e_ux.y},
                                 uyv[2] = {e_uy.x, e_uy.y}, uzv[2] = {e_uz.x, e_uz.y};
-                    float qj[C];
+                    float qj[CQ];
                     if (with_q) {
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) qj[cc] = q_s[(k0 + s) * C + cc];
+                        for (int cc = 0; cc < CQ; ++cc) qj[cc] = q_s[(k0 + s) * C + cm + cc];
                     }
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
                             for (int d = 0; d < 4; ++d) S[c][ap][d] = ffma2(av[ap], wd[d], S[c][ap][d]);
                         if (with_q) {
 #pragma unroll
-                            for (int cc = 0; cc < C; ++cc)
+                            for (int cc = 0; cc < CQ; ++cc)
 #pragma unroll
                                 for (int d = 0; d < 4; ++d) Sq[c][cc][d] = fmaf(qj[cc], wv[d], Sq[c][cc][d]);
                         }
@@ -288,14 +292,14 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ CUt
                     }
                     int base = 2 * kAG + kAH;
                     if (with_q) {
-                        if (h == 0) {
-                            if (g < C) xr[base + g] = q_s[il * C + g];
+                        if (h == 0 && g < C) xr[base + g] = q_s[il * C + g];
+                        if (C == 2 || h == 0) {
 #pragma unroll
-                            for (int cc = 0; cc < C; ++cc) {
-                                xr[base + C + cc * kG + g] = Sq[c][cc][0];
-                                svql[cc * kSvRow + g] = Sq[c][cc][1];
-                                svql[cc * kSvRow + kG + g] = Sq[c][cc][2];
-                                svql[cc * kSvRow + 2 * kG + g] = Sq[c][cc][3];
+                            for (int cc = 0; cc < CQ; ++cc) {
+                                xr[base + C + (cm + cc) * kG + g] = Sq[c][cc][0];
+                                svql[(cm + cc) * kSvRow + g] = Sq[c][cc][1];
+                                svql[(cm + cc) * kSvRow + kG + g] = Sq[c][cc][2];
+                                svql[(cm + cc) * kSvRow + 2 * kG + g] = Sq[c][cc][3];
                             }
                         }
                         base += C * (1 + kG + kH);
