@@ -399,3 +399,83 @@ def test_pysis_adapter_host_logic(monkeypatch):
     assert len(calc.calls) == n + 1 and calc.calls[-1]["forces"] is False
     p.get_forces(atoms, coords + 1.0)                                         # an energy-only entry is not a forces hit
     assert len(calc.calls) == n + 2
+
+
+def test_hessian_host_logic_on_a_quadratic_surface():
+    """The finite-difference Hessian / HVP code of the calculator (displaced molecule batches, chunking, stencil weights
+    from the realised fp32 displacements, symmetrisation, batched and padded inputs) on a fake engine whose energy is the
+    quadratic form E = x^T K x / 2 per structure: every stencil is exact there, so the Hessian must come back as K."""
+    import torch
+
+    from aimnetcentral_b200.calculator import AIMNet2Calculator
+
+    n = 5
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(3 * n, 3 * n, generator=g, dtype=torch.float64)
+    K = (A + A.T) * 0.5
+
+    class FakeEngine:
+        calls = []
+
+        def eval(self, coord, numbers, charge, mol_idx=None, forces=True, **kw):
+            B = int(charge.shape[0])
+            per = coord.shape[0] // B
+            self.calls.append(B)
+            out_e, out_f = [], []
+            for b in range(B):
+                x = coord[b * per:(b + 1) * per].double().reshape(-1)
+                m = 3 * per
+                out_e.append(0.5 * x @ K[:m, :m] @ x)
+                out_f.append((-(K[:m, :m] @ x)).reshape(per, 3).float())
+            return {"energy": torch.stack(out_e), "forces": torch.cat(out_f), "charges": torch.zeros(coord.shape[0])}
+
+    calc = AIMNet2Calculator.__new__(AIMNet2Calculator)
+    calc.device, calc.engine, calc._coulomb_method = "cpu", FakeEngine(), "simple"
+    calc._num_charge_channels, calc._mult_ignored_checked = 1, True
+    calc._upload_cache, calc._validated_numbers, calc._host_cell_cache = {}, None, None
+    x = torch.randn(n, 3, generator=g).numpy().astype(np.float32) * 2.0
+    z = np.array([6, 1, 1, 8, 7])
+    data = {"coord": x, "numbers": z, "charge": 0.0}
+    for stencil in (2, 4, 6):
+        calc.hessian_stencil = stencil
+        out = calc.eval(dict(data), hessian=True, validate_species=False)
+        H = out["hessian"].double().reshape(3 * n, 3 * n)
+        assert out["hessian"].shape == (n, 3, n, 3) and torch.equal(H, H.T)
+        assert float((H - K).abs().max()) < 2e-3 * float(K.abs().max()), stencil   # fp32 force rounding / step
+    del calc.hessian_stencil
+    # stencil weights: classical coefficients on nominal nodes, exact first derivative of polynomials on perturbed ones
+    w = calc._fd_weights(torch.tensor([[1.0, -1.0, 2.0, -2.0, 3.0, -3.0]]))[0]
+    assert torch.allclose(w, torch.tensor([3 / 4, -3 / 4, -3 / 20, 3 / 20, 1 / 60, -1 / 60], dtype=torch.float64), atol=1e-12)
+    nodes = torch.tensor([[1.0003, -0.9998, 2.0001, -1.9996]], dtype=torch.float64)
+    w = calc._fd_weights(nodes)[0]
+    poly = lambda u: 0.3 + 1.7 * u - 0.4 * u ** 2 + 0.9 * u ** 3   # noqa: E731  (derivative at 0: 1.7)
+    assert abs(float((w * poly(nodes[0])).sum()) - 1.7) < 1e-9
+    # chunks of the displaced batch (here 2 components per engine call), a stacked batch, a mol_idx batch, a padded structure
+    calc.hessian_batch_atoms = 6 * n * 2
+    calc.engine.calls.clear()
+    H1 = calc.eval(dict(data), hessian=True, validate_species=False)["hessian"]
+    assert max(calc.engine.calls) == 12 and float((H1.double().reshape(3 * n, 3 * n) - K).abs().max()) < 2e-3 * float(K.abs().max())
+    del calc.hessian_batch_atoms
+    xb = np.stack([x, x * 0.5])
+    outb = calc.eval({"coord": xb, "numbers": np.stack([z, z]), "charge": np.zeros(2, np.float32)}, hessian=True, validate_species=False)
+    assert outb["hessian"].shape == (2, n, 3, n, 3) and outb["energy"].shape == (2, 1)
+    assert float((outb["hessian"][1].double().reshape(3 * n, 3 * n) - K).abs().max()) < 2e-3 * float(K.abs().max())
+    outl = calc.eval({"coord": xb.reshape(-1, 3), "numbers": np.concatenate([z, z]), "charge": np.zeros(2, np.float32),
+                      "mol_idx": np.repeat([0, 1], n)}, hessian=True, validate_species=False)
+    assert isinstance(outl["hessian"], list) and len(outl["hessian"]) == 2 and outl["hessian"][0].shape == (n, 3, n, 3)
+    pad = {"coord": np.concatenate([x[:4], np.zeros((1, 3), np.float32)])[None], "numbers": np.array([[6, 1, 1, 8, 0]]), "charge": np.zeros(1, np.float32)}
+    Hp = calc.eval(pad, hessian=True, validate_species=False)["hessian"]
+    assert Hp.shape == (5, 3, 5, 3) and not Hp[4].any() and not Hp[:, :, 4].any()
+    assert float((Hp[:4, :, :4].double().reshape(12, 12) - K[:12, :12]).abs().max()) < 2e-3 * float(K.abs().max())
+    # Hessian-vector products: one and several directions, shape errors
+    v = torch.randn(3, n, 3, generator=g)
+    hv = calc.hessian_vector_product(dict(data), v, validate_species=False)
+    want = (K @ v.double().reshape(3, -1).T).T.reshape(3, n, 3)
+    assert hv.shape == (3, n, 3) and float((hv.double() - want).abs().max()) < 5e-3 * float(want.abs().max())
+    assert calc.hessian_vector_product(dict(data), v[0], validate_species=False).shape == (n, 3)
+    with pytest.raises(ValueError):
+        calc.hessian_vector_product(dict(data), v[:, :4], validate_species=False)
+    with pytest.raises(NotImplementedError):
+        calc.hessian_vector_product({"coord": xb, "numbers": np.stack([z, z]), "charge": np.zeros(2, np.float32)}, v[0], validate_species=False)
+    with pytest.raises(NotImplementedError):
+        calc.hessian_vector_product(dict(data), v[0], create_graph=True, validate_species=False)
